@@ -1,0 +1,533 @@
+/*
+ * msg_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see msg_oracle.h).
+ *
+ * Restates, from their published algorithms, the OpenCV functions that the reference
+ * (ShayHulud/opencv-msegment, Java) reaches through org.opencv.imgproc.Imgproc:
+ *   - Imgproc.watershed            PictureService.java:909
+ *   - Imgproc.connectedComponents  PictureService.java:441-442
+ *   - colorByIndexes (Java loop)   PictureService.java:913-936
+ * and the two Imgproc functions BASELINE.json's north_star puts on the path although the
+ * reference has no call site for them:
+ *   - Imgproc.pyrMeanShiftFiltering  (+ pyrDown / pyrUp / dilate helpers)
+ *   - Imgproc.floodFill-style region growing == colour-predicate connected components
+ * Third-party dependency restated: org.openpnp:opencv:3.4.2-1 (pom.xml:39-43), not vendored
+ * under /root/reference.  Pinned against cv2 4.13.0 (tests/golden/gen_golden.py).
+ *
+ * Written for clarity, not speed: single thread, scalar.
+ */
+#include "msg_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* cvRound: round-half-to-even (SSE cvtsd2si with default MXCSR) */
+static inline int cv_round_d(double v) { return (int)lrint(v); }
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+static inline int reflect101(int p, int n)
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) {
+        if (p < 0) p = -p;
+        else p = 2 * (n - 1) - p;
+    }
+    return p;
+}
+
+/* ------------------------------------------------------------------ pyramids (App. A.3) */
+
+void orc_pyr_down_8uc3(const uint8_t* src, size_t sstep, int w, int h, uint8_t* dst, size_t dstep)
+{
+    static const int k[5] = {1, 4, 6, 4, 1};
+    int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++)
+            for (int c = 0; c < 3; c++) {
+                int acc = 0;
+                for (int a = -2; a <= 2; a++) {
+                    int yy = reflect101(2 * y + a, h);
+                    for (int b = -2; b <= 2; b++) {
+                        int xx = reflect101(2 * x + b, w);
+                        acc += k[a + 2] * k[b + 2] * src[(size_t)yy * sstep + 3 * xx + c];
+                    }
+                }
+                dst[(size_t)y * dstep + 3 * x + c] = (uint8_t)((acc + 128) >> 8);
+            }
+}
+
+/* one separable pyrUp axis: out[2i] = s[i-1] + 6 s[i] + s[i+1], out[2i+1] = 4 (s[i] + s[i+1]),
+ * s[-1] := s[1] (reflect-101), s[n] := s[n-1] (replicate).  n==1: s[-1] := s[0]. */
+static inline int up_tap(const int* s, int n, int o)
+{
+    int i = o >> 1;
+    int sm = (i - 1 >= 0) ? s[i - 1] : s[n > 1 ? 1 : 0];
+    int sp = (i + 1 < n) ? s[i + 1] : s[n - 1];
+    return (o & 1) ? 4 * (s[i] + sp) : sm + 6 * s[i] + sp;
+}
+
+void orc_pyr_up_8uc3(const uint8_t* src, size_t sstep, int w, int h, uint8_t* dst, size_t dstep, int dw, int dh)
+{
+    int* col = (int*)malloc(sizeof(int) * (size_t)(h > w ? h : w));
+    int* tmp = (int*)malloc(sizeof(int) * (size_t)dh * (size_t)w); /* vertical pass result, per channel */
+    for (int c = 0; c < 3; c++) {
+        for (int x = 0; x < w; x++) {
+            for (int y = 0; y < h; y++) col[y] = src[(size_t)y * sstep + 3 * x + c];
+            for (int oy = 0; oy < dh; oy++) tmp[(size_t)oy * w + x] = up_tap(col, h, oy);
+        }
+        for (int oy = 0; oy < dh; oy++) {
+            const int* row = tmp + (size_t)oy * w;
+            for (int ox = 0; ox < dw; ox++) {
+                int v = up_tap(row, w, ox);
+                dst[(size_t)oy * dstep + 3 * ox + c] = (uint8_t)((v + 32) >> 6);
+            }
+        }
+    }
+    free(col);
+    free(tmp);
+}
+
+/* ------------------------------------------------------------------ mean shift (App. A.2) */
+
+static inline int sq(int v) { return v * v; }
+
+static void meanshift_level(const uint8_t* S, size_t sstep, uint8_t* D, size_t dstep, int w, int h,
+                            const uint8_t* mask, float sp, int isr2, int max_count, double eps,
+                            orc_ms_counters* ct)
+{
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++) {
+            if (mask && !mask[(size_t)i * w + j]) continue;
+            int x0 = j, y0 = i;
+            int c0 = S[(size_t)i * sstep + 3 * j], c1 = S[(size_t)i * sstep + 3 * j + 1],
+                c2 = S[(size_t)i * sstep + 3 * j + 2];
+            if (ct) ct->pixels++;
+            for (int iter = 0; iter < max_count; iter++) {
+                int minx = cv_round_f((float)x0 - sp), miny = cv_round_f((float)y0 - sp);
+                int maxx = cv_round_f((float)x0 + sp), maxy = cv_round_f((float)y0 + sp);
+                if (minx < 0) minx = 0;
+                if (miny < 0) miny = 0;
+                if (maxx > w - 1) maxx = w - 1;
+                if (maxy > h - 1) maxy = h - 1;
+                int s0 = 0, s1 = 0, s2 = 0, sx = 0, sy = 0, count = 0;
+                for (int y = miny; y <= maxy; y++) {
+                    const uint8_t* p = S + (size_t)y * sstep + 3 * minx;
+                    int row_count = 0;
+                    for (int x = minx; x <= maxx; x++, p += 3) {
+                        int t0 = p[0], t1 = p[1], t2 = p[2];
+                        if (sq(t0 - c0) + sq(t1 - c1) + sq(t2 - c2) <= isr2) {
+                            s0 += t0; s1 += t1; s2 += t2; sx += x; row_count++;
+                        }
+                    }
+                    count += row_count;
+                    sy += y * row_count;
+                }
+                if (ct) {
+                    ct->iterations++;
+                    if (maxx >= minx && maxy >= miny)
+                        ct->window_tests += (uint64_t)(maxx - minx + 1) * (uint64_t)(maxy - miny + 1);
+                    ct->hits += (uint64_t)count;
+                }
+                if (count == 0) break;
+                double icount = 1.0 / count;
+                int x1 = cv_round_d(sx * icount), y1 = cv_round_d(sy * icount);
+                int n0 = cv_round_d(s0 * icount), n1 = cv_round_d(s1 * icount), n2 = cv_round_d(s2 * icount);
+                int stop = (x0 == x1 && y0 == y1) ||
+                           (double)(abs(x1 - x0) + abs(y1 - y0) + sq(n0 - c0) + sq(n1 - c1) + sq(n2 - c2)) <= eps;
+                x0 = x1; y0 = y1; c0 = n0; c1 = n1; c2 = n2;
+                if (ct) {
+                    uint64_t dr = (uint64_t)(abs(x0 - j) > abs(y0 - i) ? abs(x0 - j) : abs(y0 - i));
+                    if (dr > ct->max_drift) ct->max_drift = dr;
+                }
+                if (stop) break;
+            }
+            uint8_t* d = D + (size_t)i * dstep + 3 * j;
+            d[0] = (uint8_t)c0; d[1] = (uint8_t)c1; d[2] = (uint8_t)c2;
+        }
+}
+
+int orc_meanshift_filter(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h,
+                         double sp0, double sr, int max_level, int term_type, int max_count, double eps,
+                         orc_ms_counters* ct)
+{
+    if (max_level < 0 || max_level > 8 || !(sp0 > 0) || !(sr > 0) || w <= 0 || h <= 0) return -1;
+    if (!(term_type & ORC_TERM_COUNT)) max_count = 5;
+    if (max_count < 1) max_count = 1;
+    if (max_count > 100) max_count = 100;
+    if (!(term_type & ORC_TERM_EPS)) eps = 1.0;
+    if (eps < 0) eps = 0;
+    int isr2 = cv_round_d(sr * sr);
+    int isr22 = isr2 > 16 ? isr2 : 16;
+    if (ct) memset(ct, 0, sizeof(*ct));
+
+    uint8_t* S[9]; uint8_t* D[9]; int W[9], H[9];
+    S[0] = (uint8_t*)src; D[0] = dst; W[0] = w; H[0] = h;
+    size_t sst[9], dst_[9];
+    sst[0] = sstep; dst_[0] = dstep;
+    for (int l = 1; l <= max_level; l++) {
+        W[l] = (W[l - 1] + 1) / 2; H[l] = (H[l - 1] + 1) / 2;
+        sst[l] = dst_[l] = (size_t)3 * W[l];
+        S[l] = (uint8_t*)malloc(sst[l] * H[l]);
+        D[l] = (uint8_t*)malloc(dst_[l] * H[l]);
+        orc_pyr_down_8uc3(S[l - 1], sst[l - 1], W[l - 1], H[l - 1], S[l], sst[l]);
+    }
+    uint8_t* mask = max_level > 0 ? (uint8_t*)malloc((size_t)w * h) : NULL;
+    uint8_t* mtmp = max_level > 0 ? (uint8_t*)malloc((size_t)w * h) : NULL;
+
+    for (int l = max_level; l >= 0; l--) {
+        float sp = (float)(sp0 / (double)(1 << l));
+        if (sp < 1.f) sp = 1.f;
+        const uint8_t* m = NULL;
+        int lw = W[l], lh = H[l];
+        if (l < max_level) {
+            int w1 = W[l + 1], h1 = H[l + 1];
+            const uint8_t* P = D[l + 1]; size_t ps = dst_[l + 1];
+            orc_pyr_up_8uc3(P, ps, w1, h1, D[l], dst_[l], lw, lh);
+            memset(mtmp, 0, (size_t)lw * lh);
+            for (int i = 1; i < h1 - 1; i++)
+                for (int j = 1; j < w1 - 1; j++) {
+                    const uint8_t* c = P + (size_t)i * ps + 3 * j;
+                    int flag = 0;
+                    for (int dy = -1; dy <= 1; dy++)
+                        for (int dx = -1; dx <= 1; dx++) {
+                            if (!dx && !dy) continue;
+                            const uint8_t* n = P + (size_t)(i + dy) * ps + 3 * (j + dx);
+                            if (sq(c[0] - n[0]) + sq(c[1] - n[1]) + sq(c[2] - n[2]) >= isr22) flag = 1;
+                        }
+                    int my = 2 * i + 1, mx = 2 * j - 1; /* empirical, exact vs cv2 */
+                    if (my < lh && mx < lw) mtmp[(size_t)my * lw + mx] = (uint8_t)flag;
+                }
+            /* dilate 3x3, outside = absent */
+            for (int y = 0; y < lh; y++)
+                for (int x = 0; x < lw; x++) {
+                    uint8_t v = 0;
+                    for (int dy = -1; dy <= 1; dy++)
+                        for (int dx = -1; dx <= 1; dx++) {
+                            int yy = y + dy, xx = x + dx;
+                            if (yy < 0 || yy >= lh || xx < 0 || xx >= lw) continue;
+                            if (mtmp[(size_t)yy * lw + xx]) v = 1;
+                        }
+                    mask[(size_t)y * lw + x] = v;
+                }
+            m = mask;
+        }
+        meanshift_level(S[l], sst[l], D[l], dst_[l], lw, lh, m, sp, isr2, max_count, eps, ct);
+    }
+    for (int l = 1; l <= max_level; l++) { free(S[l]); free(D[l]); }
+    free(mask); free(mtmp);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ union-find labelling (App. A.4) */
+
+static int32_t uf_find(int32_t* p, int32_t a)
+{
+    int32_t r = a;
+    while (p[r] != r) r = p[r];
+    while (p[a] != r) { int32_t n = p[a]; p[a] = r; a = n; }
+    return r;
+}
+static void uf_union(int32_t* p, int32_t a, int32_t b)
+{
+    a = uf_find(p, a); b = uf_find(p, b);
+    if (a < b) p[b] = a; else if (b < a) p[a] = b;
+}
+
+static inline int color_close(const uint8_t* a, const uint8_t* b, int d)
+{
+    return abs(a[0] - b[0]) <= d && abs(a[1] - b[1]) <= d && abs(a[2] - b[2]) <= d;
+}
+
+int32_t orc_relabel_canonical(int32_t* labels, size_t lstep, int w, int h)
+{
+    /* map arbitrary positive labels -> 1.. in raster order of first occurrence */
+    int32_t maxl = 0;
+    for (int y = 0; y < h; y++) {
+        const int32_t* r = (const int32_t*)((const char*)labels + (size_t)y * lstep);
+        for (int x = 0; x < w; x++) if (r[x] > maxl) maxl = r[x];
+    }
+    int32_t* map = (int32_t*)calloc((size_t)maxl + 1, sizeof(int32_t));
+    int32_t n = 0;
+    for (int y = 0; y < h; y++) {
+        int32_t* r = (int32_t*)((char*)labels + (size_t)y * lstep);
+        for (int x = 0; x < w; x++)
+            if (r[x] > 0) {
+                if (!map[r[x]]) map[r[x]] = ++n;
+                r[x] = map[r[x]];
+            }
+    }
+    free(map);
+    return n;
+}
+
+int32_t orc_label_regions(const uint8_t* bgr, size_t step, int32_t* labels, size_t lstep, int w, int h, int d)
+{
+    size_t n = (size_t)w * h;
+    int32_t* p = (int32_t*)malloc(n * sizeof(int32_t));
+    for (size_t i = 0; i < n; i++) p[i] = (int32_t)i;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* c = bgr + (size_t)y * step + 3 * x;
+            if (x > 0 && color_close(c, c - 3, d)) uf_union(p, y * w + x, y * w + x - 1);
+            if (y > 0 && color_close(c, c - step, d)) uf_union(p, y * w + x, (y - 1) * w + x);
+        }
+    for (int y = 0; y < h; y++) {
+        int32_t* r = (int32_t*)((char*)labels + (size_t)y * lstep);
+        for (int x = 0; x < w; x++) r[x] = uf_find(p, y * w + x) + 1;
+    }
+    free(p);
+    return orc_relabel_canonical(labels, lstep, w, h);
+}
+
+int32_t orc_connected_components(const uint8_t* mask, size_t step, int32_t* labels, size_t lstep, int w, int h,
+                                 int connectivity)
+{
+    size_t n = (size_t)w * h;
+    int32_t* p = (int32_t*)malloc(n * sizeof(int32_t));
+    for (size_t i = 0; i < n; i++) p[i] = (int32_t)i;
+#define FG(yy, xx) (mask[(size_t)(yy) * step + (xx)] != 0)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            if (!FG(y, x)) continue;
+            if (x > 0 && FG(y, x - 1)) uf_union(p, y * w + x, y * w + x - 1);
+            if (y > 0 && FG(y - 1, x)) uf_union(p, y * w + x, (y - 1) * w + x);
+            if (connectivity == 8 && y > 0) {
+                if (x > 0 && FG(y - 1, x - 1)) uf_union(p, y * w + x, (y - 1) * w + x - 1);
+                if (x < w - 1 && FG(y - 1, x + 1)) uf_union(p, y * w + x, (y - 1) * w + x + 1);
+            }
+        }
+    for (int y = 0; y < h; y++) {
+        int32_t* r = (int32_t*)((char*)labels + (size_t)y * lstep);
+        for (int x = 0; x < w; x++) r[x] = FG(y, x) ? uf_find(p, y * w + x) + 1 : 0;
+    }
+#undef FG
+    free(p);
+    return orc_relabel_canonical(labels, lstep, w, h) + 1;
+}
+
+/* ------------------------------------------------------------------ region merge (self-defined spec)
+ *
+ * Regions = sets of pixels with equal positive label.  Per round:
+ *   area[L], sum_c[L] (c = B,G,R);  mean_c[L] = floor((2*sum_c + area) / (2*area))   (0..255)
+ *   dist2(L,Q) = sum_c (mean_c[L] - mean_c[Q])^2
+ *   every *participating* region L selects, among the regions Q != L 4-adjacent to it, the one with the
+ *   lexicographically smallest key (dist2(L,Q), Q); the selection is *accepted* if dist2 <= limit.
+ *   All accepted selections are united simultaneously; a united component takes its smallest member label.
+ * Phase A (color_dist > 0): every region participates, limit = color_dist^2; rounds until no selection is
+ *   accepted (at most ORC_MERGE_MAX_ROUNDS).
+ * Phase B (min_size > 0): regions with area < min_size participate, limit = +inf; rounds until no region
+ *   participates-with-a-neighbour (at most ORC_MERGE_MAX_ROUNDS).
+ * Finally labels are renumbered canonically (raster order of first pixel).
+ */
+#define ORC_MERGE_MAX_ROUNDS 64
+
+static int merge_round(const uint8_t* bgr, size_t step, int32_t* labels, size_t lstep, int w, int h,
+                       int32_t maxl, int64_t size_thr, int64_t dist_limit)
+{
+    size_t nl = (size_t)maxl + 1;
+    int64_t* area = (int64_t*)calloc(nl, sizeof(int64_t));
+    int64_t* sum = (int64_t*)calloc(nl * 3, sizeof(int64_t));
+    int32_t* mean = (int32_t*)calloc(nl * 3, sizeof(int32_t));
+    uint64_t* best = (uint64_t*)malloc(nl * sizeof(uint64_t));
+    int32_t* par = (int32_t*)malloc(nl * sizeof(int32_t));
+    for (size_t i = 0; i < nl; i++) { best[i] = ~(uint64_t)0; par[i] = (int32_t)i; }
+#define LAB(yy, xx) (((const int32_t*)((const char*)labels + (size_t)(yy) * lstep))[xx])
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int32_t L = LAB(y, x);
+            if (L <= 0) continue;
+            const uint8_t* c = bgr + (size_t)y * step + 3 * x;
+            area[L]++; sum[3 * L] += c[0]; sum[3 * L + 1] += c[1]; sum[3 * L + 2] += c[2];
+        }
+    for (size_t L = 1; L < nl; L++)
+        if (area[L] > 0)
+            for (int c = 0; c < 3; c++) mean[3 * L + c] = (int32_t)((2 * sum[3 * L + c] + area[L]) / (2 * area[L]));
+    static const int dx4[4] = {-1, 1, 0, 0}, dy4[4] = {0, 0, -1, 1};
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int32_t L = LAB(y, x);
+            if (L <= 0 || area[L] >= size_thr) continue;
+            for (int k = 0; k < 4; k++) {
+                int xx = x + dx4[k], yy = y + dy4[k];
+                if (xx < 0 || yy < 0 || xx >= w || yy >= h) continue;
+                int32_t Q = LAB(yy, xx);
+                if (Q <= 0 || Q == L) continue;
+                uint64_t d2 = (uint64_t)(sq(mean[3 * L] - mean[3 * Q]) + sq(mean[3 * L + 1] - mean[3 * Q + 1]) +
+                                         sq(mean[3 * L + 2] - mean[3 * Q + 2]));
+                uint64_t key = (d2 << 32) | (uint32_t)Q;
+                if (key < best[L]) best[L] = key;
+            }
+        }
+    int accepted = 0;
+    for (size_t L = 1; L < nl; L++) {
+        if (best[L] == ~(uint64_t)0) continue;
+        int64_t d2 = (int64_t)(best[L] >> 32);
+        if (d2 > dist_limit) continue;
+        uf_union(par, (int32_t)L, (int32_t)(best[L] & 0xffffffffu));
+        accepted++;
+    }
+    if (accepted)
+        for (int y = 0; y < h; y++) {
+            int32_t* r = (int32_t*)((char*)labels + (size_t)y * lstep);
+            for (int x = 0; x < w; x++)
+                if (r[x] > 0) r[x] = uf_find(par, r[x]);
+        }
+#undef LAB
+    free(area); free(sum); free(mean); free(best); free(par);
+    return accepted;
+}
+
+int32_t orc_merge_regions(const uint8_t* bgr, size_t step, int32_t* labels, size_t lstep, int w, int h,
+                          int min_size, int color_dist)
+{
+    int32_t maxl = 0;
+    for (int y = 0; y < h; y++) {
+        const int32_t* r = (const int32_t*)((const char*)labels + (size_t)y * lstep);
+        for (int x = 0; x < w; x++) if (r[x] > maxl) maxl = r[x];
+    }
+    const int64_t INF = (int64_t)1 << 40;
+    if (color_dist > 0)
+        for (int r = 0; r < ORC_MERGE_MAX_ROUNDS; r++)
+            if (!merge_round(bgr, step, labels, lstep, w, h, maxl, INF, (int64_t)color_dist * color_dist)) break;
+    if (min_size > 0)
+        for (int r = 0; r < ORC_MERGE_MAX_ROUNDS; r++)
+            if (!merge_round(bgr, step, labels, lstep, w, h, maxl, (int64_t)min_size, INF)) break;
+    return orc_relabel_canonical(labels, lstep, w, h);
+}
+
+/* ------------------------------------------------------------------ render (PictureService.java:913-936) */
+
+void orc_render_labels(const int32_t* labels, size_t lstep, uint8_t* dst, size_t dstep, int w, int h, int depth,
+                       const uint8_t* colors_bgr)
+{
+    for (int y = 0; y < h; y++) {
+        const int32_t* r = (const int32_t*)((const char*)labels + (size_t)y * lstep);
+        uint8_t* d = dst + (size_t)y * dstep;
+        for (int x = 0; x < w; x++) {
+            int32_t L = r[x];
+            if (L > 0 && L <= depth) {
+                if (colors_bgr) { d[3 * x] = colors_bgr[3 * (L - 1)]; d[3 * x + 1] = colors_bgr[3 * (L - 1) + 1]; d[3 * x + 2] = colors_bgr[3 * (L - 1) + 2]; }
+                else d[3 * x] = d[3 * x + 1] = d[3 * x + 2] = 255;
+            } else d[3 * x] = d[3 * x + 1] = d[3 * x + 2] = 0;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ watershed (App. A.1) */
+
+void orc_watershed(const uint8_t* bgr, size_t step, int32_t* markers, size_t mstep, int w, int h)
+{
+    enum { IN_QUEUE = -2, WSHED = -1 };
+    size_t n = (size_t)w * h;
+    int32_t* next = (int32_t*)malloc(n * sizeof(int32_t));
+    int32_t head[256], tail[256];
+    for (int i = 0; i < 256; i++) head[i] = tail[i] = -1;
+#define M(yy, xx) (((int32_t*)((char*)markers + (size_t)(yy) * mstep))[xx])
+#define PIX(yy, xx) (bgr + (size_t)(yy) * step + 3 * (xx))
+#define PUSH(q, pos) do { next[pos] = -1; if (tail[q] < 0) head[q] = pos; else next[tail[q]] = pos; tail[q] = pos; } while (0)
+    if (w < 1 || h < 1) { free(next); return; }
+    for (int x = 0; x < w; x++) { M(0, x) = WSHED; M(h - 1, x) = WSHED; }
+    static const int dxs[4] = {-1, 1, 0, 0}, dys[4] = {0, 0, -1, 1};
+    for (int i = 1; i < h - 1; i++) {
+        M(i, 0) = WSHED; M(i, w - 1) = WSHED;
+        for (int j = 1; j < w - 1; j++) {
+            if (M(i, j) < 0) M(i, j) = 0;
+            if (M(i, j) != 0) continue;
+            int idx = 256;
+            for (int k = 0; k < 4; k++) {
+                int yy = i + dys[k], xx = j + dxs[k];
+                if (M(yy, xx) > 0) {
+                    const uint8_t *a = PIX(i, j), *b = PIX(yy, xx);
+                    int d0 = abs(a[0] - b[0]), d1 = abs(a[1] - b[1]), d2 = abs(a[2] - b[2]);
+                    int t = d0 > d1 ? d0 : d1; if (d2 > t) t = d2;
+                    if (t < idx) idx = t;
+                }
+            }
+            if (idx < 256) { PUSH(idx, i * w + j); M(i, j) = IN_QUEUE; }
+        }
+    }
+    int active = 0;
+    while (active < 256 && head[active] < 0) active++;
+    if (active == 256) { free(next); return; }
+    for (;;) {
+        if (head[active] < 0) {
+            while (active < 256 && head[active] < 0) active++;
+            if (active == 256) break;
+        }
+        int pos = head[active];
+        head[active] = next[pos];
+        if (head[active] < 0) tail[active] = -1;
+        int i = pos / w, j = pos % w;
+        int lab = 0;
+        for (int k = 0; k < 4; k++) {
+            int t = M(i + dys[k], j + dxs[k]);
+            if (t > 0) { if (lab == 0) lab = t; else if (t != lab) lab = WSHED; }
+        }
+        M(i, j) = lab;
+        if (lab == WSHED) continue;
+        for (int k = 0; k < 4; k++) {
+            int yy = i + dys[k], xx = j + dxs[k];
+            if (M(yy, xx) == 0) {
+                const uint8_t *a = PIX(i, j), *b = PIX(yy, xx);
+                int d0 = abs(a[0] - b[0]), d1 = abs(a[1] - b[1]), d2 = abs(a[2] - b[2]);
+                int t = d0 > d1 ? d0 : d1; if (d2 > t) t = d2;
+                PUSH(t, yy * w + xx);
+                if (t < active) active = t;
+                M(yy, xx) = IN_QUEUE;
+            }
+        }
+    }
+#undef M
+#undef PIX
+#undef PUSH
+    free(next);
+}
+
+/* ------------------------------------------------------------------ synthetic image */
+
+static inline uint64_t splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline uint64_t synth_hash(uint64_t seedmix, uint32_t a, uint32_t b, uint32_t c)
+{
+    return splitmix64(seedmix ^ (((uint64_t)a << 40) | ((uint64_t)b << 16) | (uint64_t)c));
+}
+
+void orc_synth_bgr(uint8_t* dst, size_t step, int w, int h, uint64_t seed)
+{
+    uint64_t sm = splitmix64(seed);
+    int ncx = (w + 63) / 64, ncy = (h + 63) / 64;
+    int* sxs = (int*)malloc(sizeof(int) * (size_t)ncx * ncy);
+    int* sys = (int*)malloc(sizeof(int) * (size_t)ncx * ncy);
+    uint32_t* col = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)ncx * ncy);
+    for (int cy = 0; cy < ncy; cy++)
+        for (int cx = 0; cx < ncx; cx++) {
+            sxs[cy * ncx + cx] = 64 * cx + (int)(synth_hash(sm, (uint32_t)cx, (uint32_t)cy, 0) % 64);
+            sys[cy * ncx + cx] = 64 * cy + (int)(synth_hash(sm, (uint32_t)cx, (uint32_t)cy, 1) % 64);
+            col[cy * ncx + cx] = (uint32_t)(synth_hash(sm, (uint32_t)cx, (uint32_t)cy, 2) & 0xFFFFFFu);
+        }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int cx0 = x / 64, cy0 = y / 64;
+            long best = -1; uint32_t bc = 0;
+            for (int cy = cy0 - 1; cy <= cy0 + 1; cy++)
+                for (int cx = cx0 - 1; cx <= cx0 + 1; cx++) {
+                    if (cx < 0 || cy < 0 || cx >= ncx || cy >= ncy) continue;
+                    long ddx = x - sxs[cy * ncx + cx], ddy = y - sys[cy * ncx + cx];
+                    long d = ddx * ddx + ddy * ddy;
+                    if (best < 0 || d < best) { best = d; bc = col[cy * ncx + cx]; }
+                }
+            for (int c = 0; c < 3; c++) {
+                int base = (int)((bc >> (8 * c)) & 0xFF);
+                int nz = (int)(synth_hash(sm, (uint32_t)x, (uint32_t)y, 16u + (uint32_t)c) % 13) +
+                         (int)(synth_hash(sm, (uint32_t)x, (uint32_t)y, 32u + (uint32_t)c) % 13) - 12;
+                int v = base + nz;
+                dst[(size_t)y * step + 3 * x + c] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+            }
+        }
+    free(sxs); free(sys); free(col);
+}

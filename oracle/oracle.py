@@ -1,0 +1,155 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE ONLY -- see oracle/msg_oracle.h).
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs.  Nothing under ``opencv-msegment_b200/`` may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmsg_oracle.so")
+
+TERM_COUNT = 1
+TERM_EPS = 2
+
+
+class MsCounters(C.Structure):
+    _fields_ = [("window_tests", C.c_uint64), ("hits", C.c_uint64), ("iterations", C.c_uint64),
+                ("pixels", C.c_uint64), ("max_drift", C.c_uint64)]
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "msg_oracle.c")
+    if (force or not os.path.exists(_LIB_PATH)
+            or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(src[:-2] + ".h"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libmsg_oracle.so"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p, i32p, sz, i, d = C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double
+        L.orc_pyr_down_8uc3.argtypes = [u8p, sz, i, i, u8p, sz]
+        L.orc_pyr_up_8uc3.argtypes = [u8p, sz, i, i, u8p, sz, i, i]
+        L.orc_meanshift_filter.argtypes = [u8p, sz, u8p, sz, i, i, d, d, i, i, i, d, C.POINTER(MsCounters)]
+        L.orc_meanshift_filter.restype = i
+        L.orc_label_regions.argtypes = [u8p, sz, i32p, sz, i, i, i]
+        L.orc_label_regions.restype = C.c_int32
+        L.orc_connected_components.argtypes = [u8p, sz, i32p, sz, i, i, i]
+        L.orc_connected_components.restype = C.c_int32
+        L.orc_relabel_canonical.argtypes = [i32p, sz, i, i]
+        L.orc_relabel_canonical.restype = C.c_int32
+        L.orc_merge_regions.argtypes = [u8p, sz, i32p, sz, i, i, i, i]
+        L.orc_merge_regions.restype = C.c_int32
+        L.orc_render_labels.argtypes = [i32p, sz, u8p, sz, i, i, i, u8p]
+        L.orc_watershed.argtypes = [u8p, sz, i32p, sz, i, i]
+        L.orc_synth_bgr.argtypes = [u8p, sz, i, i, C.c_uint64]
+        _lib = L
+    return _lib
+
+
+def _img(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 3
+    return a
+
+
+def pyr_down(src):
+    src = _img(src)
+    h, w = src.shape[:2]
+    dst = np.empty(((h + 1) // 2, (w + 1) // 2, 3), np.uint8)
+    lib().orc_pyr_down_8uc3(src.ctypes.data, src.strides[0], w, h, dst.ctypes.data, dst.strides[0])
+    return dst
+
+
+def pyr_up(src, dsize=None):
+    src = _img(src)
+    h, w = src.shape[:2]
+    dw, dh = dsize if dsize is not None else (2 * w, 2 * h)
+    dst = np.empty((dh, dw, 3), np.uint8)
+    lib().orc_pyr_up_8uc3(src.ctypes.data, src.strides[0], w, h, dst.ctypes.data, dst.strides[0], dw, dh)
+    return dst
+
+
+def meanshift_filter(src, sp, sr, max_level=1, term=(TERM_COUNT | TERM_EPS, 5, 1.0), counters=False):
+    src = _img(src)
+    h, w = src.shape[:2]
+    dst = np.empty_like(src)
+    ct = MsCounters()
+    rc = lib().orc_meanshift_filter(src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h,
+                                    float(sp), float(sr), int(max_level), int(term[0]), int(term[1]),
+                                    float(term[2]), C.byref(ct))
+    if rc != 0:
+        raise ValueError("orc_meanshift_filter: invalid arguments")
+    if counters:
+        return dst, {k: getattr(ct, k) for k, _ in MsCounters._fields_}
+    return dst
+
+
+def label_regions(bgr, d=2):
+    bgr = _img(bgr)
+    h, w = bgr.shape[:2]
+    lab = np.empty((h, w), np.int32)
+    n = lib().orc_label_regions(bgr.ctypes.data, bgr.strides[0], lab.ctypes.data, lab.strides[0], w, h, int(d))
+    return n, lab
+
+
+def connected_components(mask, connectivity=8):
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    h, w = mask.shape
+    lab = np.empty((h, w), np.int32)
+    n = lib().orc_connected_components(mask.ctypes.data, mask.strides[0], lab.ctypes.data, lab.strides[0], w, h,
+                                       int(connectivity))
+    return n, lab
+
+
+def relabel_canonical(labels):
+    lab = np.ascontiguousarray(labels, dtype=np.int32).copy()
+    h, w = lab.shape
+    n = lib().orc_relabel_canonical(lab.ctypes.data, lab.strides[0], w, h)
+    return n, lab
+
+
+def merge_regions(bgr, labels, min_size, color_dist):
+    bgr = _img(bgr)
+    lab = np.ascontiguousarray(labels, dtype=np.int32).copy()
+    h, w = lab.shape
+    n = lib().orc_merge_regions(bgr.ctypes.data, bgr.strides[0], lab.ctypes.data, lab.strides[0], w, h,
+                                int(min_size), int(color_dist))
+    return n, lab
+
+
+def render_labels(labels, depth, colors=None):
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    h, w = lab.shape
+    dst = np.empty((h, w, 3), np.uint8)
+    cptr = None
+    if colors is not None:
+        colors = np.ascontiguousarray(colors, dtype=np.uint8)
+        assert colors.shape == (depth, 3)
+        cptr = colors.ctypes.data
+    lib().orc_render_labels(lab.ctypes.data, lab.strides[0], dst.ctypes.data, dst.strides[0], w, h, int(depth), cptr)
+    return dst
+
+
+def watershed(bgr, markers):
+    bgr = _img(bgr)
+    m = np.ascontiguousarray(markers, dtype=np.int32).copy()
+    h, w = m.shape
+    lib().orc_watershed(bgr.ctypes.data, bgr.strides[0], m.ctypes.data, m.strides[0], w, h)
+    return m
+
+
+def synth_bgr(w, h, seed):
+    dst = np.empty((h, w, 3), np.uint8)
+    lib().orc_synth_bgr(dst.ctypes.data, dst.strides[0], w, h, int(seed))
+    return dst
