@@ -1,0 +1,207 @@
+/*
+ * msegment.h -- C ABI of libmsegment_b200.so: the B200-native (sm_100a CUDA) segmentation hot path
+ * behind the OpenCV `Imgproc` calls that ShayHulud/opencv-msegment drives through OpenCV's Java
+ * bindings.  Plain C: pointers, sizes, ints and doubles only, so that JNI, Panama FFI, ctypes and
+ * cffi bind it directly (INTEGRATION.md shows the Java side).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference; the JNI layer itself is the
+ * un-vendored org.openpnp:opencv:3.4.2-1, pom.xml:39-43):
+ *   Imgproc.connectedComponents(mask, markers, 8, CV_32S)
+ *        src/main/java/ru/shayhulud/opencvcmsegment/service/PictureService.java:441-442
+ *        -> msg_connected_components
+ *   PictureService.colorByIndexes(markers, depth, colored)         PictureService.java:913-936
+ *        -> msg_render_labels
+ *   Imgproc.pyrMeanShiftFiltering(src, dst, sp, sr[, maxLevel, termcrit])   (no call site in the
+ *        reference; named by BASELINE.json north_star subsystem 1)   -> msg_meanshift_filter
+ *   Imgproc.floodFill(...) region-growing loop (north_star subsystem 2; canonical use: OpenCV
+ *        samples/cpp/meanshift_segmentation.cpp)                     -> msg_label_regions
+ *   colour-distance + min-size region merge (north_star subsystem 2, self-defined spec in
+ *        DESIGN.md "K2b")                                            -> msg_merge_regions
+ * The CLI contract of App.main (App.java:14-31: input folder, output root, file name) is kept by
+ * the host program on top of this ABI (opencv-msegment_b200/host).
+ *
+ * Conventions
+ *   - every function returns MSG_OK (0) or a negative msg_status; the message of the last failure
+ *     of a context is msg_last_error(ctx).  Nothing aborts or throws across the ABI.
+ *   - images are row-major with a row step in BYTES (cv::Mat::step): 8UC3 BGR interleaved,
+ *     8UC1 masks, 32SC1 labels.  The caller owns all buffers; the library never retains them
+ *     past the call (or past msg_wait for submitted work).
+ *   - a msg_ctx is bound to one CUDA device and is NOT thread-safe; use one per thread / GPU.
+ *   - there is no CPU fallback: without a CUDA device msg_create fails with MSG_ECUDA.
+ */
+#ifndef MSEGMENT_H
+#define MSEGMENT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSG_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define MSG_API __attribute__((visibility("default")))
+#else
+#define MSG_API
+#endif
+
+typedef enum msg_status {
+    MSG_OK = 0,
+    MSG_EINVAL = -1,  /* bad argument (mirrors OpenCV's CV_Assert failures -> CvException) */
+    MSG_ECUDA = -2,   /* CUDA runtime / driver error (sticky per context) */
+    MSG_ENOMEM = -3,  /* host or device allocation failed */
+    MSG_ESTATE = -4   /* call sequence error (bad ticket, ...) */
+} msg_status;
+
+/* cv::TermCriteria type bits */
+#define MSG_TERM_COUNT 1
+#define MSG_TERM_EPS 2
+
+typedef struct msg_ctx msg_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+MSG_API int msg_version(void);
+MSG_API int msg_device_count(void);                       /* number of CUDA devices, 0 if none / error */
+MSG_API int msg_create(int device, msg_ctx** out);
+MSG_API void msg_destroy(msg_ctx* ctx);
+MSG_API const char* msg_last_error(const msg_ctx* ctx);   /* ctx may be NULL: last msg_create error */
+/* Use an externally owned cudaStream_t for all work of this context (NULL = the context's own). */
+MSG_API int msg_set_stream(msg_ctx* ctx, void* cuda_stream);
+MSG_API int msg_synchronize(msg_ctx* ctx);
+
+/* ---- drop-in operators on HOST buffers (synchronous; staging + H2D/D2H inside) ---------- */
+
+/* Imgproc.pyrMeanShiftFiltering.  src/dst 8UC3 (dst may equal src).  OpenCV rules: max_level in
+ * [0,8]; term_type without COUNT -> max_count=5, clamp to [1,100]; without EPS -> eps=1; eps>=0.
+ * Java's 4-argument overload = (max_level=1, term_type=COUNT|EPS, max_count=5, eps=1). */
+MSG_API int msg_meanshift_filter(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, uint8_t* dst_bgr,
+                         size_t dst_step, int width, int height, double sp, double sr, int max_level,
+                         int term_type, int max_count, double eps);
+
+/* floodFill-style region growing over the whole image: regions = connected components of
+ * "4-adjacent and per-channel |delta| <= lo_diff"; lo_diff must equal up_diff (asymmetric ranges make
+ * floodFill order dependent -> MSG_EINVAL); connectivity must be 4.  labels 32SC1, numbered 1..n in
+ * raster order of each region's first pixel (== the floodFill loop's numbering). */
+MSG_API int msg_label_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* labels, size_t labels_step,
+                      int width, int height, int lo_diff, int up_diff, int connectivity,
+                      int32_t* n_regions);
+
+/* Region merge on (image, labels): colour fuse (color_dist > 0) then min-size prune (min_size > 0);
+ * labels in/out, renumbered canonically.  Labels <= 0 are left untouched. */
+MSG_API int msg_merge_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* labels, size_t labels_step,
+                      int width, int height, int min_size, int color_dist, int32_t* n_regions);
+
+/* Imgproc.connectedComponents(image 8UC1, labels 32SC1, connectivity 4|8, CV_32S).
+ * n_labels = number of labels including background 0 (OpenCV's return value).  Foreground labels
+ * are numbered 1.. in raster order of first pixel (OpenCV's numbering is implementation defined). */
+MSG_API int msg_connected_components(msg_ctx* ctx, const uint8_t* mask, size_t step, int32_t* labels,
+                             size_t labels_step, int width, int height, int connectivity,
+                             int32_t* n_labels);
+
+/* PictureService.colorByIndexes: dst(8UC3) = (0 < label <= depth) ? colors[label-1] : (0,0,0);
+ * colors_bgr = depth*3 bytes, or NULL for all white (the CLI path, colored=false). */
+MSG_API int msg_render_labels(msg_ctx* ctx, const int32_t* labels, size_t labels_step, uint8_t* dst_bgr,
+                      size_t dst_step, int width, int height, int depth, const uint8_t* colors_bgr);
+
+/* ---- fused pipeline: filter -> label -> merge -> render, intermediates stay in HBM -------- */
+typedef struct msg_segment_params {
+    double sp, sr;
+    int max_level, term_type, max_count;
+    double eps;
+    int lo_diff;      /* label stage; < 0 skips labelling (filter only) */
+    int min_size;     /* merge stage; 0 with color_dist 0 skips it      */
+    int color_dist;
+    int render_depth; /* > 0: render with that depth; 0: depth = n_regions; < 0: skip */
+} msg_segment_params;
+
+MSG_API void msg_segment_params_default(msg_segment_params* p); /* sp=sr=10, L1, (3,5,1), lo=2, no merge */
+
+/* Any output pointer may be NULL (that product is then not downloaded). */
+MSG_API int msg_segment(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, int width, int height,
+                const msg_segment_params* params, uint8_t* filtered_bgr, size_t filtered_step,
+                int32_t* labels, size_t labels_step, uint8_t* rendered_bgr, size_t rendered_step,
+                int32_t* n_regions);
+
+/* ---- asynchronous batch interface (stream ordered within a context) ----------------------- */
+/* Buffers must stay valid until msg_wait(ticket); host buffers from msg_alloc_pinned make the
+ * copies truly asynchronous.  Up to MSG_MAX_INFLIGHT submissions may be pending per context. */
+#define MSG_MAX_INFLIGHT 4
+MSG_API int msg_submit_segment(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, int width, int height,
+                       const msg_segment_params* params, uint8_t* filtered_bgr, size_t filtered_step,
+                       int32_t* labels, size_t labels_step, uint8_t* rendered_bgr, size_t rendered_step,
+                       int* ticket);
+MSG_API int msg_wait(msg_ctx* ctx, int ticket, int32_t* n_regions);
+
+MSG_API void* msg_alloc_pinned(size_t bytes);
+MSG_API void msg_free_pinned(void* p);
+
+/* ---- device-resident interface (pointers are CUDA device pointers on the context's device;
+ *      work is enqueued on the context's stream and NOT synchronised) ------------------------ */
+MSG_API int msg_meanshift_filter_dev(msg_ctx* ctx, const uint8_t* d_src_bgr, size_t src_step, uint8_t* d_dst_bgr,
+                             size_t dst_step, int width, int height, double sp, double sr, int max_level,
+                             int term_type, int max_count, double eps);
+/* d_n_regions: device int32 (may be NULL). */
+MSG_API int msg_label_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32_t* d_labels,
+                          size_t labels_step, int width, int height, int lo_diff, int32_t* d_n_regions);
+MSG_API int msg_connected_components_dev(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int32_t* d_labels,
+                                 size_t labels_step, int width, int height, int connectivity,
+                                 int32_t* d_n_labels);
+/* merge iterates to a fixed point, so it synchronises the stream internally. */
+MSG_API int msg_merge_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32_t* d_labels,
+                          size_t labels_step, int width, int height, int min_size, int color_dist,
+                          int32_t* d_n_regions);
+MSG_API int msg_render_labels_dev(msg_ctx* ctx, const int32_t* d_labels, size_t labels_step, uint8_t* d_dst_bgr,
+                          size_t dst_step, int width, int height, int depth, const uint8_t* d_colors_bgr);
+/* Deterministic synthetic test image generated on the device. */
+MSG_API int msg_synth_bgr_dev(msg_ctx* ctx, uint8_t* d_dst_bgr, size_t step, int width, int height, uint64_t seed);
+
+/* ---- strip sharding support (one very large image over several GPUs; DESIGN.md "multi-GPU") */
+/* Mean-shift filter of rows [row0,row1) of a width x full_height image, given device rows
+ * [halo_row0, halo_row1) of the source (halo_row0 <= row0 < row1 <= halo_row1).  Coordinates are
+ * global, so the result is bit-identical to the same rows of the unsharded call provided the halo
+ * is wide enough: msg_meanshift_halo_rows().  row0 and halo_row0 must be multiples of
+ * 2^max_level.  Output: rows [row0,row1) at d_dst_bgr (row 0 of the buffer = row0). */
+MSG_API int msg_meanshift_halo_rows(double sp, int max_level, int term_type, int max_count);
+MSG_API int msg_meanshift_filter_strip_dev(msg_ctx* ctx, const uint8_t* d_src_rows, size_t src_step,
+                                   int halo_row0, int halo_row1, uint8_t* d_dst_bgr, size_t dst_step,
+                                   int width, int full_height, int row0, int row1, double sp, double sr,
+                                   int max_level, int term_type, int max_count, double eps);
+/* Labels of a strip with GLOBAL provisional labels (1 + global linear index of the component's
+ * first pixel inside the strip); seams are resolved by msg_seam_pairs_dev + msg_apply_label_map_dev. */
+MSG_API int msg_label_strip_dev(msg_ctx* ctx, const uint8_t* d_bgr_rows, size_t step, int32_t* d_labels,
+                        size_t labels_step, int width, int rows, int row0, int full_width, int lo_diff);
+/* Equivalence pairs across one seam: upper strip's last row vs lower strip's first row.
+ * Writes up to `width` (labelA,labelB) pairs to d_pairs (2*width int32), count to d_count. */
+MSG_API int msg_seam_pairs_dev(msg_ctx* ctx, const uint8_t* d_upper_row_bgr, const int32_t* d_upper_row_labels,
+                       const uint8_t* d_lower_row_bgr, const int32_t* d_lower_row_labels, int width,
+                       int lo_diff, int32_t* d_pairs, int32_t* d_count);
+/* labels[p] = map(labels[p]) where map is given as sorted (from,to) pairs (binary search). */
+MSG_API int msg_apply_label_map_dev(msg_ctx* ctx, int32_t* d_labels, size_t labels_step, int width, int rows,
+                            const int32_t* d_from_sorted, const int32_t* d_to, int n_map);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+typedef struct msg_timings { /* milliseconds of the last host-buffer call, CUDA events */
+    float h2d_ms, filter_ms, label_ms, merge_ms, render_ms, d2h_ms, total_ms;
+} msg_timings;
+MSG_API int msg_get_timings(msg_ctx* ctx, msg_timings* out);
+
+typedef struct msg_stats {
+    uint64_t kernel_launches;     /* kernels of this library launched by this context so far */
+    uint64_t ms_overflow_items;   /* mean-shift items that left their staged tile (slow path), last call */
+    uint64_t ms_active_items;     /* mean-shift pixels processed (all levels), last call */
+    uint64_t merge_rounds;        /* rounds of the last merge call */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes copied by host-buffer calls so far */
+} msg_stats;
+MSG_API int msg_get_stats(msg_ctx* ctx, msg_stats* out);
+
+/* Debug: copy pyramid plane (kind 0 = source S[level], 1 = result D[level]) of the last filter call
+ * to a host BGRX buffer (4 bytes/pixel, dense).  Writes its size to *w,*h. */
+MSG_API int msg_debug_get_plane(msg_ctx* ctx, int kind, int level, uint32_t* host_out, size_t capacity_pixels,
+                        int* w, int* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSEGMENT_H */

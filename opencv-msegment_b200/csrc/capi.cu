@@ -1,0 +1,775 @@
+// capi.cu -- the C ABI of libmsegment_b200.so (include/msegment.h): context, workspace, host staging,
+// stream-ordered pipelines.  No CPU implementation of any operator lives here: every entry point
+// ends in the CUDA kernels of k_*.cu or fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "msg_internal.h"
+
+static char g_create_err[512] = "";
+
+int msg_fail(msg_ctx* ctx, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int msg_reserve(msg_ctx* ctx, void** p, size_t* cap, size_t bytes)
+{
+    if (*cap >= bytes && *p) return MSG_OK;
+    if (*p) {
+        MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        MSG_CUDA(ctx, cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;  // head-room against ping-pong regrowth
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return msg_fail(ctx, MSG_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    *cap = want;
+    return MSG_OK;
+}
+
+#define CTX_ENTER(ctx)                                                                           \
+    do {                                                                                         \
+        if (!(ctx)) return MSG_EINVAL;                                                           \
+        if ((ctx)->cuda_failed) return msg_fail((ctx), MSG_ECUDA, "context is in a failed CUDA state"); \
+        MSG_CUDA((ctx), cudaSetDevice((ctx)->device));                                           \
+    } while (0)
+
+extern "C" {
+
+int msg_version(void) { return MSG_VERSION; }
+
+int msg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* msg_last_error(const msg_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+int msg_create(int device, msg_ctx** out)
+{
+    if (!out) return MSG_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return msg_fail(nullptr, MSG_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= n) return msg_fail(nullptr, MSG_EINVAL, "device %d out of range [0,%d)", device, n);
+    msg_ctx* ctx = (msg_ctx*)calloc(1, sizeof(msg_ctx));
+    if (!ctx) return msg_fail(nullptr, MSG_ENOMEM, "out of host memory");
+    ctx->device = device;
+#define CR(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e2 = (call);                                                                  \
+        if (e2 != cudaSuccess) {                                                                  \
+            msg_fail(nullptr, MSG_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e2));         \
+            free(ctx);                                                                            \
+            return MSG_ECUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+    CR(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CR(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        msg_fail(nullptr, MSG_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                 prop.major, prop.minor);
+        free(ctx);
+        return MSG_ECUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CR(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 8; i++) CR(cudaEventCreate(&ctx->ev[i]));
+    CR(cudaMalloc((void**)&ctx->d_counters, 64 * sizeof(int32_t)));
+    CR(cudaMemset(ctx->d_counters, 0, 64 * sizeof(int32_t)));
+    CR(cudaMallocHost((void**)&ctx->h_counters, 64 * sizeof(int32_t)));
+    memset(ctx->h_counters, 0, 64 * sizeof(int32_t));
+    for (int i = 0; i < MSG_MAX_INFLIGHT; i++) {
+        CR(cudaEventCreateWithFlags(&ctx->pend[i].done, cudaEventDisableTiming));
+        ctx->pend[i].n_regions_host = ctx->h_counters + 32 + i;
+    }
+#undef CR
+    *out = ctx;
+    return MSG_OK;
+}
+
+void msg_destroy(msg_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_out2); cudaFree(ctx->d_labels);
+    cudaFree(ctx->d_planes); cudaFree(ctx->d_ovf); cudaFree(ctx->d_scratch); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_colors);
+    cudaFreeHost(ctx->h_counters);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < MSG_MAX_INFLIGHT; i++) cudaEventDestroy(ctx->pend[i].done);
+    cudaStreamDestroy(ctx->own_stream);
+    cudaGetLastError();
+    free(ctx);
+}
+
+int msg_set_stream(msg_ctx* ctx, void* cuda_stream)
+{
+    CTX_ENTER(ctx);
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return MSG_OK;
+}
+
+int msg_synchronize(msg_ctx* ctx)
+{
+    CTX_ENTER(ctx);
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+void* msg_alloc_pinned(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void msg_free_pinned(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void msg_segment_params_default(msg_segment_params* p)
+{
+    if (!p) return;
+    p->sp = 10.0; p->sr = 10.0; p->max_level = 1;
+    p->term_type = MSG_TERM_COUNT | MSG_TERM_EPS; p->max_count = 5; p->eps = 1.0;
+    p->lo_diff = 2; p->min_size = 0; p->color_dist = 0; p->render_depth = 0;
+}
+
+int msg_get_timings(msg_ctx* ctx, msg_timings* out)
+{
+    if (!ctx || !out) return MSG_EINVAL;
+    *out = ctx->tm;
+    return MSG_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================ mean-shift pipeline
+
+struct ms_config {
+    double sp0;
+    int isr2, isr22, max_level, max_count, ieps;
+};
+
+static int ms_validate(msg_ctx* ctx, int w, int h, double sp, double sr, int max_level, int term_type, int max_count,
+                       double eps, ms_config* cfg)
+{
+    if (w <= 0 || h <= 0) return msg_fail(ctx, MSG_EINVAL, "image size %dx%d is empty", w, h);
+    if (max_level < 0 || max_level > 8)
+        return msg_fail(ctx, MSG_EINVAL, "The number of pyramid levels is too large or negative (maxLevel=%d)", max_level);
+    if (isnan(sp) || isnan(sr) || isnan(eps)) return msg_fail(ctx, MSG_EINVAL, "NaN parameter");
+    if (!(term_type & MSG_TERM_COUNT)) max_count = 5;
+    if (max_count < 1) max_count = 1;
+    if (max_count > 100) max_count = 100;
+    if (!(term_type & MSG_TERM_EPS)) eps = 1.0;
+    if (eps < 0) eps = 0;
+    double sr2 = sr * sr;
+    cfg->isr2 = sr2 >= 2147483647.0 ? 2147483647 : (int)lrint(sr2);   // cvRound(sr*sr)
+    cfg->isr22 = cfg->isr2 > 16 ? cfg->isr2 : 16;
+    cfg->sp0 = sp;
+    cfg->max_level = max_level;
+    cfg->max_count = max_count;
+    cfg->ieps = eps >= 2147483647.0 ? 2147483647 : (int)floor(eps);
+    return MSG_OK;
+}
+
+// Builds planes for rows [r0, r1) (global, level 0) of a w x hfull image whose BGR rows start at d_src
+// (row r0 first), runs all levels, leaves the result in ctx->D[0].
+static int ms_run(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, int w, int hfull, int r0, int r1, const ms_config& cfg)
+{
+    const int L = cfg.max_level;
+    int lw[MSG_MAX_LEVELS], lh[MSG_MAX_LEVELS], ly0[MSG_MAX_LEVELS], ly1[MSG_MAX_LEVELS];
+    lw[0] = w; lh[0] = hfull; ly0[0] = r0; ly1[0] = r1;
+    for (int l = 1; l <= L; l++) {
+        lw[l] = (lw[l - 1] + 1) / 2; lh[l] = (lh[l - 1] + 1) / 2;
+        ly0[l] = ly0[l - 1] / 2; ly1[l] = (ly1[l - 1] + 1) / 2;
+    }
+    size_t total = 0, offs[MSG_MAX_LEVELS];
+    for (int l = 0; l <= L; l++) {
+        offs[l] = total;
+        total += 2 * (size_t)msg_align_up(lw[l], 32) * (size_t)(ly1[l] - ly0[l]);
+    }
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, total * sizeof(uint32_t)));
+    for (int l = 0; l <= L; l++) {
+        msg_plane s;
+        s.w = lw[l]; s.rows = ly1[l] - ly0[l]; s.y0 = ly0[l]; s.hfull = lh[l]; s.pitch = msg_align_up(lw[l], 32);
+        s.p = ctx->d_planes + offs[l];
+        msg_plane d = s;
+        d.p = s.p + (size_t)s.pitch * s.rows;
+        ctx->S[l] = s; ctx->D[l] = d;
+    }
+    ctx->last_levels = L;
+    MSG_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int32_t), ctx->stream));
+    MSG_TRY(k_bgr_to_plane(ctx, d_src, sstep, ctx->S[0]));
+    for (int l = 1; l <= L; l++) MSG_TRY(k_pyr_down(ctx, ctx->S[l - 1], ctx->S[l]));
+    for (int l = L; l >= 0; l--) {
+        msg_ms_params prm;
+        float sp = (float)(cfg.sp0 / (double)(1 << l));
+        if (!(sp >= 1.f)) sp = 1.f;
+        prm.sp = sp;
+        prm.radius = (int)ceilf(sp);
+        prm.isr2 = cfg.isr2;
+        prm.max_count = cfg.max_count;
+        prm.ieps = cfg.ieps;
+        prm.use_mask = l < L;
+        if (l < L) MSG_TRY(k_pyr_up_mask(ctx, ctx->D[l + 1], ctx->D[l], cfg.isr22));
+        MSG_TRY(k_meanshift_level(ctx, ctx->S[l], ctx->D[l], prm));
+    }
+    return MSG_OK;
+}
+
+static int fetch_ms_stats(msg_ctx* ctx)
+{
+    // counters [2..3] active items (u64), [4..5] overflow items (u64)
+    MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return MSG_OK;
+}
+
+static void publish_ms_stats(msg_ctx* ctx)
+{
+    unsigned long long a, o;
+    memcpy(&a, ctx->h_counters + 2, 8);
+    memcpy(&o, ctx->h_counters + 4, 8);
+    ctx->st.ms_active_items = a;
+    ctx->st.ms_overflow_items = o;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ms;
+}
+
+static int copy_in(msg_ctx* ctx, const void* host, size_t hstep, size_t row_bytes, int rows, uint8_t** d, size_t* dcap)
+{
+    MSG_TRY(msg_reserve(ctx, (void**)d, dcap, row_bytes * (size_t)rows));
+    MSG_CUDA(ctx, cudaMemcpy2DAsync(*d, row_bytes, host, hstep, row_bytes, rows, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.h2d_bytes += row_bytes * (size_t)rows;
+    return MSG_OK;
+}
+
+static int copy_out(msg_ctx* ctx, void* host, size_t hstep, const void* d, size_t row_bytes, int rows)
+{
+    MSG_CUDA(ctx, cudaMemcpy2DAsync(host, hstep, d, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->st.d2h_bytes += row_bytes * (size_t)rows;
+    return MSG_OK;
+}
+
+static int check_img(msg_ctx* ctx, const void* p, size_t step, int w, int h, int elem, const char* what)
+{
+    if (w <= 0 || h <= 0) return msg_fail(ctx, MSG_EINVAL, "%s: empty image %dx%d", what, w, h);
+    if (!p) return msg_fail(ctx, MSG_EINVAL, "%s: null pointer", what);
+    if (step < (size_t)w * elem) return msg_fail(ctx, MSG_EINVAL, "%s: step %zu < row bytes %zu", what, step, (size_t)w * elem);
+    if ((long long)w * h > 0x7fffffffLL - 1) return msg_fail(ctx, MSG_EINVAL, "%s: more than 2^31-2 pixels", what);
+    return MSG_OK;
+}
+
+extern "C" {
+
+int msg_meanshift_filter_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w,
+                             int h, double sp, double sr, int max_level, int term_type, int max_count, double eps)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_src, sstep, w, h, 3, "meanshift src"));
+    MSG_TRY(check_img(ctx, d_dst, dstep, w, h, 3, "meanshift dst"));
+    ms_config cfg;
+    MSG_TRY(ms_validate(ctx, w, h, sp, sr, max_level, term_type, max_count, eps, &cfg));
+    MSG_TRY(ms_run(ctx, d_src, sstep, w, h, 0, h, cfg));
+    MSG_TRY(k_plane_to_bgr(ctx, ctx->D[0], 0, h, d_dst, dstep));
+    return MSG_OK;
+}
+
+int msg_meanshift_filter(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h,
+                         double sp, double sr, int max_level, int term_type, int max_count, double eps)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "meanshift src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 3, "meanshift dst"));
+    ms_config cfg;
+    MSG_TRY(ms_validate(ctx, w, h, sp, sr, max_level, term_type, max_count, eps, &cfg));
+    size_t rb = (size_t)w * 3;
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    MSG_TRY(copy_in(ctx, src, sstep, rb, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rb * h));
+    MSG_TRY(ms_run(ctx, ctx->d_in, rb, w, h, 0, h, cfg));
+    MSG_TRY(k_plane_to_bgr(ctx, ctx->D[0], 0, h, ctx->d_out, rb));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, rb, h));
+    MSG_TRY(fetch_ms_stats(ctx));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    publish_ms_stats(ctx);
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->tm.h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->tm.filter_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->tm.d2h_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[3]);
+    return MSG_OK;
+}
+
+// ============================================================================ labelling
+
+int msg_label_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32_t* d_labels, size_t lstep, int w, int h,
+                          int lo_diff, int32_t* d_n)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_bgr, step, w, h, 3, "label src"));
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, h, 4, "labels"));
+    if (lo_diff < 0) return msg_fail(ctx, MSG_EINVAL, "lo_diff must be >= 0");
+    if (lstep % 4) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of 4");
+    msg_plane s;
+    s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
+    s.p = ctx->d_planes;
+    MSG_TRY(k_bgr_to_plane(ctx, d_bgr, step, s));
+    bool dense = lstep == (size_t)w * 4;
+    int32_t* work = d_labels;
+    if (!dense) {
+        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+        work = ctx->d_labels;
+    }
+    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, work, -1, w));
+    MSG_TRY(k_relabel_canonical(ctx, work, w, h, 1, d_n, 0));
+    if (!dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
+    return MSG_OK;
+}
+
+int msg_connected_components_dev(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int32_t* d_labels, size_t lstep,
+                                 int w, int h, int connectivity, int32_t* d_n)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_mask, step, w, h, 1, "connectedComponents image"));
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, h, 4, "labels"));
+    if (connectivity != 4 && connectivity != 8) return msg_fail(ctx, MSG_EINVAL, "connectivity must be 4 or 8");
+    if (lstep % 4) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of 4");
+    bool dense = lstep == (size_t)w * 4;
+    int32_t* work = d_labels;
+    if (!dense) {
+        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+        work = ctx->d_labels;
+    }
+    MSG_TRY(k_ccl_binary(ctx, d_mask, step, w, h, connectivity, work));
+    MSG_TRY(k_relabel_canonical(ctx, work, w, h, 1, d_n, 1));   // + background label, as OpenCV counts
+    if (!dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
+    return MSG_OK;
+}
+
+int msg_merge_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32_t* d_labels, size_t lstep, int w, int h,
+                          int min_size, int color_dist, int32_t* d_n)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_bgr, step, w, h, 3, "merge image"));
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, h, 4, "labels"));
+    if (min_size < 0 || color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
+    if (lstep % 4) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of 4");
+    msg_plane s;
+    s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
+    s.p = ctx->d_planes;
+    MSG_TRY(k_bgr_to_plane(ctx, d_bgr, step, s));
+    bool dense = lstep == (size_t)w * 4;
+    int32_t* work = d_labels;
+    if (!dense) {
+        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+        work = ctx->d_labels;
+        MSG_TRY(k_copy_labels_2d(ctx, d_labels, lstep, work, (size_t)w * 4, w, h));
+    }
+    MSG_TRY(k_merge(ctx, s.p, s.pitch, work, w, h, min_size, color_dist, d_n));
+    if (!dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
+    return MSG_OK;
+}
+
+int msg_render_labels_dev(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, uint8_t* d_dst, size_t dstep, int w, int h,
+                          int depth, const uint8_t* d_colors)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, h, 4, "labels"));
+    MSG_TRY(check_img(ctx, d_dst, dstep, w, h, 3, "render dst"));
+    return k_render(ctx, d_labels, lstep, d_dst, dstep, w, h, depth, d_colors);
+}
+
+int msg_synth_bgr_dev(msg_ctx* ctx, uint8_t* d_dst, size_t step, int w, int h, uint64_t seed)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_dst, step, w, h, 3, "synth dst"));
+    return k_synth(ctx, d_dst, step, w, h, seed);
+}
+
+// ---- host-buffer label operators
+
+static int finish_count(msg_ctx* ctx, int32_t* n_out)
+{
+    MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 16, ctx->d_counters + 16, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_out) *n_out = ctx->h_counters[16];
+    return MSG_OK;
+}
+
+int msg_label_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* labels, size_t lstep, int w, int h,
+                      int lo_diff, int up_diff, int connectivity, int32_t* n_regions)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, bgr, step, w, h, 3, "label src"));
+    MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "labels"));
+    if (lo_diff != up_diff)
+        return msg_fail(ctx, MSG_EINVAL, "lo_diff (%d) != up_diff (%d): asymmetric floodFill ranges are order dependent", lo_diff, up_diff);
+    if (connectivity != 4) return msg_fail(ctx, MSG_EINVAL, "label_regions supports connectivity 4 only (got %d)", connectivity);
+    if (lo_diff < 0) return msg_fail(ctx, MSG_EINVAL, "lo_diff must be >= 0");
+    size_t rb = (size_t)w * 3;
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    MSG_TRY(copy_in(ctx, bgr, step, rb, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+    // dense device labels: msg_label_regions_dev would alias ctx->d_labels for a strided target, so go direct
+    msg_plane s;
+    s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
+    s.p = ctx->d_planes;
+    MSG_TRY(k_bgr_to_plane(ctx, ctx->d_in, rb, s));
+    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, ctx->d_labels, -1, w));
+    MSG_TRY(k_relabel_canonical(ctx, ctx->d_labels, w, h, 1, ctx->d_counters + 16, 0));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    MSG_TRY(finish_count(ctx, n_regions));
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->tm.h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->tm.label_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->tm.d2h_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[3]);
+    return MSG_OK;
+}
+
+int msg_connected_components(msg_ctx* ctx, const uint8_t* mask, size_t step, int32_t* labels, size_t lstep, int w, int h,
+                             int connectivity, int32_t* n_labels)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, mask, step, w, h, 1, "connectedComponents image"));
+    MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "labels"));
+    if (connectivity != 4 && connectivity != 8) return msg_fail(ctx, MSG_EINVAL, "connectivity must be 4 or 8 (got %d)", connectivity);
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    MSG_TRY(copy_in(ctx, mask, step, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+    MSG_TRY(k_ccl_binary(ctx, ctx->d_in, (size_t)w, w, h, connectivity, ctx->d_labels));
+    MSG_TRY(k_relabel_canonical(ctx, ctx->d_labels, w, h, 1, ctx->d_counters + 16, 1));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    MSG_TRY(finish_count(ctx, n_labels));
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->tm.h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->tm.label_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->tm.d2h_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[3]);
+    return MSG_OK;
+}
+
+int msg_merge_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* labels, size_t lstep, int w, int h,
+                      int min_size, int color_dist, int32_t* n_regions)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, bgr, step, w, h, 3, "merge image"));
+    MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "labels"));
+    if (min_size < 0 || color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
+    size_t rb = (size_t)w * 3;
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    MSG_TRY(copy_in(ctx, bgr, step, rb, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+    MSG_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_labels, (size_t)w * 4, labels, lstep, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.h2d_bytes += (size_t)w * 4 * h;
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    msg_plane s;
+    s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
+    s.p = ctx->d_planes;
+    MSG_TRY(k_bgr_to_plane(ctx, ctx->d_in, rb, s));
+    MSG_TRY(k_merge(ctx, s.p, s.pitch, ctx->d_labels, w, h, min_size, color_dist, ctx->d_counters + 16));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    MSG_TRY(finish_count(ctx, n_regions));
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->tm.h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->tm.merge_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->tm.d2h_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[3]);
+    return MSG_OK;
+}
+
+int msg_render_labels(msg_ctx* ctx, const int32_t* labels, size_t lstep, uint8_t* dst, size_t dstep, int w, int h,
+                      int depth, const uint8_t* colors)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "labels"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 3, "render dst"));
+    if (depth < 0) depth = 0;
+    size_t rb = (size_t)w * 3;
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+    MSG_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_labels, (size_t)w * 4, labels, lstep, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.h2d_bytes += (size_t)w * 4 * h;
+    const uint8_t* d_colors = nullptr;
+    if (colors && depth > 0) {
+        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_colors, &ctx->d_colors_cap, (size_t)depth * 3));
+        MSG_CUDA(ctx, cudaMemcpyAsync(ctx->d_colors, colors, (size_t)depth * 3, cudaMemcpyHostToDevice, ctx->stream));
+        d_colors = ctx->d_colors;
+    }
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out2, &ctx->d_out2_cap, rb * h));
+    MSG_TRY(k_render(ctx, ctx->d_labels, (size_t)w * 4, ctx->d_out2, rb, w, h, depth, d_colors));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out2, rb, h));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->tm.h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->tm.render_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->tm.d2h_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[3]);
+    return MSG_OK;
+}
+
+// ============================================================================ fused pipeline
+
+static int segment_enqueue(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
+                           uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered,
+                           size_t rstep, int32_t* h_n_slot)
+{
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "segment src"));
+    if (!p) return msg_fail(ctx, MSG_EINVAL, "segment: params is NULL");
+    if (filtered) MSG_TRY(check_img(ctx, filtered, fstep, w, h, 3, "segment filtered"));
+    if (labels) MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "segment labels"));
+    if (rendered) MSG_TRY(check_img(ctx, rendered, rstep, w, h, 3, "segment rendered"));
+    ms_config cfg;
+    MSG_TRY(ms_validate(ctx, w, h, p->sp, p->sr, p->max_level, p->term_type, p->max_count, p->eps, &cfg));
+    if (p->min_size < 0 || p->color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
+    const bool do_label = p->lo_diff >= 0;
+    const bool do_merge = do_label && (p->min_size > 0 || p->color_dist > 0);
+    const bool do_render = do_label && p->render_depth >= 0 && rendered;
+    size_t rb = (size_t)w * 3;
+    cudaStream_t st = ctx->stream;
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    MSG_TRY(copy_in(ctx, src, sstep, rb, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    MSG_TRY(ms_run(ctx, ctx->d_in, rb, w, h, 0, h, cfg));
+    if (filtered) {
+        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rb * h));
+        MSG_TRY(k_plane_to_bgr(ctx, ctx->D[0], 0, h, ctx->d_out, rb));
+    }
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    int32_t* d_n = ctx->d_counters + 16;
+    if (do_label) {
+        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+        MSG_TRY(k_ccl_color(ctx, ctx->D[0].p, ctx->D[0].pitch, w, h, p->lo_diff, ctx->d_labels, -1, w));
+        MSG_TRY(k_relabel_canonical(ctx, ctx->d_labels, w, h, 1, d_n, 0));
+    } else {
+        MSG_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int32_t), st));
+    }
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    if (do_merge) MSG_TRY(k_merge(ctx, ctx->D[0].p, ctx->D[0].pitch, ctx->d_labels, w, h, p->min_size, p->color_dist, d_n));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    if (do_render) {
+        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out2, &ctx->d_out2_cap, rb * h));
+        int depth = p->render_depth > 0 ? p->render_depth : 0x7fffffff;   // 0: every region renders
+        MSG_TRY(k_render(ctx, ctx->d_labels, (size_t)w * 4, ctx->d_out2, rb, w, h, depth, nullptr));
+    }
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    // all downloads last, so the stage timings above are clean
+    if (filtered) MSG_TRY(copy_out(ctx, filtered, fstep, ctx->d_out, rb, h));
+    if (do_label && labels) MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
+    if (do_render) MSG_TRY(copy_out(ctx, rendered, rstep, ctx->d_out2, rb, h));
+    MSG_CUDA(ctx, cudaMemcpyAsync(h_n_slot, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MSG_TRY(fetch_ms_stats(ctx));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+    return MSG_OK;
+}
+
+int msg_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
+                uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered, size_t rstep,
+                int32_t* n_regions)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(segment_enqueue(ctx, src, sstep, w, h, p, filtered, fstep, labels, lstep, rendered, rstep, ctx->h_counters + 16));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    publish_ms_stats(ctx);
+    if (n_regions) *n_regions = ctx->h_counters[16];
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->tm.h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->tm.filter_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->tm.label_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.merge_ms = ev_ms(ctx->ev[3], ctx->ev[4]);
+    ctx->tm.render_ms = ev_ms(ctx->ev[4], ctx->ev[5]);
+    ctx->tm.d2h_ms = ev_ms(ctx->ev[5], ctx->ev[6]);
+    ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[6]);
+    return MSG_OK;
+}
+
+int msg_submit_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
+                       uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered, size_t rstep,
+                       int* ticket)
+{
+    CTX_ENTER(ctx);
+    if (!ticket) return msg_fail(ctx, MSG_EINVAL, "submit: ticket is NULL");
+    int slot = -1;
+    for (int i = 0; i < MSG_MAX_INFLIGHT; i++)
+        if (!ctx->pend[i].used) { slot = i; break; }
+    if (slot < 0) return msg_fail(ctx, MSG_ESTATE, "submit: %d submissions already in flight; call msg_wait", MSG_MAX_INFLIGHT);
+    MSG_TRY(segment_enqueue(ctx, src, sstep, w, h, p, filtered, fstep, labels, lstep, rendered, rstep,
+                            ctx->pend[slot].n_regions_host));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->pend[slot].done, ctx->stream));
+    ctx->pend[slot].used = 1;
+    *ticket = slot;
+    return MSG_OK;
+}
+
+int msg_wait(msg_ctx* ctx, int ticket, int32_t* n_regions)
+{
+    CTX_ENTER(ctx);
+    if (ticket < 0 || ticket >= MSG_MAX_INFLIGHT || !ctx->pend[ticket].used)
+        return msg_fail(ctx, MSG_ESTATE, "wait: invalid ticket %d", ticket);
+    MSG_CUDA(ctx, cudaEventSynchronize(ctx->pend[ticket].done));
+    ctx->pend[ticket].used = 0;
+    if (n_regions) *n_regions = *ctx->pend[ticket].n_regions_host;
+    publish_ms_stats(ctx);
+    return MSG_OK;
+}
+
+int msg_get_stats(msg_ctx* ctx, msg_stats* out)
+{
+    if (!ctx || !out) return MSG_EINVAL;
+    *out = ctx->st;
+    return MSG_OK;
+}
+
+int msg_debug_get_plane(msg_ctx* ctx, int kind, int level, uint32_t* host_out, size_t cap, int* w, int* h)
+{
+    CTX_ENTER(ctx);
+    if (level < 0 || level > ctx->last_levels || (kind != 0 && kind != 1) || !ctx->d_planes)
+        return msg_fail(ctx, MSG_EINVAL, "debug_get_plane: bad kind/level");
+    msg_plane p = kind ? ctx->D[level] : ctx->S[level];
+    if (w) *w = p.w;
+    if (h) *h = p.rows;
+    if (!host_out) return MSG_OK;
+    if (cap < (size_t)p.w * p.rows) return msg_fail(ctx, MSG_EINVAL, "debug_get_plane: buffer too small");
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MSG_CUDA(ctx, cudaMemcpy2D(host_out, (size_t)p.w * 4, p.p, (size_t)p.pitch * 4, (size_t)p.w * 4, p.rows, cudaMemcpyDeviceToHost));
+    return MSG_OK;
+}
+
+// ============================================================================ strip sharding
+
+int msg_meanshift_halo_rows(double sp, int max_level, int term_type, int max_count)
+{
+    if (max_level < 0 || max_level > 8) return -1;
+    if (!(term_type & MSG_TERM_COUNT)) max_count = 5;
+    if (max_count < 1) max_count = 1;
+    if (max_count > 100) max_count = 100;
+    // Dependency cone of an output row, in level-0 rows (DESIGN.md "strip sharding"):
+    //  at level l a pixel reads S[l] within max_count*ceil(sp_l) + ceil(sp_l) rows of itself; S[l] reads S[l-1]
+    //  within 2 rows (pyrDown taps, scaled by 2); the level-l mask/pyrUp reads D[l+1] within 3 rows.
+    long need = 0;  // rows needed at the current level, accumulated from level 0 upwards
+    long halo0 = 0;
+    for (int l = 0; l <= max_level; l++) {
+        double spl = sp / (double)(1 << l);
+        if (!(spl >= 1.0)) spl = 1.0;
+        long r = (long)ceil(spl);
+        long reach_l = (long)(max_count + 1) * r;          // rows of S[l] a level-l pixel can touch
+        // to have D[l] valid on the rows that level l-1 needs (need rows at level l), S[l] is needed on need + reach_l
+        long s_rows_l = need + reach_l;
+        // rows of level 0 that S[l] on +-s_rows_l depends on: each pyrDown adds 2 rows then doubles
+        long v = s_rows_l;
+        for (int k = l; k > 0; k--) v = 2 * v + 2;
+        if (v > halo0) halo0 = v;
+        // the level l+1 rows needed by level l's pyrUp + mask (3 rows margin), for pixels within `need + 0` rows
+        need = (need + reach_l) / 2 + 4;
+    }
+    long a = 1L << max_level;
+    halo0 = (halo0 + 2 * a + a - 1) / a * a;   // multiple of 2^max_level, plus slack
+    return (int)halo0;
+}
+
+int msg_meanshift_filter_strip_dev(msg_ctx* ctx, const uint8_t* d_src_rows, size_t sstep, int halo_row0, int halo_row1,
+                                   uint8_t* d_dst, size_t dstep, int w, int full_h, int row0, int row1, double sp,
+                                   double sr, int max_level, int term_type, int max_count, double eps)
+{
+    CTX_ENTER(ctx);
+    if (!(0 <= halo_row0 && halo_row0 <= row0 && row0 < row1 && row1 <= halo_row1 && halo_row1 <= full_h))
+        return msg_fail(ctx, MSG_EINVAL, "strip: need 0 <= halo_row0 <= row0 < row1 <= halo_row1 <= full_height");
+    MSG_TRY(check_img(ctx, d_src_rows, sstep, w, halo_row1 - halo_row0, 3, "strip src"));
+    MSG_TRY(check_img(ctx, d_dst, dstep, w, row1 - row0, 3, "strip dst"));
+    ms_config cfg;
+    MSG_TRY(ms_validate(ctx, w, full_h, sp, sr, max_level, term_type, max_count, eps, &cfg));
+    int a = 1 << max_level;
+    if (halo_row0 % a || row0 % a) return msg_fail(ctx, MSG_EINVAL, "strip: row0 and halo_row0 must be multiples of 2^max_level");
+    MSG_TRY(ms_run(ctx, d_src_rows, sstep, w, full_h, halo_row0, halo_row1, cfg));
+    MSG_TRY(k_plane_to_bgr(ctx, ctx->D[0], row0 - halo_row0, row1 - row0, d_dst, dstep));
+    return MSG_OK;
+}
+
+int msg_label_strip_dev(msg_ctx* ctx, const uint8_t* d_bgr_rows, size_t step, int32_t* d_labels, size_t lstep, int w,
+                        int rows, int row0, int full_w, int lo_diff)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_bgr_rows, step, w, rows, 3, "label strip src"));
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, rows, 4, "labels"));
+    if (lstep != (size_t)w * 4) return msg_fail(ctx, MSG_EINVAL, "label strip: labels must be dense");
+    if (lo_diff < 0 || full_w != w) return msg_fail(ctx, MSG_EINVAL, "label strip: lo_diff >= 0 and full_width == width required");
+    if (((long long)row0 + rows) * (long long)full_w > 0x7fffffffLL - 1)
+        return msg_fail(ctx, MSG_EINVAL, "label strip: global label would overflow int32");
+    msg_plane s;
+    s.w = w; s.rows = rows; s.y0 = 0; s.hfull = rows; s.pitch = msg_align_up(w, 32);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * rows * sizeof(uint32_t)));
+    s.p = ctx->d_planes;
+    MSG_TRY(k_bgr_to_plane(ctx, d_bgr_rows, step, s));
+    return k_ccl_color(ctx, s.p, s.pitch, w, rows, lo_diff, d_labels, (int64_t)row0 * full_w, full_w);
+}
+
+int msg_seam_pairs_dev(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const uint8_t* lo_bgr,
+                       const int32_t* lo_lab, int w, int lo_diff, int32_t* d_pairs, int32_t* d_count)
+{
+    CTX_ENTER(ctx);
+    if (!up_bgr || !up_lab || !lo_bgr || !lo_lab || !d_pairs || !d_count || w <= 0 || lo_diff < 0)
+        return msg_fail(ctx, MSG_EINVAL, "seam_pairs: bad argument");
+    return k_seam_pairs(ctx, up_bgr, up_lab, lo_bgr, lo_lab, w, lo_diff, d_pairs, d_count);
+}
+
+int msg_apply_label_map_dev(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, const int32_t* d_from,
+                            const int32_t* d_to, int n_map)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, rows, 4, "labels"));
+    if (n_map < 0 || (n_map > 0 && (!d_from || !d_to))) return msg_fail(ctx, MSG_EINVAL, "apply_label_map: bad map");
+    return k_apply_map(ctx, d_labels, lstep, w, rows, d_from, d_to, n_map);
+}
+
+}  // extern "C"

@@ -1,0 +1,423 @@
+// k_ccl.cu -- K2a: connected-component labelling by union-find in HBM, plus canonical relabelling.
+//
+//   colour predicate, 4-connectivity  == OpenCV floodFill loop with loDiff = upDiff = d, floating range
+//                                        (samples/cpp/meanshift_segmentation.cpp)
+//   binary predicate, 4/8-connectivity == Imgproc.connectedComponents (PictureService.java:441-442)
+//
+// Passes (all HBM-bound streaming kernels, one thread per pixel, warps along rows):
+//   1 rows    : warp __ballot of "connected to left" bits -> every pixel points at the start of its
+//               run inside its 32-pixel chunk (no pointer chains inside a chunk)
+//   2 merge   : union(run, run above / previous chunk) with atomicMin on roots; redundant unions
+//               inside an overlap of two runs are skipped (only the first column of an overlap unites)
+//   3 flatten : label = find(label)   (root = smallest linear index of the component)
+//   4 relabel : roots flagged, exclusive scan in raster order, label = rank(root) + 1
+#include "msg_internal.h"
+
+namespace {
+
+constexpr int CCL_THREADS = 256;
+constexpr int SCAN_CHUNK = 4096;   // pixels per block in the rank scan (256 threads x 16)
+
+__device__ __forceinline__ bool color_close(uint32_t a, uint32_t b, int d)
+{
+    uint32_t e = __vabsdiffu4(a & 0x00FFFFFFu, b & 0x00FFFFFFu);
+    return (int)(e & 0xFF) <= d && (int)((e >> 8) & 0xFF) <= d && (int)(e >> 16) <= d;
+}
+
+__device__ __forceinline__ int uf_find(const int32_t* L, int a)
+{
+    int p = __ldcg(L + a);
+    while (p != a) { a = p; p = __ldcg(L + a); }
+    return a;
+}
+
+__device__ __forceinline__ void uf_union(int32_t* L, int a, int b)
+{
+    for (;;) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }   // a > b: link the larger root under the smaller
+        int old = atomicMin(L + a, b);
+        if (old == a) return;                     // a was still a root
+        a = old;                                  // somebody re-linked a meanwhile: keep merging
+    }
+}
+
+// ---------------------------------------------------------------- pass 1: row runs
+// PRED: 0 = colour (plane u32, pitch in pixels), 1 = binary mask (u8, step in bytes)
+template <int PRED>
+__global__ void __launch_bounds__(CCL_THREADS) ccl_rows_kernel(const void* __restrict__ img, size_t pitch, int w, int h,
+                                                               int d, int32_t* __restrict__ L)
+{
+    int x = blockIdx.x * CCL_THREADS + threadIdx.x;
+    int y = blockIdx.y;
+    int lane = threadIdx.x & 31;
+    bool in = x < w;
+    bool fg = in, cl = false;
+    if (PRED == 0) {
+        const uint32_t* row = (const uint32_t*)img + (size_t)y * pitch;
+        if (in && x > 0) cl = color_close(__ldg(row + x), __ldg(row + x - 1), d);
+    } else {
+        const uint8_t* row = (const uint8_t*)img + (size_t)y * pitch;
+        fg = in && row[x] != 0;
+        if (fg && x > 0) cl = row[x - 1] != 0;
+    }
+    unsigned bits = __ballot_sync(0xffffffffu, cl);
+    if (!in) return;
+    if (!fg) { L[(size_t)y * w + x] = -1; return; }
+    unsigned starts = (~bits | 1u) & (0xffffffffu >> (31 - lane));   // run starts at lanes <= mine
+    int start_lane = 31 - __clz(starts);
+    L[(size_t)y * w + x] = y * w + (x - lane + start_lane);
+}
+
+// ---------------------------------------------------------------- pass 2: merge runs
+template <int PRED, int CONN>
+__global__ void __launch_bounds__(CCL_THREADS) ccl_merge_kernel(const void* __restrict__ img, size_t pitch, int w, int h,
+                                                                int d, int32_t* __restrict__ L)
+{
+    int x = blockIdx.x * CCL_THREADS + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int p = y * w + x;
+    if (PRED == 0) {
+        const uint32_t* row = (const uint32_t*)img + (size_t)y * pitch;
+        uint32_t c = __ldg(row + x);
+        bool cl = x > 0 && color_close(c, __ldg(row + x - 1), d);
+        if (cl && (x & 31) == 0) uf_union(L, p, p - 1);
+        if (y > 0) {
+            const uint32_t* up = row - pitch;
+            uint32_t cu = __ldg(up + x);
+            if (color_close(c, cu, d)) {
+                bool redundant = cl && color_close(cu, __ldg(up + x - 1), d) &&
+                                 color_close(__ldg(row + x - 1), __ldg(up + x - 1), d);
+                if (!redundant) uf_union(L, p, p - w);
+            }
+        }
+    } else {
+        const uint8_t* row = (const uint8_t*)img + (size_t)y * pitch;
+        if (!row[x]) return;
+        bool left = x > 0 && row[x - 1];
+        if (left && (x & 31) == 0) uf_union(L, p, p - 1);
+        if (y > 0) {
+            const uint8_t* up = row - pitch;
+            bool u = up[x] != 0;
+            bool ul = x > 0 && up[x - 1] != 0;
+            if (u) {
+                if (!(left && ul)) uf_union(L, p, p - w);
+            } else if (CONN == 8) {
+                bool ur = x + 1 < w && up[x + 1] != 0;
+                bool right = x + 1 < w && row[x + 1] != 0;
+                if (ul && !left) uf_union(L, p, p - w - 1);   // left pixel (if any) unites with ul itself
+                if (ur && !right) uf_union(L, p, p - w + 1);  // right pixel (if any) unites with ur itself
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- pass 3: flatten
+__global__ void __launch_bounds__(CCL_THREADS) ccl_flatten_kernel(int32_t* __restrict__ L, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int v = L[i];
+    if (v < 0) return;
+    int r = uf_find(L, v);
+    if (r != v) L[i] = r;
+}
+
+// ---------------------------------------------------------------- pass 4: canonical relabel
+// MODE 0: labels are root pixel indices (>= 0), background < 0; a pixel is a "first" iff L[p] == p
+// MODE 1: labels are arbitrary positive ids (<= n), <= 0 ignored; first[] holds min pixel index per id
+template <int MODE>
+__device__ __forceinline__ bool is_first(const int32_t* __restrict__ L, const int32_t* __restrict__ first, size_t i)
+{
+    int v = L[i];
+    if (MODE == 0) return v == (int)i;
+    return v > 0 && first[v] == (int)i;
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) first_pixel_kernel(const int32_t* __restrict__ L, size_t n,
+                                                                  int32_t* __restrict__ first)
+{
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    int v = i < n ? L[i] : 0;
+    // only the first lane of each run of equal labels inside a warp issues the atomic
+    int prev = __shfl_up_sync(0xffffffffu, v, 1);
+    bool head = (threadIdx.x & 31) == 0 || prev != v;
+    if (i < n && v > 0 && head && first[v] > (int)i) atomicMin(first + v, (int)i);
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total)  // 256 threads
+{
+    __shared__ int warp_sums[CCL_THREADS / 32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    int ws = (lane < CCL_THREADS / 32) ? warp_sums[lane] : 0;
+    int wincl = ws;
+#pragma unroll
+    for (int o = 1; o < CCL_THREADS / 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += t;
+    }
+    int woff = __shfl_sync(0xffffffffu, wincl - ws, wid);
+    if (total) *total = __shfl_sync(0xffffffffu, wincl, CCL_THREADS / 32 - 1);
+    __syncthreads();
+    return woff + incl - v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CCL_THREADS) count_first_kernel(const int32_t* __restrict__ L,
+                                                                  const int32_t* __restrict__ first, size_t n,
+                                                                  int32_t* __restrict__ block_sums)
+{
+    size_t base = (size_t)blockIdx.x * SCAN_CHUNK;
+    int cnt = 0;
+    for (int k = threadIdx.x; k < SCAN_CHUNK; k += CCL_THREADS) {
+        size_t i = base + k;
+        if (i < n && is_first<MODE>(L, first, i)) cnt++;
+    }
+    int total;
+    block_exclusive_scan(cnt, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) scan_block_sums_kernel(int32_t* __restrict__ block_sums, int nb,
+                                                                      int32_t* __restrict__ total_out, int add_to_total)
+{
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += CCL_THREADS) {
+        int i = base + threadIdx.x;
+        int v = i < nb ? block_sums[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total);
+        int c = carry;
+        if (i < nb) block_sums[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry + add_to_total;
+}
+
+// rank[] is indexed by pixel (MODE 0: at the root pixel) or by label id (MODE 1)
+template <int MODE>
+__global__ void __launch_bounds__(CCL_THREADS) assign_rank_kernel(const int32_t* __restrict__ L,
+                                                                  const int32_t* __restrict__ first, size_t n,
+                                                                  const int32_t* __restrict__ block_offs,
+                                                                  int32_t* __restrict__ rank)
+{
+    // each thread owns 16 consecutive pixels of the chunk so that ranks follow raster order
+    size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * (SCAN_CHUNK / CCL_THREADS);
+    unsigned flags = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_CHUNK / CCL_THREADS; k++) {
+        size_t i = base + k;
+        if (i < n && is_first<MODE>(L, first, i)) { flags |= 1u << k; cnt++; }
+    }
+    int ex = block_exclusive_scan(cnt, nullptr) + block_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_CHUNK / CCL_THREADS; k++) {
+        if (flags & (1u << k)) {
+            size_t i = base + k;
+            if (MODE == 0) rank[i] = ex; else rank[L[i]] = ex;
+            ex++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) apply_rank_kernel(int32_t* __restrict__ L, size_t n,
+                                                                 const int32_t* __restrict__ rank, int mode)
+{
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int v = L[i];
+    if (mode == 0) L[i] = v >= 0 ? rank[v] + 1 : 0;
+    else if (v > 0) L[i] = rank[v] + 1;
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) fill_i32_kernel(int32_t* __restrict__ p, size_t n, int32_t v)
+{
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) copy_labels_2d_kernel(const int32_t* __restrict__ src, size_t sstep,
+                                                                     int32_t* __restrict__ dst, size_t dstep, int w)
+{
+    int x = blockIdx.x * CCL_THREADS + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const int32_t* s = (const int32_t*)((const char*)src + (size_t)y * sstep);
+    int32_t* d = (int32_t*)((char*)dst + (size_t)y * dstep);
+    d[x] = s[x];
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) add_label_base_kernel(int32_t* __restrict__ L, size_t n, int w, int fullw,
+                                                                     long long base)
+{
+    // strip labelling: local root index (row*w + x) -> 1 + global linear index
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int v = L[i];
+    if (v < 0) { L[i] = 0; return; }
+    L[i] = (int32_t)(base + (long long)(v / w) * fullw + (v % w) + 1);
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) seam_pairs_kernel(const uint8_t* __restrict__ up_bgr,
+                                                                 const int32_t* __restrict__ up_lab,
+                                                                 const uint8_t* __restrict__ lo_bgr,
+                                                                 const int32_t* __restrict__ lo_lab, int w, int d,
+                                                                 int32_t* __restrict__ pairs, int32_t* __restrict__ count)
+{
+    int x = blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (x >= w) return;
+    auto close = [&](const uint8_t* a, const uint8_t* b) {
+        return abs((int)a[0] - (int)b[0]) <= d && abs((int)a[1] - (int)b[1]) <= d && abs((int)a[2] - (int)b[2]) <= d;
+    };
+    if (!close(up_bgr + 3 * x, lo_bgr + 3 * x)) return;
+    int a = up_lab[x], b = lo_lab[x];
+    if (a == b) return;
+    // skip a pair identical to the one of the previous column (same two runs)
+    if (x > 0 && up_lab[x - 1] == a && lo_lab[x - 1] == b && close(up_bgr + 3 * (x - 1), lo_bgr + 3 * (x - 1))) return;
+    int slot = atomicAdd(count, 1);
+    pairs[2 * slot] = a;
+    pairs[2 * slot + 1] = b;
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) apply_map_kernel(int32_t* __restrict__ labels, size_t lstep, int w,
+                                                                const int32_t* __restrict__ from,
+                                                                const int32_t* __restrict__ to, int n)
+{
+    int x = blockIdx.x * CCL_THREADS + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int32_t* row = (int32_t*)((char*)labels + (size_t)y * lstep);
+    int v = row[x];
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        int f = __ldg(from + mid);
+        if (f == v) { row[x] = __ldg(to + mid); return; }
+        if (f < v) lo = mid + 1; else hi = mid - 1;
+    }
+}
+
+inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+
+// scratch layout for relabel: [rank: n+1 ints][first: n+1 ints (MODE 1)][block_sums: nb ints]
+static int relabel_impl(msg_ctx* ctx, int32_t* d_labels, size_t n, int mode, int32_t* d_n_out, int add_to_total)
+{
+    int nb = (int)blocks_for(n, SCAN_CHUNK);
+    size_t need = ((n + 1) * (mode ? 2 : 1) + (size_t)nb + 64) * sizeof(int32_t);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_scratch, &ctx->d_scratch_cap, need));
+    int32_t* rank = (int32_t*)ctx->d_scratch;
+    int32_t* first = mode ? rank + (n + 1) : nullptr;
+    int32_t* block_sums = rank + (n + 1) * (mode ? 2 : 1);
+    cudaStream_t st = ctx->stream;
+    if (mode) {
+        fill_i32_kernel<<<blocks_for(n + 1, CCL_THREADS), CCL_THREADS, 0, st>>>(first, n + 1, 0x7fffffff);
+        MSG_LAUNCHED(ctx);
+        first_pixel_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n, first);
+        MSG_LAUNCHED(ctx);
+        count_first_kernel<1><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums);
+    } else {
+        count_first_kernel<0><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums);
+    }
+    MSG_LAUNCHED(ctx);
+    scan_block_sums_kernel<<<1, CCL_THREADS, 0, st>>>(block_sums, nb, d_n_out, add_to_total);
+    MSG_LAUNCHED(ctx);
+    if (mode) assign_rank_kernel<1><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums, rank);
+    else assign_rank_kernel<0><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums, rank);
+    MSG_LAUNCHED(ctx);
+    apply_rank_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n, rank, mode);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_relabel_canonical(msg_ctx* ctx, int32_t* d_labels, int w, int h, int roots_are_pixels, int32_t* d_n_out,
+                        int add_to_count)
+{
+    return relabel_impl(ctx, d_labels, (size_t)w * h, roots_are_pixels ? 0 : 1, d_n_out, add_to_count);
+}
+
+// label_base < 0: canonical labels 1..n (n -> d_n via caller's relabel); otherwise strip mode
+int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int32_t* d_labels,
+                int64_t label_base, int full_w)
+{
+    dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);
+    size_t n = (size_t)w * h;
+    cudaStream_t st = ctx->stream;
+    ccl_rows_kernel<0><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
+    MSG_LAUNCHED(ctx);
+    ccl_merge_kernel<0, 4><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
+    MSG_LAUNCHED(ctx);
+    ccl_flatten_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n);
+    MSG_LAUNCHED(ctx);
+    if (label_base >= 0) {
+        add_label_base_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n, w, full_w, label_base);
+        MSG_LAUNCHED(ctx);
+    }
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_ccl_binary(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int conn, int32_t* d_labels)
+{
+    dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);
+    size_t n = (size_t)w * h;
+    cudaStream_t st = ctx->stream;
+    ccl_rows_kernel<1><<<grid, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
+    MSG_LAUNCHED(ctx);
+    if (conn == 8) ccl_merge_kernel<1, 8><<<grid, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
+    else ccl_merge_kernel<1, 4><<<grid, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
+    MSG_LAUNCHED(ctx);
+    ccl_flatten_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_copy_labels_2d(msg_ctx* ctx, const int32_t* src, size_t sstep, int32_t* dst, size_t dstep, int w, int h)
+{
+    dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);
+    copy_labels_2d_kernel<<<grid, CCL_THREADS, 0, ctx->stream>>>(src, sstep, dst, dstep, w);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_seam_pairs(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const uint8_t* lo_bgr,
+                 const int32_t* lo_lab, int w, int d, int32_t* pairs, int32_t* count)
+{
+    MSG_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t), ctx->stream));
+    seam_pairs_kernel<<<(w + CCL_THREADS - 1) / CCL_THREADS, CCL_THREADS, 0, ctx->stream>>>(up_bgr, up_lab, lo_bgr, lo_lab,
+                                                                                           w, d, pairs, count);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_apply_map(msg_ctx* ctx, int32_t* labels, size_t lstep, int w, int rows, const int32_t* from, const int32_t* to,
+                int n)
+{
+    if (n <= 0) return MSG_OK;
+    dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, rows);
+    apply_map_kernel<<<grid, CCL_THREADS, 0, ctx->stream>>>(labels, lstep, w, from, to, n);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}

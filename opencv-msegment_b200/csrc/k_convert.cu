@@ -1,0 +1,252 @@
+// k_convert.cu -- layout conversion, Gaussian pyramid (cv::pyrDown / cv::pyrUp integer formulas,
+// SURVEY.md App. A.3), the pyramid change-mask of cv::pyrMeanShiftFiltering (App. A.2), label
+// rendering helpers and the synthetic-image generator.  All HBM-bound streaming kernels.
+#include "msg_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int p, int n)
+{
+    if (n == 1) return 0;
+    // |p| < 2n always holds for the 5-tap kernels used here, but loop for safety on tiny n
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------------------ BGR (8UC3, byte step) -> plane
+__global__ void __launch_bounds__(256) bgr_to_plane_kernel(const uint8_t* __restrict__ src, size_t step,
+                                                           uint32_t* __restrict__ dst, int w, int rows, int pitch)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w || y >= rows) return;
+    const uint8_t* p = src + (size_t)y * step + 3 * (size_t)x;
+    uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | 0x01000000u;
+    dst[(size_t)y * pitch + x] = v;
+}
+
+__global__ void __launch_bounds__(256) plane_to_bgr_kernel(const uint32_t* __restrict__ src, int pitch, int w,
+                                                           int nrows, uint8_t* __restrict__ dst, size_t step)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w || y >= nrows) return;
+    uint32_t v = src[(size_t)y * pitch + x];
+    uint8_t* p = dst + (size_t)y * step + 3 * (size_t)x;
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16);
+}
+
+// ------------------------------------------------------------------ pyrDown: 5x5 [1 4 6 4 1]^2, (acc+128)>>8
+__global__ void __launch_bounds__(256) pyr_down_kernel(msg_plane s, msg_plane d)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;  // stored row of d
+    if (x >= d.w || r >= d.rows) return;
+    int y = d.y0 + r;    // global row at the coarse level
+    const int k[5] = {1, 4, 6, 4, 1};
+    int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int a = -2; a <= 2; a++) {
+        int yy = reflect101(2 * y + a, s.hfull) - s.y0;
+        yy = clampi(yy, 0, s.rows - 1);  // rows outside a strip's halo: value unused by valid outputs
+        const uint32_t* row = s.p + (size_t)yy * s.pitch;
+#pragma unroll
+        for (int b = -2; b <= 2; b++) {
+            int xx = reflect101(2 * x + b, s.w);
+            uint32_t v = __ldg(row + xx);
+            int wgt = k[a + 2] * k[b + 2];
+            a0 += wgt * (int)(v & 0xFF);
+            a1 += wgt * (int)((v >> 8) & 0xFF);
+            a2 += wgt * (int)((v >> 16) & 0xFF);
+        }
+    }
+    uint32_t o = (uint32_t)((a0 + 128) >> 8) | ((uint32_t)((a1 + 128) >> 8) << 8) |
+                 ((uint32_t)((a2 + 128) >> 8) << 16) | 0x01000000u;
+    d.p[(size_t)r * d.pitch + x] = o;
+}
+
+// ------------------------------------------------------------------ change flags of D[l+1] (App. A.2)
+// flag(i,j) = any 8-neighbour n with ||D(i,j) - D(n)||^2 >= isr22, for interior pixels; stored in byte3.
+__global__ void __launch_bounds__(256) flag_kernel(msg_plane d, int isr22)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    if (x >= d.w || r >= d.rows) return;
+    int y = d.y0 + r;
+    uint32_t c = d.p[(size_t)r * d.pitch + x] & 0x00FFFFFFu;
+    uint32_t flag = 0;
+    if (x >= 1 && x <= d.w - 2 && y >= 1 && y <= d.hfull - 2 && r >= 1 && r <= d.rows - 2) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                if (dx == 0 && dy == 0) continue;
+                uint32_t n = d.p[(size_t)(r + dy) * d.pitch + (x + dx)] & 0x00FFFFFFu;
+                uint32_t e = __vabsdiffu4(c, n);
+                if ((int)__dp4a(e, e, 0u) >= isr22) flag = 1;
+            }
+    }
+    // only byte3 changes; neighbours read bytes 0..2 (32-bit accesses are atomic, colour bits unchanged)
+    d.p[(size_t)r * d.pitch + x] = c | (flag << 24);
+}
+
+__device__ __forceinline__ void up_taps(int o, int n, int& i0, int& i1, int& i2, int& w0, int& w1, int& w2)
+{
+    int i = o >> 1;
+    if (o & 1) {  // odd: 4*(s[i] + s[i+1]), s[n] := s[n-1]
+        i0 = i; i1 = (i + 1 < n) ? i + 1 : n - 1; i2 = i;
+        w0 = 4; w1 = 4; w2 = 0;
+    } else {      // even: s[i-1] + 6 s[i] + s[i+1], s[-1] := s[1] (s[0] if n==1), s[n] := s[n-1]
+        i0 = (i - 1 >= 0) ? i - 1 : (n > 1 ? 1 : 0); i1 = i; i2 = (i + 1 < n) ? i + 1 : n - 1;
+        w0 = 1; w1 = 6; w2 = 1;
+    }
+}
+
+// D[l] = pyrUp(D[l+1]); byte3 = dilate3x3(Mraw) where Mraw[2i+1][2j-1] = flag(i,j), 1<=i<=h1-2, 1<=j<=w1-2.
+__global__ void __launch_bounds__(256) pyr_up_mask_kernel(msg_plane s /*D[l+1] with flags*/, msg_plane d)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    if (x >= d.w || r >= d.rows) return;
+    int y = d.y0 + r;
+    int yi[3], yw[3], xi[3], xw[3];
+    up_taps(y, s.hfull, yi[0], yi[1], yi[2], yw[0], yw[1], yw[2]);
+    up_taps(x, s.w, xi[0], xi[1], xi[2], xw[0], xw[1], xw[2]);
+    int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        int rr = clampi(yi[a] - s.y0, 0, s.rows - 1);
+        const uint32_t* row = s.p + (size_t)rr * s.pitch;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            int wgt = yw[a] * xw[b];
+            uint32_t v = __ldg(row + xi[b]);
+            a0 += wgt * (int)(v & 0xFF);
+            a1 += wgt * (int)((v >> 8) & 0xFF);
+            a2 += wgt * (int)((v >> 16) & 0xFF);
+        }
+    }
+    uint32_t col = (uint32_t)((a0 + 32) >> 6) | ((uint32_t)((a1 + 32) >> 6) << 8) | ((uint32_t)((a2 + 32) >> 6) << 16);
+    // mask
+    uint32_t m = 0;
+    int h1 = s.hfull, w1 = s.w;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+        int yy = y + dy;
+        if (yy < 0 || yy >= d.hfull || !(yy & 1)) continue;
+        int i = (yy - 1) >> 1;
+        if (i < 1 || i > h1 - 2) continue;
+        int ri = i - s.y0;
+        if (ri < 0 || ri >= s.rows) continue;  // outside the strip's halo (unused outputs)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+            int xx = x + dx;
+            if (xx < 0 || xx >= d.w || !(xx & 1)) continue;
+            int j = (xx + 1) >> 1;
+            if (j < 1 || j > w1 - 2) continue;
+            m |= __ldg(s.p + (size_t)ri * s.pitch + j) >> 24;
+        }
+    }
+    d.p[(size_t)r * d.pitch + x] = col | ((m ? 1u : 0u) << 24);
+}
+
+// ------------------------------------------------------------------ synthetic image
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t synth_hash(uint64_t sm, uint32_t a, uint32_t b, uint32_t c)
+{
+    return splitmix64(sm ^ (((uint64_t)a << 40) | ((uint64_t)b << 16) | (uint64_t)c));
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(uint8_t* __restrict__ dst, size_t step, int w, int h, uint64_t sm)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    int ncx = (w + 63) / 64, ncy = (h + 63) / 64;
+    int cx0 = x / 64, cy0 = y / 64;
+    long long best = -1;
+    uint32_t bc = 0;
+    for (int cy = cy0 - 1; cy <= cy0 + 1; cy++)
+        for (int cx = cx0 - 1; cx <= cx0 + 1; cx++) {
+            if (cx < 0 || cy < 0 || cx >= ncx || cy >= ncy) continue;
+            int sx = 64 * cx + (int)(synth_hash(sm, cx, cy, 0) % 64);
+            int sy = 64 * cy + (int)(synth_hash(sm, cx, cy, 1) % 64);
+            long long ddx = x - sx, ddy = y - sy, dd = ddx * ddx + ddy * ddy;
+            if (best < 0 || dd < best) { best = dd; bc = (uint32_t)(synth_hash(sm, cx, cy, 2) & 0xFFFFFFu); }
+        }
+    uint8_t* p = dst + (size_t)y * step + 3 * (size_t)x;
+    for (int c = 0; c < 3; c++) {
+        int base = (int)((bc >> (8 * c)) & 0xFF);
+        int nz = (int)(synth_hash(sm, x, y, 16u + c) % 13) + (int)(synth_hash(sm, x, y, 32u + c) % 13) - 12;
+        int v = base + nz;
+        p[c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
+uint64_t host_splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+}  // namespace
+
+int k_bgr_to_plane(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, msg_plane dst)
+{
+    dim3 grid((dst.w + 255) / 256, dst.rows);
+    bgr_to_plane_kernel<<<grid, 256, 0, ctx->stream>>>(d_bgr, step, dst.p, dst.w, dst.rows, dst.pitch);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_plane_to_bgr(msg_ctx* ctx, msg_plane src, int row_first, int nrows, uint8_t* d_bgr, size_t step)
+{
+    dim3 grid((src.w + 255) / 256, nrows);
+    plane_to_bgr_kernel<<<grid, 256, 0, ctx->stream>>>(src.p + (size_t)row_first * src.pitch, src.pitch, src.w, nrows,
+                                                      d_bgr, step);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_pyr_down(msg_ctx* ctx, msg_plane src, msg_plane dst)
+{
+    dim3 grid((dst.w + 255) / 256, dst.rows);
+    pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(src, dst);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc, msg_plane ddst, int isr22)
+{
+    dim3 g1((dsrc.w + 255) / 256, dsrc.rows);
+    flag_kernel<<<g1, 256, 0, ctx->stream>>>(dsrc, isr22);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    dim3 g2((ddst.w + 255) / 256, ddst.rows);
+    pyr_up_mask_kernel<<<g2, 256, 0, ctx->stream>>>(dsrc, ddst);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_synth(msg_ctx* ctx, uint8_t* d_bgr, size_t step, int w, int h, uint64_t seed)
+{
+    dim3 grid((w + 255) / 256, h);
+    synth_kernel<<<grid, 256, 0, ctx->stream>>>(d_bgr, step, w, h, host_splitmix64(seed));
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}

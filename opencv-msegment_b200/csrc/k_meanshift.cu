@@ -1,0 +1,373 @@
+// k_meanshift.cu -- K1: the mean-shift filtering kernels (one pyramid level per launch).
+//
+// Semantics: cv::pyrMeanShiftFiltering's per-level loop, SURVEY.md App. A.2 (bit-exact):
+//   window  = [cvRound(x0-sp), cvRound(x0+sp)] x [cvRound(y0-sp), cvRound(y0+sp)] clamped to the image
+//   in-range test ||t-c||^2 <= isr2 on 8-bit BGR; integer sums of colour and ABSOLUTE position;
+//   new state = cvRound(sum * (1.0/count)) in IEEE double, round-half-even;
+//   stop when the centre does not move or |dx|+|dy|+||dc||^2 <= eps, or after maxCount iterations.
+//
+// Design (B200, INT-ALU bound, DESIGN.md "K1"):
+//   * one CTA per 64x32 pixel tile; tile + (radius + drift) halo staged once in shared memory as
+//     packed BGRx words, out-of-image positions hold a sentinel that can never be in range, so the
+//     window loops run unclamped and warp-convergent;
+//   * work is a queue of (pixel, centre, colour) items held in shared memory and processed in
+//     rounds, ONE mean-shift iteration per item per round; converged items retire, the rest are
+//     compacted (ballot + one shared atomic per warp) into the next round's queue, so lanes never
+//     idle on pixels that converged early (iterations vary 1..maxCount per pixel);
+//   * per test: LDS + VABSDIFF4 + IDP4A + ISETP + predicated 16-bit-lane SIMD accumulates;
+//   * an item whose next window would leave the staged rectangle is pushed to a global overflow
+//     list and finished by the generic kernel (reads HBM/L2 directly, explicit clamping).
+#include "msg_internal.h"
+
+namespace {
+
+constexpr int TW = 64;            // tile width  (pixels)
+constexpr int TH = 32;            // tile height (pixels)
+constexpr int NPIX = TW * TH;     // 2048 -> 11 bits
+constexpr int MS_THREADS = 256;
+constexpr uint32_t SENTINEL = 0xFF000000u;  // byte3 = 255 vs 1 of real pixels: distance >= 254^2
+
+__device__ __forceinline__ int rnd_f(float v) { return __float2int_rn(v); }  // cvRound(float): half-even
+
+struct iter_result {
+    int x1, y1;
+    uint32_t c1;
+    int count;
+};
+
+// One mean-shift iteration epilogue: exact OpenCV arithmetic (double reciprocal, then multiplies).
+__device__ __forceinline__ iter_result ms_epilogue(int s0, int s1, int s2, long long sx, long long sy, int count)
+{
+    iter_result r;
+    double icount = __ddiv_rn(1.0, (double)count);
+    r.x1 = __double2int_rn(__dmul_rn((double)sx, icount));
+    r.y1 = __double2int_rn(__dmul_rn((double)sy, icount));
+    int n0 = __double2int_rn(__dmul_rn((double)s0, icount));
+    int n1 = __double2int_rn(__dmul_rn((double)s1, icount));
+    int n2 = __double2int_rn(__dmul_rn((double)s2, icount));
+    r.c1 = (uint32_t)n0 | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16) | 0x01000000u;
+    r.count = count;
+    return r;
+}
+
+__device__ __forceinline__ bool ms_stop(int x0, int y0, uint32_t c0, const iter_result& r, int ieps)
+{
+    if (r.x1 == x0 && r.y1 == y0) return true;
+    uint32_t e = __vabsdiffu4(c0, r.c1);  // byte3 equal (1) on both sides
+    int dc2 = (int)__dp4a(e, e, 0u);
+    return abs(r.x1 - x0) + abs(r.y1 - y0) + dc2 <= ieps;
+}
+
+// Window scan over the staged tile.  NX > 0: window is NX x NX for every item (integral sp).
+template <int NX>
+__device__ __forceinline__ void window_scan(const uint32_t* __restrict__ base, int swp, int nx, int ny, uint32_t c,
+                                            int isr2, int& s0, int& s1, int& s2, int& sxr, int& syr, int& cnt)
+{
+    s0 = s1 = s2 = sxr = syr = cnt = 0;
+    if (NX > 0) { nx = NX; ny = NX; }
+    for (int yy = 0; yy < ny; ++yy) {
+        const uint32_t* row = base + yy * swp;
+        uint32_t lo = 0, hi = 0;
+        int sx = 0;
+        if (NX > 0) {
+#pragma unroll
+            for (int xx = 0; xx < (NX > 0 ? NX : 1); ++xx) {
+                uint32_t t = row[xx];
+                uint32_t e = __vabsdiffu4(t, c);
+                if ((int)__dp4a(e, e, 0u) <= isr2) {
+                    lo += __byte_perm(t, 0u, 0x4240);  // (B, 0, R, 0)
+                    hi += __byte_perm(t, 0u, 0x4341);  // (G, 0, 1, 0)
+                    sx += xx;
+                }
+            }
+        } else {
+            for (int xx = 0; xx < nx; ++xx) {
+                uint32_t t = row[xx];
+                uint32_t e = __vabsdiffu4(t, c);
+                if ((int)__dp4a(e, e, 0u) <= isr2) {
+                    lo += __byte_perm(t, 0u, 0x4240);
+                    hi += __byte_perm(t, 0u, 0x4341);
+                    sx += xx;
+                }
+            }
+        }
+        // per-row flush of the 16-bit lanes (row length <= 257 keeps 255*n < 65536)
+        int rc = (int)(hi >> 16);
+        s0 += (int)(lo & 0xFFFFu);
+        s2 += (int)(lo >> 16);
+        s1 += (int)(hi & 0xFFFFu);
+        cnt += rc;
+        syr += yy * rc;
+        sxr += sx;
+    }
+}
+
+struct tile_geom {
+    int halo;     // radius + drift allowance
+    int sw, sh;   // staged width / height
+    int swp;      // staged row pitch (odd, to spread banks between rows)
+    int tiles_x;
+};
+
+template <int NX>
+__global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S, msg_plane D, msg_ms_params prm,
+                                                                    tile_geom g, msg_ovf_item* __restrict__ ovf,
+                                                                    int* __restrict__ ovf_count,
+                                                                    unsigned long long* __restrict__ active_count)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* stage = smem;                                  // g.sh * g.swp
+    uint2* q0 = reinterpret_cast<uint2*>(smem + ((g.sh * g.swp + 1) & ~1));
+    uint2* q1 = q0 + NPIX;
+    __shared__ int qn[2];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int tile_x = blockIdx.x % g.tiles_x, tile_y = blockIdx.x / g.tiles_x;
+    const int tx0 = tile_x * TW;                 // global x of the tile origin
+    const int ty0 = S.y0 + tile_y * TH;          // global y of the tile origin
+    const int ox = tx0 - g.halo, oy = ty0 - g.halo;  // global coords of staged (0,0)
+
+    if (tid < 2) qn[tid] = 0;
+
+    // ---- stage tile + halo (coalesced row segments; sentinel outside the image / stored rows)
+    for (int sy = tid / 32; sy < g.sh; sy += MS_THREADS / 32) {
+        int gy = oy + sy;
+        int r = gy - S.y0;
+        bool row_ok = (gy >= 0) && (gy < S.hfull) && (r >= 0) && (r < S.rows);
+        const uint32_t* srow = S.p + (size_t)(row_ok ? r : 0) * S.pitch;
+        uint32_t* drow = stage + sy * g.swp;
+        for (int sx = lane; sx < g.sw; sx += 32) {
+            int gx = ox + sx;
+            uint32_t v = SENTINEL;
+            if (row_ok && gx >= 0 && gx < S.w) v = __ldg(srow + gx);
+            drow[sx] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- initial queue: active pixels of the tile, in raster order within each warp chunk
+    for (int base = (tid / 32) * 32; base < NPIX; base += MS_THREADS) {
+        int p = base + lane;
+        int ty = p / TW, tx = p % TW;
+        int gx = tx0 + tx, gy = ty0 + ty;
+        int r = gy - S.y0;
+        bool act = (gx < S.w) && (gy < S.hfull) && (r < S.rows);
+        if (act && prm.use_mask) act = (D.p[(size_t)r * D.pitch + gx] >> 24) != 0;
+        unsigned m = __ballot_sync(0xffffffffu, act);
+        int pos = 0;
+        if (lane == 0 && m) pos = atomicAdd(&qn[0], __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (act) {
+            int slot = pos + __popc(m & ((1u << lane) - 1));
+            uint32_t w0 = (uint32_t)p | ((uint32_t)(tx + g.halo) << 12) | ((uint32_t)(ty + g.halo) << 21);
+            q0[slot] = make_uint2(w0, stage[(ty + g.halo) * g.swp + tx + g.halo]);
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && active_count) atomicAdd(active_count, (unsigned long long)qn[0]);
+
+    const float sp = prm.sp;
+    const int R = prm.radius;
+    uint2* qc = q0;
+    uint2* qnx = q1;
+    for (int it = 0; it < prm.max_count; ++it) {
+        const int cur = it & 1;
+        const int n = qn[cur];
+        if (n == 0) break;
+        __syncthreads();               // everyone has read qn[cur] / finished the previous round
+        if (tid == 0) qn[cur ^ 1] = 0;
+        __syncthreads();
+        const bool last_round = (it == prm.max_count - 1);
+        for (int ibase = (tid / 32) * 32; ibase < n; ibase += MS_THREADS) {
+            const int i = ibase + lane;
+            const bool valid = i < n;
+            uint2 item = valid ? qc[i] : make_uint2(0u, 0u);
+            const int pix = item.x & 0xFFF;
+            const int xs = (item.x >> 12) & 0x1FF, ys = (item.x >> 21) & 0x1FF;
+            const uint32_t c = item.y;
+            const int x0 = ox + xs, y0 = oy + ys;
+            bool requeue = false, to_ovf = false;
+            iter_result res;
+            res.x1 = x0; res.y1 = y0; res.c1 = c; res.count = 0;
+            if (valid) {
+                int minx = rnd_f((float)x0 - sp), maxx = rnd_f((float)x0 + sp);
+                int miny = rnd_f((float)y0 - sp), maxy = rnd_f((float)y0 + sp);
+                const uint32_t* base = stage + (miny - oy) * g.swp + (minx - ox);
+                int s0, s1, s2, sxr, syr, cnt;
+                window_scan<NX>(base, g.swp, maxx - minx + 1, maxy - miny + 1, c, prm.isr2, s0, s1, s2, sxr, syr, cnt);
+                bool fin = true;
+                if (cnt > 0) {
+                    long long sx = (long long)sxr + (long long)cnt * minx;   // absolute-coordinate sums
+                    long long sy = (long long)syr + (long long)cnt * miny;
+                    res = ms_epilogue(s0, s1, s2, sx, sy, cnt);
+                    fin = ms_stop(x0, y0, c, res, prm.ieps) || last_round;
+                }
+                if (fin) {
+                    int ty = pix / TW, tx = pix % TW;
+                    D.p[(size_t)(ty0 - S.y0 + ty) * D.pitch + (tx0 + tx)] = res.c1;
+                } else {
+                    int nxs = res.x1 - ox, nys = res.y1 - oy;
+                    bool inside = (nxs - R >= 0) && (nxs + R < g.sw) && (nys - R >= 0) && (nys + R < g.sh);
+                    requeue = inside;
+                    to_ovf = !inside;
+                }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, requeue);
+            int pos = 0;
+            if (lane == 0 && m) pos = atomicAdd(&qn[cur ^ 1], __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (requeue) {
+                int slot = pos + __popc(m & ((1u << lane) - 1));
+                uint32_t w0 = (uint32_t)pix | ((uint32_t)(res.x1 - ox) << 12) | ((uint32_t)(res.y1 - oy) << 21);
+                qnx[slot] = make_uint2(w0, res.c1);
+            }
+            if (to_ovf) {
+                int slot = atomicAdd(ovf_count, 1);
+                int ty = pix / TW, tx = pix % TW;
+                msg_ovf_item o;
+                o.pix = (uint32_t)((size_t)(ty0 - S.y0 + ty) * D.pitch + (tx0 + tx));
+                o.x0 = (int16_t)res.x1;
+                o.y0rel = (int16_t)(res.y1 - S.y0);
+                o.c = res.c1;
+                o.iter = (uint32_t)(it + 1);
+                ovf[slot] = o;
+            }
+        }
+        __syncthreads();
+        uint2* t = qc; qc = qnx; qnx = t;
+    }
+}
+
+// Generic path: explicit clamping, reads the plane through L1/L2.  Either finishes overflow items
+// (items != nullptr) or processes every (active) pixel of the plane (items == nullptr).
+__global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg_plane D, msg_ms_params prm,
+                                                                const msg_ovf_item* __restrict__ items,
+                                                                const int* __restrict__ n_items,
+                                                                unsigned long long* __restrict__ active_count,
+                                                                unsigned long long* __restrict__ ovf_total)
+{
+    const long long total = items ? (long long)*n_items : (long long)S.rows * S.w;
+    if (items && ovf_total && blockIdx.x == 0 && threadIdx.x == 0 && total > 0)
+        atomicAdd(ovf_total, (unsigned long long)total);
+    const float sp = prm.sp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int x0, y0, it0;
+        uint32_t c;
+        size_t out;
+        if (items) {
+            msg_ovf_item o = items[i];
+            x0 = o.x0; y0 = S.y0 + o.y0rel; c = o.c; it0 = (int)o.iter; out = o.pix;
+        } else {
+            int r = (int)(i / S.w), x = (int)(i % S.w);
+            out = (size_t)r * D.pitch + x;
+            if (prm.use_mask && (D.p[out] >> 24) == 0) continue;
+            x0 = x; y0 = S.y0 + r; c = S.p[(size_t)r * S.pitch + x]; it0 = 0;
+            if (active_count) atomicAdd(active_count, 1ull);
+        }
+        for (int it = it0; it < prm.max_count; ++it) {
+            int minx = max(rnd_f((float)x0 - sp), 0), maxx = min(rnd_f((float)x0 + sp), S.w - 1);
+            int miny = max(rnd_f((float)y0 - sp), 0), maxy = min(rnd_f((float)y0 + sp), S.hfull - 1);
+            // stored-row guard (strip planes): rows outside the stored range do not exist here
+            miny = max(miny, S.y0); maxy = min(maxy, S.y0 + S.rows - 1);
+            int s0 = 0, s1 = 0, s2 = 0, cnt = 0;
+            long long sx = 0, sy = 0;
+            for (int y = miny; y <= maxy; ++y) {
+                const uint32_t* row = S.p + (size_t)(y - S.y0) * S.pitch;
+                int rc = 0, rsx = 0;
+                for (int x = minx; x <= maxx; ++x) {
+                    uint32_t t = __ldg(row + x);
+                    uint32_t e = __vabsdiffu4(t, c);
+                    if ((long long)__dp4a(e, e, 0u) <= (long long)prm.isr2) {
+                        s0 += (int)(t & 0xFF); s1 += (int)((t >> 8) & 0xFF); s2 += (int)((t >> 16) & 0xFF);
+                        rsx += x; rc++;
+                    }
+                }
+                cnt += rc; sx += rsx; sy += (long long)y * rc;
+            }
+            if (cnt == 0) break;
+            iter_result res = ms_epilogue(s0, s1, s2, sx, sy, cnt);
+            bool stop = ms_stop(x0, y0, c, res, prm.ieps);
+            x0 = res.x1; y0 = res.y1; c = res.c1;
+            if (stop) break;
+        }
+        D.p[out] = c;
+    }
+}
+
+template <int NX>
+cudaError_t launch_tile(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, const tile_geom& g, int tiles,
+                        size_t smem, int* ovf_count, unsigned long long* active)
+{
+    // attribute is per function AND per device: set it on every launch (cheap, no sync)
+    cudaError_t e = cudaFuncSetAttribute(meanshift_tile_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    meanshift_tile_kernel<NX><<<tiles, MS_THREADS, smem, ctx->stream>>>(S, D, prm, g, ctx->d_ovf, ovf_count, active);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// d_counters layout: [0] overflow count of the current level, [2..3] active items (u64), [4..5] overflow total (u64)
+int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm)
+{
+    int* ovf_count = ctx->d_counters;
+    unsigned long long* active = reinterpret_cast<unsigned long long*>(ctx->d_counters + 2);
+    unsigned long long* ovf_total = reinterpret_cast<unsigned long long*>(ctx->d_counters + 4);
+
+    // tile path limits: sentinel distance 254^2 must exceed isr2; staged tile must fit shared memory
+    const int R = prm.radius;
+    int drift = R + (R + 3) / 4;  // ~1.25 * radius (covers > 99 % of measured drift)
+    if (drift < 4) drift = 4;
+    tile_geom g;
+    size_t smem = 0;
+    bool tile_ok = prm.isr2 < 254 * 254 && R <= 120 && S.rows <= 32767 && S.w <= 32767;
+    if (tile_ok) {
+        for (;; drift = drift * 3 / 4) {
+            g.halo = R + drift;
+            g.sw = TW + 2 * g.halo;
+            g.sh = TH + 2 * g.halo;
+            g.swp = g.sw | 1;
+            smem = ((size_t)((g.sh * g.swp + 1) & ~1) + 4 * (size_t)NPIX) * sizeof(uint32_t);
+            if (smem <= (size_t)ctx->max_smem_optin - 1024 && g.sw < 512 && g.sh < 512) break;
+            if (drift == 0) { tile_ok = false; break; }
+        }
+    }
+    if (!tile_ok) {
+        int blocks = ctx->sm_count * 16;
+        meanshift_generic_kernel<<<blocks, 128, 0, ctx->stream>>>(S, D, prm, nullptr, nullptr, active, nullptr);
+        MSG_LAUNCHED(ctx);
+        MSG_CHECK_LAUNCH(ctx);
+        return MSG_OK;
+    }
+
+    size_t need = (size_t)S.rows * S.w;
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, need * sizeof(msg_ovf_item)));
+    MSG_CUDA(ctx, cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
+    g.tiles_x = (S.w + TW - 1) / TW;
+    int tiles_y = (S.rows + TH - 1) / TH;
+    int tiles = g.tiles_x * tiles_y;
+
+    // integral sp -> every window is (2 sp + 1)^2: use the fully unrolled instantiations
+    int nx = 0;
+    if (prm.sp == (float)(int)prm.sp) nx = 2 * (int)prm.sp + 1;
+    cudaError_t e;
+    switch (nx) {
+        case 3: e = launch_tile<3>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
+        case 5: e = launch_tile<5>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
+        case 7: e = launch_tile<7>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
+        case 11: e = launch_tile<11>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
+        case 21: e = launch_tile<21>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
+        case 41: e = launch_tile<41>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
+        default: e = launch_tile<0>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
+    }
+    MSG_LAUNCHED(ctx);
+    MSG_CUDA(ctx, e);
+
+    // finish the items that left their tile (count is read on the device: no host sync)
+    meanshift_generic_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(S, D, prm, ctx->d_ovf, ovf_count, nullptr, ovf_total);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}

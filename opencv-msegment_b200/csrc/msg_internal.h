@@ -1,0 +1,131 @@
+// msg_internal.h -- shared declarations of libmsegment_b200 (sm_100a).  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/msegment.h"
+
+#define MSG_MAX_LEVELS 9  // max_level in [0,8]
+
+// A pyramid plane in HBM: one u32 per pixel, byte0=B byte1=G byte2=R byte3=flag.
+//   S planes: byte3 = 1 for every pixel (so the packed word can be used directly as a
+//             mean-shift "centre" and count accumulates through the same SIMD lane).
+//   D planes: byte3 = change-mask of the level below maxLevel (0 = keep pyrUp value).
+// `pitch` is in pixels (multiple of 32 -> rows start on 128-byte lines).
+// A plane may hold only rows [y0, y0+rows) of a level whose full height is `hfull`
+// (strip sharding); unsharded: y0 = 0, rows = hfull.
+struct msg_plane {
+    uint32_t* p;
+    int w;       // level width
+    int rows;    // rows stored
+    int y0;      // global row of stored row 0
+    int hfull;   // full level height
+    int pitch;   // pixels per stored row
+};
+
+struct msg_ms_params {   // per level
+    float sp;            // spatial radius of the level (float32, as OpenCV computes it)
+    int radius;          // ceil(sp): max |offset| the window can reach
+    int isr2;            // cvRound(sr*sr)
+    int max_count;
+    int ieps;            // floor(eps) clamped to int: (double)k <= eps  <=>  k <= ieps
+    int use_mask;        // level < max_level: only pixels with D.byte3 != 0 run
+};
+
+struct msg_ovf_item {    // mean-shift item that left its staged tile; finished by the generic kernel
+    uint32_t pix;        // plane-linear pixel index (row*pitch + x, stored rows)
+    int16_t x0, y0rel;   // current window centre: x global, y relative to plane.y0 (fits: <= 32767 rows/plane)
+    uint32_t c;          // packed colour, byte3 = 1
+    uint32_t iter;       // iterations already done
+};
+
+struct msg_ctx {
+    int device;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    cudaEvent_t ev[8];
+    char err[512];
+    int cuda_failed;
+    int sm_count;
+    int max_smem_optin;
+
+    // grow-only device workspace
+    uint8_t* d_in;     size_t d_in_cap;      // raw BGR / mask upload
+    uint8_t* d_out;    size_t d_out_cap;     // raw BGR download staging
+    uint8_t* d_out2;   size_t d_out2_cap;    // rendered image staging
+    int32_t* d_labels; size_t d_labels_cap;  // dense labels (w*h)
+    uint32_t* d_planes; size_t d_planes_cap; // all S and D planes, carved per call
+    msg_ovf_item* d_ovf; size_t d_ovf_cap;   // overflow queue (items)
+    uint32_t* d_scratch; size_t d_scratch_cap; // CCL / scan / merge scratch (bytes)
+    int32_t* d_counters;                     // 64 int32 device counters
+    int32_t* h_counters;                     // pinned mirror
+    uint8_t* d_colors; size_t d_colors_cap;
+
+    // pinned host staging for pageable caller buffers
+    uint8_t* h_stage; size_t h_stage_cap;
+
+    msg_plane S[MSG_MAX_LEVELS], D[MSG_MAX_LEVELS];
+    int last_levels;
+
+    msg_timings tm;
+    msg_stats st;
+
+    struct pending {
+        int used;
+        int32_t* n_regions_host;  // pinned slot
+        cudaEvent_t done;
+        // deferred host copies (pageable destinations) are not supported asynchronously:
+        // submit requires pinned or registered memory, otherwise it degrades to synchronous.
+    } pend[MSG_MAX_INFLIGHT];
+};
+
+// ---------------------------------------------------------------- error helpers
+int msg_fail(msg_ctx* ctx, int code, const char* fmt, ...);
+#define MSG_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->cuda_failed = 1;                                                           \
+            return msg_fail((ctx), MSG_ECUDA, "%s failed: %s (%s:%d)", #call,                 \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                     \
+        }                                                                                     \
+    } while (0)
+#define MSG_TRY(expr)                    \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != MSG_OK) return rc__; \
+    } while (0)
+
+int msg_reserve(msg_ctx* ctx, void** p, size_t* cap, size_t bytes);
+
+static inline int msg_align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- kernel launchers (k_*.cu)
+// conversions / pyramid
+int k_bgr_to_plane(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, msg_plane dst);          // all stored rows
+int k_plane_to_bgr(msg_ctx* ctx, msg_plane src, int row_first, int nrows, uint8_t* d_bgr, size_t step);
+int k_pyr_down(msg_ctx* ctx, msg_plane src, msg_plane dst);
+int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc /*D[l+1]*/, msg_plane ddst /*D[l]*/, int isr22);
+int k_synth(msg_ctx* ctx, uint8_t* d_bgr, size_t step, int w, int h, uint64_t seed);
+// mean shift
+int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm);
+// labelling
+int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int32_t* d_labels,
+                int64_t label_base, int lab_pitch);
+int k_ccl_binary(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int conn, int32_t* d_labels);
+int k_relabel_canonical(msg_ctx* ctx, int32_t* d_labels, int w, int h, int roots_are_pixels,
+                        int32_t* d_n_out /*device, may be NULL*/, int add_to_count);
+int k_merge(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels, int w, int h, int min_size,
+            int color_dist, int32_t* d_n_out);
+int k_render(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, uint8_t* d_dst, size_t dstep, int w, int h,
+             int depth, const uint8_t* d_colors);
+int k_copy_labels_2d(msg_ctx* ctx, const int32_t* src, size_t sstep, int32_t* dst, size_t dstep, int w, int h);
+int k_seam_pairs(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const uint8_t* lo_bgr,
+                 const int32_t* lo_lab, int w, int d, int32_t* pairs, int32_t* count);
+int k_apply_map(msg_ctx* ctx, int32_t* labels, size_t lstep, int w, int rows, const int32_t* from,
+                const int32_t* to, int n);
+
+#define MSG_LAUNCHED(ctx) ((ctx)->st.kernel_launches++)
+#define MSG_CHECK_LAUNCH(ctx) MSG_CUDA(ctx, cudaGetLastError())

@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference's operator interface for the segmentation hot path.
+
+The reference (Java) calls static methods of ``org.opencv.imgproc.Imgproc`` on ``Mat`` objects
+(PictureService.java:441-442 connectedComponents, :909 watershed, :913-936 colorByIndexes) and
+BASELINE.json's north_star adds pyrMeanShiftFiltering / floodFill-style labelling / region merge.
+This module exposes the same names with the argument meaning of the OpenCV Java/Python API on
+numpy arrays (the Python spelling of ``Mat``): ``GpuImgproc.pyrMeanShiftFiltering(src, sp, sr,
+maxLevel, termcrit)`` etc.  Every call goes through the C ABI (include/msegment.h) into CUDA; a
+non-zero status raises ``CvException`` exactly where the Java shim throws
+``org.opencv.core.CvException``.  No CPU implementation exists here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+CV_32S = 4                     # org.opencv.core.CvType.CV_32S
+TERM_COUNT, TERM_EPS = L.TERM_COUNT, L.TERM_EPS
+DEFAULT_TERMCRIT = (TERM_COUNT | TERM_EPS, 5, 1.0)   # Imgproc.pyrMeanShiftFiltering 4-arg overload
+
+
+class CvException(RuntimeError):
+    """Mirror of org.opencv.core.CvException (unchecked)."""
+
+    def __init__(self, status, message):
+        super().__init__("msegment status %d: %s" % (status, message))
+        self.status = status
+
+
+class Context:
+    """One msg_ctx: one CUDA device, one stream, a grow-only HBM workspace.  Not thread-safe."""
+
+    def __init__(self, device=0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        rc = self._lib.msg_create(int(device), C.byref(h))
+        if rc != L.MSG_OK:
+            raise CvException(rc, (self._lib.msg_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.msg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def check(self, rc):
+        if rc != L.MSG_OK:
+            raise CvException(rc, (self._lib.msg_last_error(self._h) or b"").decode())
+
+    # -- introspection
+    def timings(self):
+        t = L.Timings()
+        self.check(self._lib.msg_get_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in L.Timings._fields_}
+
+    def stats(self):
+        s = L.Stats()
+        self.check(self._lib.msg_get_stats(self._h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in L.Stats._fields_}
+
+    def set_stream(self, cuda_stream):
+        self.check(self._lib.msg_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
+
+    def synchronize(self):
+        self.check(self._lib.msg_synchronize(self._h))
+
+    def debug_plane(self, kind, level):
+        w, h = C.c_int(), C.c_int()
+        self.check(self._lib.msg_debug_get_plane(self._h, kind, level, None, 0, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint32)
+        self.check(self._lib.msg_debug_get_plane(self._h, kind, level, out.ctypes.data, out.size, C.byref(w), C.byref(h)))
+        return out
+
+
+def _mat8uc3(a, what):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+        raise CvException(L.MSG_EINVAL, "%s must be CV_8UC3 (HxWx3 uint8), got %s %s" % (what, a.dtype, a.shape))
+    if a.strides[2] != 1 or a.strides[1] != 3:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def _mat32s(a, what):
+    a = np.asarray(a)
+    if a.dtype != np.int32 or a.ndim != 2:
+        raise CvException(L.MSG_EINVAL, "%s must be CV_32SC1 (HxW int32), got %s %s" % (what, a.dtype, a.shape))
+    if a.strides[1] != 4:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class GpuImgproc:
+    """Static-method style mirror of ``Imgproc`` bound to a Context (``GpuImgproc(ctx).name(...)``)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx if ctx is not None else Context(0)
+        self._lib = self.ctx._lib
+
+    # Imgproc.pyrMeanShiftFiltering(Mat src, Mat dst, double sp, double sr, int maxLevel, TermCriteria termcrit)
+    def pyrMeanShiftFiltering(self, src, sp, sr, maxLevel=1, termcrit=DEFAULT_TERMCRIT, dst=None):
+        src = _mat8uc3(src, "src")
+        h, w = src.shape[:2]
+        if dst is None:
+            dst = np.empty((h, w, 3), np.uint8)
+        else:
+            if dst.shape != src.shape or dst.dtype != np.uint8:
+                raise CvException(L.MSG_EINVAL, "dst must have the size and type of src")
+        self.ctx.check(self._lib.msg_meanshift_filter(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data,
+                                                      dst.strides[0], w, h, float(sp), float(sr), int(maxLevel),
+                                                      int(termcrit[0]), int(termcrit[1]), float(termcrit[2])))
+        return dst
+
+    # floodFill region-growing loop of OpenCV's meanshift_segmentation sample, as one call
+    def labelRegions(self, image, loDiff=2, upDiff=2, connectivity=4):
+        image = _mat8uc3(image, "image")
+        h, w = image.shape[:2]
+        labels = np.empty((h, w), np.int32)
+        n = C.c_int32()
+        self.ctx.check(self._lib.msg_label_regions(self.ctx._h, image.ctypes.data, image.strides[0], labels.ctypes.data,
+                                                   labels.strides[0], w, h, int(loDiff), int(upDiff), int(connectivity),
+                                                   C.byref(n)))
+        return n.value, labels
+
+    def mergeRegions(self, image, labels, minSize, colorDist):
+        image = _mat8uc3(image, "image")
+        labels = _mat32s(labels, "labels").copy()
+        h, w = image.shape[:2]
+        if labels.shape != (h, w):
+            raise CvException(L.MSG_EINVAL, "labels must have the size of image")
+        n = C.c_int32()
+        self.ctx.check(self._lib.msg_merge_regions(self.ctx._h, image.ctypes.data, image.strides[0], labels.ctypes.data,
+                                                   labels.strides[0], w, h, int(minSize), int(colorDist), C.byref(n)))
+        return n.value, labels
+
+    # Imgproc.connectedComponents(Mat image, Mat labels, int connectivity, int ltype) -- PictureService.java:441-442
+    def connectedComponents(self, image, connectivity=8, ltype=CV_32S):
+        image = np.asarray(image)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise CvException(L.MSG_EINVAL, "image must be CV_8UC1")
+        if ltype != CV_32S:
+            raise CvException(L.MSG_EINVAL, "only ltype CV_32S is supported (the reference passes CvType.CV_32S)")
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        labels = np.empty((h, w), np.int32)
+        n = C.c_int32()
+        self.ctx.check(self._lib.msg_connected_components(self.ctx._h, image.ctypes.data, image.strides[0],
+                                                          labels.ctypes.data, labels.strides[0], w, h,
+                                                          int(connectivity), C.byref(n)))
+        return n.value, labels
+
+    # PictureService.colorByIndexes(Mat markers, Integer depth, boolean colored) -- PictureService.java:913-936
+    def colorByIndexes(self, markers, depth, colors=None):
+        markers = _mat32s(markers, "markers")
+        h, w = markers.shape
+        dst = np.empty((h, w, 3), np.uint8)
+        cptr = None
+        if colors is not None:
+            colors = np.ascontiguousarray(colors, dtype=np.uint8)
+            if colors.shape != (depth, 3):
+                raise CvException(L.MSG_EINVAL, "colors must be depth x 3 bytes")
+            cptr = colors.ctypes.data
+        self.ctx.check(self._lib.msg_render_labels(self.ctx._h, markers.ctypes.data, markers.strides[0], dst.ctypes.data,
+                                                   dst.strides[0], w, h, int(depth), cptr))
+        return dst
+
+    # fused pipeline
+    def segment(self, src, sp=10.0, sr=10.0, maxLevel=1, termcrit=DEFAULT_TERMCRIT, loDiff=2, minSize=0, colorDist=0,
+                renderDepth=0, want=("filtered", "labels", "rendered")):
+        src = _mat8uc3(src, "src")
+        h, w = src.shape[:2]
+        p = L.SegmentParams(float(sp), float(sr), int(maxLevel), int(termcrit[0]), int(termcrit[1]), float(termcrit[2]),
+                            int(loDiff), int(minSize), int(colorDist), int(renderDepth))
+        out = {}
+        f = np.empty((h, w, 3), np.uint8) if "filtered" in want else None
+        lab = np.empty((h, w), np.int32) if "labels" in want else None
+        r = np.empty((h, w, 3), np.uint8) if "rendered" in want else None
+        n = C.c_int32()
+        self.ctx.check(self._lib.msg_segment(
+            self.ctx._h, src.ctypes.data, src.strides[0], w, h, C.byref(p),
+            f.ctypes.data if f is not None else None, f.strides[0] if f is not None else 0,
+            lab.ctypes.data if lab is not None else None, lab.strides[0] if lab is not None else 0,
+            r.ctypes.data if r is not None else None, r.strides[0] if r is not None else 0, C.byref(n)))
+        out["n_regions"] = n.value
+        if f is not None:
+            out["filtered"] = f
+        if lab is not None:
+            out["labels"] = lab
+        if r is not None:
+            out["rendered"] = r
+        return out

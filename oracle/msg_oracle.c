@@ -91,14 +91,17 @@ void orc_pyr_up_8uc3(const uint8_t* src, size_t sstep, int w, int h, uint8_t* ds
 
 static inline int sq(int v) { return v * v; }
 
+/* One level.  The plane S (w x h) is the window [xoff, xoff+w) x [yoff, yoff+h) of a level whose full size is
+ * fullw x fullh: centres, clamping and the position sums use GLOBAL coordinates (the rounding of
+ * sum * (1/count) depends on the absolute magnitude of the sums).  Whole image: xoff = yoff = 0, full = (w,h). */
 static void meanshift_level(const uint8_t* S, size_t sstep, uint8_t* D, size_t dstep, int w, int h,
                             const uint8_t* mask, float sp, int isr2, int max_count, double eps,
-                            orc_ms_counters* ct)
+                            orc_ms_counters* ct, int xoff, int yoff, int fullw, int fullh)
 {
     for (int i = 0; i < h; i++)
         for (int j = 0; j < w; j++) {
             if (mask && !mask[(size_t)i * w + j]) continue;
-            int x0 = j, y0 = i;
+            int x0 = j + xoff, y0 = i + yoff;
             int c0 = S[(size_t)i * sstep + 3 * j], c1 = S[(size_t)i * sstep + 3 * j + 1],
                 c2 = S[(size_t)i * sstep + 3 * j + 2];
             if (ct) ct->pixels++;
@@ -107,11 +110,18 @@ static void meanshift_level(const uint8_t* S, size_t sstep, uint8_t* D, size_t d
                 int maxx = cv_round_f((float)x0 + sp), maxy = cv_round_f((float)y0 + sp);
                 if (minx < 0) minx = 0;
                 if (miny < 0) miny = 0;
-                if (maxx > w - 1) maxx = w - 1;
-                if (maxy > h - 1) maxy = h - 1;
-                int s0 = 0, s1 = 0, s2 = 0, sx = 0, sy = 0, count = 0;
+                if (maxx > fullw - 1) maxx = fullw - 1;
+                if (maxy > fullh - 1) maxy = fullh - 1;
+                /* rows / columns outside the stored window do not exist (ROI evaluation: such pixels lie in
+                 * the caller's margin and their results are discarded) */
+                if (minx < xoff) minx = xoff;
+                if (miny < yoff) miny = yoff;
+                if (maxx > xoff + w - 1) maxx = xoff + w - 1;
+                if (maxy > yoff + h - 1) maxy = yoff + h - 1;
+                int s0 = 0, s1 = 0, s2 = 0, count = 0;
+                long long sx = 0, sy = 0;
                 for (int y = miny; y <= maxy; y++) {
-                    const uint8_t* p = S + (size_t)y * sstep + 3 * minx;
+                    const uint8_t* p = S + (size_t)(y - yoff) * sstep + 3 * (size_t)(minx - xoff);
                     int row_count = 0;
                     for (int x = minx; x <= maxx; x++, p += 3) {
                         int t0 = p[0], t1 = p[1], t2 = p[2];
@@ -120,7 +130,7 @@ static void meanshift_level(const uint8_t* S, size_t sstep, uint8_t* D, size_t d
                         }
                     }
                     count += row_count;
-                    sy += y * row_count;
+                    sy += (long long)y * row_count;
                 }
                 if (ct) {
                     ct->iterations++;
@@ -136,7 +146,8 @@ static void meanshift_level(const uint8_t* S, size_t sstep, uint8_t* D, size_t d
                            (double)(abs(x1 - x0) + abs(y1 - y0) + sq(n0 - c0) + sq(n1 - c1) + sq(n2 - c2)) <= eps;
                 x0 = x1; y0 = y1; c0 = n0; c1 = n1; c2 = n2;
                 if (ct) {
-                    uint64_t dr = (uint64_t)(abs(x0 - j) > abs(y0 - i) ? abs(x0 - j) : abs(y0 - i));
+                    int ddx = abs(x0 - (j + xoff)), ddy = abs(y0 - (i + yoff));
+                    uint64_t dr = (uint64_t)(ddx > ddy ? ddx : ddy);
                     if (dr > ct->max_drift) ct->max_drift = dr;
                 }
                 if (stop) break;
@@ -150,7 +161,18 @@ int orc_meanshift_filter(const uint8_t* src, size_t sstep, uint8_t* dst, size_t 
                          double sp0, double sr, int max_level, int term_type, int max_count, double eps,
                          orc_ms_counters* ct)
 {
-    if (max_level < 0 || max_level > 8 || !(sp0 > 0) || !(sr > 0) || w <= 0 || h <= 0) return -1;
+    return orc_meanshift_filter_roi(src, sstep, dst, dstep, w, h, 0, 0, w, h, sp0, sr, max_level, term_type,
+                                    max_count, eps, ct);
+}
+
+int orc_meanshift_filter_roi(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h,
+                             int xoff, int yoff, int full_w, int full_h,
+                             double sp0, double sr, int max_level, int term_type, int max_count, double eps,
+                             orc_ms_counters* ct)
+{
+    if (max_level < 0 || max_level > 8 || w <= 0 || h <= 0) return -1; /* OpenCV validates only maxLevel */
+    if (xoff < 0 || yoff < 0 || xoff + w > full_w || yoff + h > full_h) return -1;
+    if ((xoff | yoff) & ((1 << max_level) - 1)) return -1; /* pyramid phase must match the full image */
     if (!(term_type & ORC_TERM_COUNT)) max_count = 5;
     if (max_count < 1) max_count = 1;
     if (max_count > 100) max_count = 100;
@@ -160,12 +182,13 @@ int orc_meanshift_filter(const uint8_t* src, size_t sstep, uint8_t* dst, size_t 
     int isr22 = isr2 > 16 ? isr2 : 16;
     if (ct) memset(ct, 0, sizeof(*ct));
 
-    uint8_t* S[9]; uint8_t* D[9]; int W[9], H[9];
-    S[0] = (uint8_t*)src; D[0] = dst; W[0] = w; H[0] = h;
+    uint8_t* S[9]; uint8_t* D[9]; int W[9], H[9], FW[9], FH[9];
+    S[0] = (uint8_t*)src; D[0] = dst; W[0] = w; H[0] = h; FW[0] = full_w; FH[0] = full_h;
     size_t sst[9], dst_[9];
     sst[0] = sstep; dst_[0] = dstep;
     for (int l = 1; l <= max_level; l++) {
         W[l] = (W[l - 1] + 1) / 2; H[l] = (H[l - 1] + 1) / 2;
+        FW[l] = (FW[l - 1] + 1) / 2; FH[l] = (FH[l - 1] + 1) / 2;
         sst[l] = dst_[l] = (size_t)3 * W[l];
         S[l] = (uint8_t*)malloc(sst[l] * H[l]);
         D[l] = (uint8_t*)malloc(dst_[l] * H[l]);
@@ -211,7 +234,7 @@ int orc_meanshift_filter(const uint8_t* src, size_t sstep, uint8_t* dst, size_t 
                 }
             m = mask;
         }
-        meanshift_level(S[l], sst[l], D[l], dst_[l], lw, lh, m, sp, isr2, max_count, eps, ct);
+        meanshift_level(S[l], sst[l], D[l], dst_[l], lw, lh, m, sp, isr2, max_count, eps, ct, xoff >> l, yoff >> l, FW[l], FH[l]);
     }
     for (int l = 1; l <= max_level; l++) { free(S[l]); free(D[l]); }
     free(mask); free(mtmp);

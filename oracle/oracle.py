@@ -42,6 +42,8 @@ def lib():
         L.orc_pyr_up_8uc3.argtypes = [u8p, sz, i, i, u8p, sz, i, i]
         L.orc_meanshift_filter.argtypes = [u8p, sz, u8p, sz, i, i, d, d, i, i, i, d, C.POINTER(MsCounters)]
         L.orc_meanshift_filter.restype = i
+        L.orc_meanshift_filter_roi.argtypes = [u8p, sz, u8p, sz, i, i, i, i, i, i, d, d, i, i, i, d, C.POINTER(MsCounters)]
+        L.orc_meanshift_filter_roi.restype = i
         L.orc_label_regions.argtypes = [u8p, sz, i32p, sz, i, i, i]
         L.orc_label_regions.restype = C.c_int32
         L.orc_connected_components.argtypes = [u8p, sz, i32p, sz, i, i, i]
@@ -92,6 +94,18 @@ def meanshift_filter(src, sp, sr, max_level=1, term=(TERM_COUNT | TERM_EPS, 5, 1
         raise ValueError("orc_meanshift_filter: invalid arguments")
     if counters:
         return dst, {k: getattr(ct, k) for k, _ in MsCounters._fields_}
+    return dst
+
+
+def meanshift_filter_roi(crop, xoff, yoff, full_w, full_h, sp, sr, max_level=1, term=(TERM_COUNT | TERM_EPS, 5, 1.0)):
+    crop = _img(crop)
+    h, w = crop.shape[:2]
+    dst = np.empty_like(crop)
+    rc = lib().orc_meanshift_filter_roi(crop.ctypes.data, crop.strides[0], dst.ctypes.data, dst.strides[0], w, h,
+                                        int(xoff), int(yoff), int(full_w), int(full_h), float(sp), float(sr),
+                                        int(max_level), int(term[0]), int(term[1]), float(term[2]), None)
+    if rc != 0:
+        raise ValueError("orc_meanshift_filter_roi: invalid arguments")
     return dst
 
 

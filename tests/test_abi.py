@@ -1,0 +1,66 @@
+"""CPU: the C-ABI library builds, loads without a GPU and exports every symbol include/msegment.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import msegment_b200 as mseg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "msegment.h")).read()
+    return sorted(set(re.findall(r"^MSG_API\s+[\w\s\*]+?\b(msg_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_header_declares_expected_surface():
+    syms = declared_symbols()
+    for must in ("msg_create", "msg_meanshift_filter", "msg_label_regions", "msg_merge_regions",
+                 "msg_connected_components", "msg_render_labels", "msg_segment", "msg_submit_segment", "msg_wait",
+                 "msg_alloc_pinned", "msg_meanshift_filter_dev", "msg_meanshift_filter_strip_dev"):
+        assert must in syms
+    assert len(syms) >= 30
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(mseg.lib.LIB_PATH), "run `python __graft_entry__.py build` first"
+    lib = ctypes.CDLL(mseg.lib.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_the_header():
+    assert sorted(mseg.lib.SIGNATURES) == declared_symbols()
+
+
+def test_version_and_no_cpu_fallback():
+    lib = mseg.lib.load()
+    assert lib.msg_version() == 100
+    if lib.msg_device_count() == 0:
+        with pytest.raises(mseg.CvException) as ei:
+            mseg.Context(0)
+        assert ei.value.status == mseg.lib.MSG_ECUDA
+        assert "no CPU fallback" in str(ei.value)
+
+
+def test_halo_rows_is_pure_host_function():
+    lib = mseg.lib.load()
+    h1 = lib.msg_meanshift_halo_rows(10.0, 1, 3, 5)
+    h0 = lib.msg_meanshift_halo_rows(10.0, 0, 3, 5)
+    assert h0 >= 50 and h1 >= 58 and h1 % 2 == 0
+    assert lib.msg_meanshift_halo_rows(10.0, 9, 3, 5) < 0
+
+
+def test_product_does_not_use_oracle():
+    """The product path must never import, link or call the CPU oracle."""
+    pkg = os.path.join(ROOT, "opencv-msegment_b200")
+    bad = re.compile(r"libmsg_oracle|from\s+oracle|import\s+oracle|msg_oracle\.h|\borc_\w+\s*\(")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp", ".java", ".c")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not bad.search(txt), (dirpath, f)
+    out = os.popen("ldd %s 2>/dev/null" % mseg.lib.LIB_PATH).read()
+    assert "oracle" not in out
