@@ -139,6 +139,11 @@ MSG_API void msg_free_pinned(void* p);
 
 /* ---- device-resident interface (pointers are CUDA device pointers on the context's device;
  *      work is enqueued on the context's stream and NOT synchronised) ------------------------ */
+/* msg_segment on device buffers (any output may be NULL); d_n_regions: device int32 or NULL. */
+MSG_API int msg_segment_dev(msg_ctx* ctx, const uint8_t* d_src_bgr, size_t src_step, int width, int height,
+                    const msg_segment_params* params, uint8_t* d_filtered_bgr, size_t filtered_step,
+                    int32_t* d_labels, size_t labels_step, uint8_t* d_rendered_bgr, size_t rendered_step,
+                    int32_t* d_n_regions);
 MSG_API int msg_meanshift_filter_dev(msg_ctx* ctx, const uint8_t* d_src_bgr, size_t src_step, uint8_t* d_dst_bgr,
                              size_t dst_step, int width, int height, double sp, double sr, int max_level,
                              int term_type, int max_count, double eps);
@@ -195,6 +200,20 @@ typedef struct msg_stats {
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied by host-buffer calls so far */
 } msg_stats;
 MSG_API int msg_get_stats(msg_ctx* ctx, msg_stats* out);
+
+/* Per-kernel profile of the mean-shift levels (bench.py's roofline): CUDA-event durations of the tile kernel
+ * and of the overflow kernel, and the ALGORITHMIC work they executed, counted on the device exactly as the CPU
+ * oracle counts it (window tests T = clamped window area per iteration, hits = in-range tests).  Profiling
+ * serialises the host with every level; leave it off when timing throughput. */
+typedef struct msg_kernel_profile {
+    uint64_t launches[9];       /* tile-kernel launches per pyramid level since profiling was enabled */
+    double tile_ms[9];          /* summed tile-kernel durations per level */
+    double overflow_ms[9];      /* summed overflow (generic) kernel durations per level */
+    uint64_t tile_tests[9], tile_hits[9];          /* work done by the tile kernel */
+    uint64_t overflow_tests[9], overflow_hits[9];  /* work done by the generic kernel */
+} msg_kernel_profile;
+MSG_API int msg_set_profiling(msg_ctx* ctx, int enable);      /* enabling resets the accumulated profile */
+MSG_API int msg_get_kernel_profile(msg_ctx* ctx, msg_kernel_profile* out);
 
 /* Debug: copy pyramid plane (kind 0 = source S[level], 1 = result D[level]) of the last filter call
  * to a host BGRX buffer (4 bytes/pixel, dense).  Writes its size to *w,*h. */

@@ -18,4 +18,5 @@ if _NAME not in sys.modules:
 pkg = sys.modules[_NAME]
 Context, CvException, GpuImgproc = pkg.Context, pkg.CvException, pkg.GpuImgproc
 lib = pkg._lib
+device = pkg.device
 PKG_DIR = _PKG_DIR

@@ -26,6 +26,12 @@ class Stats(C.Structure):
                                            "h2d_bytes", "d2h_bytes")]
 
 
+class KernelProfile(C.Structure):
+    _fields_ = [("launches", C.c_uint64 * 9), ("tile_ms", C.c_double * 9), ("overflow_ms", C.c_double * 9),
+                ("tile_tests", C.c_uint64 * 9), ("tile_hits", C.c_uint64 * 9),
+                ("overflow_tests", C.c_uint64 * 9), ("overflow_hits", C.c_uint64 * 9)]
+
+
 # name -> (restype, argtypes); must list every symbol include/msegment.h declares (tests/test_abi.py checks)
 _P, _SZ, _I, _D = C.c_void_p, C.c_size_t, C.c_int, C.c_double
 SIGNATURES = {
@@ -47,6 +53,7 @@ SIGNATURES = {
     "msg_wait": (_I, [_P, _I, C.POINTER(C.c_int32)]),
     "msg_alloc_pinned": (_P, [_SZ]),
     "msg_free_pinned": (None, [_P]),
+    "msg_segment_dev": (_I, [_P, _P, _SZ, _I, _I, C.POINTER(SegmentParams), _P, _SZ, _P, _SZ, _P, _SZ, _P]),
     "msg_meanshift_filter_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _D, _D, _I, _I, _I, _D]),
     "msg_label_regions_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _P]),
     "msg_connected_components_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _P]),
@@ -58,6 +65,8 @@ SIGNATURES = {
     "msg_label_strip_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, _I]),
     "msg_seam_pairs_dev": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "msg_apply_label_map_dev": (_I, [_P, _P, _SZ, _I, _I, _P, _P, _I]),
+    "msg_set_profiling": (_I, [_P, _I]),
+    "msg_get_kernel_profile": (_I, [_P, C.POINTER(KernelProfile)]),
     "msg_get_timings": (_I, [_P, C.POINTER(Timings)]),
     "msg_get_stats": (_I, [_P, C.POINTER(Stats)]),
     "msg_debug_get_plane": (_I, [_P, _I, _I, _P, _SZ, C.POINTER(_I), C.POINTER(_I)]),

@@ -38,6 +38,31 @@ int msg_reserve(msg_ctx* ctx, void** p, size_t* cap, size_t bytes)
     return MSG_OK;
 }
 
+static void prof_fold(msg_ctx* ctx, int level)
+{
+    if (!ctx->prof_pending[level]) return;
+    float a = 0, b = 0;
+    cudaEventSynchronize(ctx->prof_ev[level][2]);
+    cudaEventElapsedTime(&a, ctx->prof_ev[level][0], ctx->prof_ev[level][1]);
+    cudaEventElapsedTime(&b, ctx->prof_ev[level][1], ctx->prof_ev[level][2]);
+    ctx->prof.tile_ms[level] += a;
+    ctx->prof.overflow_ms[level] += b;
+    ctx->prof.launches[level] += 1;
+    ctx->prof_pending[level] = 0;
+}
+
+void msg_prof_begin(msg_ctx* ctx, int level)
+{
+    prof_fold(ctx, level);
+    cudaEventRecord(ctx->prof_ev[level][0], ctx->stream);
+}
+
+void msg_prof_end(msg_ctx* ctx, int level, int slot)
+{
+    cudaEventRecord(ctx->prof_ev[level][1 + slot], ctx->stream);
+    if (slot == 1) ctx->prof_pending[level] = 1;
+}
+
 #define CTX_ENTER(ctx)                                                                           \
     do {                                                                                         \
         if (!(ctx)) return MSG_EINVAL;                                                           \
@@ -100,6 +125,10 @@ int msg_create(int device, msg_ctx** out)
     CR(cudaMemset(ctx->d_counters, 0, 64 * sizeof(int32_t)));
     CR(cudaMallocHost((void**)&ctx->h_counters, 64 * sizeof(int32_t)));
     memset(ctx->h_counters, 0, 64 * sizeof(int32_t));
+    CR(cudaMalloc((void**)&ctx->d_work, MSG_MAX_LEVELS * 4 * sizeof(unsigned long long)));
+    CR(cudaMemset(ctx->d_work, 0, MSG_MAX_LEVELS * 4 * sizeof(unsigned long long)));
+    for (int l = 0; l < MSG_MAX_LEVELS; l++)
+        for (int k = 0; k < 3; k++) CR(cudaEventCreate(&ctx->prof_ev[l][k]));
     for (int i = 0; i < MSG_MAX_INFLIGHT; i++) {
         CR(cudaEventCreateWithFlags(&ctx->pend[i].done, cudaEventDisableTiming));
         ctx->pend[i].n_regions_host = ctx->h_counters + 32 + i;
@@ -116,7 +145,9 @@ void msg_destroy(msg_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_out2); cudaFree(ctx->d_labels);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_ovf); cudaFree(ctx->d_scratch); cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_colors);
+    cudaFree(ctx->d_colors); cudaFree(ctx->d_work);
+    for (int l = 0; l < MSG_MAX_LEVELS; l++)
+        for (int k = 0; k < 3; k++) cudaEventDestroy(ctx->prof_ev[l][k]);
     cudaFreeHost(ctx->h_counters);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
@@ -239,7 +270,7 @@ static int ms_run(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, int w, int h
         prm.ieps = cfg.ieps;
         prm.use_mask = l < L;
         if (l < L) MSG_TRY(k_pyr_up_mask(ctx, ctx->D[l + 1], ctx->D[l], cfg.isr22));
-        MSG_TRY(k_meanshift_level(ctx, ctx->S[l], ctx->D[l], prm));
+        MSG_TRY(k_meanshift_level(ctx, ctx->S[l], ctx->D[l], prm, l));
     }
     return MSG_OK;
 }
@@ -561,6 +592,47 @@ int msg_render_labels(msg_ctx* ctx, const int32_t* labels, size_t lstep, uint8_t
 
 // ============================================================================ fused pipeline
 
+// Device core of the fused pipeline.  All pointers are device pointers; any output may be NULL.
+// Events: ev[1] start, ev[2] after filter, ev[3] after label, ev[4] after merge, ev[5] after render.
+static int segment_core_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, int w, int h, const msg_segment_params* p,
+                            const ms_config& cfg, uint8_t* d_filtered, size_t fstep, int32_t* d_labels, size_t lstep,
+                            uint8_t* d_rendered, size_t rstep, int32_t* d_n)
+{
+    const bool do_label = p->lo_diff >= 0 && (d_labels || d_rendered || d_n);
+    const bool do_merge = do_label && (p->min_size > 0 || p->color_dist > 0);
+    const bool do_render = do_label && p->render_depth >= 0 && d_rendered;
+    cudaStream_t st = ctx->stream;
+    if (d_labels && lstep % 4) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of 4");
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    MSG_TRY(ms_run(ctx, d_src, sstep, w, h, 0, h, cfg));
+    if (d_filtered) MSG_TRY(k_plane_to_bgr(ctx, ctx->D[0], 0, h, d_filtered, fstep));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    int32_t* n_dev = d_n ? d_n : ctx->d_counters + 17;
+    int32_t* work = nullptr;
+    const bool dense = d_labels && lstep == (size_t)w * 4;
+    if (do_label) {
+        work = d_labels;
+        if (!dense) {
+            MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+            work = ctx->d_labels;
+        }
+        MSG_TRY(k_ccl_color(ctx, ctx->D[0].p, ctx->D[0].pitch, w, h, p->lo_diff, work, -1, w));
+        MSG_TRY(k_relabel_canonical(ctx, work, w, h, 1, n_dev, 0));
+    } else if (d_n) {
+        MSG_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int32_t), st));
+    }
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    if (do_merge) MSG_TRY(k_merge(ctx, ctx->D[0].p, ctx->D[0].pitch, work, w, h, p->min_size, p->color_dist, n_dev));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    if (do_label && d_labels && !dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
+    if (do_render) {
+        int depth = p->render_depth > 0 ? p->render_depth : 0x7fffffff;   // 0: every region renders
+        MSG_TRY(k_render(ctx, work, (size_t)w * 4, d_rendered, rstep, w, h, depth, nullptr));
+    }
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    return MSG_OK;
+}
+
 static int segment_enqueue(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
                            uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered,
                            size_t rstep, int32_t* h_n_slot)
@@ -574,37 +646,18 @@ static int segment_enqueue(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w
     MSG_TRY(ms_validate(ctx, w, h, p->sp, p->sr, p->max_level, p->term_type, p->max_count, p->eps, &cfg));
     if (p->min_size < 0 || p->color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
     const bool do_label = p->lo_diff >= 0;
-    const bool do_merge = do_label && (p->min_size > 0 || p->color_dist > 0);
     const bool do_render = do_label && p->render_depth >= 0 && rendered;
     size_t rb = (size_t)w * 3;
     cudaStream_t st = ctx->stream;
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     MSG_TRY(copy_in(ctx, src, sstep, rb, h, &ctx->d_in, &ctx->d_in_cap));
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    MSG_TRY(ms_run(ctx, ctx->d_in, rb, w, h, 0, h, cfg));
-    if (filtered) {
-        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rb * h));
-        MSG_TRY(k_plane_to_bgr(ctx, ctx->D[0], 0, h, ctx->d_out, rb));
-    }
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (filtered) MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rb * h));
+    if (do_label) MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+    if (do_render) MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out2, &ctx->d_out2_cap, rb * h));
     int32_t* d_n = ctx->d_counters + 16;
-    if (do_label) {
-        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
-        MSG_TRY(k_ccl_color(ctx, ctx->D[0].p, ctx->D[0].pitch, w, h, p->lo_diff, ctx->d_labels, -1, w));
-        MSG_TRY(k_relabel_canonical(ctx, ctx->d_labels, w, h, 1, d_n, 0));
-    } else {
-        MSG_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int32_t), st));
-    }
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    if (do_merge) MSG_TRY(k_merge(ctx, ctx->D[0].p, ctx->D[0].pitch, ctx->d_labels, w, h, p->min_size, p->color_dist, d_n));
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    if (do_render) {
-        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out2, &ctx->d_out2_cap, rb * h));
-        int depth = p->render_depth > 0 ? p->render_depth : 0x7fffffff;   // 0: every region renders
-        MSG_TRY(k_render(ctx, ctx->d_labels, (size_t)w * 4, ctx->d_out2, rb, w, h, depth, nullptr));
-    }
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-    // all downloads last, so the stage timings above are clean
+    MSG_TRY(segment_core_dev(ctx, ctx->d_in, rb, w, h, p, cfg, filtered ? ctx->d_out : nullptr, rb,
+                             do_label ? ctx->d_labels : nullptr, (size_t)w * 4, do_render ? ctx->d_out2 : nullptr, rb, d_n));
+    // all downloads last, so the stage timings are clean
     if (filtered) MSG_TRY(copy_out(ctx, filtered, fstep, ctx->d_out, rb, h));
     if (do_label && labels) MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
     if (do_render) MSG_TRY(copy_out(ctx, rendered, rstep, ctx->d_out2, rb, h));
@@ -612,6 +665,22 @@ static int segment_enqueue(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w
     MSG_TRY(fetch_ms_stats(ctx));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
     return MSG_OK;
+}
+
+int msg_segment_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, int w, int h, const msg_segment_params* p,
+                    uint8_t* d_filtered, size_t fstep, int32_t* d_labels, size_t lstep, uint8_t* d_rendered, size_t rstep,
+                    int32_t* d_n)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_src, sstep, w, h, 3, "segment src"));
+    if (!p) return msg_fail(ctx, MSG_EINVAL, "segment: params is NULL");
+    if (d_filtered) MSG_TRY(check_img(ctx, d_filtered, fstep, w, h, 3, "segment filtered"));
+    if (d_labels) MSG_TRY(check_img(ctx, d_labels, lstep, w, h, 4, "segment labels"));
+    if (d_rendered) MSG_TRY(check_img(ctx, d_rendered, rstep, w, h, 3, "segment rendered"));
+    ms_config cfg;
+    MSG_TRY(ms_validate(ctx, w, h, p->sp, p->sr, p->max_level, p->term_type, p->max_count, p->eps, &cfg));
+    if (p->min_size < 0 || p->color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
+    return segment_core_dev(ctx, d_src, sstep, w, h, p, cfg, d_filtered, fstep, d_labels, lstep, d_rendered, rstep, d_n);
 }
 
 int msg_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
@@ -661,6 +730,35 @@ int msg_wait(msg_ctx* ctx, int ticket, int32_t* n_regions)
     ctx->pend[ticket].used = 0;
     if (n_regions) *n_regions = *ctx->pend[ticket].n_regions_host;
     publish_ms_stats(ctx);
+    return MSG_OK;
+}
+
+int msg_set_profiling(msg_ctx* ctx, int enable)
+{
+    CTX_ENTER(ctx);
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < MSG_MAX_LEVELS; l++) ctx->prof_pending[l] = 0;
+    if (enable) {
+        memset(&ctx->prof, 0, sizeof(ctx->prof));
+        MSG_CUDA(ctx, cudaMemset(ctx->d_work, 0, MSG_MAX_LEVELS * 4 * sizeof(unsigned long long)));
+    }
+    ctx->profiling = enable ? 1 : 0;
+    return MSG_OK;
+}
+
+int msg_get_kernel_profile(msg_ctx* ctx, msg_kernel_profile* out)
+{
+    CTX_ENTER(ctx);
+    if (!out) return MSG_EINVAL;
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < MSG_MAX_LEVELS; l++) prof_fold(ctx, l);
+    unsigned long long wk[MSG_MAX_LEVELS * 4];
+    MSG_CUDA(ctx, cudaMemcpy(wk, ctx->d_work, sizeof(wk), cudaMemcpyDeviceToHost));
+    for (int l = 0; l < MSG_MAX_LEVELS; l++) {
+        ctx->prof.tile_tests[l] = wk[4 * l]; ctx->prof.tile_hits[l] = wk[4 * l + 1];
+        ctx->prof.overflow_tests[l] = wk[4 * l + 2]; ctx->prof.overflow_hits[l] = wk[4 * l + 3];
+    }
+    *out = ctx->prof;
     return MSG_OK;
 }
 

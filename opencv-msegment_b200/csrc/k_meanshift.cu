@@ -113,7 +113,8 @@ template <int NX>
 __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S, msg_plane D, msg_ms_params prm,
                                                                     tile_geom g, msg_ovf_item* __restrict__ ovf,
                                                                     int* __restrict__ ovf_count,
-                                                                    unsigned long long* __restrict__ active_count)
+                                                                    unsigned long long* __restrict__ active_count,
+                                                                    unsigned long long* __restrict__ work)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* stage = smem;                                  // g.sh * g.swp
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S,
 
     const float sp = prm.sp;
     const int R = prm.radius;
+    unsigned wk_tests = 0, wk_hits = 0;   // algorithmic work of this thread (profiling only)
     uint2* qc = q0;
     uint2* qnx = q1;
     for (int it = 0; it < prm.max_count; ++it) {
@@ -196,6 +198,11 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S,
                 const uint32_t* base = stage + (miny - oy) * g.swp + (minx - ox);
                 int s0, s1, s2, sxr, syr, cnt;
                 window_scan<NX>(base, g.swp, maxx - minx + 1, maxy - miny + 1, c, prm.isr2, s0, s1, s2, sxr, syr, cnt);
+                if (work) {   // uniform branch; counts what the CPU oracle counts: clamped window area and hits
+                    int cx = min(maxx, S.w - 1) - max(minx, 0) + 1, cy = min(maxy, S.hfull - 1) - max(miny, 0) + 1;
+                    wk_tests += (unsigned)(cx * cy);
+                    wk_hits += (unsigned)cnt;
+                }
                 bool fin = true;
                 if (cnt > 0) {
                     long long sx = (long long)sxr + (long long)cnt * minx;   // absolute-coordinate sums
@@ -237,6 +244,17 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S,
         __syncthreads();
         uint2* t = qc; qc = qnx; qnx = t;
     }
+    if (work) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            wk_tests += __shfl_xor_sync(0xffffffffu, wk_tests, o);
+            wk_hits += __shfl_xor_sync(0xffffffffu, wk_hits, o);
+        }
+        if (lane == 0) {
+            atomicAdd(work, (unsigned long long)wk_tests);
+            atomicAdd(work + 1, (unsigned long long)wk_hits);
+        }
+    }
 }
 
 // Generic path: explicit clamping, reads the plane through L1/L2.  Either finishes overflow items
@@ -245,8 +263,10 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
                                                                 const msg_ovf_item* __restrict__ items,
                                                                 const int* __restrict__ n_items,
                                                                 unsigned long long* __restrict__ active_count,
-                                                                unsigned long long* __restrict__ ovf_total)
+                                                                unsigned long long* __restrict__ ovf_total,
+                                                                unsigned long long* __restrict__ work)
 {
+    unsigned long long wk_tests = 0, wk_hits = 0;
     const long long total = items ? (long long)*n_items : (long long)S.rows * S.w;
     if (items && ovf_total && blockIdx.x == 0 && threadIdx.x == 0 && total > 0)
         atomicAdd(ovf_total, (unsigned long long)total);
@@ -286,6 +306,10 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
                 }
                 cnt += rc; sx += rsx; sy += (long long)y * rc;
             }
+            if (work && maxx >= minx && maxy >= miny) {
+                wk_tests += (unsigned long long)(maxx - minx + 1) * (unsigned long long)(maxy - miny + 1);
+                wk_hits += (unsigned long long)cnt;
+            }
             if (cnt == 0) break;
             iter_result res = ms_epilogue(s0, s1, s2, sx, sy, cnt);
             bool stop = ms_stop(x0, y0, c, res, prm.ieps);
@@ -294,24 +318,30 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
         }
         D.p[out] = c;
     }
+    if (work && (wk_tests | wk_hits)) {
+        atomicAdd(work + 2, wk_tests);
+        atomicAdd(work + 3, wk_hits);
+    }
 }
 
 template <int NX>
 cudaError_t launch_tile(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, const tile_geom& g, int tiles,
-                        size_t smem, int* ovf_count, unsigned long long* active)
+                        size_t smem, int* ovf_count, unsigned long long* active, unsigned long long* work)
 {
     // attribute is per function AND per device: set it on every launch (cheap, no sync)
     cudaError_t e = cudaFuncSetAttribute(meanshift_tile_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    meanshift_tile_kernel<NX><<<tiles, MS_THREADS, smem, ctx->stream>>>(S, D, prm, g, ctx->d_ovf, ovf_count, active);
+    meanshift_tile_kernel<NX><<<tiles, MS_THREADS, smem, ctx->stream>>>(S, D, prm, g, ctx->d_ovf, ovf_count, active, work);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 // d_counters layout: [0] overflow count of the current level, [2..3] active items (u64), [4..5] overflow total (u64)
-int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm)
+int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, int level)
 {
+    // profiling: d_work[level] = {tile tests, tile hits, generic tests, generic hits} (u64 each)
+    unsigned long long* work = ctx->profiling ? ctx->d_work + 4 * level : nullptr;
     int* ovf_count = ctx->d_counters;
     unsigned long long* active = reinterpret_cast<unsigned long long*>(ctx->d_counters + 2);
     unsigned long long* ovf_total = reinterpret_cast<unsigned long long*>(ctx->d_counters + 4);
@@ -336,7 +366,7 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     }
     if (!tile_ok) {
         int blocks = ctx->sm_count * 16;
-        meanshift_generic_kernel<<<blocks, 128, 0, ctx->stream>>>(S, D, prm, nullptr, nullptr, active, nullptr);
+        meanshift_generic_kernel<<<blocks, 128, 0, ctx->stream>>>(S, D, prm, nullptr, nullptr, active, nullptr, work);
         MSG_LAUNCHED(ctx);
         MSG_CHECK_LAUNCH(ctx);
         return MSG_OK;
@@ -353,20 +383,23 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     int nx = 0;
     if (prm.sp == (float)(int)prm.sp) nx = 2 * (int)prm.sp + 1;
     cudaError_t e;
+    if (ctx->profiling) msg_prof_begin(ctx, level);
     switch (nx) {
-        case 3: e = launch_tile<3>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
-        case 5: e = launch_tile<5>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
-        case 7: e = launch_tile<7>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
-        case 11: e = launch_tile<11>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
-        case 21: e = launch_tile<21>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
-        case 41: e = launch_tile<41>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
-        default: e = launch_tile<0>(ctx, S, D, prm, g, tiles, smem, ovf_count, active); break;
+        case 3: e = launch_tile<3>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
+        case 5: e = launch_tile<5>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
+        case 7: e = launch_tile<7>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
+        case 11: e = launch_tile<11>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
+        case 21: e = launch_tile<21>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
+        case 41: e = launch_tile<41>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
+        default: e = launch_tile<0>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
     }
     MSG_LAUNCHED(ctx);
     MSG_CUDA(ctx, e);
+    if (ctx->profiling) msg_prof_end(ctx, level, 0);
 
     // finish the items that left their tile (count is read on the device: no host sync)
-    meanshift_generic_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(S, D, prm, ctx->d_ovf, ovf_count, nullptr, ovf_total);
+    meanshift_generic_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(S, D, prm, ctx->d_ovf, ovf_count, nullptr, ovf_total, work);
+    if (ctx->profiling) msg_prof_end(ctx, level, 1);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;

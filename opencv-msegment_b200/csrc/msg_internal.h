@@ -72,6 +72,13 @@ struct msg_ctx {
     msg_timings tm;
     msg_stats st;
 
+    // optional per-kernel profiling of the mean-shift levels (msg_set_profiling)
+    int profiling;
+    unsigned long long* d_work;          // [MSG_MAX_LEVELS][4] u64 work counters
+    cudaEvent_t prof_ev[MSG_MAX_LEVELS][3];   // begin, after tile kernel, after overflow kernel
+    int prof_pending[MSG_MAX_LEVELS];
+    msg_kernel_profile prof;
+
     struct pending {
         int used;
         int32_t* n_regions_host;  // pinned slot
@@ -110,7 +117,10 @@ int k_pyr_down(msg_ctx* ctx, msg_plane src, msg_plane dst);
 int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc /*D[l+1]*/, msg_plane ddst /*D[l]*/, int isr22);
 int k_synth(msg_ctx* ctx, uint8_t* d_bgr, size_t step, int w, int h, uint64_t seed);
 // mean shift
-int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm);
+int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, int level);
+// profiling hooks (capi.cu): CUDA events around the tile kernel (slot 0) and the overflow kernel (slot 1) of a level
+void msg_prof_begin(msg_ctx* ctx, int level);
+void msg_prof_end(msg_ctx* ctx, int level, int slot);
 // labelling
 int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int32_t* d_labels,
                 int64_t label_base, int lab_pitch);

@@ -1,0 +1,100 @@
+"""Device-resident and asynchronous entry points of the C ABI (raw device / pinned pointers as ints).
+
+Used by bench.py and by callers that keep frames in HBM (e.g. behind torch tensors: pass ``t.data_ptr()`` and
+hand the torch stream to ``Context.set_stream``).  Thin ctypes forwarding only.
+"""
+import ctypes as C
+
+from . import _lib as L
+
+
+def params(sp=10.0, sr=10.0, max_level=1, termcrit=(3, 5, 1.0), lo_diff=2, min_size=0, color_dist=0, render_depth=0):
+    return L.SegmentParams(float(sp), float(sr), int(max_level), int(termcrit[0]), int(termcrit[1]), float(termcrit[2]),
+                           int(lo_diff), int(min_size), int(color_dist), int(render_depth))
+
+
+def _p(v):
+    return C.c_void_p(int(v)) if v else None
+
+
+def synth(ctx, d_dst, step, w, h, seed):
+    ctx.check(ctx._lib.msg_synth_bgr_dev(ctx._h, _p(d_dst), step, w, h, int(seed)))
+
+
+def segment(ctx, d_src, sstep, w, h, prm, d_filtered=0, fstep=0, d_labels=0, lstep=0, d_rendered=0, rstep=0, d_n=0):
+    ctx.check(ctx._lib.msg_segment_dev(ctx._h, _p(d_src), sstep, w, h, C.byref(prm), _p(d_filtered), fstep, _p(d_labels),
+                                       lstep, _p(d_rendered), rstep, _p(d_n)))
+
+
+def meanshift(ctx, d_src, sstep, d_dst, dstep, w, h, sp, sr, max_level=1, termcrit=(3, 5, 1.0)):
+    ctx.check(ctx._lib.msg_meanshift_filter_dev(ctx._h, _p(d_src), sstep, _p(d_dst), dstep, w, h, float(sp), float(sr),
+                                                int(max_level), int(termcrit[0]), int(termcrit[1]), float(termcrit[2])))
+
+
+def meanshift_strip(ctx, d_src_rows, sstep, halo_row0, halo_row1, d_dst, dstep, w, full_h, row0, row1, sp, sr,
+                    max_level=1, termcrit=(3, 5, 1.0)):
+    ctx.check(ctx._lib.msg_meanshift_filter_strip_dev(ctx._h, _p(d_src_rows), sstep, halo_row0, halo_row1, _p(d_dst), dstep,
+                                                      w, full_h, row0, row1, float(sp), float(sr), int(max_level),
+                                                      int(termcrit[0]), int(termcrit[1]), float(termcrit[2])))
+
+
+def halo_rows(sp, max_level=1, termcrit=(3, 5, 1.0)):
+    return L.load().msg_meanshift_halo_rows(float(sp), int(max_level), int(termcrit[0]), int(termcrit[1]))
+
+
+def label_regions(ctx, d_bgr, step, d_labels, lstep, w, h, lo_diff, d_n=0):
+    ctx.check(ctx._lib.msg_label_regions_dev(ctx._h, _p(d_bgr), step, _p(d_labels), lstep, w, h, int(lo_diff), _p(d_n)))
+
+
+def label_strip(ctx, d_bgr_rows, step, d_labels, lstep, w, rows, row0, full_w, lo_diff):
+    ctx.check(ctx._lib.msg_label_strip_dev(ctx._h, _p(d_bgr_rows), step, _p(d_labels), lstep, w, rows, row0, full_w,
+                                           int(lo_diff)))
+
+
+def seam_pairs(ctx, d_up_bgr, d_up_lab, d_lo_bgr, d_lo_lab, w, lo_diff, d_pairs, d_count):
+    ctx.check(ctx._lib.msg_seam_pairs_dev(ctx._h, _p(d_up_bgr), _p(d_up_lab), _p(d_lo_bgr), _p(d_lo_lab), w, int(lo_diff),
+                                          _p(d_pairs), _p(d_count)))
+
+
+def apply_label_map(ctx, d_labels, lstep, w, rows, d_from, d_to, n):
+    ctx.check(ctx._lib.msg_apply_label_map_dev(ctx._h, _p(d_labels), lstep, w, rows, _p(d_from), _p(d_to), int(n)))
+
+
+def connected_components(ctx, d_mask, step, d_labels, lstep, w, h, connectivity=8, d_n=0):
+    ctx.check(ctx._lib.msg_connected_components_dev(ctx._h, _p(d_mask), step, _p(d_labels), lstep, w, h, int(connectivity),
+                                                    _p(d_n)))
+
+
+def merge_regions(ctx, d_bgr, step, d_labels, lstep, w, h, min_size, color_dist, d_n=0):
+    ctx.check(ctx._lib.msg_merge_regions_dev(ctx._h, _p(d_bgr), step, _p(d_labels), lstep, w, h, int(min_size),
+                                             int(color_dist), _p(d_n)))
+
+
+def render_labels(ctx, d_labels, lstep, d_dst, dstep, w, h, depth, d_colors=0):
+    ctx.check(ctx._lib.msg_render_labels_dev(ctx._h, _p(d_labels), lstep, _p(d_dst), dstep, w, h, int(depth), _p(d_colors)))
+
+
+# ---- asynchronous host-buffer interface (pinned memory)
+
+def alloc_pinned(nbytes):
+    p = L.load().msg_alloc_pinned(int(nbytes))
+    if not p:
+        raise MemoryError("msg_alloc_pinned(%d) failed" % nbytes)
+    return p
+
+
+def free_pinned(p):
+    L.load().msg_free_pinned(C.c_void_p(p))
+
+
+def submit_segment(ctx, src, sstep, w, h, prm, filtered=0, fstep=0, labels=0, lstep=0, rendered=0, rstep=0):
+    t = C.c_int()
+    ctx.check(ctx._lib.msg_submit_segment(ctx._h, _p(src), sstep, w, h, C.byref(prm), _p(filtered), fstep, _p(labels), lstep,
+                                          _p(rendered), rstep, C.byref(t)))
+    return t.value
+
+
+def wait(ctx, ticket):
+    n = C.c_int32()
+    ctx.check(ctx._lib.msg_wait(ctx._h, int(ticket), C.byref(n)))
+    return n.value

@@ -72,6 +72,14 @@ class Context:
         self.check(self._lib.msg_get_stats(self._h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in L.Stats._fields_}
 
+    def set_profiling(self, enable):
+        self.check(self._lib.msg_set_profiling(self._h, 1 if enable else 0))
+
+    def kernel_profile(self):
+        p = L.KernelProfile()
+        self.check(self._lib.msg_get_kernel_profile(self._h, C.byref(p)))
+        return {n: list(getattr(p, n)) for n, _ in L.KernelProfile._fields_}
+
     def set_stream(self, cuda_stream):
         self.check(self._lib.msg_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
 
