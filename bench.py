@@ -302,7 +302,9 @@ def run_ours(args):
     h_filt = dev.alloc_pinned(B * frame_bytes)
     h_lab = dev.alloc_pinned(B * lab_bytes)
     torch.cuda.synchronize()
-    ctypes.memmove(h_src, src.cpu().numpy().ctypes.data, B * frame_bytes)
+    src_host = src.cpu().numpy()            # keep the array alive across the memmove
+    ctypes.memmove(h_src, src_host.ctypes.data, B * frame_bytes)
+    del src_host
 
     def step_e2e():
         tickets = []
