@@ -1,0 +1,103 @@
+package ru.shayhulud.opencvcmsegment.gpu;
+
+import org.opencv.core.CvException;
+import org.opencv.core.CvType;
+import org.opencv.core.Mat;
+import org.opencv.core.TermCriteria;
+
+/**
+ * Drop-in sibling of {@code org.opencv.imgproc.Imgproc} for the segmentation hot path, bound to
+ * libmsegment_b200.so (include/msegment.h) through JNI (msegment_jni.c).  Same static signatures taking
+ * {@code Mat}; swap {@code Imgproc.} for {@code GpuImgproc.} at PictureService.java:442 (connectedComponents)
+ * and :913-936 (colorByIndexes), and call pyrMeanShiftFiltering / labelRegions / mergeRegions where the
+ * mean-shift pipeline replaces the watershed stage.  NOT compiled in this repository (no JDK in the build image).
+ */
+public final class GpuImgproc {
+
+	static {
+		System.loadLibrary("msegment_jni"); // which links libmsegment_b200.so
+	}
+
+	private static final ThreadLocal<Long> CTX = ThreadLocal.withInitial(() -> check(nCreate(0)));
+
+	private GpuImgproc() {
+	}
+
+	public static void pyrMeanShiftFiltering(Mat src, Mat dst, double sp, double sr) {
+		pyrMeanShiftFiltering(src, dst, sp, sr, 1, new TermCriteria(TermCriteria.COUNT + TermCriteria.EPS, 5, 1));
+	}
+
+	public static void pyrMeanShiftFiltering(Mat src, Mat dst, double sp, double sr, int maxLevel, TermCriteria tc) {
+		require(src.type() == CvType.CV_8UC3, "src must be CV_8UC3");
+		dst.create(src.size(), src.type());
+		status(nMeanshift(CTX.get(), src.dataAddr(), src.step1() * src.elemSize1(), dst.dataAddr(),
+			dst.step1() * dst.elemSize1(), src.cols(), src.rows(), sp, sr, maxLevel, tc.type, tc.maxCount, tc.epsilon));
+	}
+
+	/** floodFill region-growing loop (loDiff == upDiff, 4-connectivity) as one call; returns the region count. */
+	public static int labelRegions(Mat image, Mat labels, int loDiff, int upDiff, int connectivity) {
+		require(image.type() == CvType.CV_8UC3, "image must be CV_8UC3");
+		labels.create(image.size(), CvType.CV_32SC1);
+		int[] n = new int[1];
+		status(nLabelRegions(CTX.get(), image.dataAddr(), image.step1(), labels.dataAddr(), labels.step1() * 4,
+			image.cols(), image.rows(), loDiff, upDiff, connectivity, n));
+		return n[0];
+	}
+
+	public static int mergeRegions(Mat image, Mat labels, int minSize, int colorDist) {
+		int[] n = new int[1];
+		status(nMergeRegions(CTX.get(), image.dataAddr(), image.step1(), labels.dataAddr(), labels.step1() * 4,
+			image.cols(), image.rows(), minSize, colorDist, n));
+		return n[0];
+	}
+
+	/** Same contract as Imgproc.connectedComponents(image, labels, connectivity, ltype) -- PictureService.java:442. */
+	public static int connectedComponents(Mat image, Mat labels, int connectivity, int ltype) {
+		require(image.type() == CvType.CV_8UC1 && ltype == CvType.CV_32S, "CV_8UC1 image and CV_32S labels only");
+		labels.create(image.size(), CvType.CV_32SC1);
+		int[] n = new int[1];
+		status(nConnectedComponents(CTX.get(), image.dataAddr(), image.step1(), labels.dataAddr(), labels.step1() * 4,
+			image.cols(), image.rows(), connectivity, n));
+		return n[0];
+	}
+
+	/** PictureService.colorByIndexes (PictureService.java:913-936); colors == null renders white. */
+	public static Mat colorByIndexes(Mat markers, int depth, byte[] colorsBgr) {
+		Mat dst = new Mat(markers.size(), CvType.CV_8UC3);
+		status(nRender(CTX.get(), markers.dataAddr(), markers.step1() * 4, dst.dataAddr(), dst.step1(), markers.cols(),
+			markers.rows(), depth, colorsBgr));
+		return dst;
+	}
+
+	private static void require(boolean ok, String msg) {
+		if (!ok) {
+			throw new CvException(msg);
+		}
+	}
+
+	private static void status(int rc) {
+		if (rc != 0) {
+			throw new CvException("msegment status " + rc + ": " + nLastError(CTX.get()));
+		}
+	}
+
+	private static long check(long handle) {
+		if (handle == 0) {
+			throw new CvException("msg_create failed: " + nLastError(0));
+		}
+		return handle;
+	}
+
+	private static native long nCreate(int device);
+	private static native String nLastError(long ctx);
+	private static native int nMeanshift(long ctx, long src, long sstep, long dst, long dstep, int w, int h, double sp,
+		double sr, int maxLevel, int termType, int maxCount, double eps);
+	private static native int nLabelRegions(long ctx, long img, long step, long labels, long lstep, int w, int h, int lo,
+		int up, int conn, int[] n);
+	private static native int nMergeRegions(long ctx, long img, long step, long labels, long lstep, int w, int h,
+		int minSize, int colorDist, int[] n);
+	private static native int nConnectedComponents(long ctx, long img, long step, long labels, long lstep, int w, int h,
+		int conn, int[] n);
+	private static native int nRender(long ctx, long labels, long lstep, long dst, long dstep, int w, int h, int depth,
+		byte[] colors);
+}

@@ -1,0 +1,73 @@
+/* msegment_jni.c -- JNI glue between GpuImgproc.java and libmsegment_b200.so.  Mechanical: every native method
+ * forwards its arguments to the C ABI of include/msegment.h.  Build (on a machine with a JDK):
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include msegment_jni.c \
+ *       -L.. -lmsegment_b200 -o libmsegment_jni.so
+ * Not built in this repository: the build image has no jni.h. */
+#include <jni.h>
+#include <stdint.h>
+
+#include "msegment.h"
+
+#define J(name) Java_ru_shayhulud_opencvcmsegment_gpu_GpuImgproc_##name
+#define P(x) ((void*)(intptr_t)(x))
+
+JNIEXPORT jlong JNICALL J(nCreate)(JNIEnv* e, jclass c, jint device)
+{
+    msg_ctx* ctx = NULL;
+    return msg_create(device, &ctx) == MSG_OK ? (jlong)(intptr_t)ctx : 0;
+}
+
+JNIEXPORT jstring JNICALL J(nLastError)(JNIEnv* e, jclass c, jlong ctx)
+{
+    return (*e)->NewStringUTF(e, msg_last_error((const msg_ctx*)P(ctx)));
+}
+
+JNIEXPORT jint JNICALL J(nMeanshift)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w,
+                                     jint h, jdouble sp, jdouble sr, jint ml, jint tt, jint mc, jdouble eps)
+{
+    return msg_meanshift_filter((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h,
+                                sp, sr, ml, tt, mc, eps);
+}
+
+JNIEXPORT jint JNICALL J(nLabelRegions)(JNIEnv* e, jclass c, jlong ctx, jlong img, jlong step, jlong lab, jlong lstep, jint w,
+                                        jint h, jint lo, jint up, jint conn, jintArray n)
+{
+    int32_t cnt = 0;
+    int rc = msg_label_regions((msg_ctx*)P(ctx), (const uint8_t*)P(img), (size_t)step, (int32_t*)P(lab), (size_t)lstep, w, h, lo,
+                               up, conn, &cnt);
+    jint v = cnt;
+    (*e)->SetIntArrayRegion(e, n, 0, 1, &v);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nMergeRegions)(JNIEnv* e, jclass c, jlong ctx, jlong img, jlong step, jlong lab, jlong lstep, jint w,
+                                        jint h, jint min_size, jint color_dist, jintArray n)
+{
+    int32_t cnt = 0;
+    int rc = msg_merge_regions((msg_ctx*)P(ctx), (const uint8_t*)P(img), (size_t)step, (int32_t*)P(lab), (size_t)lstep, w, h,
+                               min_size, color_dist, &cnt);
+    jint v = cnt;
+    (*e)->SetIntArrayRegion(e, n, 0, 1, &v);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nConnectedComponents)(JNIEnv* e, jclass c, jlong ctx, jlong img, jlong step, jlong lab, jlong lstep,
+                                               jint w, jint h, jint conn, jintArray n)
+{
+    int32_t cnt = 0;
+    int rc = msg_connected_components((msg_ctx*)P(ctx), (const uint8_t*)P(img), (size_t)step, (int32_t*)P(lab), (size_t)lstep, w,
+                                      h, conn, &cnt);
+    jint v = cnt;
+    (*e)->SetIntArrayRegion(e, n, 0, 1, &v);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nRender)(JNIEnv* e, jclass c, jlong ctx, jlong lab, jlong lstep, jlong dst, jlong dstep, jint w, jint h,
+                                  jint depth, jbyteArray colors)
+{
+    jbyte* col = colors ? (*e)->GetByteArrayElements(e, colors, NULL) : NULL;
+    int rc = msg_render_labels((msg_ctx*)P(ctx), (const int32_t*)P(lab), (size_t)lstep, (uint8_t*)P(dst), (size_t)dstep, w, h,
+                               depth, (const uint8_t*)col);
+    if (col) (*e)->ReleaseByteArrayElements(e, colors, col, JNI_ABORT);
+    return rc;
+}
