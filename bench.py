@@ -35,7 +35,7 @@ SEED0 = 2          # config 2 -> seed 2 (frame i of rank r uses see
 PARAMS = dict(sp=10.0, sr=10.0, max_level=1, termcrit=(3, 5, 1.0), lo_diff=2, min_size=50, color_dist=10)
 METRIC = "segmented_mpix_per_s"
 UNIT = "Mpix/s"
-N_STREAMS = 3      # contexts (streams + workspaces) per GPU; frames are dealt round-robin
+N_STREAMS = 4      # contexts (stream + workspace + host thread) per GPU; frames are dealt round-robin
 
 
 def workload_name():
@@ -249,11 +249,19 @@ def run_ours(args):
     labs = [torch.empty((H, W), dtype=torch.int32, device="cuda") for _ in range(N_STREAMS)]
     nreg = torch.zeros((B,), dtype=torch.int32, device="cuda")
 
-    def step_device():
-        for i in range(B):
-            k = i % N_STREAMS
+    # one host thread per context: msg_segment_dev blocks its caller while the merge stage iterates to a fixed point
+    # (one stream sync per round), so contexts must be driven concurrently for their streams to overlap on the GPU.
+    # ctypes releases the GIL for the duration of every C-ABI call.
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=N_STREAMS)
+
+    def _device_worker(k):
+        for i in range(k, B, N_STREAMS):
             dev.segment(ctxs[k], src[i].data_ptr(), 3 * W, W, H, prm, filt[k].data_ptr(), 3 * W, labs[k].data_ptr(), 4 * W,
                         0, 0, nreg[i:].data_ptr())
+
+    def step_device():
+        list(pool.map(_device_worker, range(N_STREAMS)))
 
     def barrier():
         torch.cuda.synchronize()
@@ -306,18 +314,18 @@ def run_ours(args):
     ctypes.memmove(h_src, src_host.ctypes.data, B * frame_bytes)
     del src_host
 
-    def step_e2e():
+    def _e2e_worker(k):
         tickets = []
-        for i in range(B):
-            k = i % N_STREAMS
-            if len(tickets) >= N_STREAMS * 2:          # keep at most 2 submissions in flight per context
-                kk, t = tickets.pop(0)
-                dev.wait(ctxs[kk], t)
-            t = dev.submit_segment(ctxs[k], h_src + i * frame_bytes, 3 * W, W, H, prm, h_filt + i * frame_bytes, 3 * W,
-                                   h_lab + i * lab_bytes, 4 * W)
-            tickets.append((k, t))
-        for kk, t in tickets:
-            dev.wait(ctxs[kk], t)
+        for i in range(k, B, N_STREAMS):
+            if len(tickets) >= 2:                      # at most 2 submissions in flight per context
+                dev.wait(ctxs[k], tickets.pop(0))
+            tickets.append(dev.submit_segment(ctxs[k], h_src + i * frame_bytes, 3 * W, W, H, prm,
+                                              h_filt + i * frame_bytes, 3 * W, h_lab + i * lab_bytes, 4 * W))
+        for t in tickets:
+            dev.wait(ctxs[k], t)
+
+    def step_e2e():
+        list(pool.map(_e2e_worker, range(N_STREAMS)))
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()

@@ -161,6 +161,9 @@ MSG_API int msg_render_labels_dev(msg_ctx* ctx, const int32_t* d_labels, size_t 
                           size_t dst_step, int width, int height, int depth, const uint8_t* d_colors_bgr);
 /* Deterministic synthetic test image generated on the device. */
 MSG_API int msg_synth_bgr_dev(msg_ctx* ctx, uint8_t* d_dst_bgr, size_t step, int width, int height, uint64_t seed);
+/* Rows [row0, row0+rows) of the same width x full_height image (strip-sharded generation). */
+MSG_API int msg_synth_bgr_rows_dev(msg_ctx* ctx, uint8_t* d_dst_bgr, size_t step, int width, int full_height, int row0,
+                           int rows, uint64_t seed);
 
 /* ---- strip sharding support (one very large image over several GPUs; DESIGN.md "multi-GPU") */
 /* Mean-shift filter of rows [row0,row1) of a width x full_height image, given device rows

@@ -60,6 +60,7 @@ SIGNATURES = {
     "msg_merge_regions_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, _P]),
     "msg_render_labels_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _P]),
     "msg_synth_bgr_dev": (_I, [_P, _P, _SZ, _I, _I, C.c_uint64]),
+    "msg_synth_bgr_rows_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _I, C.c_uint64]),
     "msg_meanshift_halo_rows": (_I, [_D, _I, _I, _I]),
     "msg_meanshift_filter_strip_dev": (_I, [_P, _P, _SZ, _I, _I, _P, _SZ, _I, _I, _I, _I, _D, _D, _I, _I, _I, _D]),
     "msg_label_strip_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, _I]),

@@ -451,7 +451,15 @@ int msg_synth_bgr_dev(msg_ctx* ctx, uint8_t* d_dst, size_t step, int w, int h, u
 {
     CTX_ENTER(ctx);
     MSG_TRY(check_img(ctx, d_dst, step, w, h, 3, "synth dst"));
-    return k_synth(ctx, d_dst, step, w, h, seed);
+    return k_synth(ctx, d_dst, step, w, h, 0, h, seed);
+}
+
+int msg_synth_bgr_rows_dev(msg_ctx* ctx, uint8_t* d_dst, size_t step, int w, int full_h, int row0, int rows, uint64_t seed)
+{
+    CTX_ENTER(ctx);
+    if (row0 < 0 || rows <= 0 || row0 + rows > full_h) return msg_fail(ctx, MSG_EINVAL, "synth rows: bad row range");
+    MSG_TRY(check_img(ctx, d_dst, step, w, rows, 3, "synth dst"));
+    return k_synth(ctx, d_dst, step, w, full_h, row0, rows, seed);
 }
 
 // ---- host-buffer label operators

@@ -165,11 +165,12 @@ __device__ __forceinline__ uint64_t synth_hash(uint64_t sm, uint32_t a, uint32_t
     return splitmix64(sm ^ (((uint64_t)a << 40) | ((uint64_t)b << 16) | (uint64_t)c));
 }
 
-__global__ void __launch_bounds__(256) synth_kernel(uint8_t* __restrict__ dst, size_t step, int w, int h, uint64_t sm)
+__global__ void __launch_bounds__(256) synth_kernel(uint8_t* __restrict__ dst, size_t step, int w, int h, int row0, int rows,
+                                                    uint64_t sm)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= w || y >= h) return;
+    int y = row0 + blockIdx.y;      // global row; the buffer holds rows [row0, row0 + rows)
+    if (x >= w || (int)blockIdx.y >= rows || y >= h) return;
     int ncx = (w + 63) / 64, ncy = (h + 63) / 64;
     int cx0 = x / 64, cy0 = y / 64;
     long long best = -1;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) synth_kernel(uint8_t* __restrict__ dst, s
             long long ddx = x - sx, ddy = y - sy, dd = ddx * ddx + ddy * ddy;
             if (best < 0 || dd < best) { best = dd; bc = (uint32_t)(synth_hash(sm, cx, cy, 2) & 0xFFFFFFu); }
         }
-    uint8_t* p = dst + (size_t)y * step + 3 * (size_t)x;
+    uint8_t* p = dst + (size_t)(y - row0) * step + 3 * (size_t)x;
     for (int c = 0; c < 3; c++) {
         int base = (int)((bc >> (8 * c)) & 0xFF);
         int nz = (int)(synth_hash(sm, x, y, 16u + c) % 13) + (int)(synth_hash(sm, x, y, 32u + c) % 13) - 12;
@@ -242,10 +243,10 @@ int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc, msg_plane ddst, int isr22)
     return MSG_OK;
 }
 
-int k_synth(msg_ctx* ctx, uint8_t* d_bgr, size_t step, int w, int h, uint64_t seed)
+int k_synth(msg_ctx* ctx, uint8_t* d_bgr, size_t step, int w, int h, int row0, int rows, uint64_t seed)
 {
-    dim3 grid((w + 255) / 256, h);
-    synth_kernel<<<grid, 256, 0, ctx->stream>>>(d_bgr, step, w, h, host_splitmix64(seed));
+    dim3 grid((w + 255) / 256, rows);
+    synth_kernel<<<grid, 256, 0, ctx->stream>>>(d_bgr, step, w, h, row0, rows, host_splitmix64(seed));
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;

@@ -7,7 +7,7 @@
 //   stop when the centre does not move or |dx|+|dy|+||dc||^2 <= eps, or after maxCount iterations.
 //
 // Design (B200, INT-ALU bound, DESIGN.md "K1"):
-//   * one CTA per 64x32 pixel tile; tile + (radius + drift) halo staged once in shared memory as
+//   * one CTA per 64x32 (large planes) or 32x32 (small planes: shorter tail) pixel tile; tile + (radius + drift) halo staged once in shared memory as
 //     packed BGRx words, out-of-image positions hold a sentinel that can never be in range, so the
 //     window loops run unclamped and warp-convergent;
 //   * work is a queue of (pixel, centre, colour) items held in shared memory and processed in
@@ -16,15 +16,14 @@
 //     idle on pixels that converged early (iterations vary 1..maxCount per pixel);
 //   * per test: LDS + VABSDIFF4 + IDP4A + ISETP + predicated 16-bit-lane SIMD accumulates;
 //   * an item whose next window would leave the staged rectangle is pushed to a global overflow
-//     list and finished by the generic kernel (reads HBM/L2 directly, explicit clamping).
+//     list and finished by the warp-cooperative generic kernel (reads HBM/L2 directly, explicit clamping).
+#include <stdlib.h>
+
 #include "msg_internal.h"
 
 namespace {
 
-constexpr int TW = 64;            // tile width  (pixels)
-constexpr int TH = 32;            // tile height (pixels)
-constexpr int NPIX = TW * TH;     // 2048 -> 11 bits
-constexpr int MS_THREADS = 256;
+constexpr int TH = 32;            // tile height (pixels); tile width TW is 64 (256 threads) or 32 (128 threads)
 constexpr uint32_t SENTINEL = 0xFF000000u;  // byte3 = 255 vs 1 of real pixels: distance >= 254^2
 
 __device__ __forceinline__ int rnd_f(float v) { return __float2int_rn(v); }  // cvRound(float): half-even
@@ -59,47 +58,102 @@ __device__ __forceinline__ bool ms_stop(int x0, int y0, uint32_t c0, const iter_
 }
 
 // Window scan over the staged tile.  NX > 0: window is NX x NX for every item (integral sp).
-template <int NX>
+// Per test: LDS + VABSDIFF4 + IDP4A + ISETP + 3 predicated IDP4A (B, G, R sums; FMA pipe) + 1 predicated add of the
+// immediate (1 << 16 | xx) (hit count and sum of x in one register; ALU pipe) = 8 issue slots, 4 FMA : 3 ALU : 1 LSU.
+__device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// In-range accumulate, branch free: the packed pixel is zeroed on a miss (1 SEL, ALU pipe) and the three colour sums
+// are unconditional IDP4A (FMA pipe); hit count and sum of x share one register via a predicated immediate add.
+// Per test: LDS + VABSDIFF4 + IDP4A + ISETP + SEL + 3 IDP4A + 1 add = 9 issue slots, 4 ALU : 4 FMA : 1 LSU.
+__device__ __forceinline__ void accumulate_if_hit(uint32_t d2, int isr2, uint32_t t, uint32_t add_cx, uint32_t& a0,
+                                                  uint32_t& a1, uint32_t& a2, uint32_t& cx)
+{
+    uint32_t tm;
+    // one predicate, one select, one predicated add -- spelled in PTX so that the add stays predicated
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.le.s32 p, %2, %3;\n\t"
+        "selp.u32 %0, %4, 0, p;\n\t"
+        "@p add.u32 %1, %1, %5;\n\t"
+        "}"
+        : "=r"(tm), "+r"(cx)
+        : "r"(d2), "r"(isr2), "r"(t), "r"(add_cx));
+    a0 = dp4a_u(tm, 0x00000001u, a0);
+    a1 = dp4a_u(tm, 0x00000100u, a1);
+    a2 = dp4a_u(tm, 0x00010000u, a2);
+}
+
+// ACC = 1: IDP4A accumulates (above).  ACC = 0: 16-bit-lane SIMD accumulates (PRMT + predicated adds; 5 ALU : 3 FMA).
+template <int NX, int ACC>
 __device__ __forceinline__ void window_scan(const uint32_t* __restrict__ base, int swp, int nx, int ny, uint32_t c,
                                             int isr2, int& s0, int& s1, int& s2, int& sxr, int& syr, int& cnt)
 {
-    s0 = s1 = s2 = sxr = syr = cnt = 0;
+    uint32_t a0 = 0, a1 = 0, a2 = 0;
+    sxr = syr = cnt = 0;
     if (NX > 0) { nx = NX; ny = NX; }
     for (int yy = 0; yy < ny; ++yy) {
         const uint32_t* row = base + yy * swp;
-        uint32_t lo = 0, hi = 0;
-        int sx = 0;
-        if (NX > 0) {
+        if (ACC == 1) {
+            uint32_t cx = 0;   // (hits << 16) | sum of xx over the hits of this row (nx <= 241: both fields fit)
+            if (NX > 0) {
 #pragma unroll
-            for (int xx = 0; xx < (NX > 0 ? NX : 1); ++xx) {
-                uint32_t t = row[xx];
-                uint32_t e = __vabsdiffu4(t, c);
-                if ((int)__dp4a(e, e, 0u) <= isr2) {
-                    lo += __byte_perm(t, 0u, 0x4240);  // (B, 0, R, 0)
-                    hi += __byte_perm(t, 0u, 0x4341);  // (G, 0, 1, 0)
-                    sx += xx;
+                for (int xx = 0; xx < (NX > 0 ? NX : 1); ++xx) {
+                    uint32_t t = row[xx];
+                    uint32_t e = __vabsdiffu4(t, c);
+                    accumulate_if_hit(dp4a_u(e, e, 0u), isr2, t, 0x10000u + (uint32_t)xx, a0, a1, a2, cx);
+                }
+            } else {
+                for (int xx = 0; xx < nx; ++xx) {
+                    uint32_t t = row[xx];
+                    uint32_t e = __vabsdiffu4(t, c);
+                    accumulate_if_hit(dp4a_u(e, e, 0u), isr2, t, 0x10000u + (uint32_t)xx, a0, a1, a2, cx);
                 }
             }
+            int rc = (int)(cx >> 16);
+            cnt += rc;
+            syr += yy * rc;
+            sxr += (int)(cx & 0xFFFFu);
         } else {
-            for (int xx = 0; xx < nx; ++xx) {
-                uint32_t t = row[xx];
-                uint32_t e = __vabsdiffu4(t, c);
-                if ((int)__dp4a(e, e, 0u) <= isr2) {
-                    lo += __byte_perm(t, 0u, 0x4240);
-                    hi += __byte_perm(t, 0u, 0x4341);
-                    sx += xx;
+            uint32_t lo = 0, hi = 0;
+            int sx = 0;
+            if (NX > 0) {
+#pragma unroll
+                for (int xx = 0; xx < (NX > 0 ? NX : 1); ++xx) {
+                    uint32_t t = row[xx];
+                    uint32_t e = __vabsdiffu4(t, c);
+                    if ((int)__dp4a(e, e, 0u) <= isr2) {
+                        lo += __byte_perm(t, 0u, 0x4240);  // (B, 0, R, 0)
+                        hi += __byte_perm(t, 0u, 0x4341);  // (G, 0, 1, 0)
+                        sx += xx;
+                    }
+                }
+            } else {
+                for (int xx = 0; xx < nx; ++xx) {
+                    uint32_t t = row[xx];
+                    uint32_t e = __vabsdiffu4(t, c);
+                    if ((int)__dp4a(e, e, 0u) <= isr2) {
+                        lo += __byte_perm(t, 0u, 0x4240);
+                        hi += __byte_perm(t, 0u, 0x4341);
+                        sx += xx;
+                    }
                 }
             }
+            // per-row flush of the 16-bit lanes (row length <= 257 keeps 255*n < 65536)
+            int rc = (int)(hi >> 16);
+            a0 += lo & 0xFFFFu;
+            a2 += lo >> 16;
+            a1 += hi & 0xFFFFu;
+            cnt += rc;
+            syr += yy * rc;
+            sxr += sx;
         }
-        // per-row flush of the 16-bit lanes (row length <= 257 keeps 255*n < 65536)
-        int rc = (int)(hi >> 16);
-        s0 += (int)(lo & 0xFFFFu);
-        s2 += (int)(lo >> 16);
-        s1 += (int)(hi & 0xFFFFu);
-        cnt += rc;
-        syr += yy * rc;
-        sxr += sx;
     }
+    s0 = (int)a0; s1 = (int)a1; s2 = (int)a2;
 }
 
 struct tile_geom {
@@ -109,13 +163,14 @@ struct tile_geom {
     int tiles_x;
 };
 
-template <int NX>
-__global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S, msg_plane D, msg_ms_params prm,
-                                                                    tile_geom g, msg_ovf_item* __restrict__ ovf,
-                                                                    int* __restrict__ ovf_count,
-                                                                    unsigned long long* __restrict__ active_count,
-                                                                    unsigned long long* __restrict__ work)
+template <int NX, int TW, int ACC>
+__global__ void __launch_bounds__(TW * 4) meanshift_tile_kernel(msg_plane S, msg_plane D, msg_ms_params prm, tile_geom g,
+                                                                msg_ovf_item* __restrict__ ovf, int* __restrict__ ovf_count,
+                                                                unsigned long long* __restrict__ active_count,
+                                                                unsigned long long* __restrict__ work)
 {
+    constexpr int NT = TW * 4;        // threads per CTA
+    constexpr int NPIX = TW * TH;     // <= 2048 -> 11 bits
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* stage = smem;                                  // g.sh * g.swp
     uint2* q0 = reinterpret_cast<uint2*>(smem + ((g.sh * g.swp + 1) & ~1));
@@ -132,7 +187,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S,
     if (tid < 2) qn[tid] = 0;
 
     // ---- stage tile + halo (coalesced row segments; sentinel outside the image / stored rows)
-    for (int sy = tid / 32; sy < g.sh; sy += MS_THREADS / 32) {
+    for (int sy = tid / 32; sy < g.sh; sy += NT / 32) {
         int gy = oy + sy;
         int r = gy - S.y0;
         bool row_ok = (gy >= 0) && (gy < S.hfull) && (r >= 0) && (r < S.rows);
@@ -148,7 +203,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S,
     __syncthreads();
 
     // ---- initial queue: active pixels of the tile, in raster order within each warp chunk
-    for (int base = (tid / 32) * 32; base < NPIX; base += MS_THREADS) {
+    for (int base = (tid / 32) * 32; base < NPIX; base += NT) {
         int p = base + lane;
         int ty = p / TW, tx = p % TW;
         int gx = tx0 + tx, gy = ty0 + ty;
@@ -181,7 +236,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S,
         if (tid == 0) qn[cur ^ 1] = 0;
         __syncthreads();
         const bool last_round = (it == prm.max_count - 1);
-        for (int ibase = (tid / 32) * 32; ibase < n; ibase += MS_THREADS) {
+        for (int ibase = (tid / 32) * 32; ibase < n; ibase += NT) {
             const int i = ibase + lane;
             const bool valid = i < n;
             uint2 item = valid ? qc[i] : make_uint2(0u, 0u);
@@ -197,7 +252,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S,
                 int miny = rnd_f((float)y0 - sp), maxy = rnd_f((float)y0 + sp);
                 const uint32_t* base = stage + (miny - oy) * g.swp + (minx - ox);
                 int s0, s1, s2, sxr, syr, cnt;
-                window_scan<NX>(base, g.swp, maxx - minx + 1, maxy - miny + 1, c, prm.isr2, s0, s1, s2, sxr, syr, cnt);
+                window_scan<NX, ACC>(base, g.swp, maxx - minx + 1, maxy - miny + 1, c, prm.isr2, s0, s1, s2, sxr, syr, cnt);
                 if (work) {   // uniform branch; counts what the CPU oracle counts: clamped window area and hits
                     int cx = min(maxx, S.w - 1) - max(minx, 0) + 1, cy = min(maxy, S.hfull - 1) - max(miny, 0) + 1;
                     wk_tests += (unsigned)(cx * cy);
@@ -257,8 +312,10 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_tile_kernel(msg_plane S,
     }
 }
 
-// Generic path: explicit clamping, reads the plane through L1/L2.  Either finishes overflow items
-// (items != nullptr) or processes every (active) pixel of the plane (items == nullptr).
+// Generic path, one WARP per item: lanes stride over the columns of the (explicitly clamped) window, rows are looped,
+// partial sums are combined with shuffles and every lane evaluates the (identical) epilogue, so control flow stays
+// warp-uniform.  Reads the plane through L1/L2.  Either finishes overflow items (items != nullptr) or processes every
+// (active) pixel of the plane (items == nullptr: parameter corners the tile kernel does not serve).
 __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg_plane D, msg_ms_params prm,
                                                                 const msg_ovf_item* __restrict__ items,
                                                                 const int* __restrict__ n_items,
@@ -266,13 +323,15 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
                                                                 unsigned long long* __restrict__ ovf_total,
                                                                 unsigned long long* __restrict__ work)
 {
-    unsigned long long wk_tests = 0, wk_hits = 0;
     const long long total = items ? (long long)*n_items : (long long)S.rows * S.w;
     if (items && ovf_total && blockIdx.x == 0 && threadIdx.x == 0 && total > 0)
         atomicAdd(ovf_total, (unsigned long long)total);
     const float sp = prm.sp;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long wk_tests = 0, wk_hits = 0;
+    for (long long i = warp0; i < total; i += nwarps) {
         int x0, y0, it0;
         uint32_t c;
         size_t out;
@@ -282,9 +341,9 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
         } else {
             int r = (int)(i / S.w), x = (int)(i % S.w);
             out = (size_t)r * D.pitch + x;
-            if (prm.use_mask && (D.p[out] >> 24) == 0) continue;
+            if (prm.use_mask && (D.p[out] >> 24) == 0) continue;      // warp-uniform
             x0 = x; y0 = S.y0 + r; c = S.p[(size_t)r * S.pitch + x]; it0 = 0;
-            if (active_count) atomicAdd(active_count, 1ull);
+            if (active_count && lane == 0) atomicAdd(active_count, 1ull);
         }
         for (int it = it0; it < prm.max_count; ++it) {
             int minx = max(rnd_f((float)x0 - sp), 0), maxx = min(rnd_f((float)x0 + sp), S.w - 1);
@@ -296,7 +355,7 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
             for (int y = miny; y <= maxy; ++y) {
                 const uint32_t* row = S.p + (size_t)(y - S.y0) * S.pitch;
                 int rc = 0, rsx = 0;
-                for (int x = minx; x <= maxx; ++x) {
+                for (int x = minx + lane; x <= maxx; x += 32) {
                     uint32_t t = __ldg(row + x);
                     uint32_t e = __vabsdiffu4(t, c);
                     if ((long long)__dp4a(e, e, 0u) <= (long long)prm.isr2) {
@@ -306,7 +365,16 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
                 }
                 cnt += rc; sx += rsx; sy += (long long)y * rc;
             }
-            if (work && maxx >= minx && maxy >= miny) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            }
+            if (work && lane == 0 && maxx >= minx && maxy >= miny) {
                 wk_tests += (unsigned long long)(maxx - minx + 1) * (unsigned long long)(maxy - miny + 1);
                 wk_hits += (unsigned long long)cnt;
             }
@@ -316,7 +384,7 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
             x0 = res.x1; y0 = res.y1; c = res.c1;
             if (stop) break;
         }
-        D.p[out] = c;
+        if (lane == 0) D.p[out] = c;
     }
     if (work && (wk_tests | wk_hits)) {
         atomicAdd(work + 2, wk_tests);
@@ -324,15 +392,30 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
     }
 }
 
-template <int NX>
+template <int NX, int TW, int ACC>
 cudaError_t launch_tile(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, const tile_geom& g, int tiles,
                         size_t smem, int* ovf_count, unsigned long long* active, unsigned long long* work)
 {
     // attribute is per function AND per device: set it on every launch (cheap, no sync)
-    cudaError_t e = cudaFuncSetAttribute(meanshift_tile_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(meanshift_tile_kernel<NX, TW, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    meanshift_tile_kernel<NX><<<tiles, MS_THREADS, smem, ctx->stream>>>(S, D, prm, g, ctx->d_ovf, ovf_count, active, work);
+    meanshift_tile_kernel<NX, TW, ACC><<<tiles, TW * 4, smem, ctx->stream>>>(S, D, prm, g, ctx->d_ovf, ovf_count, active, work);
     return cudaGetLastError();
+}
+
+template <int TW, int ACC>
+cudaError_t dispatch_tile(int nx, msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, const tile_geom& g,
+                          int tiles, size_t smem, int* ovf_count, unsigned long long* active, unsigned long long* work)
+{
+    switch (nx) {   // integral sp -> every window is (2 sp + 1)^2: fully unrolled instantiations
+        case 3: return launch_tile<3, TW, ACC>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
+        case 5: return launch_tile<5, TW, ACC>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
+        case 7: return launch_tile<7, TW, ACC>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
+        case 11: return launch_tile<11, TW, ACC>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
+        case 21: return launch_tile<21, TW, ACC>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
+        case 41: return launch_tile<41, TW, ACC>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
+        default: return launch_tile<0, TW, ACC>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
+    }
 }
 
 }  // namespace
@@ -346,6 +429,15 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     unsigned long long* active = reinterpret_cast<unsigned long long*>(ctx->d_counters + 2);
     unsigned long long* ovf_total = reinterpret_cast<unsigned long long*>(ctx->d_counters + 4);
 
+    // tile width: 64 (256 threads) when the plane gives enough 64x32 tiles for several waves, else 32 (128 threads):
+    // small planes would otherwise run 1-2 waves of unequal tiles and idle SMs in the tail
+    const long long tiles64 = (long long)((S.w + 63) / 64) * ((S.rows + TH - 1) / TH);
+    int TWsel = tiles64 >= (long long)ctx->sm_count * 18 ? 64 : 32;
+    int acc = 1;
+    // tuning overrides (experiments only): MSG_TILE_W = 32 | 64, MSG_ACC = 0 | 1
+    if (const char* e = getenv("MSG_TILE_W")) { int v = atoi(e); if (v == 32 || v == 64) TWsel = v; }
+    if (const char* e = getenv("MSG_ACC")) acc = atoi(e) ? 1 : 0;
+
     // tile path limits: sentinel distance 254^2 must exceed isr2; staged tile must fit shared memory
     const int R = prm.radius;
     int drift = R + (R + 3) / 4;  // ~1.25 * radius (covers > 99 % of measured drift)
@@ -356,10 +448,10 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     if (tile_ok) {
         for (;; drift = drift * 3 / 4) {
             g.halo = R + drift;
-            g.sw = TW + 2 * g.halo;
+            g.sw = TWsel + 2 * g.halo;
             g.sh = TH + 2 * g.halo;
             g.swp = g.sw | 1;
-            smem = ((size_t)((g.sh * g.swp + 1) & ~1) + 4 * (size_t)NPIX) * sizeof(uint32_t);
+            smem = ((size_t)((g.sh * g.swp + 1) & ~1) + 4 * (size_t)(TWsel * TH)) * sizeof(uint32_t);
             if (smem <= (size_t)ctx->max_smem_optin - 1024 && g.sw < 512 && g.sh < 512) break;
             if (drift == 0) { tile_ok = false; break; }
         }
@@ -375,24 +467,20 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     size_t need = (size_t)S.rows * S.w;
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, need * sizeof(msg_ovf_item)));
     MSG_CUDA(ctx, cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
-    g.tiles_x = (S.w + TW - 1) / TW;
+    g.tiles_x = (S.w + TWsel - 1) / TWsel;
     int tiles_y = (S.rows + TH - 1) / TH;
     int tiles = g.tiles_x * tiles_y;
 
-    // integral sp -> every window is (2 sp + 1)^2: use the fully unrolled instantiations
     int nx = 0;
     if (prm.sp == (float)(int)prm.sp) nx = 2 * (int)prm.sp + 1;
-    cudaError_t e;
     if (ctx->profiling) msg_prof_begin(ctx, level);
-    switch (nx) {
-        case 3: e = launch_tile<3>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
-        case 5: e = launch_tile<5>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
-        case 7: e = launch_tile<7>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
-        case 11: e = launch_tile<11>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
-        case 21: e = launch_tile<21>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
-        case 41: e = launch_tile<41>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
-        default: e = launch_tile<0>(ctx, S, D, prm, g, tiles, smem, ovf_count, active, work); break;
-    }
+    cudaError_t e;
+    if (TWsel == 64)
+        e = acc ? dispatch_tile<64, 1>(nx, ctx, S, D, prm, g, tiles, smem, ovf_count, active, work)
+                : dispatch_tile<64, 0>(nx, ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
+    else
+        e = acc ? dispatch_tile<32, 1>(nx, ctx, S, D, prm, g, tiles, smem, ovf_count, active, work)
+                : dispatch_tile<32, 0>(nx, ctx, S, D, prm, g, tiles, smem, ovf_count, active, work);
     MSG_LAUNCHED(ctx);
     MSG_CUDA(ctx, e);
     if (ctx->profiling) msg_prof_end(ctx, level, 0);

@@ -115,7 +115,7 @@ int k_bgr_to_plane(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, msg_plane ds
 int k_plane_to_bgr(msg_ctx* ctx, msg_plane src, int row_first, int nrows, uint8_t* d_bgr, size_t step);
 int k_pyr_down(msg_ctx* ctx, msg_plane src, msg_plane dst);
 int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc /*D[l+1]*/, msg_plane ddst /*D[l]*/, int isr22);
-int k_synth(msg_ctx* ctx, uint8_t* d_bgr, size_t step, int w, int h, uint64_t seed);
+int k_synth(msg_ctx* ctx, uint8_t* d_bgr, size_t step, int w, int h, int row0, int rows, uint64_t seed);
 // mean shift
 int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, int level);
 // profiling hooks (capi.cu): CUDA events around the tile kernel (slot 0) and the overflow kernel (slot 1) of a level

@@ -21,6 +21,10 @@ def synth(ctx, d_dst, step, w, h, seed):
     ctx.check(ctx._lib.msg_synth_bgr_dev(ctx._h, _p(d_dst), step, w, h, int(seed)))
 
 
+def synth_rows(ctx, d_dst, step, w, full_h, row0, rows, seed):
+    ctx.check(ctx._lib.msg_synth_bgr_rows_dev(ctx._h, _p(d_dst), step, w, full_h, row0, rows, int(seed)))
+
+
 def segment(ctx, d_src, sstep, w, h, prm, d_filtered=0, fstep=0, d_labels=0, lstep=0, d_rendered=0, rstep=0, d_n=0):
     ctx.check(ctx._lib.msg_segment_dev(ctx._h, _p(d_src), sstep, w, h, C.byref(prm), _p(d_filtered), fstep, _p(d_labels),
                                        lstep, _p(d_rendered), rstep, _p(d_n)))

@@ -1,0 +1,109 @@
+"""Row-strip sharding of one very large image over several GPUs (BASELINE.json config 5).
+
+Host-side logic only (numpy + an injected communicator); all pixel work happens in the C-ABI strip entry points:
+    msg_meanshift_filter_strip_dev   filter rows [row0,row1) from a buffer holding rows [halo0,halo1) (global coordinates)
+    msg_label_strip_dev              union-find labels of a strip, provisional label = 1 + global index of first pixel
+    msg_seam_pairs_dev               equivalence pairs across a seam (upper strip's last row vs lower strip's first row)
+    msg_apply_label_map_dev          rewrite a strip with the resolved equivalences
+The only communication is (1) input halo rows / one boundary row per seam between neighbours (NVLink P2P copies or
+NCCL send/recv) and (2) an all-gather of the seam pair lists (NCCL); every rank then solves the same small union-find.
+There is no oracle and no CPU pixel path in here.
+"""
+import numpy as np
+
+
+def plan_strips(height, n_strips, max_level):
+    """Row ranges [(row0,row1), ...]: contiguous, non-empty, every row0 a multiple of 2^max_level (pyramid phase)."""
+    a = 1 << max_level
+    if n_strips < 1:
+        raise ValueError("n_strips must be >= 1")
+    units = (height + a - 1) // a
+    if units < n_strips:
+        raise ValueError("image too small for %d strips at alignment %d" % (n_strips, a))
+    bounds = [min(height, ((units * k) // n_strips) * a) for k in range(n_strips)] + [height]
+    return [(bounds[k], bounds[k + 1]) for k in range(n_strips)]
+
+
+def halo_range(row0, row1, height, halo, max_level):
+    """Rows a rank must hold to filter [row0,row1): clipped to the image, start aligned to 2^max_level."""
+    a = 1 << max_level
+    h0 = max(0, row0 - halo)
+    h0 -= h0 % a
+    h1 = min(height, row1 + halo)
+    return h0, h1
+
+
+def resolve_pairs(pairs):
+    """Union-find over seam equivalence pairs.
+
+    pairs: int array (n,2) of global provisional labels (any order, duplicates allowed).
+    Returns (from_sorted, to): every label that must change and the label (smallest of its class) it becomes.
+    Deterministic: all ranks compute the same map from the same gathered pairs."""
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    if len(pairs) == 0:
+        return np.zeros(0, np.int32), np.zeros(0, np.int32)
+    labels, inv = np.unique(pairs, return_inverse=True)
+    inv = inv.reshape(-1, 2)
+    parent = np.arange(len(labels))
+
+    def find(i):
+        r = i
+        while parent[r] != r:
+            r = parent[r]
+        while parent[i] != r:
+            parent[i], i = r, parent[i]
+        return r
+
+    for a, b in inv:
+        ra, rb = find(a), find(b)
+        if ra != rb:            # labels is sorted, so the smaller index is the smaller label
+            if ra < rb:
+                parent[rb] = ra
+            else:
+                parent[ra] = rb
+    roots = np.array([find(i) for i in range(len(labels))])
+    changed = roots != np.arange(len(labels))
+    return labels[changed].astype(np.int32), labels[roots[changed]].astype(np.int32)
+
+
+def first_pixel_labels(dense_labels):
+    """Converts dense canonical labels (1..n in raster order of first pixel) to the sharded representation
+    (1 + linear index of the region's first pixel); used to compare sharded and unsharded results."""
+    flat = np.asarray(dense_labels).ravel()
+    out = np.zeros_like(flat)
+    pos = flat > 0
+    _, first = np.unique(flat[pos], return_index=True)
+    idx = np.flatnonzero(pos)[first]            # first pixel of label k+1 (labels are 1..n, sorted by np.unique)
+    out[pos] = (idx + 1)[flat[pos] - 1]
+    return out.reshape(np.asarray(dense_labels).shape)
+
+
+def dense_from_first_pixel(labels):
+    """Inverse of first_pixel_labels on a full (gathered) label image: dense 1..n by ascending first pixel."""
+    flat = np.asarray(labels).ravel()
+    out = np.zeros_like(flat)
+    pos = flat > 0
+    u, inv = np.unique(flat[pos], return_inverse=True)
+    out[pos] = inv + 1
+    return len(u), out.reshape(np.asarray(labels).shape)
+
+
+def allgather_pairs(dist, pairs, device=None):
+    """All-gathers variable-length (n,2) int32 pair lists with torch.distributed (NCCL on GPU tensors, gloo on CPU).
+    Returns the concatenation over ranks as a numpy (m,2) array, identical on every rank."""
+    import torch
+    world = dist.get_world_size()
+    t = torch.as_tensor(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+    if device is not None:
+        t = t.to(device)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    cap = max(1, max(counts))
+    padded = torch.zeros((cap, 2), dtype=torch.int32, device=t.device)
+    padded[:t.shape[0]] = t
+    out = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded)
+    parts = [o[:c].cpu().numpy() for o, c in zip(out, counts)]
+    return np.concatenate(parts, axis=0) if parts else np.zeros((0, 2), np.int32)

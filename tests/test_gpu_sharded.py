@@ -1,0 +1,81 @@
+"""GPU (B200): strip sharding must be bit-identical to the unsharded result.  N strips are evaluated one after the
+other on one GPU (each call sees only its rows + halo), which is how the multi-GPU path is checked without a cluster;
+tools/shard_large_image.py runs the same calls with one process per GPU."""
+import numpy as np
+import pytest
+
+import msegment_b200 as mseg
+from oracle import oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+dev = mseg.device
+sh = mseg.pkg.sharded
+
+
+def _sharded_run(ctx, src, w, h, n_strips, sp, sr, ml, lo):
+    """src: torch uint8 [h,w,3] on the GPU.  Returns (filtered [h,w,3], labels [h,w] in first-pixel form)."""
+    halo = dev.halo_rows(sp, ml)
+    strips = sh.plan_strips(h, n_strips, ml)
+    filt = torch.zeros_like(src)
+    lab = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    for (r0, r1) in strips:
+        h0, h1 = sh.halo_range(r0, r1, h, halo, ml)
+        rows = src[h0:h1].contiguous()                 # what a rank would hold: its strip + halo rows only
+        out = torch.empty((r1 - r0, w, 3), dtype=torch.uint8, device="cuda")
+        dev.meanshift_strip(ctx, rows.data_ptr(), 3 * w, h0, h1, out.data_ptr(), 3 * w, w, h, r0, r1, sp, sr, ml)
+        filt[r0:r1] = out
+    for (r0, r1) in strips:
+        rows = filt[r0:r1].contiguous()
+        l = torch.empty((r1 - r0, w), dtype=torch.int32, device="cuda")
+        dev.label_strip(ctx, rows.data_ptr(), 3 * w, l.data_ptr(), 4 * w, w, r1 - r0, r0, w, lo)
+        lab[r0:r1] = l
+    pairs_all = []
+    pairs = torch.zeros((w, 2), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    for (r0, r1) in strips[1:]:
+        dev.seam_pairs(ctx, filt[r0 - 1].data_ptr(), lab[r0 - 1].data_ptr(), filt[r0].data_ptr(), lab[r0].data_ptr(), w, lo,
+                       pairs.data_ptr(), cnt.data_ptr())
+        ctx.synchronize()
+        pairs_all.append(pairs[:int(cnt.item())].cpu().numpy().copy())
+    frm, to = sh.resolve_pairs(np.concatenate(pairs_all) if pairs_all else np.zeros((0, 2), np.int32))
+    if len(frm):
+        d_from, d_to = torch.from_numpy(frm).cuda(), torch.from_numpy(to).cuda()
+        dev.apply_label_map(ctx, lab.data_ptr(), 4 * w, w, h, d_from.data_ptr(), d_to.data_ptr(), len(frm))
+    ctx.synchronize()
+    return filt, lab
+
+
+@pytest.mark.parametrize("w,h,n,sp,sr,ml", [(600, 518, 3, 10, 10, 1), (333, 400, 4, 6, 15, 2), (257, 300, 2, 8, 12, 0),
+                                           (420, 300, 5, 10, 10, 1)])
+def test_strips_bit_identical(w, h, n, sp, sr, ml):
+    ctx = mseg.Context(0)
+    im = orc.synth_bgr(w, h, 17)
+    src = torch.from_numpy(im).cuda()
+    full = torch.empty_like(src)
+    dev.meanshift(ctx, src.data_ptr(), 3 * w, full.data_ptr(), 3 * w, w, h, sp, sr, ml)
+    lab_full = torch.empty((h, w), dtype=torch.int32, device="cuda")
+    dev.label_regions(ctx, full.data_ptr(), 3 * w, lab_full.data_ptr(), 4 * w, w, h, 2)
+    ctx.synchronize()
+    filt, lab = _sharded_run(ctx, src, w, h, n, sp, sr, ml, 2)
+    bad = (filt != full).any(dim=2)
+    assert not bad.any(), "filtered differs at %d pixels, rows %s" % (int(bad.sum()), torch.nonzero(bad.any(dim=1)).flatten()[:8].tolist())
+    want = sh.first_pixel_labels(lab_full.cpu().numpy())
+    got = lab.cpu().numpy()
+    assert np.array_equal(got, want), int((got != want).sum())
+    # and the unsharded GPU result is the oracle's
+    assert np.array_equal(full.cpu().numpy(), orc.meanshift_filter(im, sp, sr, ml))
+    ctx.close()
+
+
+def test_synth_rows_matches_full():
+    ctx = mseg.Context(0)
+    w, h = 300, 200
+    a = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+    dev.synth(ctx, a.data_ptr(), 3 * w, w, h, 5)
+    b = torch.empty((60, w, 3), dtype=torch.uint8, device="cuda")
+    dev.synth_rows(ctx, b.data_ptr(), 3 * w, w, h, 70, 60, 5)
+    ctx.synchronize()
+    assert torch.equal(a[70:130], b)
+    assert np.array_equal(a.cpu().numpy(), orc.synth_bgr(w, h, 5))
+    ctx.close()

@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""BASELINE.json config 5: one very large synthetic image, row strips over the GPUs of one box.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/shard_large_image.py \
+        --size 16384 [--verify]
+
+Each rank generates ITS rows of the image on its GPU, fetches the halo rows it needs from its neighbours with NCCL
+point-to-point (NVLink), filters and labels its strip through the C ABI, exchanges one boundary row (colour + labels)
+with the rank above, and the seam equivalence pairs are all-gathered (NCCL); every rank solves the same union-find and
+rewrites its strip.  --verify (sizes that fit one GPU) gathers the result on rank 0 and compares it bit for bit with
+the unsharded single-GPU call.  Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import msegment_b200 as mseg  # noqa: E402
+
+dev = mseg.device
+sh = mseg.pkg.sharded
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=5)
+    ap.add_argument("--sp", type=float, default=10.0)
+    ap.add_argument("--sr", type=float, default=10.0)
+    ap.add_argument("--max-level", type=int, default=1)
+    ap.add_argument("--lo", type=int, default=2)
+    ap.add_argument("--verify", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    h = args.size
+    w = args.width or args.size
+    ml = args.max_level
+    ctx = mseg.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    halo = dev.halo_rows(args.sp, ml)
+    strips = sh.plan_strips(h, world, ml)
+    r0, r1 = strips[rank]
+    h0, h1 = sh.halo_range(r0, r1, h, halo, ml)
+
+    # own rows, generated in place inside the halo buffer
+    buf = torch.empty((h1 - h0, w, 3), dtype=torch.uint8, device="cuda")
+    dev.synth_rows(ctx, buf[r0 - h0:].data_ptr(), 3 * w, w, h, r0, r1 - r0, args.seed)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_start = time.perf_counter()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+
+    # ---- halo exchange (input rows only): rows [h0,r0) come from ranks above, rows [r1,h1) from ranks below
+    ops, keep = [], []
+    for peer, (p0, p1) in enumerate(strips):
+        if peer == rank:
+            continue
+        ph0, ph1 = sh.halo_range(p0, p1, h, halo, ml)
+        # what the peer needs from me
+        for (a, b) in ((max(ph0, r0), min(p0, r1)), (max(p1, r0), min(ph1, r1))):
+            if a < b:
+                t = buf[a - h0:b - h0]
+                ops.append(dist.P2POp(dist.isend, t, peer))
+        # what I need from the peer
+        for (a, b) in ((max(h0, p0), min(r0, p1)), (max(r1, p0), min(h1, p1))):
+            if a < b:
+                t = buf[a - h0:b - h0]
+                ops.append(dist.P2POp(dist.irecv, t, peer))
+    halo_bytes = sum(op.tensor.numel() for op in ops if op.op == dist.irecv)
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    ev[1].record()
+
+    # ---- filter + label the strip
+    filt = torch.empty((r1 - r0, w, 3), dtype=torch.uint8, device="cuda")
+    dev.meanshift_strip(ctx, buf.data_ptr(), 3 * w, h0, h1, filt.data_ptr(), 3 * w, w, h, r0, r1, args.sp, args.sr, ml)
+    ev[2].record()
+    lab = torch.empty((r1 - r0, w), dtype=torch.int32, device="cuda")
+    dev.label_strip(ctx, filt.data_ptr(), 3 * w, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, args.lo)
+    ev[3].record()
+
+    # ---- seam: my first row against the last row of the rank above
+    up_bgr = torch.empty((w, 3), dtype=torch.uint8, device="cuda")
+    up_lab = torch.empty((w,), dtype=torch.int32, device="cuda")
+    ops = []
+    if rank + 1 < world:
+        ops += [dist.P2POp(dist.isend, filt[-1].contiguous(), rank + 1), dist.P2POp(dist.isend, lab[-1].contiguous(), rank + 1)]
+    if rank > 0:
+        ops += [dist.P2POp(dist.irecv, up_bgr, rank - 1), dist.P2POp(dist.irecv, up_lab, rank - 1)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    pairs = torch.zeros((w, 2), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    if rank > 0:
+        dev.seam_pairs(ctx, up_bgr.data_ptr(), up_lab.data_ptr(), filt[0].data_ptr(), lab[0].data_ptr(), w, args.lo,
+                       pairs.data_ptr(), cnt.data_ptr())
+    torch.cuda.synchronize()
+    mine = pairs[:int(cnt.item())].cpu().numpy()
+    allp = sh.allgather_pairs(dist, mine, device="cuda")
+    frm, to = sh.resolve_pairs(allp)
+    if len(frm):
+        d_from, d_to = torch.from_numpy(frm).cuda(), torch.from_numpy(to).cuda()
+        dev.apply_label_map(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, d_from.data_ptr(), d_to.data_ptr(), len(frm))
+    ev[4].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.perf_counter() - t_start
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+    tmax = torch.tensor(ms + [wall * 1e3], device="cuda")
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    # regions: labels that still point at themselves
+    idx = torch.arange(r0 * w + 1, r1 * w + 1, device="cuda", dtype=torch.int32).reshape(r1 - r0, w)
+    nreg = (lab == idx).sum().to(torch.int64)
+    dist.all_reduce(nreg)
+
+    ok = None
+    if args.verify:
+        parts_f = [torch.empty((b - a, w, 3), dtype=torch.uint8, device="cuda") for a, b in strips]
+        parts_l = [torch.empty((b - a, w), dtype=torch.int32, device="cuda") for a, b in strips]
+        dist.all_gather(parts_f, filt) if len({b - a for a, b in strips}) == 1 else None
+        if len({b - a for a, b in strips}) == 1:
+            dist.all_gather(parts_l, lab)
+            if rank == 0:
+                full_f, full_l = torch.cat(parts_f), torch.cat(parts_l)
+                src = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+                dev.synth(ctx, src.data_ptr(), 3 * w, w, h, args.seed)
+                ref_f = torch.empty_like(src)
+                dev.meanshift(ctx, src.data_ptr(), 3 * w, ref_f.data_ptr(), 3 * w, w, h, args.sp, args.sr, ml)
+                ref_l = torch.empty((h, w), dtype=torch.int32, device="cuda")
+                dev.label_regions(ctx, ref_f.data_ptr(), 3 * w, ref_l.data_ptr(), 4 * w, w, h, args.lo)
+                ctx.synchronize()
+                same_f = bool(torch.equal(full_f, ref_f))
+                want = sh.first_pixel_labels(ref_l.cpu().numpy())
+                same_l = bool(np.array_equal(full_l.cpu().numpy(), want))
+                ok = {"filtered_bit_identical": same_f, "labels_bit_identical": same_l}
+        else:
+            ok = {"skipped": "unequal strips"}
+    if rank == 0:
+        t = [float(x) for x in tmax.tolist()]
+        print(json.dumps({"config": "strip-sharded %dx%d over %d GPUs, sp=%g sr=%g maxLevel=%d lo=%d" % (w, h, world, args.sp, args.sr, ml, args.lo),
+                          "n_gpus": world, "halo_rows": halo, "halo_bytes_received_rank0": int(halo_bytes),
+                          "seam_pairs_total": int(len(allp)), "regions": int(nreg.item()),
+                          "ms_max_over_ranks": {"halo_exchange": round(t[0], 3), "meanshift": round(t[1], 3), "label": round(t[2], 3),
+                                                "seams": round(t[3], 3), "wall": round(t[4], 3)},
+                          "mpix_per_s": round(w * h / 1e6 / (t[4] / 1e3), 1), "verify": ok}))
+    dist.barrier()
+    dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
