@@ -67,7 +67,8 @@ MSG_API int msg_device_count(void);                       /* number of CUDA devi
 MSG_API int msg_create(int device, msg_ctx** out);
 MSG_API void msg_destroy(msg_ctx* ctx);
 MSG_API const char* msg_last_error(const msg_ctx* ctx);   /* ctx may be NULL: last msg_create error */
-/* Use an externally owned cudaStream_t for all work of this context (NULL = the context's own). */
+/* Use an externally owned cudaStream_t for all work of this context (NULL = the context's own stream;
+ * pass cudaStreamLegacy, (void*)1, for the legacy default stream). */
 MSG_API int msg_set_stream(msg_ctx* ctx, void* cuda_stream);
 MSG_API int msg_synchronize(msg_ctx* ctx);
 

@@ -81,7 +81,13 @@ class Context:
         return {n: list(getattr(p, n)) for n, _ in L.KernelProfile._fields_}
 
     def set_stream(self, cuda_stream):
-        self.check(self._lib.msg_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
+        """cuda_stream: a cudaStream_t handle as int; None = the context's own stream; 0 = the legacy default stream
+        (what torch.cuda.current_stream().cuda_stream returns outside a stream context), passed as cudaStreamLegacy."""
+        if cuda_stream is None:
+            handle = None
+        else:
+            handle = int(cuda_stream) or 1          # cudaStreamLegacy == (cudaStream_t)0x1
+        self.check(self._lib.msg_set_stream(self._h, C.c_void_p(handle)))
 
     def synchronize(self):
         self.check(self._lib.msg_synchronize(self._h))

@@ -50,6 +50,7 @@ def _sharded_run(ctx, src, w, h, n_strips, sp, sr, ml, lo):
                                            (420, 300, 5, 10, 10, 1)])
 def test_strips_bit_identical(w, h, n, sp, sr, ml):
     ctx = mseg.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)    # torch copies and C-ABI kernels on one stream
     im = orc.synth_bgr(w, h, 17)
     src = torch.from_numpy(im).cuda()
     full = torch.empty_like(src)
@@ -70,6 +71,7 @@ def test_strips_bit_identical(w, h, n, sp, sr, ml):
 
 def test_synth_rows_matches_full():
     ctx = mseg.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     w, h = 300, 200
     a = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
     dev.synth(ctx, a.data_ptr(), 3 * w, w, h, 5)
