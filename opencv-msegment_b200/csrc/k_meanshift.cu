@@ -432,8 +432,10 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     // tile width: 64 (256 threads) when the plane gives enough 64x32 tiles for several waves, else 32 (128 threads):
     // small planes would otherwise run 1-2 waves of unequal tiles and idle SMs in the tail
     const long long tiles64 = (long long)((S.w + 63) / 64) * ((S.rows + TH - 1) / TH);
-    int TWsel = tiles64 >= (long long)ctx->sm_count * 18 ? 64 : 32;
-    int acc = 1;
+    // Measured on B200 (tools/k1_matrix.py, profiles/r01_k1_matrix.md): 64-wide tiles win whenever they fill the SMs once;
+    // IDP4A accumulates win for narrow windows (row flush amortised over few tests), 16-bit lanes for wide ones.
+    int TWsel = tiles64 >= (long long)ctx->sm_count ? 64 : 32;
+    int acc = (prm.sp == (float)(int)prm.sp && 2 * (int)prm.sp + 1 >= 21) ? 0 : 1;
     // tuning overrides (experiments only): MSG_TILE_W = 32 | 64, MSG_ACC = 0 | 1
     if (const char* e = getenv("MSG_TILE_W")) { int v = atoi(e); if (v == 32 || v == 64) TWsel = v; }
     if (const char* e = getenv("MSG_ACC")) acc = atoi(e) ? 1 : 0;

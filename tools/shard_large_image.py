@@ -55,6 +55,16 @@ def main():
     # own rows, generated in place inside the halo buffer
     buf = torch.empty((h1 - h0, w, 3), dtype=torch.uint8, device="cuda")
     dev.synth_rows(ctx, buf[r0 - h0:].data_ptr(), 3 * w, w, h, r0, r1 - r0, args.seed)
+    # warm up NCCL (communicator + P2P channels to both neighbours are created lazily on first use)
+    warm = torch.zeros(1024, device="cuda")
+    dist.all_reduce(warm)
+    wops = []
+    for peer in (rank - 1, rank + 1):
+        if 0 <= peer < world:
+            wops += [dist.P2POp(dist.isend, warm, peer), dist.P2POp(dist.irecv, torch.empty_like(warm), peer)]
+    if wops:
+        for req in dist.batch_isend_irecv(wops):
+            req.wait()
     torch.cuda.synchronize()
     dist.barrier()
     t_start = time.perf_counter()
