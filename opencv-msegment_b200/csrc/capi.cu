@@ -289,6 +289,7 @@ static void publish_ms_stats(msg_ctx* ctx)
     memcpy(&o, ctx->h_counters + 4, 8);
     ctx->st.ms_active_items = a;
     ctx->st.ms_overflow_items = o;
+    ctx->st.merge_rounds = (uint64_t)ctx->h_counters[10];
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
@@ -433,7 +434,7 @@ int msg_merge_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32
         work = ctx->d_labels;
         MSG_TRY(k_copy_labels_2d(ctx, d_labels, lstep, work, (size_t)w * 4, w, h));
     }
-    MSG_TRY(k_merge(ctx, s.p, s.pitch, work, w, h, min_size, color_dist, d_n));
+    MSG_TRY(k_merge(ctx, s.p, s.pitch, work, w, h, min_size, color_dist, nullptr, d_n));
     if (!dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
     return MSG_OK;
 }
@@ -552,11 +553,12 @@ int msg_merge_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* la
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
     s.p = ctx->d_planes;
     MSG_TRY(k_bgr_to_plane(ctx, ctx->d_in, rb, s));
-    MSG_TRY(k_merge(ctx, s.p, s.pitch, ctx->d_labels, w, h, min_size, color_dist, ctx->d_counters + 16));
+    MSG_TRY(k_merge(ctx, s.p, s.pitch, ctx->d_labels, w, h, min_size, color_dist, nullptr, ctx->d_counters + 16));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     MSG_TRY(finish_count(ctx, n_regions));
+    ctx->st.merge_rounds = (uint64_t)ctx->h_counters[10];
     memset(&ctx->tm, 0, sizeof(ctx->tm));
     ctx->tm.h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
     ctx->tm.merge_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
@@ -630,7 +632,7 @@ static int segment_core_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, in
         MSG_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int32_t), st));
     }
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    if (do_merge) MSG_TRY(k_merge(ctx, ctx->D[0].p, ctx->D[0].pitch, work, w, h, p->min_size, p->color_dist, n_dev));
+    if (do_merge) MSG_TRY(k_merge(ctx, ctx->D[0].p, ctx->D[0].pitch, work, w, h, p->min_size, p->color_dist, n_dev, n_dev));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     if (do_label && d_labels && !dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
     if (do_render) {

@@ -5,7 +5,11 @@
 // smallest (dist2 of rounded mean colours, label) key, accepted selections are united
 // simultaneously (union by smallest label); phase A = colour fuse, phase B = min-size prune.
 // K2c = PictureService.colorByIndexes (PictureService.java:913-936).
+#include <cooperative_groups.h>
+
 #include "msg_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -29,91 +33,6 @@ __global__ void __launch_bounds__(MT) max_label_kernel(const int32_t* __restrict
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 
-__global__ void __launch_bounds__(MT) init_tables_kernel(merge_tables t, int nl)
-{
-    int i = blockIdx.x * MT + threadIdx.x;
-    if (i >= nl) return;
-    t.area[i] = 0;
-    t.sum[3 * (size_t)i] = 0; t.sum[3 * (size_t)i + 1] = 0; t.sum[3 * (size_t)i + 2] = 0;
-    t.best[i] = ~0ull;
-    t.par[i] = i;
-}
-
-// per-pixel statistics with warp-level run aggregation (pixels of one warp lie in one row)
-__global__ void __launch_bounds__(MT) stats_kernel(const uint32_t* __restrict__ plane, int pitch,
-                                                   const int32_t* __restrict__ L, int w, int h, merge_tables t)
-{
-    int x = blockIdx.x * MT + threadIdx.x;
-    int y = blockIdx.y;
-    int lane = threadIdx.x & 31;
-    int lab = 0;
-    unsigned cnt = 0, b = 0, g = 0, r = 0;
-    if (x < w) {
-        lab = L[(size_t)y * w + x];
-        if (lab > 0) {
-            uint32_t c = __ldg(plane + (size_t)y * pitch + x);
-            cnt = 1; b = c & 0xFF; g = (c >> 8) & 0xFF; r = (c >> 16) & 0xFF;
-        }
-    }
-    int prev = __shfl_up_sync(0xffffffffu, lab, 1);
-    bool head = lane == 0 || prev != lab;
-    unsigned heads = __ballot_sync(0xffffffffu, head);
-    unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
-    int seg_end = above ? lane + __ffs(above) - 1 : 31;   // last lane of my run
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned c2 = __shfl_down_sync(0xffffffffu, cnt, o);
-        unsigned b2 = __shfl_down_sync(0xffffffffu, b, o);
-        unsigned g2 = __shfl_down_sync(0xffffffffu, g, o);
-        unsigned r2 = __shfl_down_sync(0xffffffffu, r, o);
-        if (lane + o <= seg_end) { cnt += c2; b += b2; g += g2; r += r2; }
-    }
-    if (head && lab > 0) {
-        atomicAdd(t.area + lab, cnt);
-        atomicAdd(t.sum + 3 * (size_t)lab, (unsigned long long)b);
-        atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
-        atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
-    }
-}
-
-__global__ void __launch_bounds__(MT) mean_kernel(merge_tables t, int nl)
-{
-    int i = blockIdx.x * MT + threadIdx.x;
-    if (i >= nl || i == 0) return;
-    unsigned long long a = t.area[i];
-    if (!a) { t.mean[i] = 0; return; }
-    uint32_t m = 0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) m |= (uint32_t)((2ull * t.sum[3 * (size_t)i + c] + a) / (2ull * a)) << (8 * c);
-    t.mean[i] = m;
-}
-
-__global__ void __launch_bounds__(MT) edges_kernel(const int32_t* __restrict__ L, int w, int h, merge_tables t,
-                                                   long long size_thr)
-{
-    int x = blockIdx.x * MT + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= w) return;
-    size_t p = (size_t)y * w + x;
-    int lab = L[p];
-    if (lab <= 0 || (long long)t.area[lab] >= size_thr) return;
-    uint32_t ml = t.mean[lab];
-    unsigned long long bestk = ~0ull;
-    int q[4];
-    q[0] = x > 0 ? L[p - 1] : 0;
-    q[1] = x + 1 < w ? L[p + 1] : 0;
-    q[2] = y > 0 ? L[p - w] : 0;
-    q[3] = y + 1 < h ? L[p + w] : 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (q[k] <= 0 || q[k] == lab) continue;
-        uint32_t e = __vabsdiffu4(ml, t.mean[q[k]]);
-        unsigned long long key = ((unsigned long long)__dp4a(e, e, 0u) << 32) | (unsigned)q[k];
-        bestk = key < bestk ? key : bestk;
-    }
-    if (bestk != ~0ull && bestk < t.best[lab]) atomicMin(t.best + lab, bestk);
-}
-
 __device__ __forceinline__ int pf_find(const int32_t* P, int a)
 {
     int p = __ldcg(P + a);
@@ -121,34 +40,226 @@ __device__ __forceinline__ int pf_find(const int32_t* P, int a)
     return a;
 }
 
-__global__ void __launch_bounds__(MT) select_kernel(merge_tables t, int nl, long long dist_limit, int32_t* __restrict__ accepted)
+// ---------------------------------------------------------------- persistent merge (one cooperative launch)
+// All rounds of both phases inside one kernel with grid-wide barriers: no host round trip, no per-round pixel
+// passes for statistics (per-label sums are folded into the surviving roots) and the final renumbering is a scan
+// over the label table (valid because input labels are numbered by first pixel and unions keep the smallest label).
+struct merge_persist_args {
+    const uint32_t* plane; int pitch;
+    int32_t* labels; int w, h;
+    const int32_t* n_in;      // device: number of input labels (labels are 1..*n_in)
+    int cap;                  // table capacity in labels
+    merge_tables t;
+    int32_t* newid;           // [cap+1]
+    int32_t* bsum;            // [gridDim.x + 1]
+    int32_t* accepted;        // device counter
+    int32_t* n_out;           // device: number of regions after the merge
+    int32_t* rounds_out;      // device: rounds executed (statistics)
+    int min_size, color_dist;
+};
+
+__device__ __forceinline__ void persist_union(int32_t* par, int a, int b)
 {
-    int i = blockIdx.x * MT + threadIdx.x;
-    if (i >= nl || i == 0) return;
-    unsigned long long k = t.best[i];
-    if (k == ~0ull) return;
-    if ((long long)(k >> 32) > dist_limit) return;
-    int a = i, b = (int)(k & 0xffffffffu);
     for (;;) {
-        a = pf_find(t.par, a);
-        b = pf_find(t.par, b);
-        if (a == b) break;
+        a = pf_find(par, a);
+        b = pf_find(par, b);
+        if (a == b) return;
         if (a < b) { int s = a; a = b; b = s; }
-        int old = atomicMin(t.par + a, b);
-        if (old == a) break;
+        int old = atomicMin(par + a, b);
+        if (old == a) return;
         a = old;
     }
-    atomicAdd(accepted, 1);
 }
 
-__global__ void __launch_bounds__(MT) apply_par_kernel(int32_t* __restrict__ L, size_t n, const int32_t* __restrict__ par)
+__global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args A)
 {
-    size_t i = (size_t)blockIdx.x * MT + threadIdx.x;
-    if (i >= n) return;
-    int v = L[i];
-    if (v > 0) {
-        int r = pf_find(par, v);
-        if (r != v) L[i] = r;
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const long long gtid = (long long)blockIdx.x * MT + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * MT;
+    const long long gwarp = gtid >> 5, nwarps = nthreads >> 5;
+    int nin = *A.n_in;
+    if (nin > A.cap) nin = A.cap;
+    const int nl = nin + 1;
+    const int w = A.w, h = A.h;
+    const int cpr = (w + 31) / 32;                      // 32-pixel chunks per row
+    const long long nchunks = (long long)cpr * h;
+    merge_tables t = A.t;
+
+    // ---- init tables
+    for (long long i = gtid; i < nl; i += nthreads) {
+        t.area[i] = 0;
+        t.sum[3 * i] = 0; t.sum[3 * i + 1] = 0; t.sum[3 * i + 2] = 0;
+        t.par[i] = (int)i;
+    }
+    if (gtid == 0) { *A.accepted = 0; *A.rounds_out = 0; }
+    grid.sync();
+
+    // ---- statistics from pixels, once (warp-level run aggregation)
+    for (long long c = gwarp; c < nchunks; c += nwarps) {
+        int y = (int)(c / cpr), x = (int)(c % cpr) * 32 + lane;
+        int lab = 0;
+        unsigned cnt = 0, b = 0, g = 0, r = 0;
+        if (x < w) {
+            lab = A.labels[(size_t)y * w + x];
+            if (lab > nin) lab = 0;
+            if (lab > 0) {
+                uint32_t col = __ldg(A.plane + (size_t)y * A.pitch + x);
+                cnt = 1; b = col & 0xFF; g = (col >> 8) & 0xFF; r = (col >> 16) & 0xFF;
+            }
+        }
+        int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+        bool head = lane == 0 || prev != lab;
+        unsigned heads = __ballot_sync(0xffffffffu, head);
+        unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+        int seg_end = above ? lane + __ffs(above) - 1 : 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned c2 = __shfl_down_sync(0xffffffffu, cnt, o);
+            unsigned b2 = __shfl_down_sync(0xffffffffu, b, o);
+            unsigned g2 = __shfl_down_sync(0xffffffffu, g, o);
+            unsigned r2 = __shfl_down_sync(0xffffffffu, r, o);
+            if (lane + o <= seg_end) { cnt += c2; b += b2; g += g2; r += r2; }
+        }
+        if (head && lab > 0) {
+            atomicAdd(t.area + lab, cnt);
+            atomicAdd(t.sum + 3 * (size_t)lab, (unsigned long long)b);
+            atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
+            atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
+        }
+    }
+    grid.sync();
+
+    const long long INF = 1ll << 40;
+    int rounds = 0;
+    for (int phase = 0; phase < 2; phase++) {
+        long long size_thr, dist_limit;
+        if (phase == 0) { if (A.color_dist <= 0) continue; size_thr = INF; dist_limit = (long long)A.color_dist * A.color_dist; }
+        else { if (A.min_size <= 0) continue; size_thr = A.min_size; dist_limit = INF; }
+        for (int round = 0; round < MERGE_MAX_ROUNDS; round++) {
+            // means of the live roots, reset the selection keys
+            for (long long i = gtid; i < nl; i += nthreads) {
+                unsigned long long a = t.area[i];
+                uint32_t m = 0;
+                if (i > 0 && a) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) m |= (uint32_t)((2ull * t.sum[3 * i + c] + a) / (2ull * a)) << (8 * c);
+                }
+                t.mean[i] = m;
+                t.best[i] = ~0ull;
+            }
+            if (gtid == 0) *A.accepted = 0;
+            grid.sync();
+            // region adjacency through the (flattened) parent table
+            for (long long c = gwarp; c < nchunks; c += nwarps) {
+                int y = (int)(c / cpr), x = (int)(c % cpr) * 32 + lane;
+                if (x >= w) continue;
+                size_t p = (size_t)y * w + x;
+                int l0 = A.labels[p];
+                if (l0 <= 0 || l0 > nin) continue;
+                int lab = __ldcg(t.par + l0);
+                if ((long long)t.area[lab] >= size_thr) continue;
+                uint32_t ml = t.mean[lab];
+                unsigned long long bestk = ~0ull;
+                int q[4];
+                q[0] = x > 0 ? A.labels[p - 1] : 0;
+                q[1] = x + 1 < w ? A.labels[p + 1] : 0;
+                q[2] = y > 0 ? A.labels[p - w] : 0;
+                q[3] = y + 1 < h ? A.labels[p + w] : 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (q[k] <= 0 || q[k] > nin || q[k] == l0) continue;
+                    int ql = __ldcg(t.par + q[k]);
+                    if (ql == lab) continue;
+                    uint32_t e = __vabsdiffu4(ml, t.mean[ql]);
+                    unsigned long long key = ((unsigned long long)__dp4a(e, e, 0u) << 32) | (unsigned)ql;
+                    bestk = key < bestk ? key : bestk;
+                }
+                if (bestk != ~0ull && bestk < t.best[lab]) atomicMin(t.best + lab, bestk);
+            }
+            grid.sync();
+            // accepted selections are united (smallest label wins)
+            for (long long i = gtid; i < nl; i += nthreads) {
+                if (i == 0) continue;
+                unsigned long long k = t.best[i];
+                if (k == ~0ull || (long long)(k >> 32) > dist_limit) continue;
+                persist_union(t.par, (int)i, (int)(k & 0xffffffffu));
+                atomicAdd(A.accepted, 1);
+            }
+            grid.sync();
+            rounds++;
+            const int acc = *((volatile int32_t*)A.accepted);
+            if (acc == 0) break;                              // uniform: every thread reads the same value
+            // fold: flatten parents, move the statistics of absorbed labels into their roots
+            for (long long i = gtid; i < nl; i += nthreads) {
+                if (i == 0) continue;
+                int r = pf_find(t.par, (int)i);
+                if (r != (int)i) {
+                    t.par[i] = r;
+                    unsigned a = t.area[i];
+                    if (a) {
+                        atomicAdd(t.area + r, a);
+                        atomicAdd(t.sum + 3 * (size_t)r, t.sum[3 * i]);
+                        atomicAdd(t.sum + 3 * (size_t)r + 1, t.sum[3 * i + 1]);
+                        atomicAdd(t.sum + 3 * (size_t)r + 2, t.sum[3 * i + 2]);
+                        t.area[i] = 0;
+                    }
+                }
+            }
+            grid.sync();
+        }
+    }
+
+    // ---- dense renumbering of the surviving roots (ascending label == ascending first pixel)
+    const int per = (nl + gridDim.x - 1) / gridDim.x;          // labels per block
+    {
+        __shared__ int carry;
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        const int lo = blockIdx.x * per, hi = min(nl, lo + per);
+        for (int base = lo; base < hi; base += MT) {
+            int i = base + threadIdx.x;
+            int alive = (i < hi && i > 0 && t.par[i] == i && t.area[i] > 0) ? 1 : 0;
+            // block exclusive scan of `alive`
+            __shared__ int wsum[MT / 32];
+            int incl = alive;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) wsum[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            int ws = lane < MT / 32 ? wsum[lane] : 0, wincl = ws;
+#pragma unroll
+            for (int o = 1; o < MT / 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, wincl, o);
+                if (lane >= o) wincl += v;
+            }
+            int woff = __shfl_sync(0xffffffffu, wincl - ws, threadIdx.x >> 5);
+            int total = __shfl_sync(0xffffffffu, wincl, MT / 32 - 1);
+            int c0 = carry;
+            if (i < hi) A.newid[i] = c0 + woff + incl - alive;
+            __syncthreads();
+            if (threadIdx.x == 0) carry = c0 + total;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) A.bsum[blockIdx.x] = carry;
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int run = 0;
+        for (unsigned b = 0; b < gridDim.x; b++) { int v = A.bsum[b]; A.bsum[b] = run; run += v; }
+        *A.n_out = run;
+        *A.rounds_out = rounds;
+    }
+    grid.sync();
+    // ---- rewrite the pixels
+    for (long long p = gtid; p < (long long)w * h; p += nthreads) {
+        int l0 = A.labels[p];
+        if (l0 <= 0 || l0 > nin) continue;
+        int r = __ldcg(t.par + l0);
+        A.labels[p] = A.newid[r] + A.bsum[r / per] + 1;
     }
 }
 
@@ -180,63 +291,67 @@ int k_render(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, uint8_t* d_dst
     return MSG_OK;
 }
 
-// d_counters: [8] max label, [9] accepted
+// d_n_in: device count of input labels, which must be canonical (1..n by first pixel).
+// d_counters: [8] max label, [9] accepted, [10] rounds, [11] spare n_out
+static int merge_persistent(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels, int w, int h, int min_size,
+                       int color_dist, const int32_t* d_n_in, int32_t* d_n_out)
+{
+    size_t n = (size_t)w * h;
+    int cap = (int)n;                                 // worst case: every pixel its own region
+    int blocks_per_sm = 0;
+    MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_persistent_kernel, MT, 0));
+    if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
+    int grid = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+    size_t nl = (size_t)cap + 1;
+    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256;
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));
+    char* base = (char*)ctx->d_ovf;
+    merge_persist_args A;
+    A.t.sum = (unsigned long long*)base;   base += nl * 24;
+    A.t.best = (unsigned long long*)base;  base += nl * 8;
+    A.t.area = (unsigned int*)base;        base += nl * 4;
+    A.t.mean = (uint32_t*)base;            base += nl * 4;
+    A.t.par = (int32_t*)base;              base += nl * 4;
+    A.newid = (int32_t*)base;              base += nl * 4;
+    A.bsum = (int32_t*)base;
+    A.plane = d_plane; A.pitch = pitch; A.labels = d_labels; A.w = w; A.h = h;
+    A.n_in = d_n_in; A.cap = cap;
+    A.accepted = ctx->d_counters + 9;
+    A.rounds_out = ctx->d_counters + 10;
+    A.n_out = d_n_out ? d_n_out : ctx->d_counters + 11;
+    A.min_size = min_size; A.color_dist = color_dist;
+    void* args[] = {&A};
+    MSG_CUDA(ctx, cudaLaunchCooperativeKernel((void*)merge_persistent_kernel, dim3(grid), dim3(MT), args, 0, ctx->stream));
+    MSG_LAUNCHED(ctx);
+    return MSG_OK;
+}
+
+// Merge entry: d_n_in != NULL promises canonical labels 1..*d_n_in (the fused pipeline); otherwise the labels are
+// validated (<= w*h, needs one stream sync) and renumbered canonically first.
 int k_merge(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels, int w, int h, int min_size,
-            int color_dist, int32_t* d_n_out)
+            int color_dist, const int32_t* d_n_in, int32_t* d_n_out)
 {
     cudaStream_t st = ctx->stream;
     size_t n = (size_t)w * h;
-    int32_t* d_max = ctx->d_counters + 8;
-    int32_t* d_acc = ctx->d_counters + 9;
-    ctx->st.merge_rounds = 0;
-    MSG_CUDA(ctx, cudaMemsetAsync(d_max, 0, sizeof(int32_t), st));
-    max_label_kernel<<<ctx->sm_count * 8, MT, 0, st>>>(d_labels, n, d_max);
-    MSG_LAUNCHED(ctx);
-    MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 8, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    MSG_CUDA(ctx, cudaStreamSynchronize(st));
-    long long maxl = ctx->h_counters[8];
-    if (maxl > (long long)n) return msg_fail(ctx, MSG_EINVAL, "merge: labels must be <= width*height (max label %lld)", maxl);
-    if (maxl > 0 && (min_size > 0 || color_dist > 0)) {
-        int nl = (int)maxl + 1;
-        size_t bytes = (size_t)nl * (4 + 24 + 4 + 8 + 4) + 256;
-        // tables live after the relabel scratch region? keep them in their own allocation: d_colors is small,
-        // so use a dedicated grow-only buffer carved from d_ovf (unused outside mean shift).
-        MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));
-        char* base = (char*)ctx->d_ovf;
-        merge_tables t;
-        t.sum = (unsigned long long*)base;                         base += (size_t)nl * 24;
-        t.best = (unsigned long long*)base;                        base += (size_t)nl * 8;
-        t.area = (unsigned int*)base;                              base += (size_t)nl * 4;
-        t.mean = (uint32_t*)base;                                  base += (size_t)nl * 4;
-        t.par = (int32_t*)base;
-        dim3 pgrid((w + MT - 1) / MT, h);
-        unsigned lgrid = (unsigned)((nl + MT - 1) / MT);
-        const long long INF = 1ll << 40;
-        for (int phase = 0; phase < 2; phase++) {
-            long long size_thr, dist_limit;
-            if (phase == 0) { if (color_dist <= 0) continue; size_thr = INF; dist_limit = (long long)color_dist * color_dist; }
-            else { if (min_size <= 0) continue; size_thr = min_size; dist_limit = INF; }
-            for (int round = 0; round < MERGE_MAX_ROUNDS; round++) {
-                init_tables_kernel<<<lgrid, MT, 0, st>>>(t, nl);
-                MSG_LAUNCHED(ctx);
-                stats_kernel<<<pgrid, MT, 0, st>>>(d_plane, pitch, d_labels, w, h, t);
-                MSG_LAUNCHED(ctx);
-                mean_kernel<<<lgrid, MT, 0, st>>>(t, nl);
-                MSG_LAUNCHED(ctx);
-                edges_kernel<<<pgrid, MT, 0, st>>>(d_labels, w, h, t, size_thr);
-                MSG_LAUNCHED(ctx);
-                MSG_CUDA(ctx, cudaMemsetAsync(d_acc, 0, sizeof(int32_t), st));
-                select_kernel<<<lgrid, MT, 0, st>>>(t, nl, dist_limit, d_acc);
-                MSG_LAUNCHED(ctx);
-                MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 9, d_acc, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-                MSG_CUDA(ctx, cudaStreamSynchronize(st));
-                ctx->st.merge_rounds++;
-                if (ctx->h_counters[9] == 0) break;
-                apply_par_kernel<<<(unsigned)((n + MT - 1) / MT), MT, 0, st>>>(d_labels, n, t.par);
-                MSG_LAUNCHED(ctx);
-            }
-        }
-        MSG_CHECK_LAUNCH(ctx);
+    int32_t* d_n_tmp = ctx->d_counters + 12;
+    if (!d_n_in) {
+        int32_t* d_max = ctx->d_counters + 8;
+        MSG_CUDA(ctx, cudaMemsetAsync(d_max, 0, sizeof(int32_t), st));
+        max_label_kernel<<<ctx->sm_count * 8, MT, 0, st>>>(d_labels, n, d_max);
+        MSG_LAUNCHED(ctx);
+        MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 8, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MSG_CUDA(ctx, cudaStreamSynchronize(st));
+        long long maxl = ctx->h_counters[8];
+        if (maxl > (long long)n) return msg_fail(ctx, MSG_EINVAL, "merge: labels must be <= width*height (max label %lld)", maxl);
+        MSG_TRY(k_relabel_canonical(ctx, d_labels, w, h, 0, d_n_tmp, 0));
+        d_n_in = d_n_tmp;
     }
-    return k_relabel_canonical(ctx, d_labels, w, h, 0, d_n_out, 0);
+    if (min_size <= 0 && color_dist <= 0) {      // identity after canonical renumbering
+        if (d_n_out && d_n_out != d_n_in)
+            MSG_CUDA(ctx, cudaMemcpyAsync(d_n_out, d_n_in, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        return MSG_OK;
+    }
+    MSG_TRY(merge_persistent(ctx, d_plane, pitch, d_labels, w, h, min_size, color_dist, d_n_in, d_n_out));
+    MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 10, ctx->d_counters + 10, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return MSG_OK;
 }

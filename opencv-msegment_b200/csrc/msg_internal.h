@@ -128,7 +128,7 @@ int k_ccl_binary(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h,
 int k_relabel_canonical(msg_ctx* ctx, int32_t* d_labels, int w, int h, int roots_are_pixels,
                         int32_t* d_n_out /*device, may be NULL*/, int add_to_count);
 int k_merge(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels, int w, int h, int min_size,
-            int color_dist, int32_t* d_n_out);
+            int color_dist, const int32_t* d_n_in /*NULL: labels not known canonical*/, int32_t* d_n_out);
 int k_render(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, uint8_t* d_dst, size_t dstep, int w, int h,
              int depth, const uint8_t* d_colors);
 int k_copy_labels_2d(msg_ctx* ctx, const int32_t* src, size_t sstep, int32_t* dst, size_t dstep, int w, int h);
