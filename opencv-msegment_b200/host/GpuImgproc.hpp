@@ -1,0 +1,119 @@
+// GpuImgproc.hpp -- C++ host-side mirror of the reference's operator interface for the segmentation hot path.
+//
+// The reference is Java: static methods of org.opencv.imgproc.Imgproc on org.opencv.core.Mat
+// (PictureService.java:441-442 connectedComponents, :913-936 colorByIndexes; pyrMeanShiftFiltering / floodFill-style
+// labelling / merge per BASELINE.json north_star).  The build image has no JDK, so this header gives the same static
+// signatures in C++ over a minimal Mat (rows, cols, type, byte step, data) and forwards to the C ABI
+// (include/msegment.h).  Non-zero status -> CvException, exactly where the Java shim (java/GpuImgproc.java) throws
+// org.opencv.core.CvException.  Header only; no CPU implementation of any operator.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "msegment.h"
+
+namespace msegment {
+
+enum MatType { CV_8UC1 = 0, CV_8UC3 = 16, CV_32SC1 = 4 };   // OpenCV's CvType codes
+
+struct CvException : std::runtime_error {
+    int status;
+    CvException(int st, const std::string& msg) : std::runtime_error("msegment status " + std::to_string(st) + ": " + msg), status(st) {}
+};
+
+struct Mat {   // row-major, continuous (like every Mat the reference creates: imread / clone / zeros)
+    int rows = 0, cols = 0, type = CV_8UC3;
+    std::vector<uint8_t> buf;
+    Mat() = default;
+    Mat(int r, int c, int t) { create(r, c, t); }
+    static int elemSize(int t) { return t == CV_8UC3 ? 3 : (t == CV_32SC1 ? 4 : 1); }
+    void create(int r, int c, int t) { rows = r; cols = c; type = t; buf.assign((size_t)r * c * elemSize(t), 0); }
+    size_t step() const { return (size_t)cols * elemSize(type); }
+    uint8_t* data() { return buf.data(); }
+    const uint8_t* data() const { return buf.data(); }
+    bool empty() const { return buf.empty(); }
+};
+
+struct TermCriteria {
+    enum { COUNT = 1, EPS = 2 };
+    int type = COUNT + EPS, maxCount = 5;
+    double epsilon = 1.0;
+    TermCriteria() = default;
+    TermCriteria(int t, int c, double e) : type(t), maxCount(c), epsilon(e) {}
+};
+
+class GpuImgproc {
+public:
+    // one context per thread, like the Java shim's ThreadLocal
+    static msg_ctx* ctx()
+    {
+        thread_local struct Holder {
+            msg_ctx* c = nullptr;
+            ~Holder() { if (c) msg_destroy(c); }
+        } h;
+        if (!h.c) {
+            int rc = msg_create(0, &h.c);
+            if (rc != MSG_OK) throw CvException(rc, msg_last_error(nullptr));
+        }
+        return h.c;
+    }
+
+    static void pyrMeanShiftFiltering(const Mat& src, Mat& dst, double sp, double sr, int maxLevel = 1,
+                                      TermCriteria tc = TermCriteria())
+    {
+        require(src.type == CV_8UC3, "src must be CV_8UC3");
+        dst.create(src.rows, src.cols, CV_8UC3);
+        check(msg_meanshift_filter(ctx(), src.data(), src.step(), dst.data(), dst.step(), src.cols, src.rows, sp, sr, maxLevel,
+                                   tc.type, tc.maxCount, tc.epsilon));
+    }
+
+    static int labelRegions(const Mat& image, Mat& labels, int loDiff = 2, int upDiff = 2, int connectivity = 4)
+    {
+        require(image.type == CV_8UC3, "image must be CV_8UC3");
+        labels.create(image.rows, image.cols, CV_32SC1);
+        int32_t n = 0;
+        check(msg_label_regions(ctx(), image.data(), image.step(), (int32_t*)labels.data(), labels.step(), image.cols, image.rows,
+                                loDiff, upDiff, connectivity, &n));
+        return n;
+    }
+
+    static int mergeRegions(const Mat& image, Mat& labels, int minSize, int colorDist)
+    {
+        require(image.type == CV_8UC3 && labels.type == CV_32SC1 && labels.rows == image.rows && labels.cols == image.cols,
+                "image CV_8UC3 and labels CV_32SC1 of equal size required");
+        int32_t n = 0;
+        check(msg_merge_regions(ctx(), image.data(), image.step(), (int32_t*)labels.data(), labels.step(), image.cols, image.rows,
+                                minSize, colorDist, &n));
+        return n;
+    }
+
+    // Imgproc.connectedComponents(image, labels, connectivity, ltype)  -- PictureService.java:441-442
+    static int connectedComponents(const Mat& image, Mat& labels, int connectivity = 8, int ltype = CV_32SC1)
+    {
+        require(image.type == CV_8UC1 && ltype == CV_32SC1, "CV_8UC1 image and CV_32S labels only");
+        labels.create(image.rows, image.cols, CV_32SC1);
+        int32_t n = 0;
+        check(msg_connected_components(ctx(), image.data(), image.step(), (int32_t*)labels.data(), labels.step(), image.cols,
+                                       image.rows, connectivity, &n));
+        return n;
+    }
+
+    // PictureService.colorByIndexes(markers, depth, colored) -- PictureService.java:913-936 (colors == nullptr: white)
+    static Mat colorByIndexes(const Mat& markers, int depth, const uint8_t* colorsBgr = nullptr)
+    {
+        require(markers.type == CV_32SC1, "markers must be CV_32SC1");
+        Mat dst(markers.rows, markers.cols, CV_8UC3);
+        check(msg_render_labels(ctx(), (const int32_t*)markers.data(), markers.step(), dst.data(), dst.step(), markers.cols,
+                                markers.rows, depth, colorsBgr));
+        return dst;
+    }
+
+private:
+    static void require(bool ok, const char* msg) { if (!ok) throw CvException(MSG_EINVAL, msg); }
+    static void check(int rc) { if (rc != MSG_OK) throw CvException(rc, msg_last_error(ctx())); }
+};
+
+}  // namespace msegment

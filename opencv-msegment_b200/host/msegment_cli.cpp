@@ -1,0 +1,127 @@
+// msegment_cli.cpp -- the reference's console entry point (App.java:14-31) over the B200 path.
+//
+// Contract kept from App.main: exactly three positional arguments (input folder, output root, input file name);
+// any other count prints "error parsing args" and returns normally; the arguments are echoed as "arg i: v".
+// The reference then runs its two watershed pipelines and (at HEAD) writes nothing; its file writer
+// (PictureService.saveResultsToFS, PictureService.java:194-234) names results
+//   <imageDir>/<name>_output/<yyyyMMdd'T'HHmmss>/<SegMethod>_<name>_<step %05d>_<stepName>.png
+// This program runs the mean-shift segmentation pass named by BASELINE.json (filter -> label -> merge -> render) and writes
+// that batch with the same naming scheme.  Image IO is binary PNM (P6 in; P6/P5 out): the image has no PNG/JPEG codec and
+// decoding is outside the hot path.  Optional environment: MSG_SP, MSG_SR, MSG_MIN_SIZE, MSG_COLOR_DIST.
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "GpuImgproc.hpp"
+
+using namespace msegment;
+
+static bool read_ppm(const std::string& path, Mat& img)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::string magic;
+    f >> magic;
+    if (magic != "P6") return false;
+    auto next_int = [&](int& v) {
+        for (;;) {
+            f >> std::ws;
+            if (f.peek() == '#') { std::string line; std::getline(f, line); continue; }
+            break;
+        }
+        f >> v;
+    };
+    int w = 0, h = 0, maxv = 0;
+    next_int(w); next_int(h); next_int(maxv);
+    f.get();
+    if (!f || w <= 0 || h <= 0 || maxv != 255) return false;
+    std::vector<uint8_t> rgb((size_t)w * h * 3);
+    f.read((char*)rgb.data(), (std::streamsize)rgb.size());
+    if (!f) return false;
+    img.create(h, w, CV_8UC3);                      // OpenCV order: BGR
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        img.buf[3 * i] = rgb[3 * i + 2]; img.buf[3 * i + 1] = rgb[3 * i + 1]; img.buf[3 * i + 2] = rgb[3 * i];
+    }
+    return true;
+}
+
+static void write_pnm(const std::string& path, const Mat& m, int multiplier)
+{
+    std::ofstream f(path, std::ios::binary);
+    if (m.type == CV_8UC3) {
+        f << "P6\n" << m.cols << " " << m.rows << "\n255\n";
+        std::vector<uint8_t> rgb(m.buf.size());
+        for (size_t i = 0; i < (size_t)m.rows * m.cols; i++) {
+            rgb[3 * i] = m.buf[3 * i + 2]; rgb[3 * i + 1] = m.buf[3 * i + 1]; rgb[3 * i + 2] = m.buf[3 * i];
+        }
+        f.write((const char*)rgb.data(), (std::streamsize)rgb.size());
+    } else if (m.type == CV_32SC1) {                // Core.multiply(m, multiplier) then saturate to 8 bit, as imwrite would
+        f << "P5\n" << m.cols << " " << m.rows << "\n255\n";
+        const int32_t* p = (const int32_t*)m.data();
+        std::vector<uint8_t> g((size_t)m.rows * m.cols);
+        for (size_t i = 0; i < g.size(); i++) {
+            long long v = (long long)p[i] * multiplier;
+            g[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+        f.write((const char*)g.data(), (std::streamsize)g.size());
+    } else {
+        f << "P5\n" << m.cols << " " << m.rows << "\n255\n";
+        f.write((const char*)m.data(), (std::streamsize)m.buf.size());
+    }
+}
+
+static double env_or(const char* k, double d) { const char* v = getenv(k); return v ? atof(v) : d; }
+
+int main(int argc, char** argv)
+{
+    if (argc - 1 != 3) {                            // App.java:17-20
+        std::cout << "error parsing args" << std::endl;
+        return 0;
+    }
+    for (int i = 1; i < argc; i++) std::cout << "arg " << (i - 1) << ": " << argv[i] << std::endl;   // App.java:22-24
+    const std::string dir = argv[1], out_root = argv[2], file = argv[3];
+    (void)out_root;                                 // dead in the reference too (PictureService.java:118, :130)
+    Mat src;
+    if (!read_ppm(dir + "/" + file, src)) {         // readPicture: dataAddr()==0 -> IOException -> logged, pipeline returns null
+        std::cerr << "There is an error with file stream processing: cannot read binary PPM " << dir << "/" << file << std::endl;
+        return 0;
+    }
+    const std::string name = file.substr(0, file.find('.'));   // ImageInfo: text before the first '.'
+    char stamp[32];
+    std::time_t t = std::time(nullptr);
+    std::strftime(stamp, sizeof(stamp), "%Y%m%dT%H%M%S", std::localtime(&t));
+    const std::string odir1 = dir + "/" + name + "_output", odir = odir1 + "/" + stamp;
+    mkdir(odir1.c_str(), 0755);
+    mkdir(odir.c_str(), 0755);
+    auto out = [&](int step, const char* step_name, const char* ext) {
+        char b[64];
+        snprintf(b, sizeof(b), "%05d", step);
+        return odir + "/MEANSHIFT_METHOD_" + name + "_" + b + "_" + step_name + ext;
+    };
+    try {
+        const double sp = env_or("MSG_SP", 10), sr = env_or("MSG_SR", 10);
+        const int min_size = (int)env_or("MSG_MIN_SIZE", 50), color_dist = (int)env_or("MSG_COLOR_DIST", 10);
+        int step = 0;
+        Mat filtered, labels;
+        GpuImgproc::pyrMeanShiftFiltering(src, filtered, sp, sr);
+        write_pnm(out(++step, "meanshift_filtered", ".ppm"), filtered, 1);
+        int n = GpuImgproc::labelRegions(filtered, labels, 2, 2, 4);
+        write_pnm(out(++step, "markers", ".pgm"), labels, 1);
+        std::cout << "regions after labelling: " << n << std::endl;
+        n = GpuImgproc::mergeRegions(filtered, labels, min_size, color_dist);
+        write_pnm(out(++step, "merged_markers", ".pgm"), labels, 1);
+        std::cout << "regions after merge: " << n << std::endl;
+        Mat result = GpuImgproc::colorByIndexes(labels, n);           // colored=false -> white (CLI path, PictureService.java:293)
+        write_pnm(out(++step, "result", ".ppm"), result, 1);
+        std::cout << "results written to " << odir << std::endl;
+    } catch (const CvException& e) {                // the reference lets CvException propagate: uncaught -> non-zero exit
+        std::cerr << "CvException: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}
