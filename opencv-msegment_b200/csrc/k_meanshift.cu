@@ -161,10 +161,11 @@ struct tile_geom {
     int sw, sh;   // staged width / height
     int swp;      // staged row pitch (odd, to spread banks between rows)
     int tiles_x;
+    int use_tma;  // interior tiles are staged with cp.async.bulk (requires halo, sw, swp multiples of 4 pixels)
 };
 
 template <int NX, int TW, int ACC>
-__global__ void __launch_bounds__(TW * 4) meanshift_tile_kernel(msg_plane S, msg_plane D, msg_ms_params prm, tile_geom g,
+__global__ void __launch_bounds__(TW * 4, 3) meanshift_tile_kernel(msg_plane S, msg_plane D, msg_ms_params prm, tile_geom g,
                                                                 msg_ovf_item* __restrict__ ovf, int* __restrict__ ovf_count,
                                                                 unsigned long long* __restrict__ active_count,
                                                                 unsigned long long* __restrict__ work)
@@ -186,18 +187,52 @@ __global__ void __launch_bounds__(TW * 4) meanshift_tile_kernel(msg_plane S, msg
 
     if (tid < 2) qn[tid] = 0;
 
-    // ---- stage tile + halo (coalesced row segments; sentinel outside the image / stored rows)
-    for (int sy = tid / 32; sy < g.sh; sy += NT / 32) {
-        int gy = oy + sy;
-        int r = gy - S.y0;
-        bool row_ok = (gy >= 0) && (gy < S.hfull) && (r >= 0) && (r < S.rows);
-        const uint32_t* srow = S.p + (size_t)(row_ok ? r : 0) * S.pitch;
-        uint32_t* drow = stage + sy * g.swp;
-        for (int sx = lane; sx < g.sw; sx += 32) {
-            int gx = ox + sx;
-            uint32_t v = SENTINEL;
-            if (row_ok && gx >= 0 && gx < S.w) v = __ldg(srow + gx);
-            drow[sx] = v;
+    // ---- stage tile + halo.  Interior tiles (staged rectangle entirely inside the stored plane, i.e. no sentinel needed):
+    //      one TMA bulk copy (cp.async.bulk, global -> shared, SASS UBLKCP) per staged row, issued by lane 0 of each warp and tracked by an
+    //      mbarrier transaction count; the rows are 16-byte aligned by construction (halo and pitch are multiples of 4 pixels).
+    //      Border tiles: plain loads, with the out-of-image sentinel.
+    const bool interior = g.use_tma && ox >= 0 && ox + g.sw <= S.w && oy >= 0 && oy + g.sh <= S.hfull &&
+                          oy - S.y0 >= 0 && oy - S.y0 + g.sh <= S.rows;
+    if (interior) {
+        __shared__ __align__(8) unsigned long long mbar;
+        const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"((uint32_t)(g.sh * g.sw * 4)) : "memory");
+        }
+        if (lane == 0) {   // one elected lane per warp issues that warp's share of the row copies
+            const uint32_t row_bytes = (uint32_t)g.sw * 4u;
+            for (int sy = tid / 32; sy < g.sh; sy += NT / 32) {
+                const uint32_t* src = S.p + (size_t)(oy - S.y0 + sy) * S.pitch + ox;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + sy * g.swp);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(src), "r"(row_bytes), "r"(mbar_a) : "memory");
+            }
+        }
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar_a) : "memory");
+        }
+    } else {
+        for (int sy = tid / 32; sy < g.sh; sy += NT / 32) {
+            int gy = oy + sy;
+            int r = gy - S.y0;
+            bool row_ok = (gy >= 0) && (gy < S.hfull) && (r >= 0) && (r < S.rows);
+            const uint32_t* srow = S.p + (size_t)(row_ok ? r : 0) * S.pitch;
+            uint32_t* drow = stage + sy * g.swp;
+            for (int sx = lane; sx < g.sw; sx += 32) {
+                int gx = ox + sx;
+                uint32_t v = SENTINEL;
+                if (row_ok && gx >= 0 && gx < S.w) v = __ldg(srow + gx);
+                drow[sx] = v;
+            }
         }
     }
     __syncthreads();
@@ -449,10 +484,14 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     bool tile_ok = prm.isr2 < 254 * 254 && R <= 120 && S.rows <= 32767 && S.w <= 32767;
     if (tile_ok) {
         for (;; drift = drift * 3 / 4) {
-            g.halo = R + drift;
+            g.halo = (R + drift + 2) & ~3;           // nearest multiple of 4 pixels: staged rows start 16-byte aligned
+            if (g.halo < R + 1) g.halo += 4;
             g.sw = TWsel + 2 * g.halo;
             g.sh = TH + 2 * g.halo;
-            g.swp = g.sw | 1;
+            // row pitch: a multiple of 4 words (TMA bulk copies need 16-byte aligned destinations) whose residue mod 32 banks
+            // keeps runs of active pixels on neighbouring rows apart (measured: residues 12..24 give the fewest conflicts)
+            g.swp = g.sw;
+            while (g.swp % 32 < 12 || g.swp % 32 > 24) g.swp += 4;
             smem = ((size_t)((g.sh * g.swp + 1) & ~1) + 4 * (size_t)(TWsel * TH)) * sizeof(uint32_t);
             if (smem <= (size_t)ctx->max_smem_optin - 1024 && g.sw < 512 && g.sh < 512) break;
             if (drift == 0) { tile_ok = false; break; }
@@ -470,6 +509,8 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, need * sizeof(msg_ovf_item)));
     MSG_CUDA(ctx, cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
     g.tiles_x = (S.w + TWsel - 1) / TWsel;
+    g.use_tma = 1;
+    if (const char* e = getenv("MSG_TMA")) g.use_tma = atoi(e) ? 1 : 0;   // A/B switch (experiments)
     int tiles_y = (S.rows + TH - 1) / TH;
     int tiles = g.tiles_x * tiles_y;
 
