@@ -5,12 +5,13 @@
 //   binary predicate, 4/8-connectivity == Imgproc.connectedComponents (PictureService.java:441-442)
 //
 // Passes (all HBM-bound streaming kernels, one thread per pixel, warps along rows):
-//   1 rows    : warp __ballot of "connected to left" bits -> every pixel points at the start of its
-//               run inside its 32-pixel chunk (no pointer chains inside a chunk)
-//   2 merge   : union(run, run above / previous chunk) with atomicMin on roots; redundant unions
-//               inside an overlap of two runs are skipped (only the first column of an overlap unites)
-//   3 flatten : label = find(label)   (root = smallest linear index of the component)
-//   4 relabel : roots flagged, exclusive scan in raster order, label = rank(root) + 1
+//   1 rows    : one CTA per row; warp __ballot of "connected to left" bits per 32-pixel chunk, runs crossing chunk
+//               borders resolved by a prefix-max over the chunks -> every pixel points at the exact start of its row run
+//   2 merge   : union(run, run above) with atomicMin on roots and path halving; redundant unions inside an overlap of
+//               two runs are skipped (only the first column of an overlap unites)
+//   3 flatten + count : label = find(label) (root = smallest linear index of the component), roots flagged and ranked
+//               inside 4096-pixel chunks in the same pass
+//   4 scan of the chunk totals, 5 apply: label = chunk offset + local rank of the root + 1 (raster order of first pixel)
 #include "msg_internal.h"
 
 namespace {
@@ -31,11 +32,24 @@ __device__ __forceinline__ int uf_find(const int32_t* L, int a)
     return a;
 }
 
+// find with path halving: every visited node is re-pointed at its grandparent.  Racing writers only ever store
+// ancestors (parents decrease monotonically towards the root), so the forest stays valid.
+__device__ __forceinline__ int uf_find_halve(int32_t* L, int a)
+{
+    int p = __ldcg(L + a);
+    while (p != a) {
+        int g = __ldcg(L + p);
+        if (g != p) L[a] = g;
+        a = p; p = g;
+    }
+    return a;
+}
+
 __device__ __forceinline__ void uf_union(int32_t* L, int a, int b)
 {
     for (;;) {
-        a = uf_find(L, a);
-        b = uf_find(L, b);
+        a = uf_find_halve(L, a);
+        b = uf_find_halve(L, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }   // a > b: link the larger root under the smaller
         int old = atomicMin(L + a, b);
@@ -46,29 +60,71 @@ __device__ __forceinline__ void uf_union(int32_t* L, int a, int b)
 
 // ---------------------------------------------------------------- pass 1: row runs
 // PRED: 0 = colour (plane u32, pitch in pixels), 1 = binary mask (u8, step in bytes)
+// One CTA per image row.  Phase 1: per 32-pixel chunk a warp __ballot of "connected to the left" bits (kept in shared
+// memory).  Phase 2: one warp resolves runs that cross chunk borders with a prefix-max over the chunks ("start of the run
+// that reaches the end of chunk c", undefined when the whole chunk is one open run).  Phase 3: every pixel is pointed at the
+// exact start of its row run, so no pointer chains exist along rows and the merge pass only unites vertically.
+constexpr int CCL_MAX_CHUNKS = 1024;   // rows up to 32768 pixels
+
 template <int PRED>
 __global__ void __launch_bounds__(CCL_THREADS) ccl_rows_kernel(const void* __restrict__ img, size_t pitch, int w, int h,
                                                                int d, int32_t* __restrict__ L)
 {
-    int x = blockIdx.x * CCL_THREADS + threadIdx.x;
-    int y = blockIdx.y;
-    int lane = threadIdx.x & 31;
-    bool in = x < w;
-    bool fg = in, cl = false;
-    if (PRED == 0) {
-        const uint32_t* row = (const uint32_t*)img + (size_t)y * pitch;
-        if (in && x > 0) cl = color_close(__ldg(row + x), __ldg(row + x - 1), d);
-    } else {
-        const uint8_t* row = (const uint8_t*)img + (size_t)y * pitch;
-        fg = in && row[x] != 0;
-        if (fg && x > 0) cl = row[x - 1] != 0;
+    __shared__ unsigned s_bits[CCL_MAX_CHUNKS];    // connected-to-left bits per chunk
+    __shared__ unsigned s_fg[CCL_MAX_CHUNKS];      // foreground bits per chunk (binary predicate)
+    __shared__ int s_open[CCL_MAX_CHUNKS];         // global x of the run start that enters chunk c from the left
+    const int y = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunks = (w + 31) / 32;
+    for (int c = warp; c < nchunks; c += CCL_THREADS / 32) {
+        int x = c * 32 + lane;
+        bool in = x < w, fg = in, cl = false;
+        if (PRED == 0) {
+            const uint32_t* row = (const uint32_t*)img + (size_t)y * pitch;
+            if (in && x > 0) cl = color_close(__ldg(row + x), __ldg(row + x - 1), d);
+        } else {
+            const uint8_t* row = (const uint8_t*)img + (size_t)y * pitch;
+            fg = in && row[x] != 0;
+            if (fg && x > 0) cl = row[x - 1] != 0;
+        }
+        unsigned bits = __ballot_sync(0xffffffffu, cl);
+        unsigned fgb = __ballot_sync(0xffffffffu, fg);
+        if (lane == 0) { s_bits[c] = bits; s_fg[c] = fgb; }
     }
-    unsigned bits = __ballot_sync(0xffffffffu, cl);
-    if (!in) return;
-    if (!fg) { L[(size_t)y * w + x] = -1; return; }
-    unsigned starts = (~bits | 1u) & (0xffffffffu >> (31 - lane));   // run starts at lanes <= mine
-    int start_lane = 31 - __clz(starts);
-    L[(size_t)y * w + x] = y * w + (x - lane + start_lane);
+    __syncthreads();
+    if (warp == 0) {
+        // E[c] = start x of the run containing the last pixel of chunk c, or -1 if that run is open to the left
+        int carry = -1;
+        for (int base = 0; base < nchunks; base += 32) {
+            int c = base + lane;
+            int e = -1;
+            if (c < nchunks) {
+                unsigned bits = s_bits[c];
+                if (bits != 0xffffffffu) e = c * 32 + (31 - __clz(~bits));     // highest lane whose bit is clear
+            }
+            int incl = e;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl = max(incl, v);
+            }
+            int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            excl = lane == 0 ? carry : max(excl, carry);
+            if (c < nchunks) s_open[c] = excl;
+            carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+        }
+    }
+    __syncthreads();
+    for (int c = warp; c < nchunks; c += CCL_THREADS / 32) {
+        int x = c * 32 + lane;
+        if (x >= w) continue;
+        size_t p = (size_t)y * w + x;
+        if (!((s_fg[c] >> lane) & 1u)) { L[p] = -1; continue; }
+        unsigned bits = s_bits[c];
+        unsigned starts = ~bits & (0xffffffffu >> (31 - lane));      // clear bits at lanes <= mine start a run
+        int sx = starts ? c * 32 + (31 - __clz(starts)) : s_open[c];
+        L[p] = y * w + sx;
+    }
 }
 
 // ---------------------------------------------------------------- pass 2: merge runs
@@ -84,7 +140,6 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_merge_kernel(const void* __re
         const uint32_t* row = (const uint32_t*)img + (size_t)y * pitch;
         uint32_t c = __ldg(row + x);
         bool cl = x > 0 && color_close(c, __ldg(row + x - 1), d);
-        if (cl && (x & 31) == 0) uf_union(L, p, p - 1);
         if (y > 0) {
             const uint32_t* up = row - pitch;
             uint32_t cu = __ldg(up + x);
@@ -98,7 +153,6 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_merge_kernel(const void* __re
         const uint8_t* row = (const uint8_t*)img + (size_t)y * pitch;
         if (!row[x]) return;
         bool left = x > 0 && row[x - 1];
-        if (left && (x & 31) == 0) uf_union(L, p, p - 1);
         if (y > 0) {
             const uint8_t* up = row - pitch;
             bool u = up[x] != 0;
@@ -246,6 +300,76 @@ __global__ void __launch_bounds__(CCL_THREADS) apply_rank_kernel(int32_t* __rest
     else if (v > 0) L[i] = rank[v] + 1;
 }
 
+// MODE 0 fast path: flatten + root flags + block-local ranks in ONE pass.  A block owns 4096 consecutive pixels and walks
+// them in 16 coalesced sweeps of 256 (pixel = base + sweep * 256 + thread, i.e. raster order = sweep-major); the root flags
+// of every (sweep, warp) are kept as ballots in shared memory, one warp turns their popcounts into exclusive prefixes and
+// lrank[root pixel] = number of roots before it inside the block's 4096 pixels.
+__global__ void __launch_bounds__(CCL_THREADS) flatten_count_kernel(int32_t* __restrict__ L, size_t n,
+                                                                    int32_t* __restrict__ block_sums,
+                                                                    int32_t* __restrict__ lrank)
+{
+    constexpr int SWEEPS = SCAN_CHUNK / CCL_THREADS;      // 16
+    constexpr int WARPS = CCL_THREADS / 32;               // 8
+    __shared__ unsigned s_ballot[SWEEPS * WARPS];
+    __shared__ int s_prefix[SWEEPS * WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t base = (size_t)blockIdx.x * SCAN_CHUNK;
+    int v[SWEEPS];
+#pragma unroll
+    for (int k = 0; k < SWEEPS; k++) {
+        size_t i = base + (size_t)k * CCL_THREADS + threadIdx.x;
+        v[k] = i < n ? L[i] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < SWEEPS; k++) {
+        size_t i = base + (size_t)k * CCL_THREADS + threadIdx.x;
+        bool is_root = false;
+        if (v[k] >= 0) {
+            int r = uf_find(L, v[k]);
+            if (r != v[k]) L[i] = r;
+            is_root = r == (int)i;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, is_root);
+        if (lane == 0) s_ballot[k * WARPS + warp] = bal;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive prefix over the 128 popcounts, in raster order (sweep-major, warp-minor)
+        int carry = 0;
+#pragma unroll
+        for (int q = 0; q < SWEEPS * WARPS / 32; q++) {
+            int c = __popc(s_ballot[q * 32 + lane]);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            s_prefix[q * 32 + lane] = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) block_sums[blockIdx.x] = carry;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SWEEPS; k++) {
+        unsigned bal = s_ballot[k * WARPS + warp];
+        if ((bal >> lane) & 1u) {
+            size_t i = base + (size_t)k * CCL_THREADS + threadIdx.x;
+            lrank[i] = s_prefix[k * WARPS + warp] + __popc(bal & ((1u << lane) - 1));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) apply_lrank_kernel(int32_t* __restrict__ L, size_t n,
+                                                                  const int32_t* __restrict__ block_offs,
+                                                                  const int32_t* __restrict__ lrank)
+{
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int v = L[i];
+    L[i] = v >= 0 ? __ldg(block_offs + v / SCAN_CHUNK) + __ldg(lrank + v) + 1 : 0;
+}
+
 __global__ void __launch_bounds__(CCL_THREADS) fill_i32_kernel(int32_t* __restrict__ p, size_t n, int32_t v)
 {
     size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
@@ -327,20 +451,25 @@ static int relabel_impl(msg_ctx* ctx, int32_t* d_labels, size_t n, int mode, int
     int32_t* first = mode ? rank + (n + 1) : nullptr;
     int32_t* block_sums = rank + (n + 1) * (mode ? 2 : 1);
     cudaStream_t st = ctx->stream;
-    if (mode) {
-        fill_i32_kernel<<<blocks_for(n + 1, CCL_THREADS), CCL_THREADS, 0, st>>>(first, n + 1, 0x7fffffff);
+    if (!mode) {   // labels are union-find parents (pixel indices): flatten, count, rank, apply = 3 launches
+        flatten_count_kernel<<<nb, CCL_THREADS, 0, st>>>(d_labels, n, block_sums, rank);
         MSG_LAUNCHED(ctx);
-        first_pixel_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n, first);
+        scan_block_sums_kernel<<<1, CCL_THREADS, 0, st>>>(block_sums, nb, d_n_out, add_to_total);
         MSG_LAUNCHED(ctx);
-        count_first_kernel<1><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums);
-    } else {
-        count_first_kernel<0><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums);
+        apply_lrank_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n, block_sums, rank);
+        MSG_LAUNCHED(ctx);
+        MSG_CHECK_LAUNCH(ctx);
+        return MSG_OK;
     }
+    fill_i32_kernel<<<blocks_for(n + 1, CCL_THREADS), CCL_THREADS, 0, st>>>(first, n + 1, 0x7fffffff);
+    MSG_LAUNCHED(ctx);
+    first_pixel_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n, first);
+    MSG_LAUNCHED(ctx);
+    count_first_kernel<1><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums);
     MSG_LAUNCHED(ctx);
     scan_block_sums_kernel<<<1, CCL_THREADS, 0, st>>>(block_sums, nb, d_n_out, add_to_total);
     MSG_LAUNCHED(ctx);
-    if (mode) assign_rank_kernel<1><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums, rank);
-    else assign_rank_kernel<0><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums, rank);
+    assign_rank_kernel<1><<<nb, CCL_THREADS, 0, st>>>(d_labels, first, n, block_sums, rank);
     MSG_LAUNCHED(ctx);
     apply_rank_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n, rank, mode);
     MSG_LAUNCHED(ctx);
@@ -361,13 +490,14 @@ int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, 
     dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);
     size_t n = (size_t)w * h;
     cudaStream_t st = ctx->stream;
-    ccl_rows_kernel<0><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
+    if (w > CCL_MAX_CHUNKS * 32) return msg_fail(ctx, MSG_EINVAL, "labelling supports rows up to %d pixels", CCL_MAX_CHUNKS * 32);
+    ccl_rows_kernel<0><<<h, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
     MSG_LAUNCHED(ctx);
     ccl_merge_kernel<0, 4><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
     MSG_LAUNCHED(ctx);
-    ccl_flatten_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n);
-    MSG_LAUNCHED(ctx);
-    if (label_base >= 0) {
+    if (label_base >= 0) {      // strip mode: no canonical relabel follows, flatten here
+        ccl_flatten_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n);
+        MSG_LAUNCHED(ctx);
         add_label_base_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n, w, full_w, label_base);
         MSG_LAUNCHED(ctx);
     }
@@ -380,12 +510,12 @@ int k_ccl_binary(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h,
     dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);
     size_t n = (size_t)w * h;
     cudaStream_t st = ctx->stream;
-    ccl_rows_kernel<1><<<grid, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
+    if (w > CCL_MAX_CHUNKS * 32) return msg_fail(ctx, MSG_EINVAL, "labelling supports rows up to %d pixels", CCL_MAX_CHUNKS * 32);
+    (void)n;
+    ccl_rows_kernel<1><<<h, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
     MSG_LAUNCHED(ctx);
     if (conn == 8) ccl_merge_kernel<1, 8><<<grid, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
     else ccl_merge_kernel<1, 4><<<grid, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
-    MSG_LAUNCHED(ctx);
-    ccl_flatten_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;
