@@ -55,6 +55,9 @@ struct merge_persist_args {
     int32_t* accepted;        // device counter
     int32_t* n_out;           // device: number of regions after the merge
     int32_t* rounds_out;      // device: rounds executed (statistics)
+    int2* pairs;              // [pair_cap] adjacent (label, label) pairs found by the statistics pass
+    int32_t* npairs;          // device counter
+    long long pair_cap;
     int min_size, color_dist;
 };
 
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
         t.sum[3 * i] = 0; t.sum[3 * i + 1] = 0; t.sum[3 * i + 2] = 0;
         t.par[i] = (int)i;
     }
-    if (gtid == 0) { *A.accepted = 0; *A.rounds_out = 0; }
+    if (gtid == 0) { *A.accepted = 0; *A.rounds_out = 0; *A.npairs = 0; }
     grid.sync();
 
     // ---- statistics from pixels, once (warp-level run aggregation)
@@ -127,8 +130,27 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
             atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
             atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
         }
+        // region adjacency list: every 4-adjacent pixel pair with two different positive labels, found once here; the
+        // rounds then iterate over this list (a few % of the pixels) instead of over the image
+        int lr = 0, ld = 0;
+        if (lab > 0) {
+            if (x + 1 < w) { lr = A.labels[(size_t)y * w + x + 1]; if (lr > nin || lr == lab) lr = 0; }
+            if (y + 1 < h) { ld = A.labels[(size_t)(y + 1) * w + x]; if (ld > nin || ld == lab) ld = 0; }
+        }
+        unsigned mr = __ballot_sync(0xffffffffu, lr > 0), md = __ballot_sync(0xffffffffu, ld > 0);
+        int tot = __popc(mr) + __popc(md);
+        if (tot) {
+            long long pos = 0;
+            if (lane == 0) pos = (long long)atomicAdd(A.npairs, tot);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            unsigned lt = (1u << lane) - 1;
+            if (lr > 0) { long long k = pos + __popc(mr & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, lr); }
+            if (ld > 0) { long long k = pos + __popc(mr) + __popc(md & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, ld); }
+        }
     }
     grid.sync();
+    long long npairs = *((volatile int32_t*)A.npairs);
+    if (npairs > A.pair_cap) npairs = A.pair_cap;
 
     const long long INF = 1ll << 40;
     int rounds = 0;
@@ -150,32 +172,17 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
             }
             if (gtid == 0) *A.accepted = 0;
             grid.sync();
-            // region adjacency through the (flattened) parent table
-            for (long long c = gwarp; c < nchunks; c += nwarps) {
-                int y = (int)(c / cpr), x = (int)(c % cpr) * 32 + lane;
-                if (x >= w) continue;
-                size_t p = (size_t)y * w + x;
-                int l0 = A.labels[p];
-                if (l0 <= 0 || l0 > nin) continue;
-                int lab = __ldcg(t.par + l0);
-                if ((long long)t.area[lab] >= size_thr) continue;
-                uint32_t ml = t.mean[lab];
-                unsigned long long bestk = ~0ull;
-                int q[4];
-                q[0] = x > 0 ? A.labels[p - 1] : 0;
-                q[1] = x + 1 < w ? A.labels[p + 1] : 0;
-                q[2] = y > 0 ? A.labels[p - w] : 0;
-                q[3] = y + 1 < h ? A.labels[p + w] : 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (q[k] <= 0 || q[k] > nin || q[k] == l0) continue;
-                    int ql = __ldcg(t.par + q[k]);
-                    if (ql == lab) continue;
-                    uint32_t e = __vabsdiffu4(ml, t.mean[ql]);
-                    unsigned long long key = ((unsigned long long)__dp4a(e, e, 0u) << 32) | (unsigned)ql;
-                    bestk = key < bestk ? key : bestk;
-                }
-                if (bestk != ~0ull && bestk < t.best[lab]) atomicMin(t.best + lab, bestk);
+            // region adjacency through the (flattened) parent table: both ends of every recorded pair
+            for (long long i = gtid; i < npairs; i += nthreads) {
+                int2 pr = A.pairs[i];
+                int ra = __ldcg(t.par + pr.x), rb = __ldcg(t.par + pr.y);
+                if (ra == rb) continue;
+                bool pa = (long long)t.area[ra] < size_thr, pb = (long long)t.area[rb] < size_thr;
+                if (!pa && !pb) continue;
+                uint32_t e = __vabsdiffu4(t.mean[ra], t.mean[rb]);
+                unsigned long long d2 = (unsigned long long)__dp4a(e, e, 0u) << 32;
+                if (pa) { unsigned long long key = d2 | (unsigned)rb; if (key < t.best[ra]) atomicMin(t.best + ra, key); }
+                if (pb) { unsigned long long key = d2 | (unsigned)ra; if (key < t.best[rb]) atomicMin(t.best + rb, key); }
             }
             grid.sync();
             // accepted selections are united (smallest label wins)
@@ -303,7 +310,8 @@ static int merge_persistent(msg_ctx* ctx, const uint32_t* d_plane, int pitch, in
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
     int grid = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
     size_t nl = (size_t)cap + 1;
-    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256;
+    size_t pair_cap = 2 * n;                        // every pixel has at most a right and a down neighbour
+    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256 + pair_cap * sizeof(int2);
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));
     char* base = (char*)ctx->d_ovf;
     merge_persist_args A;
@@ -313,7 +321,10 @@ static int merge_persistent(msg_ctx* ctx, const uint32_t* d_plane, int pitch, in
     A.t.mean = (uint32_t*)base;            base += nl * 4;
     A.t.par = (int32_t*)base;              base += nl * 4;
     A.newid = (int32_t*)base;              base += nl * 4;
-    A.bsum = (int32_t*)base;
+    A.bsum = (int32_t*)base;               base += ((size_t)(grid + 1) * 4 + 15) / 16 * 16;
+    A.pairs = (int2*)base;
+    A.pair_cap = (long long)pair_cap;
+    A.npairs = ctx->d_counters + 13;
     A.plane = d_plane; A.pitch = pitch; A.labels = d_labels; A.w = w; A.h = h;
     A.n_in = d_n_in; A.cap = cap;
     A.accepted = ctx->d_counters + 9;
