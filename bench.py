@@ -352,9 +352,18 @@ def run_ours(args):
         t0_ms = prof["tile_ms"][0]
         achieved = ops0 / (t0_ms * 1e-3) / 1e12 if t0_ms > 0 else 0.0
         all_ms = sum(prof["tile_ms"]) + sum(prof["overflow_ms"])
-        roof = {"bound": "int_alu", "kernel": "meanshift_tile_kernel<21> (level 0, sp=10)",
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (not measurable live)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+            traffic_src = tj["source"]
+        except Exception:
+            pass
+        roof = {"bound": "int_alu", "kernel": "meanshift_tile_kernel<21,64,0> (level 0, sp=10)",
                 "achieved": round(achieved, 3), "peak": peak["tiops"], "unit": "Tiop/s",
-                "frac": round(achieved / peak["tiops"], 4) if peak["tiops"] else None, "traffic": None,
+                "frac": round(achieved / peak["tiops"], 4) if peak["tiops"] else None, "traffic": traffic,
+                "traffic_unit": "bytes/launch (algorithmic HBM bytes: 8.3 MB, one pass over the 1080p source plane)",
+                "traffic_source": traffic_src,
                 "peak_source": peak["source"], "ops_model": "9*T + 5*Hit int-ops (SURVEY 8(d)); T, Hit counted on device",
                 "launches": prof["launches"][0], "avg_launch_ms": round(t0_ms / max(1, prof["launches"][0]), 4),
                 "tests_per_pixel_L0": round(prof["tile_tests"][0] / (B * W * H), 2),
