@@ -1,7 +1,4 @@
 mkdir -p gpurun_out
-python tools/profile_step.py 2 > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:meanshift_tile -s 4 -c 2 -o gpurun_out/prof_k1_final python tools/profile_step.py 2 > gpurun_out/ncu2.log 2>&1
-echo "full rc=$?"
-python tools/profile_step.py 2 > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_final.csv python tools/profile_step.py 2 > gpurun_out/ncu1.log 2>&1
-echo "list rc=$?"
+timeout 1200 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest.log
+timeout 300 python tools/k1_matrix.py 2>&1 | grep -E "tile_w=64" | tee gpurun_out/k1_carry.log
