@@ -35,7 +35,7 @@ SEED0 = 2          # config 2 -> seed 2 (frame i of rank r uses see
 PARAMS = dict(sp=10.0, sr=10.0, max_level=1, termcrit=(3, 5, 1.0), lo_diff=2, min_size=50, color_dist=10)
 METRIC = "segmented_mpix_per_s"
 UNIT = "Mpix/s"
-N_STREAMS = 4      # contexts (stream + workspace + host thread) per GPU; frames are dealt round-robin
+N_STREAMS = int(os.environ.get("BENCH_STREAMS", "6"))   # contexts (stream + workspace + host thread) per GPU; frames dealt round-robin
 
 
 def workload_name():

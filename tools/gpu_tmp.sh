@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"
-tail -3 gpurun_out/pytest.log
-timeout 300 python tools/k1_matrix.py 2>&1 | grep -E "tile_w=64" | tee gpurun_out/k1_carry.log
+for s in 3 4 6 8; do BENCH_STREAMS=$s timeout 600 python bench.py --steps 4 --warmup 2 --no-cpu 2>/dev/null | python -c "
+import json,sys
+j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('streams', $s, 'value', j['value'], 'e2e', j['e2e']['value'])"; done | tee gpurun_out/streams.log
