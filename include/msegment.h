@@ -190,6 +190,20 @@ MSG_API int msg_seam_pairs_dev(msg_ctx* ctx, const uint8_t* d_upper_row_bgr, con
 MSG_API int msg_apply_label_map_dev(msg_ctx* ctx, int32_t* d_labels, size_t labels_step, int width, int rows,
                             const int32_t* d_from_sorted, const int32_t* d_to, int n_map);
 
+/* Dense global numbering of strip labels (after msg_apply_label_map_dev): regions are renumbered 1..N over the WHOLE image in
+ * raster order of their first pixel, exactly as the unsharded call numbers them.  Three steps per strip (the context keeps
+ * the ranks between them): (1) count the roots this strip owns -> *d_count; the caller exclusive-scans the counts over the
+ * strips (an all-gather of one int per rank) to get `offset`; (2) dense ids of owned roots named in d_query (the labels other
+ * strips were mapped onto; 0 for labels not owned) -> d_out, which the ranks all-gather into a sorted (label, dense) table;
+ * (3) rewrite the strip: owned roots through the ranks, foreign roots through the table (binary search). */
+MSG_API int msg_strip_rank_dev(msg_ctx* ctx, const int32_t* d_labels, size_t labels_step, int width, int rows, int row0,
+                       int full_width, int32_t* d_count);
+MSG_API int msg_strip_query_dense_dev(msg_ctx* ctx, const int32_t* d_query, int n_query, int width, int rows, int row0,
+                              int full_width, int offset, int32_t* d_out);
+MSG_API int msg_strip_apply_dense_dev(msg_ctx* ctx, int32_t* d_labels, size_t labels_step, int width, int rows, int row0,
+                              int full_width, int offset, const int32_t* d_remote_labels_sorted,
+                              const int32_t* d_remote_dense, int n_remote);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 typedef struct msg_timings { /* milliseconds of the last host-buffer call, CUDA events */
     float h2d_ms, filter_ms, label_ms, merge_ms, render_ms, d2h_ms, total_ms;

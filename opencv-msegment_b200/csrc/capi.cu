@@ -880,4 +880,32 @@ int msg_apply_label_map_dev(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w
     return k_apply_map(ctx, d_labels, lstep, w, rows, d_from, d_to, n_map);
 }
 
+int msg_strip_rank_dev(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, int w, int rows, int row0, int full_w,
+                       int32_t* d_count)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, rows, 4, "labels"));
+    if (!d_count || full_w != w || row0 < 0 || lstep % 4) return msg_fail(ctx, MSG_EINVAL, "strip_rank: bad argument");
+    return k_strip_rank(ctx, d_labels, lstep, w, rows, (long long)row0 * full_w, d_count);
+}
+
+int msg_strip_query_dense_dev(msg_ctx* ctx, const int32_t* d_query, int nq, int w, int rows, int row0, int full_w, int offset,
+                              int32_t* d_out)
+{
+    CTX_ENTER(ctx);
+    if (nq < 0 || (nq > 0 && (!d_query || !d_out)) || full_w != w) return msg_fail(ctx, MSG_EINVAL, "strip_query: bad argument");
+    if (!ctx->d_scratch) return msg_fail(ctx, MSG_ESTATE, "strip_query: call msg_strip_rank_dev first");
+    return k_strip_query(ctx, d_query, nq, w, rows, (long long)row0 * full_w, offset, d_out);
+}
+
+int msg_strip_apply_dense_dev(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, int row0, int full_w, int offset,
+                              const int32_t* d_rlab, const int32_t* d_rdense, int nr)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, rows, 4, "labels"));
+    if (nr < 0 || (nr > 0 && (!d_rlab || !d_rdense)) || full_w != w || lstep % 4) return msg_fail(ctx, MSG_EINVAL, "strip_apply_dense: bad argument");
+    if (!ctx->d_scratch) return msg_fail(ctx, MSG_ESTATE, "strip_apply_dense: call msg_strip_rank_dev first");
+    return k_strip_apply_dense(ctx, d_labels, lstep, w, rows, (long long)row0 * full_w, offset, d_rlab, d_rdense, nr);
+}
+
 }  // extern "C"

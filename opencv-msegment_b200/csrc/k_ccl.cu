@@ -437,6 +437,92 @@ __global__ void __launch_bounds__(CCL_THREADS) apply_map_kernel(int32_t* __restr
     }
 }
 
+// ---------------------------------------------------------------- strip sharding: dense global numbering
+// Labels of a strip after seam resolution are 1 + GLOBAL index of the component's first pixel.  A pixel is an owned root
+// iff its label points at itself.  Ranks of owned roots inside 4096-pixel chunks (same layout as flatten_count_kernel).
+__global__ void __launch_bounds__(CCL_THREADS) strip_rank_kernel(const int32_t* __restrict__ L, size_t lstep_words, int w,
+                                                                 size_t n, long long base, int32_t* __restrict__ block_sums,
+                                                                 int32_t* __restrict__ lrank)
+{
+    constexpr int SWEEPS = SCAN_CHUNK / CCL_THREADS;
+    constexpr int WARPS = CCL_THREADS / 32;
+    __shared__ unsigned s_ballot[SWEEPS * WARPS];
+    __shared__ int s_prefix[SWEEPS * WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t cbase = (size_t)blockIdx.x * SCAN_CHUNK;
+#pragma unroll
+    for (int k = 0; k < SWEEPS; k++) {
+        size_t i = cbase + (size_t)k * CCL_THREADS + threadIdx.x;
+        bool is_root = false;
+        if (i < n) {
+            int v = L[(i / w) * lstep_words + (i % w)];
+            is_root = (long long)v == base + (long long)i + 1;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, is_root);
+        if (lane == 0) s_ballot[k * WARPS + warp] = bal;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+#pragma unroll
+        for (int q = 0; q < SWEEPS * WARPS / 32; q++) {
+            int c = __popc(s_ballot[q * 32 + lane]);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            s_prefix[q * 32 + lane] = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) block_sums[blockIdx.x] = carry;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SWEEPS; k++) {
+        unsigned bal = s_ballot[k * WARPS + warp];
+        if ((bal >> lane) & 1u) {
+            size_t i = cbase + (size_t)k * CCL_THREADS + threadIdx.x;
+            lrank[i] = s_prefix[k * WARPS + warp] + __popc(bal & ((1u << lane) - 1));
+        }
+    }
+}
+
+// dense id of owned root labels: out[q] = offset + rank(label) + 1 (0 if the label is not an owned root position)
+__global__ void __launch_bounds__(CCL_THREADS) strip_query_kernel(const int32_t* __restrict__ q, int nq, long long base, size_t n,
+                                                                  int offset, const int32_t* __restrict__ block_offs,
+                                                                  const int32_t* __restrict__ lrank, int32_t* __restrict__ out)
+{
+    int i = blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i >= nq) return;
+    long long loc = (long long)q[i] - 1 - base;
+    out[i] = (loc >= 0 && loc < (long long)n) ? offset + block_offs[loc / SCAN_CHUNK] + lrank[loc] + 1 : 0;
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) strip_apply_dense_kernel(int32_t* __restrict__ L, size_t lstep_words, int w, size_t n,
+                                                                        long long base, int offset,
+                                                                        const int32_t* __restrict__ block_offs,
+                                                                        const int32_t* __restrict__ lrank,
+                                                                        const int32_t* __restrict__ rlab,
+                                                                        const int32_t* __restrict__ rdense, int nr)
+{
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int32_t* p = L + (i / w) * lstep_words + (i % w);
+    int v = *p;
+    if (v <= 0) return;
+    long long loc = (long long)v - 1 - base;
+    if (loc >= 0 && loc < (long long)n) { *p = offset + block_offs[loc / SCAN_CHUNK] + lrank[loc] + 1; return; }
+    int lo = 0, hi = nr - 1;                     // root owned by another strip: look its dense id up
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        int f = __ldg(rlab + mid);
+        if (f == v) { *p = __ldg(rdense + mid); return; }
+        if (f < v) lo = mid + 1; else hi = mid - 1;
+    }
+}
+
 inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace
@@ -547,6 +633,45 @@ int k_apply_map(msg_ctx* ctx, int32_t* labels, size_t lstep, int w, int rows, co
     if (n <= 0) return MSG_OK;
     dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, rows);
     apply_map_kernel<<<grid, CCL_THREADS, 0, ctx->stream>>>(labels, lstep, w, from, to, n);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+// ---- strip dense numbering launchers (scratch layout: [lrank: n ints][block_sums: nb ints]; kept between the calls)
+int k_strip_rank(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, int w, int rows, long long base, int32_t* d_count)
+{
+    size_t n = (size_t)w * rows;
+    int nb = (int)blocks_for(n, SCAN_CHUNK);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_scratch, &ctx->d_scratch_cap, (n + (size_t)nb + 64) * sizeof(int32_t)));
+    int32_t* lrank = (int32_t*)ctx->d_scratch;
+    int32_t* block_sums = lrank + n;
+    strip_rank_kernel<<<nb, CCL_THREADS, 0, ctx->stream>>>(d_labels, lstep / 4, w, n, base, block_sums, lrank);
+    MSG_LAUNCHED(ctx);
+    scan_block_sums_kernel<<<1, CCL_THREADS, 0, ctx->stream>>>(block_sums, nb, d_count, 0);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_strip_query(msg_ctx* ctx, const int32_t* d_q, int nq, int w, int rows, long long base, int offset, int32_t* d_out)
+{
+    if (nq <= 0) return MSG_OK;
+    size_t n = (size_t)w * rows;
+    int32_t* lrank = (int32_t*)ctx->d_scratch;
+    strip_query_kernel<<<blocks_for((size_t)nq, CCL_THREADS), CCL_THREADS, 0, ctx->stream>>>(d_q, nq, base, n, offset, lrank + n, lrank, d_out);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_strip_apply_dense(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, long long base, int offset,
+                        const int32_t* d_rlab, const int32_t* d_rdense, int nr)
+{
+    size_t n = (size_t)w * rows;
+    int32_t* lrank = (int32_t*)ctx->d_scratch;
+    strip_apply_dense_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, ctx->stream>>>(d_labels, lstep / 4, w, n, base, offset,
+                                                                                          lrank + n, lrank, d_rlab, d_rdense, nr);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;

@@ -137,5 +137,10 @@ int k_seam_pairs(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, con
 int k_apply_map(msg_ctx* ctx, int32_t* labels, size_t lstep, int w, int rows, const int32_t* from,
                 const int32_t* to, int n);
 
+int k_strip_rank(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, int w, int rows, long long base, int32_t* d_count);
+int k_strip_query(msg_ctx* ctx, const int32_t* d_q, int nq, int w, int rows, long long base, int offset, int32_t* d_out);
+int k_strip_apply_dense(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, long long base, int offset,
+                        const int32_t* d_rlab, const int32_t* d_rdense, int nr);
+
 #define MSG_LAUNCHED(ctx) ((ctx)->st.kernel_launches++)
 #define MSG_CHECK_LAUNCH(ctx) MSG_CUDA(ctx, cudaGetLastError())

@@ -64,6 +64,19 @@ def apply_label_map(ctx, d_labels, lstep, w, rows, d_from, d_to, n):
     ctx.check(ctx._lib.msg_apply_label_map_dev(ctx._h, _p(d_labels), lstep, w, rows, _p(d_from), _p(d_to), int(n)))
 
 
+def strip_rank(ctx, d_labels, lstep, w, rows, row0, full_w, d_count):
+    ctx.check(ctx._lib.msg_strip_rank_dev(ctx._h, _p(d_labels), lstep, w, rows, row0, full_w, _p(d_count)))
+
+
+def strip_query_dense(ctx, d_query, nq, w, rows, row0, full_w, offset, d_out):
+    ctx.check(ctx._lib.msg_strip_query_dense_dev(ctx._h, _p(d_query), int(nq), w, rows, row0, full_w, int(offset), _p(d_out)))
+
+
+def strip_apply_dense(ctx, d_labels, lstep, w, rows, row0, full_w, offset, d_rlab, d_rdense, nr):
+    ctx.check(ctx._lib.msg_strip_apply_dense_dev(ctx._h, _p(d_labels), lstep, w, rows, row0, full_w, int(offset), _p(d_rlab),
+                                                 _p(d_rdense), int(nr)))
+
+
 def connected_components(ctx, d_mask, step, d_labels, lstep, w, h, connectivity=8, d_n=0):
     ctx.check(ctx._lib.msg_connected_components_dev(ctx._h, _p(d_mask), step, _p(d_labels), lstep, w, h, int(connectivity),
                                                     _p(d_n)))

@@ -43,7 +43,7 @@ def _sharded_run(ctx, src, w, h, n_strips, sp, sr, ml, lo):
         d_from, d_to = torch.from_numpy(frm).cuda(), torch.from_numpy(to).cuda()
         dev.apply_label_map(ctx, lab.data_ptr(), 4 * w, w, h, d_from.data_ptr(), d_to.data_ptr(), len(frm))
     ctx.synchronize()
-    return filt, lab
+    return filt, lab, strips, to
 
 
 @pytest.mark.parametrize("w,h,n,sp,sr,ml", [(600, 518, 3, 10, 10, 1), (333, 400, 4, 6, 15, 2), (257, 300, 2, 8, 12, 0),
@@ -58,7 +58,7 @@ def test_strips_bit_identical(w, h, n, sp, sr, ml):
     lab_full = torch.empty((h, w), dtype=torch.int32, device="cuda")
     dev.label_regions(ctx, full.data_ptr(), 3 * w, lab_full.data_ptr(), 4 * w, w, h, 2)
     ctx.synchronize()
-    filt, lab = _sharded_run(ctx, src, w, h, n, sp, sr, ml, 2)
+    filt, lab, strips, to = _sharded_run(ctx, src, w, h, n, sp, sr, ml, 2)
     bad = (filt != full).any(dim=2)
     assert not bad.any(), "filtered differs at %d pixels, rows %s" % (int(bad.sum()), torch.nonzero(bad.any(dim=1)).flatten()[:8].tolist())
     want = sh.first_pixel_labels(lab_full.cpu().numpy())
@@ -66,6 +66,34 @@ def test_strips_bit_identical(w, h, n, sp, sr, ml):
     assert np.array_equal(got, want), int((got != want).sum())
     # and the unsharded GPU result is the oracle's
     assert np.array_equal(full.cpu().numpy(), orc.meanshift_filter(im, sp, sr, ml))
+    # dense global numbering: one context per simulated rank (each keeps its ranks between the three steps)
+    ctxs = [mseg.Context(0) for _ in strips]
+    for c in ctxs:
+        c.set_stream(torch.cuda.current_stream().cuda_stream)
+    cnt = torch.zeros(len(strips), dtype=torch.int32, device="cuda")
+    for k, (r0, r1) in enumerate(strips):
+        dev.strip_rank(ctxs[k], lab[r0:r1].data_ptr(), 4 * w, w, r1 - r0, r0, w, cnt[k:].data_ptr())
+    counts = cnt.cpu().numpy().astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    uniq_to = np.unique(to).astype(np.int32)
+    dense_of_to = np.zeros(len(uniq_to), np.int32)
+    for k, (r0, r1) in enumerate(strips):
+        own = np.flatnonzero((uniq_to > r0 * w) & (uniq_to <= r1 * w))
+        if len(own):
+            q = torch.from_numpy(uniq_to[own]).cuda()
+            o = torch.zeros(len(own), dtype=torch.int32, device="cuda")
+            dev.strip_query_dense(ctxs[k], q.data_ptr(), len(own), w, r1 - r0, r0, w, int(offsets[k]), o.data_ptr())
+            dense_of_to[own] = o.cpu().numpy()
+    assert (dense_of_to > 0).all()
+    d_lab, d_dense = torch.from_numpy(uniq_to).cuda(), torch.from_numpy(dense_of_to).cuda()
+    for k, (r0, r1) in enumerate(strips):
+        dev.strip_apply_dense(ctxs[k], lab[r0:r1].data_ptr(), 4 * w, w, r1 - r0, r0, w, int(offsets[k]), d_lab.data_ptr(),
+                              d_dense.data_ptr(), len(uniq_to))
+    torch.cuda.synchronize()
+    assert int(counts.sum()) == int(lab_full.max().item())
+    assert torch.equal(lab, lab_full), int((lab != lab_full).sum().item())      # identical to the unsharded dense numbering
+    for c in ctxs:
+        c.close()
     ctx.close()
 
 
