@@ -65,94 +65,100 @@ def main():
     if wops:
         for req in dist.batch_isend_irecv(wops):
             req.wait()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t_start = time.perf_counter()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    ev[0].record()
+    def process():
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_start = time.perf_counter()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
 
-    # ---- halo exchange (input rows only): rows [h0,r0) come from ranks above, rows [r1,h1) from ranks below
-    ops, keep = [], []
-    for peer, (p0, p1) in enumerate(strips):
-        if peer == rank:
-            continue
-        ph0, ph1 = sh.halo_range(p0, p1, h, halo, ml)
-        # what the peer needs from me
-        for (a, b) in ((max(ph0, r0), min(p0, r1)), (max(p1, r0), min(ph1, r1))):
-            if a < b:
-                t = buf[a - h0:b - h0]
-                ops.append(dist.P2POp(dist.isend, t, peer))
-        # what I need from the peer
-        for (a, b) in ((max(h0, p0), min(r0, p1)), (max(r1, p0), min(h1, p1))):
-            if a < b:
-                t = buf[a - h0:b - h0]
-                ops.append(dist.P2POp(dist.irecv, t, peer))
-    halo_bytes = sum(op.tensor.numel() for op in ops if op.op == dist.irecv)
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    ev[1].record()
+        # ---- halo exchange (input rows only): rows [h0,r0) come from ranks above, rows [r1,h1) from ranks below
+        ops, keep = [], []
+        for peer, (p0, p1) in enumerate(strips):
+            if peer == rank:
+                continue
+            ph0, ph1 = sh.halo_range(p0, p1, h, halo, ml)
+            # what the peer needs from me
+            for (a, b) in ((max(ph0, r0), min(p0, r1)), (max(p1, r0), min(ph1, r1))):
+                if a < b:
+                    t = buf[a - h0:b - h0]
+                    ops.append(dist.P2POp(dist.isend, t, peer))
+            # what I need from the peer
+            for (a, b) in ((max(h0, p0), min(r0, p1)), (max(r1, p0), min(h1, p1))):
+                if a < b:
+                    t = buf[a - h0:b - h0]
+                    ops.append(dist.P2POp(dist.irecv, t, peer))
+        halo_bytes = sum(op.tensor.numel() for op in ops if op.op == dist.irecv)
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        ev[1].record()
 
-    # ---- filter + label the strip
-    filt = torch.empty((r1 - r0, w, 3), dtype=torch.uint8, device="cuda")
-    dev.meanshift_strip(ctx, buf.data_ptr(), 3 * w, h0, h1, filt.data_ptr(), 3 * w, w, h, r0, r1, args.sp, args.sr, ml)
-    ev[2].record()
-    lab = torch.empty((r1 - r0, w), dtype=torch.int32, device="cuda")
-    dev.label_strip(ctx, filt.data_ptr(), 3 * w, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, args.lo)
-    ev[3].record()
+        # ---- filter + label the strip
+        filt = torch.empty((r1 - r0, w, 3), dtype=torch.uint8, device="cuda")
+        dev.meanshift_strip(ctx, buf.data_ptr(), 3 * w, h0, h1, filt.data_ptr(), 3 * w, w, h, r0, r1, args.sp, args.sr, ml)
+        ev[2].record()
+        lab = torch.empty((r1 - r0, w), dtype=torch.int32, device="cuda")
+        dev.label_strip(ctx, filt.data_ptr(), 3 * w, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, args.lo)
+        ev[3].record()
 
-    # ---- seam: my first row against the last row of the rank above
-    up_bgr = torch.empty((w, 3), dtype=torch.uint8, device="cuda")
-    up_lab = torch.empty((w,), dtype=torch.int32, device="cuda")
-    ops = []
-    if rank + 1 < world:
-        ops += [dist.P2POp(dist.isend, filt[-1].contiguous(), rank + 1), dist.P2POp(dist.isend, lab[-1].contiguous(), rank + 1)]
-    if rank > 0:
-        ops += [dist.P2POp(dist.irecv, up_bgr, rank - 1), dist.P2POp(dist.irecv, up_lab, rank - 1)]
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    pairs = torch.zeros((w, 2), dtype=torch.int32, device="cuda")
-    cnt = torch.zeros((1,), dtype=torch.int32, device="cuda")
-    if rank > 0:
-        dev.seam_pairs(ctx, up_bgr.data_ptr(), up_lab.data_ptr(), filt[0].data_ptr(), lab[0].data_ptr(), w, args.lo,
-                       pairs.data_ptr(), cnt.data_ptr())
-    torch.cuda.synchronize()
-    mine = pairs[:int(cnt.item())].cpu().numpy()
-    allp = sh.allgather_pairs(dist, mine, device="cuda")
-    frm, to = sh.resolve_pairs(allp)
-    if len(frm):
-        d_from, d_to = torch.from_numpy(frm).cuda(), torch.from_numpy(to).cuda()
-        dev.apply_label_map(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, d_from.data_ptr(), d_to.data_ptr(), len(frm))
-    # ---- dense global numbering (1..N in raster order of first pixel, as the unsharded call numbers regions)
-    cnt_d = torch.zeros((1,), dtype=torch.int32, device="cuda")
-    dev.strip_rank(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, cnt_d.data_ptr())
-    counts = [torch.zeros_like(cnt_d) for _ in range(world)]
-    dist.all_gather(counts, cnt_d)
-    counts = [int(c.item()) for c in counts]
-    offset = sum(counts[:rank])
-    uniq_to = np.unique(to).astype(np.int32) if len(frm) else np.zeros(0, np.int32)
-    own = np.flatnonzero((uniq_to > r0 * w) & (uniq_to <= r1 * w))
-    mine_tab = np.zeros((len(own), 2), np.int32)
-    if len(own):
-        q = torch.from_numpy(uniq_to[own]).cuda()
-        o = torch.zeros(len(own), dtype=torch.int32, device="cuda")
-        dev.strip_query_dense(ctx, q.data_ptr(), len(own), w, r1 - r0, r0, w, offset, o.data_ptr())
-        mine_tab[:, 0] = uniq_to[own]
-        mine_tab[:, 1] = o.cpu().numpy()
-    tab = sh.allgather_pairs(dist, mine_tab, device="cuda")
-    tab = tab[np.argsort(tab[:, 0], kind="stable")] if len(tab) else tab
-    d_rl = torch.from_numpy(np.ascontiguousarray(tab[:, 0])).cuda() if len(tab) else torch.zeros(1, dtype=torch.int32, device="cuda")
-    d_rd = torch.from_numpy(np.ascontiguousarray(tab[:, 1])).cuda() if len(tab) else torch.zeros(1, dtype=torch.int32, device="cuda")
-    dev.strip_apply_dense(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, offset, d_rl.data_ptr(), d_rd.data_ptr(), len(tab))
-    ev[4].record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    wall = time.perf_counter() - t_start
-    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
-    tmax = torch.tensor(ms + [wall * 1e3], device="cuda")
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    nreg = torch.tensor([sum(counts)], device="cuda", dtype=torch.int64)
+        # ---- seam: my first row against the last row of the rank above
+        up_bgr = torch.empty((w, 3), dtype=torch.uint8, device="cuda")
+        up_lab = torch.empty((w,), dtype=torch.int32, device="cuda")
+        ops = []
+        if rank + 1 < world:
+            ops += [dist.P2POp(dist.isend, filt[-1].contiguous(), rank + 1), dist.P2POp(dist.isend, lab[-1].contiguous(), rank + 1)]
+        if rank > 0:
+            ops += [dist.P2POp(dist.irecv, up_bgr, rank - 1), dist.P2POp(dist.irecv, up_lab, rank - 1)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        pairs = torch.zeros((w, 2), dtype=torch.int32, device="cuda")
+        cnt = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        if rank > 0:
+            dev.seam_pairs(ctx, up_bgr.data_ptr(), up_lab.data_ptr(), filt[0].data_ptr(), lab[0].data_ptr(), w, args.lo,
+                           pairs.data_ptr(), cnt.data_ptr())
+        torch.cuda.synchronize()
+        mine = pairs[:int(cnt.item())].cpu().numpy()
+        allp = sh.allgather_pairs(dist, mine, device="cuda")
+        frm, to = sh.resolve_pairs(allp)
+        if len(frm):
+            d_from, d_to = torch.from_numpy(frm).cuda(), torch.from_numpy(to).cuda()
+            dev.apply_label_map(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, d_from.data_ptr(), d_to.data_ptr(), len(frm))
+        # ---- dense global numbering (1..N in raster order of first pixel, as the unsharded call numbers regions)
+        cnt_d = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        dev.strip_rank(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, cnt_d.data_ptr())
+        counts = [torch.zeros_like(cnt_d) for _ in range(world)]
+        dist.all_gather(counts, cnt_d)
+        counts = [int(c.item()) for c in counts]
+        offset = sum(counts[:rank])
+        uniq_to = np.unique(to).astype(np.int32) if len(frm) else np.zeros(0, np.int32)
+        own = np.flatnonzero((uniq_to > r0 * w) & (uniq_to <= r1 * w))
+        mine_tab = np.zeros((len(own), 2), np.int32)
+        if len(own):
+            q = torch.from_numpy(uniq_to[own]).cuda()
+            o = torch.zeros(len(own), dtype=torch.int32, device="cuda")
+            dev.strip_query_dense(ctx, q.data_ptr(), len(own), w, r1 - r0, r0, w, offset, o.data_ptr())
+            mine_tab[:, 0] = uniq_to[own]
+            mine_tab[:, 1] = o.cpu().numpy()
+        tab = sh.allgather_pairs(dist, mine_tab, device="cuda")
+        tab = tab[np.argsort(tab[:, 0], kind="stable")] if len(tab) else tab
+        d_rl = torch.from_numpy(np.ascontiguousarray(tab[:, 0])).cuda() if len(tab) else torch.zeros(1, dtype=torch.int32, device="cuda")
+        d_rd = torch.from_numpy(np.ascontiguousarray(tab[:, 1])).cuda() if len(tab) else torch.zeros(1, dtype=torch.int32, device="cuda")
+        dev.strip_apply_dense(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, offset, d_rl.data_ptr(), d_rd.data_ptr(), len(tab))
+        ev[4].record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        wall = time.perf_counter() - t_start
+        ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        tmax = torch.tensor(ms + [wall * 1e3], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        nreg = torch.tensor([sum(counts)], device="cuda", dtype=torch.int64)
+
+        return filt, lab, halo_bytes, allp, nreg, tmax
+
+    process()                                    # warm-up pass: workspace allocation, first-launch overheads
+    filt, lab, halo_bytes, allp, nreg, tmax = process()
 
     ok = None
     if args.verify:
