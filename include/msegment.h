@@ -106,6 +106,21 @@ MSG_API int msg_connected_components(msg_ctx* ctx, const uint8_t* mask, size_t s
 MSG_API int msg_render_labels(msg_ctx* ctx, const int32_t* labels, size_t labels_step, uint8_t* dst_bgr,
                       size_t dst_step, int width, int height, int depth, const uint8_t* colors_bgr);
 
+/* ---- pre-filters the reference calls around its segmentation stage (exact integer forms) ------------- */
+/* Laplacian sharpen chain of PictureService.java:323-333: filter2D(src, lap, CV_32F, K); src.convertTo(CV_32F);
+ * subtract; convertTo(CV_8UC3)  ==  dst = saturate_u8(src - sum_K taps * src), BORDER_REFLECT_101, anchor at the kernel centre.
+ * taps: krows*kcols small integers, row-major; the reference's MatOfFloat(1,1,1,1,-8,1,1,1,1) is 9x1 read literally and 3x3 as
+ * intended -- the kernel is data, so either reading is one call.  krows, kcols odd, krows*kcols <= 1024. */
+MSG_API int msg_laplacian_sharpen(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, uint8_t* dst_bgr, size_t dst_step,
+                          int width, int height, const int8_t* taps, int krows, int kcols);
+/* Imgproc.cvtColor(src, dst, COLOR_BGR2GRAY) (PictureService.java:405, :940): (3735 B + 19235 G + 9798 R + 16384) >> 15,
+ * the cv2 4.13 fixed-point form (OpenCV 3.4.2's scalar path differs by 1 LSB on 0.26 % of colours). */
+MSG_API int msg_bgr2gray(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, uint8_t* dst_gray, size_t dst_step, int width,
+                 int height);
+/* Imgproc.medianBlur(src 8UC1, dst, ksize) (PictureService.java:408, :436): odd ksize in [1, 127], BORDER_REPLICATE. */
+MSG_API int msg_median_blur(msg_ctx* ctx, const uint8_t* src_gray, size_t src_step, uint8_t* dst_gray, size_t dst_step, int width,
+                    int height, int ksize);
+
 /* ---- fused pipeline: filter -> label -> merge -> render, intermediates stay in HBM -------- */
 typedef struct msg_segment_params {
     double sp, sr;

@@ -47,6 +47,9 @@ SIGNATURES = {
     "msg_merge_regions": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, C.POINTER(C.c_int32)]),
     "msg_connected_components": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, C.POINTER(C.c_int32)]),
     "msg_render_labels": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _P]),
+    "msg_laplacian_sharpen": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _P, _I, _I]),
+    "msg_bgr2gray": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I]),
+    "msg_median_blur": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I]),
     "msg_segment_params_default": (None, [C.POINTER(SegmentParams)]),
     "msg_segment": (_I, [_P, _P, _SZ, _I, _I, C.POINTER(SegmentParams), _P, _SZ, _P, _SZ, _P, _SZ, C.POINTER(C.c_int32)]),
     "msg_submit_segment": (_I, [_P, _P, _SZ, _I, _I, C.POINTER(SegmentParams), _P, _SZ, _P, _SZ, _P, _SZ, C.POINTER(_I)]),

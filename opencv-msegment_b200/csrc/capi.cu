@@ -908,4 +908,48 @@ int msg_strip_apply_dense_dev(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int
     return k_strip_apply_dense(ctx, d_labels, lstep, w, rows, (long long)row0 * full_w, offset, d_rlab, d_rdense, nr);
 }
 
+// ============================================================================ pre-filters (8(f2))
+
+static int filter_host(msg_ctx* ctx, const uint8_t* src, size_t sstep, int in_ch, uint8_t* dst, size_t dstep, int out_ch, int w,
+                       int h, int which, const int8_t* taps, int krows, int kcols, int ksize)
+{
+    size_t rin = (size_t)w * in_ch, rout = (size_t)w * out_ch;
+    MSG_TRY(copy_in(ctx, src, sstep, rin, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rout * h));
+    if (which == 0) MSG_TRY(k_sharpen(ctx, ctx->d_in, rin, ctx->d_out, rout, w, h, taps, krows, kcols));
+    else if (which == 1) MSG_TRY(k_gray(ctx, ctx->d_in, rin, ctx->d_out, rout, w, h));
+    else MSG_TRY(k_median(ctx, ctx->d_in, rin, ctx->d_out, rout, w, h, ksize));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, rout, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+int msg_laplacian_sharpen(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h,
+                          const int8_t* taps, int krows, int kcols)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "sharpen src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 3, "sharpen dst"));
+    if (!taps || krows < 1 || kcols < 1 || !(krows & 1) || !(kcols & 1) || krows * kcols > 1024)
+        return msg_fail(ctx, MSG_EINVAL, "sharpen: kernel must be odd x odd with at most 1024 taps");
+    return filter_host(ctx, src, sstep, 3, dst, dstep, 3, w, h, 0, taps, krows, kcols, 0);
+}
+
+int msg_bgr2gray(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "cvtColor src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 1, "cvtColor dst"));
+    return filter_host(ctx, src, sstep, 3, dst, dstep, 1, w, h, 1, nullptr, 0, 0, 0);
+}
+
+int msg_median_blur(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, int ksize)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 1, "medianBlur src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 1, "medianBlur dst"));
+    if (ksize < 1 || ksize > 127 || !(ksize & 1)) return msg_fail(ctx, MSG_EINVAL, "medianBlur: ksize must be odd and in [1,127] (got %d)", ksize);
+    return filter_host(ctx, src, sstep, 1, dst, dstep, 1, w, h, 2, nullptr, 0, 0, ksize);
+}
+
 }  // extern "C"

@@ -142,5 +142,11 @@ int k_strip_query(msg_ctx* ctx, const int32_t* d_q, int nq, int w, int rows, lon
 int k_strip_apply_dense(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, long long base, int offset,
                         const int32_t* d_rlab, const int32_t* d_rdense, int nr);
 
+// pre-filters (k_filters.cu)
+int k_sharpen(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, const int8_t* taps,
+              int krows, int kcols);
+int k_gray(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h);
+int k_median(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, int k);
+
 #define MSG_LAUNCHED(ctx) ((ctx)->st.kernel_launches++)
 #define MSG_CHECK_LAUNCH(ctx) MSG_CUDA(ctx, cudaGetLastError())

@@ -111,6 +111,32 @@ public:
         return dst;
     }
 
+    // ---- pre-filters the reference calls around the segmentation stage
+    // filter2D + convertTo + subtract + convertTo chain of PictureService.java:323-333; kernel = integer taps (krows x kcols)
+    static void sharpenLaplacian(const Mat& src, Mat& dst, const int8_t* taps, int krows, int kcols)
+    {
+        require(src.type == CV_8UC3, "src must be CV_8UC3");
+        dst.create(src.rows, src.cols, CV_8UC3);
+        check(msg_laplacian_sharpen(ctx(), src.data(), src.step(), dst.data(), dst.step(), src.cols, src.rows, taps, krows, kcols));
+    }
+
+    // Imgproc.cvtColor(src, dst, COLOR_BGR2GRAY)
+    static void cvtColorBGR2GRAY(const Mat& src, Mat& dst)
+    {
+        require(src.type == CV_8UC3, "src must be CV_8UC3");
+        dst.create(src.rows, src.cols, CV_8UC1);
+        check(msg_bgr2gray(ctx(), src.data(), src.step(), dst.data(), dst.step(), src.cols, src.rows));
+    }
+
+    // Imgproc.medianBlur(src, dst, ksize) on CV_8UC1
+    static void medianBlur(const Mat& src, Mat& dst, int ksize)
+    {
+        require(src.type == CV_8UC1, "src must be CV_8UC1");
+        Mat out(src.rows, src.cols, CV_8UC1);
+        check(msg_median_blur(ctx(), src.data(), src.step(), out.data(), out.step(), src.cols, src.rows, ksize));
+        dst = out;
+    }
+
 private:
     static void require(bool ok, const char* msg) { if (!ok) throw CvException(MSG_EINVAL, msg); }
     static void check(int rc) { if (rc != MSG_OK) throw CvException(rc, msg_last_error(ctx())); }

@@ -193,6 +193,40 @@ class GpuImgproc:
                                                    dst.strides[0], w, h, int(depth), cptr))
         return dst
 
+    # ---- pre-filters the reference calls around the segmentation stage
+    # filter2D + convertTo + subtract + convertTo chain of PictureService.java:323-333 as one call; kernel = integer taps
+    def sharpenLaplacian(self, src, kernel):
+        src = _mat8uc3(src, "src")
+        taps = np.ascontiguousarray(kernel, dtype=np.int8)
+        if taps.ndim != 2:
+            raise CvException(L.MSG_EINVAL, "kernel must be 2-D (MatOfFloat(...) is N x 1)")
+        h, w = src.shape[:2]
+        dst = np.empty_like(src)
+        self.ctx.check(self._lib.msg_laplacian_sharpen(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data,
+                                                       dst.strides[0], w, h, taps.ctypes.data, taps.shape[0], taps.shape[1]))
+        return dst
+
+    # Imgproc.cvtColor(src, dst, Imgproc.COLOR_BGR2GRAY)
+    def cvtColorBGR2GRAY(self, src):
+        src = _mat8uc3(src, "src")
+        h, w = src.shape[:2]
+        dst = np.empty((h, w), np.uint8)
+        self.ctx.check(self._lib.msg_bgr2gray(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h))
+        return dst
+
+    # Imgproc.medianBlur(src, dst, ksize)
+    def medianBlur(self, src, ksize):
+        src = np.asarray(src)
+        if src.dtype != np.uint8 or src.ndim != 2:
+            raise CvException(L.MSG_EINVAL, "medianBlur: CV_8UC1 only (the reference blurs gray images)")
+        if src.strides[1] != 1:
+            src = np.ascontiguousarray(src)
+        h, w = src.shape
+        dst = np.empty_like(src)
+        self.ctx.check(self._lib.msg_median_blur(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0],
+                                                 w, h, int(ksize)))
+        return dst
+
     # fused pipeline
     def segment(self, src, sp=10.0, sr=10.0, maxLevel=1, termcrit=DEFAULT_TERMCRIT, loDiff=2, minSize=0, colorDist=0,
                 renderDepth=0, want=("filtered", "labels", "rendered")):

@@ -69,6 +69,29 @@ public final class GpuImgproc {
 		return dst;
 	}
 
+	/** filter2D(CV_32F, kernel) + convertTo + subtract + convertTo(CV_8UC3) of PictureService.java:323-333 as one call. */
+	public static void sharpenLaplacian(Mat src, Mat dst, byte[] taps, int krows, int kcols) {
+		require(src.type() == CvType.CV_8UC3, "src must be CV_8UC3");
+		dst.create(src.size(), src.type());
+		status(nSharpen(CTX.get(), src.dataAddr(), src.step1(), dst.dataAddr(), dst.step1(), src.cols(), src.rows(), taps,
+			krows, kcols));
+	}
+
+	/** Imgproc.cvtColor(src, dst, Imgproc.COLOR_BGR2GRAY). */
+	public static void cvtColorBGR2GRAY(Mat src, Mat dst) {
+		require(src.type() == CvType.CV_8UC3, "src must be CV_8UC3");
+		dst.create(src.size(), CvType.CV_8UC1);
+		status(nGray(CTX.get(), src.dataAddr(), src.step1(), dst.dataAddr(), dst.step1(), src.cols(), src.rows()));
+	}
+
+	/** Imgproc.medianBlur(src, dst, ksize) for CV_8UC1 (PictureService.java:408, :436). */
+	public static void medianBlur(Mat src, Mat dst, int ksize) {
+		require(src.type() == CvType.CV_8UC1, "src must be CV_8UC1");
+		Mat out = new Mat(src.size(), CvType.CV_8UC1);
+		status(nMedian(CTX.get(), src.dataAddr(), src.step1(), out.dataAddr(), out.step1(), src.cols(), src.rows(), ksize));
+		out.copyTo(dst);
+	}
+
 	private static void require(boolean ok, String msg) {
 		if (!ok) {
 			throw new CvException(msg);
@@ -98,6 +121,10 @@ public final class GpuImgproc {
 		int minSize, int colorDist, int[] n);
 	private static native int nConnectedComponents(long ctx, long img, long step, long labels, long lstep, int w, int h,
 		int conn, int[] n);
+	private static native int nSharpen(long ctx, long src, long sstep, long dst, long dstep, int w, int h, byte[] taps,
+		int krows, int kcols);
+	private static native int nGray(long ctx, long src, long sstep, long dst, long dstep, int w, int h);
+	private static native int nMedian(long ctx, long src, long sstep, long dst, long dstep, int w, int h, int ksize);
 	private static native int nRender(long ctx, long labels, long lstep, long dst, long dstep, int w, int h, int depth,
 		byte[] colors);
 }

@@ -71,3 +71,24 @@ JNIEXPORT jint JNICALL J(nRender)(JNIEnv* e, jclass c, jlong ctx, jlong lab, jlo
     if (col) (*e)->ReleaseByteArrayElements(e, colors, col, JNI_ABORT);
     return rc;
 }
+
+JNIEXPORT jint JNICALL J(nSharpen)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h,
+                                   jbyteArray taps, jint krows, jint kcols)
+{
+    jbyte* t = (*e)->GetByteArrayElements(e, taps, NULL);
+    int rc = msg_laplacian_sharpen((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h,
+                                   (const int8_t*)t, krows, kcols);
+    (*e)->ReleaseByteArrayElements(e, taps, t, JNI_ABORT);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nGray)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h)
+{
+    return msg_bgr2gray((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h);
+}
+
+JNIEXPORT jint JNICALL J(nMedian)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h,
+                                  jint ksize)
+{
+    return msg_median_blur((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h, ksize);
+}

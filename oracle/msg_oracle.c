@@ -554,3 +554,62 @@ void orc_synth_bgr(uint8_t* dst, size_t step, int w, int h, uint64_t seed)
         }
     free(sxs); free(sys); free(col);
 }
+
+/* ------------------------------------------------------------------ f2 "next" row: the pre-filters the reference really calls
+ * (PictureService.java:323-333 Laplacian sharpen chain, :405/:940 cvtColor BGR2GRAY, :408/:436 medianBlur).
+ * All three have exact integer forms, pinned on cv2 by tests/golden/filters.npz. */
+
+/* filter2D(src, lap, CV_32F, K) ; src.convertTo(CV_32F) ; subtract ; convertTo(CV_8U)  ==  saturate(src - sum_K taps * src),
+ * correlation with the anchor at the kernel centre, BORDER_REFLECT_101; taps are small integers (the reference's
+ * MatOfFloat(1,1,1,1,-8,1,1,1,1) as 9x1 -- the literal reading -- or 3x3 -- the intended one). */
+void orc_laplacian_sharpen(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h,
+                           const int8_t* taps, int krows, int kcols)
+{
+    int ay = krows / 2, ax = kcols / 2;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            for (int c = 0; c < 3; c++) {
+                int acc = 0;
+                for (int a = 0; a < krows; a++) {
+                    int yy = reflect101(y + a - ay, h);
+                    for (int b = 0; b < kcols; b++) {
+                        int xx = reflect101(x + b - ax, w);
+                        acc += taps[a * kcols + b] * src[(size_t)yy * sstep + 3 * xx + c];
+                    }
+                }
+                int v = src[(size_t)y * sstep + 3 * x + c] - acc;
+                dst[(size_t)y * dstep + 3 * x + c] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+            }
+}
+
+/* cv::medianBlur on 8UC1, odd k, BORDER_REPLICATE: the (k*k/2)-th smallest of the window. */
+void orc_median_blur_8uc1(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, int k)
+{
+    int r = k / 2, need = (k * k) / 2 + 1;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int hist[256];
+            memset(hist, 0, sizeof(hist));
+            for (int a = -r; a <= r; a++) {
+                int yy = y + a; yy = yy < 0 ? 0 : (yy >= h ? h - 1 : yy);
+                for (int b = -r; b <= r; b++) {
+                    int xx = x + b; xx = xx < 0 ? 0 : (xx >= w ? w - 1 : xx);
+                    hist[src[(size_t)yy * sstep + xx]]++;
+                }
+            }
+            int acc = 0, v = 0;
+            for (; v < 256; v++) { acc += hist[v]; if (acc >= need) break; }
+            dst[(size_t)y * dstep + x] = (uint8_t)v;
+        }
+}
+
+/* cvtColor(COLOR_BGR2GRAY) as cv2 4.13 computes it: (3735 B + 19235 G + 9798 R + 16384) >> 15
+ * (OpenCV 3.4.2's scalar path used 14-bit coefficients: +-1 LSB on 0.26 % of colours). */
+void orc_bgr2gray(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p = src + (size_t)y * sstep + 3 * x;
+            dst[(size_t)y * dstep + x] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15);
+        }
+}

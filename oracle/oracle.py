@@ -55,6 +55,9 @@ def lib():
         L.orc_render_labels.argtypes = [i32p, sz, u8p, sz, i, i, i, u8p]
         L.orc_watershed.argtypes = [u8p, sz, i32p, sz, i, i]
         L.orc_synth_bgr.argtypes = [u8p, sz, i, i, C.c_uint64]
+        L.orc_laplacian_sharpen.argtypes = [u8p, sz, u8p, sz, i, i, C.c_void_p, i, i]
+        L.orc_median_blur_8uc1.argtypes = [u8p, sz, u8p, sz, i, i, i]
+        L.orc_bgr2gray.argtypes = [u8p, sz, u8p, sz, i, i]
         _lib = L
     return _lib
 
@@ -166,4 +169,31 @@ def watershed(bgr, markers):
 def synth_bgr(w, h, seed):
     dst = np.empty((h, w, 3), np.uint8)
     lib().orc_synth_bgr(dst.ctypes.data, dst.strides[0], w, h, int(seed))
+    return dst
+
+
+def laplacian_sharpen(src, taps):
+    src = _img(src)
+    taps = np.ascontiguousarray(taps, dtype=np.int8)
+    assert taps.ndim == 2
+    h, w = src.shape[:2]
+    dst = np.empty_like(src)
+    lib().orc_laplacian_sharpen(src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h, taps.ctypes.data,
+                                taps.shape[0], taps.shape[1])
+    return dst
+
+
+def median_blur(gray, k):
+    gray = np.ascontiguousarray(gray, dtype=np.uint8)
+    h, w = gray.shape
+    dst = np.empty_like(gray)
+    lib().orc_median_blur_8uc1(gray.ctypes.data, gray.strides[0], dst.ctypes.data, dst.strides[0], w, h, int(k))
+    return dst
+
+
+def bgr2gray(src):
+    src = _img(src)
+    h, w = src.shape[:2]
+    dst = np.empty((h, w), np.uint8)
+    lib().orc_bgr2gray(src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h)
     return dst

@@ -139,6 +139,24 @@ def main():
         cv2.watershed(im, out)
         ws["out/%d" % k] = out
     np.savez_compressed(os.path.join(HERE, "watershed.npz"), **ws)
+    # f2 pre-filters the reference really calls: sharpen chain (PictureService.java:323-333), medianBlur (:408, :436), gray
+    fl = {}
+    k91 = np.array([1, 1, 1, 1, -8, 1, 1, 1, 1], np.float32).reshape(9, 1)   # literal MatOfFloat reading (9x1 column)
+    k33 = k91.reshape(3, 3)                                                 # intended 3x3 Laplacian
+    for name in ("synth96x80", "noise41x47", "guide_crop90x75", "row50", "col50"):
+        if name not in ins:
+            continue
+        im = ins[name]
+        fl["in/" + name] = im
+        for tag, kern in (("k91", k91), ("k33", k33)):
+            lap = cv2.filter2D(im, cv2.CV_32F, kern)
+            res = im.astype(np.float32) - lap
+            fl["sharp_%s/%s" % (tag, name)] = np.clip(np.rint(res), 0, 255).astype(np.uint8)   # == convertTo(CV_8U)
+        gray = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)
+        fl["gray/" + name] = gray
+        for k in (3, 5, 7, 11):
+            fl["median%d/%s" % (k, name)] = cv2.medianBlur(gray, k)
+    np.savez_compressed(os.path.join(HERE, "filters.npz"), **fl)
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         f.write("generated by tests/golden/gen_golden.py with cv2 %s, numpy %s\n" % (cv2.__version__, np.__version__))
     for fn in sorted(os.listdir(HERE)):
