@@ -19,4 +19,5 @@ pkg = sys.modules[_NAME]
 Context, CvException, GpuImgproc = pkg.Context, pkg.CvException, pkg.GpuImgproc
 lib = pkg._lib
 device = pkg.device
+synth_bgr = pkg.synth.synth_bgr
 PKG_DIR = _PKG_DIR

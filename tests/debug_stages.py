@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""GPU debugging aid: runs the mean-shift pipeline stage by stage and reports where it first departs from the
+"""GPU debugging aid (lives under tests/ because it uses the oracle): runs the mean-shift pipeline stage by stage and reports where it first departs from the
 oracle (pyramid planes, top-level result, final result).  Test infrastructure, not product."""
 import os
 import sys

@@ -64,3 +64,21 @@ def test_product_does_not_use_oracle():
                 assert not bad.search(txt), (dirpath, f)
     out = os.popen("ldd %s 2>/dev/null" % mseg.lib.LIB_PATH).read()
     assert "oracle" not in out
+
+
+def test_numpy_synth_matches_oracle_generator():
+    """Three generators (numpy in the package, C in the oracle, CUDA kernel -- checked on the GPU) must agree byte for byte."""
+    import numpy as np
+    from oracle import oracle as orc
+    for (w, h, s) in [(200, 150, 1), (64, 64, 7), (333, 129, 5), (1, 1, 2), (70, 200, 1000)]:
+        assert np.array_equal(mseg.synth_bgr(w, h, s), orc.synth_bgr(w, h, s)), (w, h, s)
+
+
+def test_only_allowed_files_touch_the_oracle():
+    """tools/ and the package must not import the oracle; tests/, __graft_entry__.smoke() and bench.py's CPU legs may."""
+    bad = re.compile(r"^\s*(from\s+oracle|import\s+oracle)", re.M)
+    for d in ("tools", "opencv-msegment_b200"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                if f.endswith(".py"):
+                    assert not bad.search(open(os.path.join(dirpath, f)).read()), (dirpath, f)
