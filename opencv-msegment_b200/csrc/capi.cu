@@ -145,7 +145,7 @@ void msg_destroy(msg_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_out2); cudaFree(ctx->d_labels);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_ovf); cudaFree(ctx->d_scratch); cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_colors); cudaFree(ctx->d_work);
+    cudaFree(ctx->d_colors); cudaFree(ctx->d_work); cudaFree(ctx->d_cells);
     for (int l = 0; l < MSG_MAX_LEVELS; l++)
         for (int k = 0; k < 3; k++) cudaEventDestroy(ctx->prof_ev[l][k]);
     cudaFreeHost(ctx->h_counters);
@@ -269,7 +269,14 @@ static int ms_run(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, int w, int h
         prm.max_count = cfg.max_count;
         prm.ieps = cfg.ieps;
         prm.use_mask = l < L;
-        if (l < L) MSG_TRY(k_pyr_up_mask(ctx, ctx->D[l + 1], ctx->D[l], cfg.isr22));
+        if (l < L) {
+            // per-cell activity counts (32x32 cells) for the heavy-first tile order of this level's mean-shift kernel
+            int cells_x = (ctx->D[l].w + 31) / 32, cells_y = (ctx->D[l].rows + 31) / 32;
+            size_t ncell = (size_t)cells_x * cells_y;
+            MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_cells, &ctx->d_cells_cap, (2 * ncell + 4096) * sizeof(int32_t)));
+            MSG_CUDA(ctx, cudaMemsetAsync(ctx->d_cells, 0, ncell * sizeof(int32_t), ctx->stream));
+            MSG_TRY(k_pyr_up_mask(ctx, ctx->D[l + 1], ctx->D[l], cfg.isr22, ctx->d_cells, cells_x));
+        }
         MSG_TRY(k_meanshift_level(ctx, ctx->S[l], ctx->D[l], prm, l));
     }
     return MSG_OK;

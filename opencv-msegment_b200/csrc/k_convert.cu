@@ -92,64 +92,75 @@ __global__ void __launch_bounds__(256) flag_kernel(msg_plane d, int isr22)
     d.p[(size_t)r * d.pitch + x] = c | (flag << 24);
 }
 
+// pyrUp taps along one axis for output index o (n = source length): source indices (i0, i1, i2) with weights
+// even o: (1, 6, 1) on (i-1, i, i+1); odd o: (0, 4, 4) on (-, i, i+1); s[-1] := s[1] (s[0] if n == 1), s[n] := s[n-1].
 __device__ __forceinline__ void up_taps(int o, int n, int& i0, int& i1, int& i2, int& w0, int& w1, int& w2)
 {
-    int i = o >> 1;
-    if (o & 1) {  // odd: 4*(s[i] + s[i+1]), s[n] := s[n-1]
-        i0 = i; i1 = (i + 1 < n) ? i + 1 : n - 1; i2 = i;
-        w0 = 4; w1 = 4; w2 = 0;
-    } else {      // even: s[i-1] + 6 s[i] + s[i+1], s[-1] := s[1] (s[0] if n==1), s[n] := s[n-1]
-        i0 = (i - 1 >= 0) ? i - 1 : (n > 1 ? 1 : 0); i1 = i; i2 = (i + 1 < n) ? i + 1 : n - 1;
-        w0 = 1; w1 = 6; w2 = 1;
-    }
+    const int i = o >> 1;
+    const bool odd = o & 1;
+    i1 = i;
+    i2 = (i + 1 < n) ? i + 1 : n - 1;
+    i0 = (i - 1 >= 0) ? i - 1 : (n > 1 ? 1 : 0);
+    w0 = odd ? 0 : 1;
+    w1 = odd ? 4 : 6;
+    w2 = odd ? 4 : 1;
 }
 
 // D[l] = pyrUp(D[l+1]); byte3 = dilate3x3(Mraw) where Mraw[2i+1][2j-1] = flag(i,j), 1<=i<=h1-2, 1<=j<=w1-2.
-__global__ void __launch_bounds__(256) pyr_up_mask_kernel(msg_plane s /*D[l+1] with flags*/, msg_plane d)
+// Channel sums are kept in 16-bit lanes of two registers ((B,R) and (G,-)): the weights sum to 64, so a lane never exceeds
+// 64 * 255, and `(v + 32) >> 6` is applied to both lanes at once.
+__global__ void __launch_bounds__(256) pyr_up_mask_kernel(msg_plane s /*D[l+1] with flags*/, msg_plane d,
+                                                          int* __restrict__ cell_count, int cells_x)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int r = blockIdx.y;
     if (x >= d.w || r >= d.rows) return;
     int y = d.y0 + r;
-    int yi[3], yw[3], xi[3], xw[3];
-    up_taps(y, s.hfull, yi[0], yi[1], yi[2], yw[0], yw[1], yw[2]);
-    up_taps(x, s.w, xi[0], xi[1], xi[2], xw[0], xw[1], xw[2]);
-    int a0 = 0, a1 = 0, a2 = 0;
+    int y0i, y1i, y2i, wy0, wy1, wy2, x0i, x1i, x2i, wx0, wx1, wx2;
+    up_taps(y, s.hfull, y0i, y1i, y2i, wy0, wy1, wy2);
+    up_taps(x, s.w, x0i, x1i, x2i, wx0, wx1, wx2);
+    uint32_t lo = 0, hi = 0;
+    const int yi[3] = {y0i, y1i, y2i}, yw[3] = {wy0, wy1, wy2};
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         int rr = clampi(yi[a] - s.y0, 0, s.rows - 1);
         const uint32_t* row = s.p + (size_t)rr * s.pitch;
-#pragma unroll
-        for (int b = 0; b < 3; b++) {
-            int wgt = yw[a] * xw[b];
-            uint32_t v = __ldg(row + xi[b]);
-            a0 += wgt * (int)(v & 0xFF);
-            a1 += wgt * (int)((v >> 8) & 0xFF);
-            a2 += wgt * (int)((v >> 16) & 0xFF);
-        }
+        uint32_t v0 = __ldg(row + x0i), v1 = __ldg(row + x1i), v2 = __ldg(row + x2i);
+        // horizontal combination first (weights <= 6, lanes <= 8 * 255), then the vertical weight
+        uint32_t hl = (uint32_t)wx0 * (v0 & 0x00FF00FFu) + (uint32_t)wx1 * (v1 & 0x00FF00FFu) + (uint32_t)wx2 * (v2 & 0x00FF00FFu);
+        uint32_t hh = (uint32_t)wx0 * ((v0 >> 8) & 0xFFu) + (uint32_t)wx1 * ((v1 >> 8) & 0xFFu) + (uint32_t)wx2 * ((v2 >> 8) & 0xFFu);
+        lo += (uint32_t)yw[a] * hl;
+        hi += (uint32_t)yw[a] * hh;
     }
-    uint32_t col = (uint32_t)((a0 + 32) >> 6) | ((uint32_t)((a1 + 32) >> 6) << 8) | ((uint32_t)((a2 + 32) >> 6) << 16);
-    // mask
+    lo = ((lo + 0x00200020u) >> 6) & 0x00FF00FFu;        // (B, R)
+    hi = ((hi + 32u) >> 6) & 0xFFu;                      // G
+    uint32_t col = lo | (hi << 8);
+    // mask = OR of the flags whose raw position (2i+1, 2j-1) lies in the 3x3 neighbourhood of (y, x):
+    //   rows: i = y>>1 (raw row 2i+1 in {y, y+1}) and, for even y, i = (y>>1) - 1 (raw row y-1)
+    //   cols: j = (x+1)>>1 (raw col 2j-1 in {x, x-1}) and, for even x, j + 1 (raw col x+1)
     uint32_t m = 0;
-    int h1 = s.hfull, w1 = s.w;
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++) {
-        int yy = y + dy;
-        if (yy < 0 || yy >= d.hfull || !(yy & 1)) continue;
-        int i = (yy - 1) >> 1;
-        if (i < 1 || i > h1 - 2) continue;
-        int ri = i - s.y0;
-        if (ri < 0 || ri >= s.rows) continue;  // outside the strip's halo (unused outputs)
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-            int xx = x + dx;
-            if (xx < 0 || xx >= d.w || !(xx & 1)) continue;
-            int j = (xx + 1) >> 1;
-            if (j < 1 || j > w1 - 2) continue;
-            m |= __ldg(s.p + (size_t)ri * s.pitch + j) >> 24;
-        }
+    const int h1 = s.hfull, w1 = s.w;
+    const int ihi = y >> 1, ilo = ihi - 1;
+    const int jlo = (x + 1) >> 1, jhi = jlo + 1;
+    const bool r_hi = (2 * ihi + 1 < d.hfull) && ihi >= 1 && ihi <= h1 - 2 && (ihi - s.y0) >= 0 && (ihi - s.y0) < s.rows;
+    const bool r_lo = !(y & 1) && ilo >= 1 && ilo <= h1 - 2 && (ilo - s.y0) >= 0 && (ilo - s.y0) < s.rows;
+    const bool c_lo = jlo >= 1 && jlo <= w1 - 2;
+    const bool c_hi = !(x & 1) && (x + 1 < d.w) && jhi >= 1 && jhi <= w1 - 2;
+    if (r_hi) {
+        const uint32_t* row = s.p + (size_t)(ihi - s.y0) * s.pitch;
+        if (c_lo) m |= __ldg(row + jlo) >> 24;
+        if (c_hi) m |= __ldg(row + jhi) >> 24;
+    }
+    if (r_lo) {
+        const uint32_t* row = s.p + (size_t)(ilo - s.y0) * s.pitch;
+        if (c_lo) m |= __ldg(row + jlo) >> 24;
+        if (c_hi) m |= __ldg(row + jhi) >> 24;
     }
     d.p[(size_t)r * d.pitch + x] = col | ((m ? 1u : 0u) << 24);
+    if (cell_count) {   // active pixels per 32x32 cell (one atomic per warp): lets the mean-shift kernel run heavy tiles first
+        unsigned bal = __ballot_sync(__activemask(), m != 0);
+        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(cell_count + (r / 32) * cells_x + (x / 32), __popc(bal));
+    }
 }
 
 // ------------------------------------------------------------------ synthetic image
@@ -230,14 +241,14 @@ int k_pyr_down(msg_ctx* ctx, msg_plane src, msg_plane dst)
     return MSG_OK;
 }
 
-int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc, msg_plane ddst, int isr22)
+int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc, msg_plane ddst, int isr22, int* d_cell_count, int cells_x)
 {
     dim3 g1((dsrc.w + 255) / 256, dsrc.rows);
     flag_kernel<<<g1, 256, 0, ctx->stream>>>(dsrc, isr22);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     dim3 g2((ddst.w + 255) / 256, ddst.rows);
-    pyr_up_mask_kernel<<<g2, 256, 0, ctx->stream>>>(dsrc, ddst);
+    pyr_up_mask_kernel<<<g2, 256, 0, ctx->stream>>>(dsrc, ddst, d_cell_count, cells_x);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;

@@ -161,6 +161,7 @@ struct tile_geom {
     int sw, sh;   // staged width / height
     int swp;      // staged row pitch (odd, to spread banks between rows)
     int tiles_x;
+    const int* order;   // tile processing order (heaviest first) or nullptr = raster order
     int use_tma;  // interior tiles are staged with cp.async.bulk (requires halo, sw, swp multiples of 4 pixels)
 };
 
@@ -180,7 +181,8 @@ __global__ void __launch_bounds__(TW * 4, 3) meanshift_tile_kernel(msg_plane S, 
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int tile_x = blockIdx.x % g.tiles_x, tile_y = blockIdx.x / g.tiles_x;
+    const int tile = g.order ? g.order[blockIdx.x] : (int)blockIdx.x;
+    const int tile_x = tile % g.tiles_x, tile_y = tile / g.tiles_x;
     const int tx0 = tile_x * TW;                 // global x of the tile origin
     const int ty0 = S.y0 + tile_y * TH;          // global y of the tile origin
     const int ox = tx0 - g.halo, oy = ty0 - g.halo;  // global coords of staged (0,0)
@@ -427,6 +429,55 @@ __global__ void __launch_bounds__(128) meanshift_generic_kernel(msg_plane S, msg
     }
 }
 
+// Heavy-first tile order.  CTAs are dispatched roughly in blockIdx order, so a launch whose tiles differ a lot in work (the
+// masked levels: 0..2048 active pixels per tile) ends with a long tail if heavy tiles start late.  One small CTA sorts the
+// tiles by active-pixel count, descending (counting sort over 2049 keys), from the 32x32-cell counts the pyrUp+mask kernel
+// left; the tile kernel then maps blockIdx through this order.
+__global__ void __launch_bounds__(256) tile_order_kernel(const int* __restrict__ cells, int cells_x, int cells_y, int tiles_x,
+                                                         int tiles_y, int tw_cells, int* __restrict__ order)
+{
+    __shared__ int hist[2050];
+    const int nt = tiles_x * tiles_y;
+    for (int i = threadIdx.x; i < 2050; i += 256) hist[i] = 0;
+    __syncthreads();
+    auto weight = [&](int t) {
+        int tx = t % tiles_x, ty = t / tiles_x, c = 0;
+        for (int k = 0; k < tw_cells; k++) {
+            int cx = tx * tw_cells + k;
+            if (cx < cells_x && ty < cells_y) c += cells[ty * cells_x + cx];
+        }
+        return min(c, 2048);
+    };
+    for (int t = threadIdx.x; t < nt; t += 256) atomicAdd(&hist[2048 - weight(t)], 1);
+    __syncthreads();
+    {   // exclusive prefix over the 2049 keys: 9 consecutive keys per thread, then a block scan of the 256 partial sums
+        __shared__ int wsum[8];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int k0 = threadIdx.x * 9;
+        int local[9], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) { local[k] = (k0 + k <= 2048) ? hist[k0 + k] : 0; sum += local[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int k = 0; k < warp; k++) woff += wsum[k];
+        int run = woff + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            if (k0 + k <= 2048) hist[k0 + k] = run;
+            run += local[k];
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nt; t += 256) order[atomicAdd(&hist[2048 - weight(t)], 1)] = t;
+}
+
 template <int NX, int TW, int ACC>
 cudaError_t launch_tile(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, const tile_geom& g, int tiles,
                         size_t smem, int* ovf_count, unsigned long long* active, unsigned long long* work)
@@ -509,10 +560,18 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, need * sizeof(msg_ovf_item)));
     MSG_CUDA(ctx, cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
     g.tiles_x = (S.w + TWsel - 1) / TWsel;
+    g.order = nullptr;
     g.use_tma = 1;
     if (const char* e = getenv("MSG_TMA")) g.use_tma = atoi(e) ? 1 : 0;   // A/B switch (experiments)
     int tiles_y = (S.rows + TH - 1) / TH;
     int tiles = g.tiles_x * tiles_y;
+    if (prm.use_mask && ctx->d_cells && !getenv("MSG_NO_ORDER")) {
+        int cells_x = (S.w + 31) / 32, cells_y = (S.rows + 31) / 32;
+        int* order = ctx->d_cells + (size_t)cells_x * cells_y;       // second half of the cell buffer
+        tile_order_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_cells, cells_x, cells_y, g.tiles_x, tiles_y, TWsel / 32, order);
+        MSG_LAUNCHED(ctx);
+        g.order = order;
+    }
 
     int nx = 0;
     if (prm.sp == (float)(int)prm.sp) nx = 2 * (int)prm.sp + 1;

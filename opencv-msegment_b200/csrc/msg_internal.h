@@ -62,6 +62,7 @@ struct msg_ctx {
     int32_t* d_counters;                     // 64 int32 device counters
     int32_t* h_counters;                     // pinned mirror
     uint8_t* d_colors; size_t d_colors_cap;
+    int32_t* d_cells;  size_t d_cells_cap;   // active pixels per 32x32 cell of the current level + tile order (K1 scheduling)
 
     // pinned host staging for pageable caller buffers
     uint8_t* h_stage; size_t h_stage_cap;
@@ -114,7 +115,7 @@ static inline int msg_align_up(int v, int a) { return (v + a - 1) / a * a; }
 int k_bgr_to_plane(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, msg_plane dst);          // all stored rows
 int k_plane_to_bgr(msg_ctx* ctx, msg_plane src, int row_first, int nrows, uint8_t* d_bgr, size_t step);
 int k_pyr_down(msg_ctx* ctx, msg_plane src, msg_plane dst);
-int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc /*D[l+1]*/, msg_plane ddst /*D[l]*/, int isr22);
+int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc /*D[l+1]*/, msg_plane ddst /*D[l]*/, int isr22, int* d_cell_count, int cells_x);
 int k_synth(msg_ctx* ctx, uint8_t* d_bgr, size_t step, int w, int h, int row0, int rows, uint64_t seed);
 // mean shift
 int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, int level);
