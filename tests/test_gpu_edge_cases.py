@@ -147,3 +147,15 @@ def test_device_entry_points_with_torch():
     n2, l2 = orc.connected_components(mask.cpu().numpy(), 8)
     assert int(n.item()) == n2 and np.array_equal(lab.cpu().numpy(), l2)
     c.close()
+
+
+@pytest.mark.parametrize("w,h,sp,sr,ml", [(260, 180, 40, 20, 0),      # wide windows: runtime-width tile kernel, drift shrunk to fit smem
+                                          (150, 110, 64, 15, 1),      # radius 64 at level 0, 32 at level 1
+                                          (120, 90, 130, 25, 0),      # radius > 120: generic warp-per-pixel kernel for every pixel
+                                          (140, 100, 12, 255, 1)])    # sr >= 254: sentinel cannot be used -> generic kernel
+def test_extreme_parameters_vs_oracle(ctx, w, h, sp, sr, ml):
+    gi = mseg.GpuImgproc(ctx)
+    im = orc.synth_bgr(w, h, 31)
+    want = orc.meanshift_filter(im, sp, sr, ml)
+    got = gi.pyrMeanShiftFiltering(im, sp, sr, ml)
+    assert np.array_equal(got, want), int((got != want).any(axis=2).sum())
