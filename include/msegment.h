@@ -82,8 +82,8 @@ MSG_API int msg_meanshift_filter(msg_ctx* ctx, const uint8_t* src_bgr, size_t sr
                          int term_type, int max_count, double eps);
 
 /* floodFill-style region growing over the whole image: regions = connected components of
- * "4-adjacent and per-channel |delta| <= lo_diff"; lo_diff must equal up_diff (asymmetric ranges make
- * floodFill order dependent -> MSG_EINVAL); connectivity must be 4.  labels 32SC1, numbered 1..n in
+ * "adjacent (4- or 8-neighbourhood) and per-channel |delta| <= lo_diff"; lo_diff must equal up_diff (asymmetric ranges make
+ * floodFill order dependent -> MSG_EINVAL); connectivity 4 or 8 (floodFill's flag).  labels 32SC1, numbered 1..n in
  * raster order of each region's first pixel (== the floodFill loop's numbering). */
 MSG_API int msg_label_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* labels, size_t labels_step,
                       int width, int height, int lo_diff, int up_diff, int connectivity,
@@ -130,6 +130,7 @@ typedef struct msg_segment_params {
     int min_size;     /* merge stage; 0 with color_dist 0 skips it      */
     int color_dist;
     int render_depth; /* > 0: render with that depth; 0: depth = n_regions; < 0: skip */
+    int connectivity; /* label stage: 4 (default, also for 0) or 8 */
 } msg_segment_params;
 
 MSG_API void msg_segment_params_default(msg_segment_params* p); /* sp=sr=10, L1, (3,5,1), lo=2, no merge */
@@ -165,7 +166,8 @@ MSG_API int msg_meanshift_filter_dev(msg_ctx* ctx, const uint8_t* d_src_bgr, siz
                              int term_type, int max_count, double eps);
 /* d_n_regions: device int32 (may be NULL). */
 MSG_API int msg_label_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32_t* d_labels,
-                          size_t labels_step, int width, int height, int lo_diff, int32_t* d_n_regions);
+                          size_t labels_step, int width, int height, int lo_diff, int connectivity,
+                          int32_t* d_n_regions);
 MSG_API int msg_connected_components_dev(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int32_t* d_labels,
                                  size_t labels_step, int width, int height, int connectivity,
                                  int32_t* d_n_labels);

@@ -14,7 +14,7 @@ MAX_INFLIGHT = 4
 class SegmentParams(C.Structure):
     _fields_ = [("sp", C.c_double), ("sr", C.c_double), ("max_level", C.c_int), ("term_type", C.c_int),
                 ("max_count", C.c_int), ("eps", C.c_double), ("lo_diff", C.c_int), ("min_size", C.c_int),
-                ("color_dist", C.c_int), ("render_depth", C.c_int)]
+                ("color_dist", C.c_int), ("render_depth", C.c_int), ("connectivity", C.c_int)]
 
 
 class Timings(C.Structure):
@@ -58,7 +58,7 @@ SIGNATURES = {
     "msg_free_pinned": (None, [_P]),
     "msg_segment_dev": (_I, [_P, _P, _SZ, _I, _I, C.POINTER(SegmentParams), _P, _SZ, _P, _SZ, _P, _SZ, _P]),
     "msg_meanshift_filter_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _D, _D, _I, _I, _I, _D]),
-    "msg_label_regions_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _P]),
+    "msg_label_regions_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, _P]),
     "msg_connected_components_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _P]),
     "msg_merge_regions_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, _P]),
     "msg_render_labels_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _P]),

@@ -189,7 +189,7 @@ void msg_segment_params_default(msg_segment_params* p)
     if (!p) return;
     p->sp = 10.0; p->sr = 10.0; p->max_level = 1;
     p->term_type = MSG_TERM_COUNT | MSG_TERM_EPS; p->max_count = 5; p->eps = 1.0;
-    p->lo_diff = 2; p->min_size = 0; p->color_dist = 0; p->render_depth = 0;
+    p->lo_diff = 2; p->min_size = 0; p->color_dist = 0; p->render_depth = 0; p->connectivity = 4;
 }
 
 int msg_get_timings(msg_ctx* ctx, msg_timings* out)
@@ -377,12 +377,13 @@ int msg_meanshift_filter(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t
 // ============================================================================ labelling
 
 int msg_label_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32_t* d_labels, size_t lstep, int w, int h,
-                          int lo_diff, int32_t* d_n)
+                          int lo_diff, int connectivity, int32_t* d_n)
 {
     CTX_ENTER(ctx);
     MSG_TRY(check_img(ctx, d_bgr, step, w, h, 3, "label src"));
     MSG_TRY(check_img(ctx, d_labels, lstep, w, h, 4, "labels"));
     if (lo_diff < 0) return msg_fail(ctx, MSG_EINVAL, "lo_diff must be >= 0");
+    if (connectivity != 4 && connectivity != 8) return msg_fail(ctx, MSG_EINVAL, "connectivity must be 4 or 8");
     if (lstep % 4) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of 4");
     msg_plane s;
     s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
@@ -395,7 +396,7 @@ int msg_label_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32
         MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
         work = ctx->d_labels;
     }
-    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, work, -1, w));
+    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, connectivity, work, -1, w));
     MSG_TRY(k_relabel_canonical(ctx, work, w, h, 1, d_n, 0));
     if (!dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
     return MSG_OK;
@@ -489,7 +490,7 @@ int msg_label_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* la
     MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "labels"));
     if (lo_diff != up_diff)
         return msg_fail(ctx, MSG_EINVAL, "lo_diff (%d) != up_diff (%d): asymmetric floodFill ranges are order dependent", lo_diff, up_diff);
-    if (connectivity != 4) return msg_fail(ctx, MSG_EINVAL, "label_regions supports connectivity 4 only (got %d)", connectivity);
+    if (connectivity != 4 && connectivity != 8) return msg_fail(ctx, MSG_EINVAL, "connectivity must be 4 or 8 (got %d)", connectivity);
     if (lo_diff < 0) return msg_fail(ctx, MSG_EINVAL, "lo_diff must be >= 0");
     size_t rb = (size_t)w * 3;
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -502,7 +503,7 @@ int msg_label_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* la
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
     s.p = ctx->d_planes;
     MSG_TRY(k_bgr_to_plane(ctx, ctx->d_in, rb, s));
-    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, ctx->d_labels, -1, w));
+    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, connectivity, ctx->d_labels, -1, w));
     MSG_TRY(k_relabel_canonical(ctx, ctx->d_labels, w, h, 1, ctx->d_counters + 16, 0));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
@@ -633,7 +634,7 @@ static int segment_core_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, in
             MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
             work = ctx->d_labels;
         }
-        MSG_TRY(k_ccl_color(ctx, ctx->D[0].p, ctx->D[0].pitch, w, h, p->lo_diff, work, -1, w));
+        MSG_TRY(k_ccl_color(ctx, ctx->D[0].p, ctx->D[0].pitch, w, h, p->lo_diff, p->connectivity == 8 ? 8 : 4, work, -1, w));
         MSG_TRY(k_relabel_canonical(ctx, work, w, h, 1, n_dev, 0));
     } else if (d_n) {
         MSG_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int32_t), st));
@@ -662,6 +663,7 @@ static int segment_enqueue(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w
     ms_config cfg;
     MSG_TRY(ms_validate(ctx, w, h, p->sp, p->sr, p->max_level, p->term_type, p->max_count, p->eps, &cfg));
     if (p->min_size < 0 || p->color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
+    if (p->connectivity != 0 && p->connectivity != 4 && p->connectivity != 8) return msg_fail(ctx, MSG_EINVAL, "connectivity must be 4 or 8");
     const bool do_label = p->lo_diff >= 0;
     const bool do_render = do_label && p->render_depth >= 0 && rendered;
     size_t rb = (size_t)w * 3;
@@ -866,7 +868,7 @@ int msg_label_strip_dev(msg_ctx* ctx, const uint8_t* d_bgr_rows, size_t step, in
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * rows * sizeof(uint32_t)));
     s.p = ctx->d_planes;
     MSG_TRY(k_bgr_to_plane(ctx, d_bgr_rows, step, s));
-    return k_ccl_color(ctx, s.p, s.pitch, w, rows, lo_diff, d_labels, (int64_t)row0 * full_w, full_w);
+    return k_ccl_color(ctx, s.p, s.pitch, w, rows, lo_diff, 4, d_labels, (int64_t)row0 * full_w, full_w);
 }
 
 int msg_seam_pairs_dev(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const uint8_t* lo_bgr,

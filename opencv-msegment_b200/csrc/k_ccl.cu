@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_merge_kernel(const void* __re
                                  color_close(__ldg(row + x - 1), __ldg(up + x - 1), d);
                 if (!redundant) uf_union(L, p, p - w);
             }
+            if (CONN == 8) {   // floodFill with the 8-connectivity flag: the two upper diagonals are edges of their own
+                if (x > 0 && color_close(c, __ldg(up + x - 1), d)) uf_union(L, p, p - w - 1);
+                if (x + 1 < w && color_close(c, __ldg(up + x + 1), d)) uf_union(L, p, p - w + 1);
+            }
         }
     } else {
         const uint8_t* row = (const uint8_t*)img + (size_t)y * pitch;
@@ -570,7 +574,7 @@ int k_relabel_canonical(msg_ctx* ctx, int32_t* d_labels, int w, int h, int roots
 }
 
 // label_base < 0: canonical labels 1..n (n -> d_n via caller's relabel); otherwise strip mode
-int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int32_t* d_labels,
+int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int conn, int32_t* d_labels,
                 int64_t label_base, int full_w)
 {
     dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);
@@ -579,7 +583,8 @@ int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, 
     if (w > CCL_MAX_CHUNKS * 32) return msg_fail(ctx, MSG_EINVAL, "labelling supports rows up to %d pixels", CCL_MAX_CHUNKS * 32);
     ccl_rows_kernel<0><<<h, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
     MSG_LAUNCHED(ctx);
-    ccl_merge_kernel<0, 4><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
+    if (conn == 8) ccl_merge_kernel<0, 8><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
+    else ccl_merge_kernel<0, 4><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
     MSG_LAUNCHED(ctx);
     if (label_base >= 0) {      // strip mode: no canonical relabel follows, flatten here
         ccl_flatten_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n);

@@ -123,7 +123,7 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
 void msg_prof_begin(msg_ctx* ctx, int level);
 void msg_prof_end(msg_ctx* ctx, int level, int slot);
 // labelling
-int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int32_t* d_labels,
+int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int conn, int32_t* d_labels,
                 int64_t label_base, int lab_pitch);
 int k_ccl_binary(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int conn, int32_t* d_labels);
 int k_relabel_canonical(msg_ctx* ctx, int32_t* d_labels, int w, int h, int roots_are_pixels,

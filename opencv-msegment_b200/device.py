@@ -8,9 +8,10 @@ import ctypes as C
 from . import _lib as L
 
 
-def params(sp=10.0, sr=10.0, max_level=1, termcrit=(3, 5, 1.0), lo_diff=2, min_size=0, color_dist=0, render_depth=0):
+def params(sp=10.0, sr=10.0, max_level=1, termcrit=(3, 5, 1.0), lo_diff=2, min_size=0, color_dist=0, render_depth=0,
+           connectivity=4):
     return L.SegmentParams(float(sp), float(sr), int(max_level), int(termcrit[0]), int(termcrit[1]), float(termcrit[2]),
-                           int(lo_diff), int(min_size), int(color_dist), int(render_depth))
+                           int(lo_diff), int(min_size), int(color_dist), int(render_depth), int(connectivity))
 
 
 def _p(v):
@@ -46,8 +47,9 @@ def halo_rows(sp, max_level=1, termcrit=(3, 5, 1.0)):
     return L.load().msg_meanshift_halo_rows(float(sp), int(max_level), int(termcrit[0]), int(termcrit[1]))
 
 
-def label_regions(ctx, d_bgr, step, d_labels, lstep, w, h, lo_diff, d_n=0):
-    ctx.check(ctx._lib.msg_label_regions_dev(ctx._h, _p(d_bgr), step, _p(d_labels), lstep, w, h, int(lo_diff), _p(d_n)))
+def label_regions(ctx, d_bgr, step, d_labels, lstep, w, h, lo_diff, d_n=0, connectivity=4):
+    ctx.check(ctx._lib.msg_label_regions_dev(ctx._h, _p(d_bgr), step, _p(d_labels), lstep, w, h, int(lo_diff),
+                                             int(connectivity), _p(d_n)))
 
 
 def label_strip(ctx, d_bgr_rows, step, d_labels, lstep, w, rows, row0, full_w, lo_diff):

@@ -229,11 +229,11 @@ class GpuImgproc:
 
     # fused pipeline
     def segment(self, src, sp=10.0, sr=10.0, maxLevel=1, termcrit=DEFAULT_TERMCRIT, loDiff=2, minSize=0, colorDist=0,
-                renderDepth=0, want=("filtered", "labels", "rendered")):
+                renderDepth=0, want=("filtered", "labels", "rendered"), connectivity=4):
         src = _mat8uc3(src, "src")
         h, w = src.shape[:2]
         p = L.SegmentParams(float(sp), float(sr), int(maxLevel), int(termcrit[0]), int(termcrit[1]), float(termcrit[2]),
-                            int(loDiff), int(minSize), int(colorDist), int(renderDepth))
+                            int(loDiff), int(minSize), int(colorDist), int(renderDepth), int(connectivity))
         out = {}
         f = np.empty((h, w, 3), np.uint8) if "filtered" in want else None
         lab = np.empty((h, w), np.int32) if "labels" in want else None

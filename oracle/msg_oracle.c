@@ -285,6 +285,12 @@ int32_t orc_relabel_canonical(int32_t* labels, size_t lstep, int w, int h)
 
 int32_t orc_label_regions(const uint8_t* bgr, size_t step, int32_t* labels, size_t lstep, int w, int h, int d)
 {
+    return orc_label_regions_conn(bgr, step, labels, lstep, w, h, d, 4);
+}
+
+int32_t orc_label_regions_conn(const uint8_t* bgr, size_t step, int32_t* labels, size_t lstep, int w, int h, int d,
+                               int connectivity)
+{
     size_t n = (size_t)w * h;
     int32_t* p = (int32_t*)malloc(n * sizeof(int32_t));
     for (size_t i = 0; i < n; i++) p[i] = (int32_t)i;
@@ -293,6 +299,10 @@ int32_t orc_label_regions(const uint8_t* bgr, size_t step, int32_t* labels, size
             const uint8_t* c = bgr + (size_t)y * step + 3 * x;
             if (x > 0 && color_close(c, c - 3, d)) uf_union(p, y * w + x, y * w + x - 1);
             if (y > 0 && color_close(c, c - step, d)) uf_union(p, y * w + x, (y - 1) * w + x);
+            if (connectivity == 8 && y > 0) {   /* floodFill with flags & 8: diagonal neighbours too */
+                if (x > 0 && color_close(c, c - step - 3, d)) uf_union(p, y * w + x, (y - 1) * w + x - 1);
+                if (x < w - 1 && color_close(c, c - step + 3, d)) uf_union(p, y * w + x, (y - 1) * w + x + 1);
+            }
         }
     for (int y = 0; y < h; y++) {
         int32_t* r = (int32_t*)((char*)labels + (size_t)y * lstep);

@@ -46,6 +46,8 @@ def lib():
         L.orc_meanshift_filter_roi.restype = i
         L.orc_label_regions.argtypes = [u8p, sz, i32p, sz, i, i, i]
         L.orc_label_regions.restype = C.c_int32
+        L.orc_label_regions_conn.argtypes = [u8p, sz, i32p, sz, i, i, i, i]
+        L.orc_label_regions_conn.restype = C.c_int32
         L.orc_connected_components.argtypes = [u8p, sz, i32p, sz, i, i, i]
         L.orc_connected_components.restype = C.c_int32
         L.orc_relabel_canonical.argtypes = [i32p, sz, i, i]
@@ -112,11 +114,12 @@ def meanshift_filter_roi(crop, xoff, yoff, full_w, full_h, sp, sr, max_level=1, 
     return dst
 
 
-def label_regions(bgr, d=2):
+def label_regions(bgr, d=2, connectivity=4):
     bgr = _img(bgr)
     h, w = bgr.shape[:2]
     lab = np.empty((h, w), np.int32)
-    n = lib().orc_label_regions(bgr.ctypes.data, bgr.strides[0], lab.ctypes.data, lab.strides[0], w, h, int(d))
+    n = lib().orc_label_regions_conn(bgr.ctypes.data, bgr.strides[0], lab.ctypes.data, lab.strides[0], w, h, int(d),
+                                     int(connectivity))
     return n, lab
 
 

@@ -56,7 +56,7 @@ MS_PARAMS = [  # sp, sr, maxLevel, (type, maxCount, eps)
 ]
 
 
-def floodfill_labels(img, d):
+def floodfill_labels(img, d, conn=4):
     """OpenCV samples/cpp/meanshift_segmentation.cpp floodFillPostprocess, recording region ids."""
     h, w = img.shape[:2]
     mask = np.zeros((h + 2, w + 2), np.uint8)
@@ -68,7 +68,7 @@ def floodfill_labels(img, d):
                 n += 1
                 before = mask[1:-1, 1:-1] != 0
                 cv2.floodFill(img, mask, (x, y), (0, 0, 0), (d, d, d), (d, d, d),
-                              4 | cv2.FLOODFILL_MASK_ONLY | (1 << 8))
+                              conn | cv2.FLOODFILL_MASK_ONLY | (1 << 8))
                 lab[(mask[1:-1, 1:-1] != 0) & ~before] = n
     return n, lab
 
@@ -117,6 +117,8 @@ def main():
         for d in (0, 2, 5):
             n, l = floodfill_labels(f.copy(), d)
             lab["ff%d/%s" % (d, name)] = l
+        n, l = floodfill_labels(f.copy(), 2, 8)
+        lab["ff2c8/%s" % name] = l
     for k, (w, h, p) in enumerate([(64, 48, .5), (101, 37, .3), (17, 90, .7), (1, 9, .5), (9, 1, .5), (40, 40, .95)]):
         m = (rng.random((h, w)) < p).astype(np.uint8) * 255
         lab["mask/%d" % k] = m

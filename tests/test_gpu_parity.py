@@ -45,6 +45,9 @@ def test_label_regions_golden(gi, golden_dir):
             want = g["ff%d/%s" % (d, name)]
             n, lab = gi.labelRegions(f, d, d, 4)
             assert n == want.max() and np.array_equal(lab, want), (name, d, n, want.max(), _diff(lab, want))
+        want8 = g["ff2c8/" + name]
+        n, lab = gi.labelRegions(f, 2, 2, 8)
+        assert n == want8.max() and np.array_equal(lab, want8), (name, "8-conn", _diff(lab, want8))
 
 
 def test_connected_components_golden(gi, golden_dir):
@@ -108,6 +111,8 @@ def test_meanshift_strided_input_and_errors(gi):
     with pytest.raises(mseg.CvException):
         gi.labelRegions(big, 2, 3, 4)              # asymmetric range rejected
     with pytest.raises(mseg.CvException):
+        gi.labelRegions(big, 2, 2, 6)              # connectivity must be 4 or 8
+    with pytest.raises(mseg.CvException):
         gi.connectedComponents(np.zeros((4, 4), np.uint8), 6)
 
 
@@ -119,6 +124,11 @@ def test_label_and_merge_vs_oracle(gi, w, h, seed):
         n0, l0 = orc.label_regions(f, d)
         n1, l1 = gi.labelRegions(f, d, d, 4)
         assert n0 == n1 and np.array_equal(l0, l1), (d, n0, n1, _diff(l1, l0))
+    n8, l8 = orc.label_regions(f, 3, 8)
+    m8, g8 = gi.labelRegions(f, 3, 3, 8)
+    assert n8 == m8 and np.array_equal(l8, g8), ("8-conn", n8, m8)
+    out8 = gi.segment(im, 6, 12, 1, loDiff=3, connectivity=8, want=("labels",))
+    assert out8["n_regions"] == n8 and np.array_equal(out8["labels"], l8)
     n0, l0 = orc.label_regions(f, 2)
     for min_size, cd in ((20, 0), (0, 10), (50, 10), (10**9, 0)):
         m0, lm0 = orc.merge_regions(f, l0, min_size, cd)

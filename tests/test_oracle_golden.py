@@ -46,6 +46,9 @@ def test_label_regions_golden(golden_dir):
             want = g["ff%d/%s" % (d, name)]
             n, lab = orc.label_regions(f, d)
             assert n == want.max() and np.array_equal(lab, want), (name, d)
+        want8 = g["ff2c8/" + name]                      # floodFill with the 8-connectivity flag
+        n, lab = orc.label_regions(f, 2, 8)
+        assert n == want8.max() and np.array_equal(lab, want8), name
 
 
 def test_connected_components_golden(golden_dir):

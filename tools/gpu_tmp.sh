@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_edge_cases.py -m gpu -q --timeout 900 -k extreme > gpurun_out/pytest_ext.log 2>&1; echo "pytest rc=$?"
-tail -12 gpurun_out/pytest_ext.log
+timeout 1200 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"
+tail -8 gpurun_out/pytest.log
