@@ -44,25 +44,33 @@ def resolve_pairs(pairs):
         return np.zeros(0, np.int32), np.zeros(0, np.int32)
     labels, inv = np.unique(pairs, return_inverse=True)
     inv = inv.reshape(-1, 2)
-    parent = np.arange(len(labels))
+    n = len(labels)
+    try:                                          # C-speed connected components of the pair graph
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+        g = coo_matrix((np.ones(len(inv), np.int8), (inv[:, 0], inv[:, 1])), shape=(n, n))
+        _, comp = connected_components(g, directed=False)
+    except ImportError:                           # same result with a plain union-find
+        parent = np.arange(n)
 
-    def find(i):
-        r = i
-        while parent[r] != r:
-            r = parent[r]
-        while parent[i] != r:
-            parent[i], i = r, parent[i]
-        return r
+        def find(i):
+            r = i
+            while parent[r] != r:
+                r = parent[r]
+            while parent[i] != r:
+                parent[i], i = r, parent[i]
+            return r
 
-    for a, b in inv:
-        ra, rb = find(a), find(b)
-        if ra != rb:            # labels is sorted, so the smaller index is the smaller label
-            if ra < rb:
-                parent[rb] = ra
-            else:
-                parent[ra] = rb
-    roots = np.array([find(i) for i in range(len(labels))])
-    changed = roots != np.arange(len(labels))
+        for a, b in inv:
+            ra, rb = find(a), find(b)
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+        comp = np.array([find(i) for i in range(n)])
+    # smallest label of every component (labels is sorted ascending, so the first index of a component is its minimum)
+    first = np.full(comp.max() + 1, n, np.int64)
+    np.minimum.at(first, comp, np.arange(n))
+    roots = first[comp]
+    changed = roots != np.arange(n)
     return labels[changed].astype(np.int32), labels[roots[changed]].astype(np.int32)
 
 
@@ -88,12 +96,29 @@ def dense_from_first_pixel(labels):
     return len(u), out.reshape(np.asarray(labels).shape)
 
 
-def allgather_pairs(dist, pairs, device=None):
+def allgather_pairs(dist, pairs, device=None, cap=None):
     """All-gathers variable-length (n,2) int32 pair lists with torch.distributed (NCCL on GPU tensors, gloo on CPU).
-    Returns the concatenation over ranks as a numpy (m,2) array, identical on every rank."""
+    Returns the concatenation over ranks as a numpy (m,2) array, identical on every rank.
+    cap: an upper bound on n known to every rank (e.g. the image width for seam pairs) -> ONE collective on a fixed-size
+    buffer whose row 0 carries the count; without it the counts are gathered first (two collectives)."""
     import torch
     world = dist.get_world_size()
-    t = torch.as_tensor(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+    arr = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+    if cap is not None:
+        if len(arr) > cap:
+            raise ValueError("allgather_pairs: %d pairs exceed cap %d" % (len(arr), cap))
+        buf = np.zeros((cap + 1, 2), np.int32)
+        buf[0, 0] = len(arr)
+        buf[1:1 + len(arr)] = arr
+        t = torch.from_numpy(buf)
+        if device is not None:
+            t = t.to(device)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        host = torch.stack(out).cpu().numpy()
+        parts = [host[r, 1:1 + int(host[r, 0, 0])] for r in range(world)]
+        return np.concatenate(parts, axis=0) if parts else np.zeros((0, 2), np.int32)
+    t = torch.as_tensor(arr)
     if device is not None:
         t = t.to(device)
     n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)

@@ -86,6 +86,8 @@ def _rank_main(rank, world, port, q):
         up_lab = up[3 * w:].view(np.int32)
         pairs = _seam_pairs_np(up_bgr, up_lab, f[r0], fp[0], d)
     allp = s.allgather_pairs(dist, pairs)
+    allp1 = s.allgather_pairs(dist, pairs, cap=w)              # single-collective form must agree
+    assert np.array_equal(allp, allp1)
     frm, to = s.resolve_pairs(allp)
     if len(frm):
         idx = np.searchsorted(frm, fp)

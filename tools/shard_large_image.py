@@ -120,7 +120,7 @@ def main():
                            pairs.data_ptr(), cnt.data_ptr())
         torch.cuda.synchronize()
         mine = pairs[:int(cnt.item())].cpu().numpy()
-        allp = sh.allgather_pairs(dist, mine, device="cuda")
+        allp = sh.allgather_pairs(dist, mine, device="cuda", cap=w)
         frm, to = sh.resolve_pairs(allp)
         if len(frm):
             d_from, d_to = torch.from_numpy(frm).cuda(), torch.from_numpy(to).cuda()
@@ -141,7 +141,7 @@ def main():
             dev.strip_query_dense(ctx, q.data_ptr(), len(own), w, r1 - r0, r0, w, offset, o.data_ptr())
             mine_tab[:, 0] = uniq_to[own]
             mine_tab[:, 1] = o.cpu().numpy()
-        tab = sh.allgather_pairs(dist, mine_tab, device="cuda")
+        tab = sh.allgather_pairs(dist, mine_tab, device="cuda", cap=max(1, len(uniq_to)))
         tab = tab[np.argsort(tab[:, 0], kind="stable")] if len(tab) else tab
         d_rl = torch.from_numpy(np.ascontiguousarray(tab[:, 0])).cuda() if len(tab) else torch.zeros(1, dtype=torch.int32, device="cuda")
         d_rd = torch.from_numpy(np.ascontiguousarray(tab[:, 1])).cuda() if len(tab) else torch.zeros(1, dtype=torch.int32, device="cuda")
