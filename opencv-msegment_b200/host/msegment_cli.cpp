@@ -6,8 +6,10 @@
 // (PictureService.saveResultsToFS, PictureService.java:194-234) names results
 //   <imageDir>/<name>_output/<yyyyMMdd'T'HHmmss>/<SegMethod>_<name>_<step %05d>_<stepName>.png
 // This program runs the mean-shift segmentation pass named by BASELINE.json (filter -> label -> merge -> render) and writes
-// that batch with the same naming scheme.  Image IO is binary PNM (P6 in; P6/P5 out): the image has no PNG/JPEG codec and
-// decoding is outside the hot path.  Optional environment: MSG_SP, MSG_SR, MSG_MIN_SIZE, MSG_COLOR_DIST.
+// that batch with the same naming scheme and file type (.png, written by the small codec in png_io.hpp; MSG_OUT_FORMAT=pnm
+// switches to binary P6/P5).  Inputs: PNG (non-interlaced, 8 bit or palette) or binary PPM; JPEG decoding is not provided
+// (no codec in the image, and decoding is outside the hot path).  Optional environment: MSG_SP, MSG_SR, MSG_MIN_SIZE,
+// MSG_COLOR_DIST, MSG_OUT_FORMAT.
 #include <sys/stat.h>
 
 #include <cstdio>
@@ -18,6 +20,7 @@
 #include <sstream>
 
 #include "GpuImgproc.hpp"
+#include "png_io.hpp"
 
 using namespace msegment;
 
@@ -50,6 +53,47 @@ static bool read_ppm(const std::string& path, Mat& img)
     return true;
 }
 
+static bool read_image(const std::string& path, Mat& img)
+{
+    if (read_ppm(path, img)) return true;
+    std::vector<uint8_t> bgr;
+    int w = 0, h = 0;
+    if (!png::read_bgr(path, bgr, w, h)) return false;
+    img.create(h, w, CV_8UC3);
+    img.buf = bgr;
+    return true;
+}
+
+// Core.multiply(m, multiplier) then the 8-bit saturation imwrite applies to CV_32S (PictureService.java:209-216)
+static std::vector<uint8_t> labels_to_gray(const Mat& m, int multiplier)
+{
+    const int32_t* p = (const int32_t*)m.data();
+    std::vector<uint8_t> g((size_t)m.rows * m.cols);
+    for (size_t i = 0; i < g.size(); i++) {
+        long long v = (long long)p[i] * multiplier;
+        g[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+    return g;
+}
+
+static void write_png(const std::string& path, const Mat& m, int multiplier)
+{
+    bool ok;
+    if (m.type == CV_8UC3) {
+        std::vector<uint8_t> rgb(m.buf.size());
+        for (size_t i = 0; i < (size_t)m.rows * m.cols; i++) {
+            rgb[3 * i] = m.buf[3 * i + 2]; rgb[3 * i + 1] = m.buf[3 * i + 1]; rgb[3 * i + 2] = m.buf[3 * i];
+        }
+        ok = png::write(path, rgb.data(), (size_t)m.cols * 3, m.cols, m.rows, 3);
+    } else if (m.type == CV_32SC1) {
+        std::vector<uint8_t> g = labels_to_gray(m, multiplier);
+        ok = png::write(path, g.data(), (size_t)m.cols, m.cols, m.rows, 1);
+    } else {
+        ok = png::write(path, m.data(), (size_t)m.cols, m.cols, m.rows, 1);
+    }
+    if (!ok) std::cerr << "cannot write " << path << std::endl;
+}
+
 static void write_pnm(const std::string& path, const Mat& m, int multiplier)
 {
     std::ofstream f(path, std::ios::binary);
@@ -62,12 +106,7 @@ static void write_pnm(const std::string& path, const Mat& m, int multiplier)
         f.write((const char*)rgb.data(), (std::streamsize)rgb.size());
     } else if (m.type == CV_32SC1) {                // Core.multiply(m, multiplier) then saturate to 8 bit, as imwrite would
         f << "P5\n" << m.cols << " " << m.rows << "\n255\n";
-        const int32_t* p = (const int32_t*)m.data();
-        std::vector<uint8_t> g((size_t)m.rows * m.cols);
-        for (size_t i = 0; i < g.size(); i++) {
-            long long v = (long long)p[i] * multiplier;
-            g[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
-        }
+        std::vector<uint8_t> g = labels_to_gray(m, multiplier);
         f.write((const char*)g.data(), (std::streamsize)g.size());
     } else {
         f << "P5\n" << m.cols << " " << m.rows << "\n255\n";
@@ -87,8 +126,8 @@ int main(int argc, char** argv)
     const std::string dir = argv[1], out_root = argv[2], file = argv[3];
     (void)out_root;                                 // dead in the reference too (PictureService.java:118, :130)
     Mat src;
-    if (!read_ppm(dir + "/" + file, src)) {         // readPicture: dataAddr()==0 -> IOException -> logged, pipeline returns null
-        std::cerr << "There is an error with file stream processing: cannot read binary PPM " << dir << "/" << file << std::endl;
+    if (!read_image(dir + "/" + file, src)) {         // readPicture: dataAddr()==0 -> IOException -> logged, pipeline returns null
+        std::cerr << "There is an error with file stream processing: cannot read PNG / binary PPM " << dir << "/" << file << std::endl;
         return 0;
     }
     const std::string name = file.substr(0, file.find('.'));   // ImageInfo: text before the first '.'
@@ -98,10 +137,14 @@ int main(int argc, char** argv)
     const std::string odir1 = dir + "/" + name + "_output", odir = odir1 + "/" + stamp;
     mkdir(odir1.c_str(), 0755);
     mkdir(odir.c_str(), 0755);
-    auto out = [&](int step, const char* step_name, const char* ext) {
+    const char* fmt = getenv("MSG_OUT_FORMAT");
+    const bool pnm = fmt && std::string(fmt) == "pnm";
+    auto save = [&](int step, const char* step_name, const Mat& m, int multiplier) {
         char b[64];
         snprintf(b, sizeof(b), "%05d", step);
-        return odir + "/MEANSHIFT_METHOD_" + name + "_" + b + "_" + step_name + ext;
+        const std::string stem = odir + "/MEANSHIFT_METHOD_" + name + "_" + b + "_" + step_name;
+        if (pnm) write_pnm(stem + (m.type == CV_8UC3 ? ".ppm" : ".pgm"), m, multiplier);
+        else write_png(stem + ".png", m, multiplier);
     };
     try {
         const double sp = env_or("MSG_SP", 10), sr = env_or("MSG_SR", 10);
@@ -109,15 +152,15 @@ int main(int argc, char** argv)
         int step = 0;
         Mat filtered, labels;
         GpuImgproc::pyrMeanShiftFiltering(src, filtered, sp, sr);
-        write_pnm(out(++step, "meanshift_filtered", ".ppm"), filtered, 1);
+        save(++step, "meanshift_filtered", filtered, 1);
         int n = GpuImgproc::labelRegions(filtered, labels, 2, 2, 4);
-        write_pnm(out(++step, "markers", ".pgm"), labels, 1);
+        save(++step, "markers", labels, 1);
         std::cout << "regions after labelling: " << n << std::endl;
         n = GpuImgproc::mergeRegions(filtered, labels, min_size, color_dist);
-        write_pnm(out(++step, "merged_markers", ".pgm"), labels, 1);
+        save(++step, "merged_markers", labels, 1);
         std::cout << "regions after merge: " << n << std::endl;
         Mat result = GpuImgproc::colorByIndexes(labels, n);           // colored=false -> white (CLI path, PictureService.java:293)
-        write_pnm(out(++step, "result", ".ppm"), result, 1);
+        save(++step, "result", result, 1);
         std::cout << "results written to " << odir << std::endl;
     } catch (const CvException& e) {                // the reference lets CvException propagate: uncaught -> non-zero exit
         std::cerr << "CvException: " << e.what() << std::endl;

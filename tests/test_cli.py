@@ -1,6 +1,8 @@
 """The C++ host program keeps the reference CLI contract (App.java:14-31) and, on a GPU, writes the output batch."""
 import os
+import struct
 import subprocess
+import zlib
 
 import numpy as np
 import pytest
@@ -25,6 +27,101 @@ def _read_pnm(path):
         f.readline()
         data = np.frombuffer(f.read(), np.uint8)
     return data.reshape(h, w, 3)[..., ::-1] if magic == b"P6" else data.reshape(h, w)
+
+
+def _read_png(path):
+    """Independent PNG decoder (python zlib) for 8-bit gray / RGB, any filter type."""
+    d = open(path, "rb").read()
+    assert d[:8] == b"\x89PNG\r\n\x1a\n"
+    o, idat = 8, b""
+    while o < len(d):
+        n, tag = struct.unpack(">I4s", d[o:o + 8])
+        body = d[o + 8:o + 8 + n]
+        assert zlib.crc32(d[o + 4:o + 8 + n]) == struct.unpack(">I", d[o + 8 + n:o + 12 + n])[0], "bad chunk CRC"
+        if tag == b"IHDR":
+            w, h, depth, ctype, _, _, interlace = struct.unpack(">IIBBBBB", body)
+            assert depth == 8 and ctype in (0, 2) and interlace == 0
+        elif tag == b"IDAT":
+            idat += body
+        o += 12 + n
+    ch = 3 if ctype == 2 else 1
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, w * ch + 1)
+    assert not raw[:, 0].any()                       # our writer uses filter 0 only
+    px = raw[:, 1:]
+    return px.reshape(h, w, 3)[..., ::-1] if ch == 3 else px.reshape(h, w)
+
+
+def _write_png_filtered(path, rgb, palette=None):
+    """PNG encoder that cycles through all five filter types and compresses (dynamic Huffman blocks)."""
+    h, w = rgb.shape[:2]
+    ch = 1 if rgb.ndim == 2 else rgb.shape[2]
+    rows = rgb.reshape(h, w * ch).astype(np.int32)
+    out = bytearray()
+    prev = np.zeros(w * ch, np.int32)
+    for y in range(h):
+        cur = rows[y]
+        a = np.concatenate([np.zeros(ch, np.int32), cur[:-ch]])
+        c = np.concatenate([np.zeros(ch, np.int32), prev[:-ch]])
+        ft = y % 5
+        if ft == 0:
+            f = cur
+        elif ft == 1:
+            f = cur - a
+        elif ft == 2:
+            f = cur - prev
+        elif ft == 3:
+            f = cur - ((a + prev) >> 1)
+        else:
+            p = a + prev - c
+            pa, pb, pc = abs(p - a), abs(p - prev), abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+            f = cur - pred
+        out.append(ft)
+        out += (f & 255).astype(np.uint8).tobytes()
+        prev = cur
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body))
+    ctype = 3 if palette is not None else {1: 0, 2: 4, 3: 2, 4: 6}[ch]
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0))
+    if palette is not None:
+        data += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    data += chunk(b"IDAT", zlib.compress(bytes(out), 9)) + chunk(b"IEND", b"")
+    open(path, "wb").write(data)
+
+
+@pytest.mark.parametrize("kind", ["rgb", "rgba", "gray", "palette", "noise_stored"])
+def test_png_codec_roundtrip(tmp_path, kind):
+    """host/png_io.hpp: inflate + unfilter + palette on read, stored-deflate on write, checked against python zlib."""
+    rt = os.path.join(mseg.PKG_DIR, "host", "png_roundtrip")
+    assert os.path.exists(rt), "run `python __graft_entry__.py` first"
+    rng = np.random.default_rng(5)
+    bgr = orc.synth_bgr(300, 231, 4)                 # > 65535 raw bytes: several stored blocks on write
+    rgb = bgr[..., ::-1]
+    src = str(tmp_path / "in.png")
+    if kind == "rgb":
+        _write_png_filtered(src, rgb)
+        want = bgr
+    elif kind == "rgba":
+        _write_png_filtered(src, np.dstack([rgb, rng.integers(0, 256, rgb.shape[:2], dtype=np.uint8)]))
+        want = bgr
+    elif kind == "gray":
+        _write_png_filtered(src, rgb[..., 0])
+        want = np.repeat(rgb[..., :1], 3, axis=2)
+    elif kind == "palette":
+        pal = rng.integers(0, 256, (200, 3), dtype=np.uint8)
+        idx = (rgb[..., 0].astype(np.int32) * 199 // 255).astype(np.uint8)
+        _write_png_filtered(src, idx, palette=pal)
+        want = pal[idx][..., ::-1]
+    else:
+        noise = rng.integers(0, 256, (97, 61, 3), dtype=np.uint8)     # incompressible: zlib emits stored blocks
+        _write_png_filtered(src, noise)
+        want = noise[..., ::-1]
+    dst = str(tmp_path / "out.png")
+    r = subprocess.run([rt, src, dst])
+    assert r.returncode == 0
+    assert np.array_equal(_read_png(dst), want)
+    assert subprocess.run([rt, str(tmp_path / "missing.png"), dst]).returncode == 2
 
 
 def test_cli_argument_contract():
@@ -55,12 +152,21 @@ def test_cli_batch_matches_oracle(tmp_path):
     outdir = tmp_path / "input_output"
     stamp = sorted(os.listdir(outdir))[0]
     files = sorted(os.listdir(outdir / stamp))
-    assert files == ["MEANSHIFT_METHOD_input_00001_meanshift_filtered.ppm", "MEANSHIFT_METHOD_input_00002_markers.pgm",
-                     "MEANSHIFT_METHOD_input_00003_merged_markers.pgm", "MEANSHIFT_METHOD_input_00004_result.ppm"]
+    # same naming scheme and file type as PictureService.saveResultsToFS (PictureService.java:209-216)
+    assert files == ["MEANSHIFT_METHOD_input_00001_meanshift_filtered.png", "MEANSHIFT_METHOD_input_00002_markers.png",
+                     "MEANSHIFT_METHOD_input_00003_merged_markers.png", "MEANSHIFT_METHOD_input_00004_result.png"]
     f = orc.meanshift_filter(im, 10, 10, 1)
-    assert np.array_equal(_read_pnm(str(outdir / stamp / files[0])), f)
+    assert np.array_equal(_read_png(str(outdir / stamp / files[0])), f)
     n0, l0 = orc.label_regions(f, 2)
     n1, l1 = orc.merge_regions(f, l0, 50, 10)
-    assert np.array_equal(_read_pnm(str(outdir / stamp / files[2])), np.clip(l1, 0, 255).astype(np.uint8))
-    assert np.array_equal(_read_pnm(str(outdir / stamp / files[3])), orc.render_labels(l1, n1))
+    assert np.array_equal(_read_png(str(outdir / stamp / files[2])), np.clip(l1, 0, 255).astype(np.uint8))
+    assert np.array_equal(_read_png(str(outdir / stamp / files[3])), orc.render_labels(l1, n1))
     assert "regions after merge: %d" % n1 in r.stdout
+    # PNG input + PNM output switch
+    _write_png_filtered(str(tmp_path / "second.png"), im[..., ::-1])
+    r = subprocess.run([CLI, str(tmp_path), "unused_out_root", "second.png"], capture_output=True, text=True,
+                       env=dict(os.environ, MSG_OUT_FORMAT="pnm"))
+    assert r.returncode == 0, r.stderr
+    outdir = tmp_path / "second_output"
+    stamp = sorted(os.listdir(outdir))[0]
+    assert np.array_equal(_read_pnm(str(outdir / stamp / "MEANSHIFT_METHOD_second_00001_meanshift_filtered.ppm")), f)
