@@ -121,6 +121,30 @@ MSG_API int msg_bgr2gray(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, 
 MSG_API int msg_median_blur(msg_ctx* ctx, const uint8_t* src_gray, size_t src_step, uint8_t* dst_gray, size_t dst_step, int width,
                     int height, int ksize);
 
+/* ---- shape-method marker generator (PictureService.java:404-442) ------------------------------ */
+/* Imgproc.Canny(image 8UC1, edges, threshold1, threshold2) (PictureService.java:416): aperture 3, L1 gradient; thresholds are
+ * swapped if threshold1 > threshold2 and floored, as cv::Canny does.  edges = 0 / 255. */
+MSG_API int msg_canny(msg_ctx* ctx, const uint8_t* src_gray, size_t src_step, uint8_t* dst_edges, size_t dst_step, int width,
+              int height, double threshold1, double threshold2);
+/* Imgproc.dilate(src 8UC1, dst, Mat.ones(kh, kw)) (PictureService.java:428-429): anchor at the centre, border pixels ignored. */
+MSG_API int msg_dilate(msg_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step, int width, int height,
+               int kw, int kh);
+/* Core.subtract(a, b, dst) on 8UC1 (PictureService.java:430): saturating. */
+MSG_API int msg_subtract(msg_ctx* ctx, const uint8_t* a, size_t a_step, const uint8_t* b, size_t b_step, uint8_t* dst,
+                 size_t dst_step, int width, int height);
+/* The whole generator, intermediates in HBM: cvtColor(BGR2GRAY) -> medianBlur(median_ksize) -> Canny(t1, t2) -> dilate 3x3 ->
+ * dilate 5x5 -> subtract -> medianBlur 3 -> connectedComponents(8, CV_32S).  markers: 0 background, 1..n-1 in raster order of
+ * first pixel; *n_labels counts the background like OpenCV.  stages (optional, NULL to skip): 4 planes of `height` rows of
+ * stage_step bytes each, back to back: blurred gray, Canny edges, dilate-dilate-subtract band, its 3x3 median -- the images
+ * the reference saves as "blured_by_KxK", "gray_borders", "dde_step", "dde_step_blurred_3x3". */
+MSG_API int msg_shape_seeds(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, int width, int height, int median_ksize,
+                    double threshold1, double threshold2, int32_t* markers, size_t markers_step, int32_t* n_labels,
+                    uint8_t* stages, size_t stage_step);
+/* Device-resident form: all pointers are device memory on ctx's device; d_stages (optional) = 4 dense width*height planes. */
+MSG_API int msg_shape_seeds_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int width, int height, int median_ksize,
+                        double threshold1, double threshold2, int32_t* d_markers, size_t markers_step, int32_t* d_n_labels,
+                        uint8_t* d_stages);
+
 /* ---- fused pipeline: filter -> label -> merge -> render, intermediates stay in HBM -------- */
 typedef struct msg_segment_params {
     double sp, sr;

@@ -50,6 +50,11 @@ SIGNATURES = {
     "msg_laplacian_sharpen": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _P, _I, _I]),
     "msg_bgr2gray": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I]),
     "msg_median_blur": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I]),
+    "msg_canny": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _D, _D]),
+    "msg_dilate": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I]),
+    "msg_subtract": (_I, [_P, _P, _SZ, _P, _SZ, _P, _SZ, _I, _I]),
+    "msg_shape_seeds": (_I, [_P, _P, _SZ, _I, _I, _I, _D, _D, _P, _SZ, _P, _P, _SZ]),
+    "msg_shape_seeds_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _D, _D, _P, _SZ, _P, _P]),
     "msg_segment_params_default": (None, [C.POINTER(SegmentParams)]),
     "msg_segment": (_I, [_P, _P, _SZ, _I, _I, C.POINTER(SegmentParams), _P, _SZ, _P, _SZ, _P, _SZ, C.POINTER(C.c_int32)]),
     "msg_submit_segment": (_I, [_P, _P, _SZ, _I, _I, C.POINTER(SegmentParams), _P, _SZ, _P, _SZ, _P, _SZ, C.POINTER(_I)]),

@@ -145,7 +145,7 @@ void msg_destroy(msg_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_out2); cudaFree(ctx->d_labels);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_ovf); cudaFree(ctx->d_scratch); cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_colors); cudaFree(ctx->d_work); cudaFree(ctx->d_cells);
+    cudaFree(ctx->d_colors); cudaFree(ctx->d_work); cudaFree(ctx->d_cells); cudaFree(ctx->d_aux);
     for (int l = 0; l < MSG_MAX_LEVELS; l++)
         for (int k = 0; k < 3; k++) cudaEventDestroy(ctx->prof_ev[l][k]);
     cudaFreeHost(ctx->h_counters);
@@ -959,6 +959,128 @@ int msg_median_blur(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst
     MSG_TRY(check_img(ctx, dst, dstep, w, h, 1, "medianBlur dst"));
     if (ksize < 1 || ksize > 127 || !(ksize & 1)) return msg_fail(ctx, MSG_EINVAL, "medianBlur: ksize must be odd and in [1,127] (got %d)", ksize);
     return filter_host(ctx, src, sstep, 1, dst, dstep, 1, w, h, 2, nullptr, 0, 0, ksize);
+}
+
+// ============================================================================ shape-method seeds (8(f3), row a7)
+
+static int canny_thresholds(msg_ctx* ctx, double low, double high, int* lo, int* hi)
+{
+    if (!(low == low) || !(high == high)) return msg_fail(ctx, MSG_EINVAL, "Canny: thresholds must be numbers");
+    if (low > high) { double t = low; low = high; high = t; }                 // cv::Canny swaps them
+    *lo = (int)floor(fmin(fmax(low, -1.0), 1e9));
+    *hi = (int)floor(fmin(fmax(high, -1.0), 1e9));
+    return MSG_OK;
+}
+
+// d_src: gray plane (step sstep); d_dst: edges 0/255.  Uses d_aux[0..2n) (classes, flags) and d_labels as scratch.
+static int canny_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, int lo, int hi,
+                     uint8_t* d_cls, uint8_t* d_flag)
+{
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+    MSG_TRY(k_canny_nms(ctx, d_src, sstep, d_cls, (size_t)w, w, h, lo, hi));
+    return k_hysteresis(ctx, d_cls, w, h, ctx->d_labels, d_flag, d_dst, dstep);
+}
+
+int msg_canny(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, double low, double high)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 1, "Canny src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 1, "Canny dst"));
+    int lo, hi;
+    MSG_TRY(canny_thresholds(ctx, low, high, &lo, &hi));
+    size_t n = (size_t)w * h;
+    MSG_TRY(copy_in(ctx, src, sstep, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, n));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_aux, &ctx->d_aux_cap, 2 * n));
+    MSG_TRY(canny_dev(ctx, ctx->d_in, (size_t)w, ctx->d_out, (size_t)w, w, h, lo, hi, ctx->d_aux, ctx->d_aux + n));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+int msg_dilate(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, int kw, int kh)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 1, "dilate src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 1, "dilate dst"));
+    if (kw < 1 || kh < 1 || kw > 63 || kh > 63) return msg_fail(ctx, MSG_EINVAL, "dilate: kernel must be 1..63 x 1..63 (got %dx%d)", kw, kh);
+    MSG_TRY(copy_in(ctx, src, sstep, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, (size_t)w * h));
+    MSG_TRY(k_dilate(ctx, ctx->d_in, (size_t)w, ctx->d_out, (size_t)w, w, h, kw, kh));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+int msg_subtract(msg_ctx* ctx, const uint8_t* a, size_t astep, const uint8_t* b, size_t bstep, uint8_t* dst, size_t dstep, int w,
+                 int h)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, a, astep, w, h, 1, "subtract src1"));
+    MSG_TRY(check_img(ctx, b, bstep, w, h, 1, "subtract src2"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 1, "subtract dst"));
+    size_t n = (size_t)w * h;
+    MSG_TRY(copy_in(ctx, a, astep, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_aux, &ctx->d_aux_cap, n));
+    MSG_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_aux, (size_t)w, b, bstep, (size_t)w, h, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.h2d_bytes += n;
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, n));
+    MSG_TRY(k_subtract(ctx, ctx->d_in, (size_t)w, ctx->d_aux, (size_t)w, ctx->d_out, (size_t)w, w, h));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+// d_stages (optional): 4 dense planes of w*h bytes: blurred gray, Canny edges, dilate-dilate-subtract band, its 3x3 median
+int msg_shape_seeds_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int w, int h, int median_ksize, double low, double high,
+                        int32_t* d_markers, size_t lstep, int32_t* d_n, uint8_t* d_stages)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_bgr, step, w, h, 3, "shape seeds src"));
+    MSG_TRY(check_img(ctx, d_markers, lstep, w, h, 4, "markers"));
+    if (median_ksize < 1 || median_ksize > 127 || !(median_ksize & 1))
+        return msg_fail(ctx, MSG_EINVAL, "shape seeds: median ksize must be odd and in [1,127] (got %d)", median_ksize);
+    if (!d_n) return msg_fail(ctx, MSG_EINVAL, "shape seeds: null count pointer");
+    int lo, hi;
+    MSG_TRY(canny_thresholds(ctx, low, high, &lo, &hi));
+    size_t n = (size_t)w * h;
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_aux, &ctx->d_aux_cap, 7 * n));
+    uint8_t* a = ctx->d_aux;                     // [cls][flag][gray / d3][blurred][edges][dde][dde3]
+    uint8_t *cls = a, *flag = a + n, *gray = a + 2 * n;
+    uint8_t* blurred = d_stages ? d_stages : a + 3 * n;
+    uint8_t* edges = d_stages ? d_stages + n : a + 4 * n;
+    uint8_t* dde = d_stages ? d_stages + 2 * n : a + 5 * n;
+    uint8_t* dde3 = d_stages ? d_stages + 3 * n : a + 6 * n;
+    MSG_TRY(k_gray(ctx, d_bgr, step, gray, (size_t)w, w, h));                                   // PictureService.java:405
+    MSG_TRY(k_median(ctx, gray, (size_t)w, blurred, (size_t)w, w, h, median_ksize));            // :408
+    MSG_TRY(canny_dev(ctx, blurred, (size_t)w, edges, (size_t)w, w, h, lo, hi, cls, flag));     // :416
+    uint8_t* d3 = gray;                                                                         // gray is dead from here on
+    MSG_TRY(k_dilate(ctx, edges, (size_t)w, d3, (size_t)w, w, h, 3, 3));                        // :428
+    MSG_TRY(k_dilate(ctx, d3, (size_t)w, cls, (size_t)w, w, h, 5, 5));                          // :429 (classes are dead)
+    MSG_TRY(k_subtract(ctx, cls, (size_t)w, d3, (size_t)w, dde, (size_t)w, w, h));              // :430
+    MSG_TRY(k_median(ctx, dde, (size_t)w, dde3, (size_t)w, w, h, 3));                           // :436
+    return msg_connected_components_dev(ctx, dde3, (size_t)w, d_markers, lstep, w, h, 8, d_n);  // :441-442
+}
+
+int msg_shape_seeds(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, int median_ksize, double low, double high,
+                    int32_t* markers, size_t lstep, int32_t* n_labels, uint8_t* stages, size_t stage_step)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "shape seeds src"));
+    MSG_TRY(check_img(ctx, markers, lstep, w, h, 4, "markers"));
+    if (stages) MSG_TRY(check_img(ctx, stages, stage_step, w, h, 1, "shape seeds stages"));
+    size_t n = (size_t)w * h;
+    MSG_TRY(copy_in(ctx, src, sstep, (size_t)w * 3, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, 4 * n));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out2, &ctx->d_out2_cap, 4 * n));
+    int32_t* d_mark = (int32_t*)ctx->d_out2;
+    MSG_TRY(msg_shape_seeds_dev(ctx, ctx->d_in, (size_t)w * 3, w, h, median_ksize, low, high, d_mark, (size_t)w * 4,
+                                ctx->d_counters + 16, ctx->d_out));
+    MSG_TRY(copy_out(ctx, markers, lstep, d_mark, (size_t)w * 4, h));
+    if (stages)
+        for (int k = 0; k < 4; k++)
+            MSG_TRY(copy_out(ctx, stages + (size_t)k * stage_step * h, stage_step, ctx->d_out + (size_t)k * n, (size_t)w, h));
+    return finish_count(ctx, n_labels);
 }
 
 }  // extern "C"

@@ -529,7 +529,43 @@ __global__ void __launch_bounds__(CCL_THREADS) strip_apply_dense_kernel(int32_t*
 
 inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
+// ---------------------------------------------------------------- Canny hysteresis on top of the binary union-find
+// cls: 0 none, 1 candidate, 2 strong candidate (k_seeds.cu).  L = union-find parents of the 8-connected candidate set.
+__global__ void __launch_bounds__(CCL_THREADS) hyst_mark_kernel(const uint8_t* __restrict__ cls, const int32_t* __restrict__ L,
+                                                                size_t n, uint8_t* __restrict__ flag)
+{
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i >= n || cls[i] != 2) return;
+    flag[uf_find(L, (int)i)] = 1;
+}
+
+__global__ void __launch_bounds__(CCL_THREADS) hyst_out_kernel(const uint8_t* __restrict__ cls, const int32_t* __restrict__ L,
+                                                               int w, const uint8_t* __restrict__ flag,
+                                                               uint8_t* __restrict__ dst, size_t dstep)
+{
+    int x = blockIdx.x * CCL_THREADS + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    size_t i = (size_t)y * w + x;
+    dst[(size_t)y * dstep + x] = (cls[i] && flag[uf_find(L, (int)i)]) ? 255 : 0;
+}
+
 }  // namespace
+
+// edges = candidates whose 8-connected component holds a strong candidate.  d_cls: w*h bytes (step w); d_labels: w*h int32
+// scratch; d_flag: w*h bytes scratch.
+int k_hysteresis(msg_ctx* ctx, const uint8_t* d_cls, int w, int h, int32_t* d_labels, uint8_t* d_flag, uint8_t* d_dst, size_t dstep)
+{
+    size_t n = (size_t)w * h;
+    MSG_TRY(k_ccl_binary(ctx, d_cls, (size_t)w, w, h, 8, d_labels));
+    MSG_CUDA(ctx, cudaMemsetAsync(d_flag, 0, n, ctx->stream));
+    hyst_mark_kernel<<<(unsigned)((n + CCL_THREADS - 1) / CCL_THREADS), CCL_THREADS, 0, ctx->stream>>>(d_cls, d_labels, n, d_flag);
+    MSG_LAUNCHED(ctx);
+    dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);
+    hyst_out_kernel<<<grid, CCL_THREADS, 0, ctx->stream>>>(d_cls, d_labels, w, d_flag, d_dst, dstep);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
 
 // scratch layout for relabel: [rank: n+1 ints][first: n+1 ints (MODE 1)][block_sums: nb ints]
 static int relabel_impl(msg_ctx* ctx, int32_t* d_labels, size_t n, int mode, int32_t* d_n_out, int add_to_total)

@@ -62,6 +62,7 @@ struct msg_ctx {
     int32_t* d_counters;                     // 64 int32 device counters
     int32_t* h_counters;                     // pinned mirror
     uint8_t* d_colors; size_t d_colors_cap;
+    uint8_t* d_aux;    size_t d_aux_cap;     // 8-bit planes of the seed generator (gray, blurred, classes, edges, ...)
     int32_t* d_cells;  size_t d_cells_cap;   // active pixels per 32x32 cell of the current level + tile order (K1 scheduling)
 
     // pinned host staging for pageable caller buffers
@@ -148,6 +149,13 @@ int k_sharpen(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, 
               int krows, int kcols);
 int k_gray(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h);
 int k_median(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, int k);
+
+// k_seeds.cu / k_ccl.cu: shape-method marker generator (8(f3))
+int k_canny_nms(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_cls, size_t cstep, int w, int h, int low, int high);
+int k_hysteresis(msg_ctx* ctx, const uint8_t* d_cls, int w, int h, int32_t* d_labels, uint8_t* d_flag, uint8_t* d_dst, size_t dstep);
+int k_dilate(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, int kw, int kh);
+int k_subtract(msg_ctx* ctx, const uint8_t* d_a, size_t astep, const uint8_t* d_b, size_t bstep, uint8_t* d_dst, size_t dstep,
+               int w, int h);
 
 #define MSG_LAUNCHED(ctx) ((ctx)->st.kernel_launches++)
 #define MSG_CHECK_LAUNCH(ctx) MSG_CUDA(ctx, cudaGetLastError())

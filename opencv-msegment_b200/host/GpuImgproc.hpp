@@ -137,6 +137,55 @@ public:
         dst = out;
     }
 
+    // ---- shape-method marker generator (PictureService.java:404-442)
+    static void Canny(const Mat& image, Mat& edges, double threshold1, double threshold2)
+    {
+        require(image.type == CV_8UC1, "image must be CV_8UC1");
+        Mat out(image.rows, image.cols, CV_8UC1);
+        check(msg_canny(ctx(), image.data(), image.step(), out.data(), out.step(), image.cols, image.rows, threshold1, threshold2));
+        edges = out;
+    }
+
+    // Imgproc.dilate(src, dst, Mat.ones(krows, kcols, type))
+    static void dilate(const Mat& src, Mat& dst, int krows, int kcols)
+    {
+        require(src.type == CV_8UC1, "src must be CV_8UC1");
+        Mat out(src.rows, src.cols, CV_8UC1);
+        check(msg_dilate(ctx(), src.data(), src.step(), out.data(), out.step(), src.cols, src.rows, kcols, krows));
+        dst = out;
+    }
+
+    // Core.subtract(src1, src2, dst)
+    static void subtract(const Mat& a, const Mat& b, Mat& dst)
+    {
+        require(a.type == CV_8UC1 && b.type == CV_8UC1 && a.rows == b.rows && a.cols == b.cols, "subtract: CV_8UC1 of equal size");
+        Mat out(a.rows, a.cols, CV_8UC1);
+        check(msg_subtract(ctx(), a.data(), a.step(), b.data(), b.step(), out.data(), out.step(), a.cols, a.rows));
+        dst = out;
+    }
+
+    // PictureService.calculateSizeOfSquareBlurMask (PictureService.java:877-899)
+    static int calculateSizeOfSquareBlurMask(int cols, int rows)
+    {
+        int m = cols <= rows ? cols : rows;
+        if (m < 3) return 1;
+        if (m <= 100) return 5;
+        double scale = m <= 360 ? 0.025 : m <= 480 ? 0.02 : m <= 720 ? 0.015 : m <= 1080 ? 0.01 : 0.005;
+        int r = (int)(m * scale);
+        return r % 2 == 0 ? r + 1 : r;
+    }
+
+    // marker half of shapeAutoMarkerWatershed (:404-442); returns the label count (background included)
+    static int shapeSeeds(const Mat& src, Mat& markers, double lowThreshold = 5, double ratio = 10)
+    {
+        require(src.type == CV_8UC3, "src must be CV_8UC3");
+        markers.create(src.rows, src.cols, CV_32SC1);
+        int32_t n = 0;
+        check(msg_shape_seeds(ctx(), src.data(), src.step(), src.cols, src.rows, calculateSizeOfSquareBlurMask(src.cols, src.rows),
+                              lowThreshold, lowThreshold * ratio, (int32_t*)markers.data(), markers.step(), &n, nullptr, 0));
+        return n;
+    }
+
 private:
     static void require(bool ok, const char* msg) { if (!ok) throw CvException(MSG_EINVAL, msg); }
     static void check(int rc) { if (rc != MSG_OK) throw CvException(rc, msg_last_error(ctx())); }

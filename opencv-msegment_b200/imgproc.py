@@ -227,6 +227,70 @@ class GpuImgproc:
                                                  w, h, int(ksize)))
         return dst
 
+    # ---- shape-method marker generator (PictureService.java:404-442)
+    def _gray(self, a, what):
+        a = np.asarray(a)
+        if a.dtype != np.uint8 or a.ndim != 2:
+            raise CvException(L.MSG_EINVAL, "%s: CV_8UC1 only" % what)
+        return a if a.strides[1] == 1 else np.ascontiguousarray(a)
+
+    # Imgproc.Canny(image, edges, threshold1, threshold2)
+    def Canny(self, image, threshold1, threshold2):
+        image = self._gray(image, "Canny")
+        h, w = image.shape
+        dst = np.empty((h, w), np.uint8)
+        self.ctx.check(self._lib.msg_canny(self.ctx._h, image.ctypes.data, image.strides[0], dst.ctypes.data, dst.strides[0], w, h,
+                                           float(threshold1), float(threshold2)))
+        return dst
+
+    # Imgproc.dilate(src, dst, Mat.ones(kh, kw, CV_8U))
+    def dilate(self, src, kernel_shape):
+        src = self._gray(src, "dilate")
+        kh, kw = kernel_shape
+        h, w = src.shape
+        dst = np.empty((h, w), np.uint8)
+        self.ctx.check(self._lib.msg_dilate(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h,
+                                            int(kw), int(kh)))
+        return dst
+
+    # Core.subtract(src1, src2, dst)
+    def subtract(self, src1, src2):
+        a, b = self._gray(src1, "subtract"), self._gray(src2, "subtract")
+        if a.shape != b.shape:
+            raise CvException(L.MSG_EINVAL, "subtract: sizes differ")
+        h, w = a.shape
+        dst = np.empty((h, w), np.uint8)
+        self.ctx.check(self._lib.msg_subtract(self.ctx._h, a.ctypes.data, a.strides[0], b.ctypes.data, b.strides[0],
+                                              dst.ctypes.data, dst.strides[0], w, h))
+        return dst
+
+    @staticmethod
+    def calculateSizeOfSquareBlurMask(cols, rows):
+        """PictureService.calculateSizeOfSquareBlurMask (PictureService.java:877-899)."""
+        m = min(cols, rows)
+        if m < 3:
+            return 1
+        if m <= 100:
+            return 5
+        scale = 0.025 if m <= 360 else 0.02 if m <= 480 else 0.015 if m <= 720 else 0.01 if m <= 1080 else 0.005
+        r = int(m * scale)
+        return r + 1 if r % 2 == 0 else r
+
+    # the marker half of PictureService.shapeAutoMarkerWatershed (:404-442) as one call, intermediates on the device
+    def shapeSeeds(self, src, lowThreshold=5, ratio=10, medianKsize=None, stages=False):
+        src = _mat8uc3(src, "src")
+        h, w = src.shape[:2]
+        k = self.calculateSizeOfSquareBlurMask(w, h) if medianKsize is None else int(medianKsize)
+        markers = np.empty((h, w), np.int32)
+        st = np.empty((4, h, w), np.uint8) if stages else None
+        n = C.c_int32(0)
+        self.ctx.check(self._lib.msg_shape_seeds(self.ctx._h, src.ctypes.data, src.strides[0], w, h, k, float(lowThreshold),
+                                                 float(lowThreshold * ratio), markers.ctypes.data, markers.strides[0],
+                                                 C.byref(n), st.ctypes.data if stages else None, w))
+        if stages:
+            return n.value, markers, {"blurred": st[0], "edges": st[1], "dde": st[2], "dde3": st[3], "k": k}
+        return n.value, markers
+
     # fused pipeline
     def segment(self, src, sp=10.0, sr=10.0, maxLevel=1, termcrit=DEFAULT_TERMCRIT, loDiff=2, minSize=0, colorDist=0,
                 renderDepth=0, want=("filtered", "labels", "rendered"), connectivity=4):

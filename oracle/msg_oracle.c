@@ -623,3 +623,96 @@ void orc_bgr2gray(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, 
             dst[(size_t)y * dstep + x] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15);
         }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Shape-method seeds (PictureService.java:416-442): Canny, dilate, subtract.  Restated from the published OpenCV
+ * algorithm (imgproc canny.cpp / morph.cpp semantics), pinned on cv2 4.13.0 by tests/golden/seeds.npz.
+ * ------------------------------------------------------------------------------------------------------------------ */
+static int clampi_(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+void orc_canny(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, double low_d, double high_d)
+{
+    if (low_d > high_d) { double t = low_d; low_d = high_d; high_d = t; }
+    const int low = (int)floor(low_d), high = (int)floor(high_d);
+    const size_t n = (size_t)w * h;
+    short* dx = (short*)malloc(n * sizeof(short));
+    short* dy = (short*)malloc(n * sizeof(short));
+    int* mag = (int*)calloc((size_t)(w + 2) * (h + 2), sizeof(int));       /* zero frame: magnitude outside the image */
+    uint8_t* cls = (uint8_t*)calloc(n, 1);                                  /* 0 none, 1 candidate, 2 strong candidate */
+    const size_t mp = (size_t)w + 2;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* r0 = src + (size_t)clampi_(y - 1, 0, h - 1) * sstep;
+            const uint8_t* r1 = src + (size_t)y * sstep;
+            const uint8_t* r2 = src + (size_t)clampi_(y + 1, 0, h - 1) * sstep;
+            int xl = clampi_(x - 1, 0, w - 1), xr = clampi_(x + 1, 0, w - 1);
+            int gx = (r0[xr] + 2 * r1[xr] + r2[xr]) - (r0[xl] + 2 * r1[xl] + r2[xl]);
+            int gy = (r2[xl] + 2 * r2[x] + r2[xr]) - (r0[xl] + 2 * r0[x] + r0[xr]);
+            dx[(size_t)y * w + x] = (short)gx;
+            dy[(size_t)y * w + x] = (short)gy;
+            mag[(size_t)(y + 1) * mp + x + 1] = abs(gx) + abs(gy);
+        }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const int* m = mag + (size_t)(y + 1) * mp + x + 1;
+            int v = m[0];
+            if (v <= low) continue;
+            int xs = dx[(size_t)y * w + x], ys = dy[(size_t)y * w + x];
+            int ax = abs(xs), ay = abs(ys) << 15;
+            int tg22 = ax * 13573;
+            int keep;
+            if (ay < tg22) keep = v > m[-1] && v >= m[1];
+            else {
+                int tg67 = tg22 + (ax << 16);
+                if (ay > tg67) keep = v > m[-(long)mp] && v >= m[mp];
+                else {
+                    int s = (xs ^ ys) < 0 ? -1 : 1;
+                    keep = v > m[-(long)mp - s] && v > m[(long)mp + s];
+                }
+            }
+            if (keep) cls[(size_t)y * w + x] = v > high ? 2 : 1;
+        }
+    /* hysteresis: flood from strong candidates over 8-connected candidates (order-independent result) */
+    int* stack = (int*)malloc((n ? n : 1) * sizeof(int));
+    size_t top = 0;
+    for (int y = 0; y < h; y++) memset(dst + (size_t)y * dstep, 0, (size_t)w);
+    for (size_t i = 0; i < n; i++)
+        if (cls[i] == 2) { stack[top++] = (int)i; dst[(i / w) * dstep + i % w] = 255; }
+    while (top) {
+        int i = stack[--top], y = i / w, x = i % w;
+        for (int yy = y - 1; yy <= y + 1; yy++)
+            for (int xx = x - 1; xx <= x + 1; xx++) {
+                if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+                if (cls[(size_t)yy * w + xx] && !dst[(size_t)yy * dstep + xx]) {
+                    dst[(size_t)yy * dstep + xx] = 255;
+                    stack[top++] = yy * w + xx;
+                }
+            }
+    }
+    free(stack); free(cls); free(mag); free(dx); free(dy);
+}
+
+void orc_dilate_rect(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, int kw, int kh)
+{
+    const int ax = kw / 2, ay = kh / 2;
+    uint8_t* out = (uint8_t*)malloc((size_t)w * h);                         /* src and dst may alias */
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int best = 0;
+            for (int yy = y - ay; yy < y - ay + kh; yy++)
+                for (int xx = x - ax; xx < x - ax + kw; xx++)
+                    if (yy >= 0 && yy < h && xx >= 0 && xx < w && src[(size_t)yy * sstep + xx] > best) best = src[(size_t)yy * sstep + xx];
+            out[(size_t)y * w + x] = (uint8_t)best;
+        }
+    for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * dstep, out + (size_t)y * w, (size_t)w);
+    free(out);
+}
+
+void orc_subtract_u8(const uint8_t* a, size_t astep, const uint8_t* b, size_t bstep, uint8_t* dst, size_t dstep, int w, int h)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int v = (int)a[(size_t)y * astep + x] - (int)b[(size_t)y * bstep + x];
+            dst[(size_t)y * dstep + x] = (uint8_t)(v < 0 ? 0 : v);
+        }
+}

@@ -60,6 +60,9 @@ def lib():
         L.orc_laplacian_sharpen.argtypes = [u8p, sz, u8p, sz, i, i, C.c_void_p, i, i]
         L.orc_median_blur_8uc1.argtypes = [u8p, sz, u8p, sz, i, i, i]
         L.orc_bgr2gray.argtypes = [u8p, sz, u8p, sz, i, i]
+        L.orc_canny.argtypes = [u8p, sz, u8p, sz, i, i, d, d]
+        L.orc_dilate_rect.argtypes = [u8p, sz, u8p, sz, i, i, i, i]
+        L.orc_subtract_u8.argtypes = [u8p, sz, u8p, sz, u8p, sz, i, i]
         _lib = L
     return _lib
 
@@ -200,3 +203,54 @@ def bgr2gray(src):
     dst = np.empty((h, w), np.uint8)
     lib().orc_bgr2gray(src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h)
     return dst
+
+
+def canny(gray, low, high):
+    gray = np.ascontiguousarray(gray, dtype=np.uint8)
+    h, w = gray.shape
+    dst = np.empty_like(gray)
+    lib().orc_canny(gray.ctypes.data, gray.strides[0], dst.ctypes.data, dst.strides[0], w, h, float(low), float(high))
+    return dst
+
+
+def dilate_rect(img, kw, kh):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    dst = np.empty_like(img)
+    lib().orc_dilate_rect(img.ctypes.data, img.strides[0], dst.ctypes.data, dst.strides[0], w, h, int(kw), int(kh))
+    return dst
+
+
+def subtract_u8(a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    h, w = a.shape
+    dst = np.empty_like(a)
+    lib().orc_subtract_u8(a.ctypes.data, a.strides[0], b.ctypes.data, b.strides[0], dst.ctypes.data, dst.strides[0], w, h)
+    return dst
+
+
+def blur_mask_size(w, h):
+    """PictureService.calculateSizeOfSquareBlurMask (PictureService.java:877-899)."""
+    m = min(w, h)
+    if m < 3:
+        return 1
+    if m <= 100:
+        return 5
+    scale = 0.025 if m <= 360 else 0.02 if m <= 480 else 0.015 if m <= 720 else 0.01 if m <= 1080 else 0.005
+    r = int(m * scale)
+    return r + 1 if r % 2 == 0 else r
+
+
+def shape_seeds(bgr, low=5, high=50):
+    """Shape-method marker generator (PictureService.java:404-442): returns (n_labels, markers int32, stages dict)."""
+    g = bgr2gray(bgr)
+    k = blur_mask_size(g.shape[1], g.shape[0])
+    blurred = median_blur(g, k)
+    edges = canny(blurred, low, high)
+    d3 = dilate_rect(edges, 3, 3)
+    d5 = dilate_rect(d3, 5, 5)
+    dde = subtract_u8(d5, d3)
+    dde3 = median_blur(dde, 3)
+    n, markers = connected_components(dde3, 8)
+    return n, markers, {"gray": g, "blurred": blurred, "edges": edges, "dde": dde, "dde3": dde3, "k": k}

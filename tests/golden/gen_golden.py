@@ -159,6 +159,35 @@ def main():
         for k in (3, 5, 7, 11):
             fl["median%d/%s" % (k, name)] = cv2.medianBlur(gray, k)
     np.savez_compressed(os.path.join(HERE, "filters.npz"), **fl)
+    # f3 shape-method seed generator (PictureService.java:404-442): Canny, dilate, subtract and the whole chain
+    sd = {}
+    for name in ("synth96x80", "noise41x47", "smooth131x97", "hkp_crop96", "guide_crop90x75", "row50", "col50", "flat20x33"):
+        if name not in ins:
+            continue
+        im = ins[name]
+        gray = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)
+        sd["in/" + name] = im
+        for k, (lo, hi) in enumerate([(5, 50), (100, 200), (0, 0), (20.7, 60.2)]):
+            sd["canny%d/%s" % (k, name)] = cv2.Canny(gray, lo, hi)
+        for kw, kh in ((3, 3), (5, 5), (7, 2)):
+            sd["dilate%dx%d/%s" % (kw, kh, name)] = cv2.dilate(gray, np.ones((kh, kw), np.uint8))
+        h, w = gray.shape
+        m = min(w, h)                                    # calculateSizeOfSquareBlurMask (PictureService.java:877-899)
+        ksz = 1 if m < 3 else 5                          # all golden inputs are <= 100 px on the short side
+        blurred = cv2.medianBlur(gray, ksz)
+        edges = cv2.Canny(blurred, 5, 50)                # :416
+        d3 = cv2.dilate(edges, np.ones((3, 3), np.uint8))   # :428
+        d5 = cv2.dilate(d3, np.ones((5, 5), np.uint8))      # :429
+        dde = cv2.subtract(d5, d3)                          # :430
+        dde3 = cv2.medianBlur(dde, 3)                       # :436
+        n, l = cv2.connectedComponents(dde3, connectivity=8, ltype=cv2.CV_32S)   # :441-442
+        sd["chain_edges/" + name] = edges
+        sd["chain_dde/" + name] = dde
+        sd["chain_dde3/" + name] = dde3
+        sd["chain_markers/" + name] = canonical(l)
+        sd["chain_n/" + name] = np.int32(n)
+    sd["canny_params"] = np.array([(5, 50), (100, 200), (0, 0), (20.7, 60.2)], np.float64)
+    np.savez_compressed(os.path.join(HERE, "seeds.npz"), **sd)
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         f.write("generated by tests/golden/gen_golden.py with cv2 %s, numpy %s\n" % (cv2.__version__, np.__version__))
     for fn in sorted(os.listdir(HERE)):
