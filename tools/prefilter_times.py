@@ -40,7 +40,9 @@ def main():
                          "sharpen_3x3": round(best(lambda: gi.sharpenLaplacian(im, taps.reshape(3, 3))), 3),
                          "bgr2gray": round(best(lambda: gi.cvtColorBGR2GRAY(im)), 3),
                          "median_3": round(best(lambda: gi.medianBlur(gray, 3)), 3),
-                         "median_11": round(best(lambda: gi.medianBlur(gray, 11)), 3)}
+                         "median_11": round(best(lambda: gi.medianBlur(gray, 11)), 3),
+                         "canny_5_50": round(best(lambda: gi.Canny(gray, 5, 50)), 3),
+                         "shape_seeds_chain": round(best(lambda: gi.shapeSeeds(im)), 3)}
     if cv2 is not None:
         k91 = taps.reshape(9, 1).astype(np.float32)
 
@@ -50,7 +52,17 @@ def main():
         out["cv2_ms"] = {"sharpen_9x1": round(best(sharp, 3), 3),
                          "bgr2gray": round(best(lambda: cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)), 3),
                          "median_3": round(best(lambda: cv2.medianBlur(gray, 3)), 3),
-                         "median_11": round(best(lambda: cv2.medianBlur(gray, 11)), 3)}
+                         "median_11": round(best(lambda: cv2.medianBlur(gray, 11)), 3),
+                         "canny_5_50": round(best(lambda: cv2.Canny(gray, 5, 50)), 3)}
+
+        def chain():
+            g = cv2.medianBlur(cv2.cvtColor(im, cv2.COLOR_BGR2GRAY), 11)
+            e = cv2.Canny(g, 5, 50)
+            d3 = cv2.dilate(e, np.ones((3, 3), np.uint8))
+            d5 = cv2.dilate(d3, np.ones((5, 5), np.uint8))
+            m = cv2.medianBlur(cv2.subtract(d5, d3), 3)
+            return cv2.connectedComponents(m, connectivity=8, ltype=cv2.CV_32S)
+        out["cv2_ms"]["shape_seeds_chain"] = round(best(chain, 3), 3)
     print(json.dumps(out))
 
 
