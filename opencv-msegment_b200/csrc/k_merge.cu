@@ -6,6 +6,8 @@
 // simultaneously (union by smallest label); phase A = colour fuse, phase B = min-size prune.
 // K2c = PictureService.colorByIndexes (PictureService.java:913-936).
 #include <cooperative_groups.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "msg_internal.h"
 
@@ -59,7 +61,17 @@ struct merge_persist_args {
     int32_t* npairs;          // device counter
     long long pair_cap;
     int min_size, color_dist;
+    int vec;                     // 1: w % 4 == 0 and labels 16-byte aligned -> 16-byte loads in the pixel passes
+    unsigned long long* trace;   // [32] globaltimer at phase boundaries, or NULL (MSG_MERGE_TRACE=1 diagnostics)
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MERGE_TRACE(slot) do { if (A.trace && gtid == 0 && (slot) < 32) A.trace[(slot)] = global_ns(); } while (0)
 
 __device__ __forceinline__ void persist_union(int32_t* par, int a, int b)
 {
@@ -71,6 +83,119 @@ __device__ __forceinline__ void persist_union(int32_t* par, int a, int b)
         int old = atomicMin(par + a, b);
         if (old == a) return;
         a = old;
+    }
+}
+
+
+// add one run (label, pixel count, colour sums) to the tables
+__device__ __forceinline__ void stats_flush(const merge_tables& t, int lab, unsigned cnt, unsigned b, unsigned g, unsigned r)
+{
+    atomicAdd(t.area + lab, cnt);
+    atomicAdd(t.sum + 3 * (size_t)lab, (unsigned long long)b);
+    atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
+    atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
+}
+
+// Statistics + adjacency pass, 16-byte loads (requires w % 4 == 0 and 16-byte aligned label rows): a warp walks the image
+// as a flat array in chunks of 128 pixels, 4 consecutive pixels per lane.  Runs of equal labels are summed inside the
+// lane, then across lanes (segmented shuffle reduction of every lane's last run), so a region costs a few atomics per
+// chunk.  Adjacent-pair list: a right pair is skipped when the row above holds the same pair, a down pair when the pixel
+// to the left holds the same pair (the first occurrence is always emitted), which keeps roughly one entry per boundary
+// corner instead of one per boundary pixel.
+__device__ __forceinline__ void stats_pass_vec4(const merge_persist_args& A, const merge_tables& t, int nin, int lane,
+                                                long long gwarp, long long nwarps)
+{
+    const int w = A.w, h = A.h;
+    const long long n = (long long)w * h;
+    const long long nchunks = (n + 127) / 128;
+    const unsigned FULL = 0xffffffffu;
+    for (long long c = gwarp; c < nchunks; c += nwarps) {
+        const long long p = c * 128 + lane * 4;
+        const bool in = p < n;
+        int y = 0, x = 0;
+        int4 L4 = make_int4(0, 0, 0, 0), D4 = L4, U4 = L4;
+        uint4 C4 = make_uint4(0, 0, 0, 0);
+        if (in) {
+            y = (int)(p / w); x = (int)(p - (long long)y * w);
+            L4 = *reinterpret_cast<const int4*>(A.labels + p);
+            C4 = __ldg(reinterpret_cast<const uint4*>(A.plane + (size_t)y * A.pitch + x));
+            if (y + 1 < h) D4 = *reinterpret_cast<const int4*>(A.labels + p + w);
+            if (y > 0) U4 = *reinterpret_cast<const int4*>(A.labels + p - w);
+        }
+        int lab[4] = {L4.x, L4.y, L4.z, L4.w}, dn[4] = {D4.x, D4.y, D4.z, D4.w}, up[5] = {U4.x, U4.y, U4.z, U4.w, 0};
+        const uint32_t col[4] = {C4.x, C4.y, C4.z, C4.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (lab[k] > nin || lab[k] < 0) lab[k] = 0;
+            if (dn[k] > nin || dn[k] < 0) dn[k] = 0;
+        }
+        // label right of my 4th pixel (and of the pixel above it): the next lane's first pixel, or one scalar load
+        int nx = __shfl_down_sync(FULL, lab[0], 1), nu = __shfl_down_sync(FULL, up[0], 1);
+        const bool has_right = in && x + 4 < w;
+        if (lane == 31 && has_right) {
+            nx = A.labels[p + 4];
+            if (nx > nin || nx < 0) nx = 0;
+            nu = y > 0 ? A.labels[p + 4 - w] : 0;
+        }
+        if (!has_right) nx = 0;
+        up[4] = nu;
+        // ---- sums: runs inside the lane, the last run continues into the next lanes
+        int cur = lab[0];
+        unsigned cnt = cur > 0, b = 0, g = 0, r = 0;
+        if (cur > 0) { b = col[0] & 0xFF; g = (col[0] >> 8) & 0xFF; r = (col[0] >> 16) & 0xFF; }
+        bool uniform = true;
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+            if (lab[k] != cur) {
+                if (cur > 0) stats_flush(t, cur, cnt, b, g, r);
+                cur = lab[k]; cnt = 0; b = g = r = 0; uniform = false;
+            }
+            if (cur > 0) { cnt++; b += col[k] & 0xFF; g += (col[k] >> 8) & 0xFF; r += (col[k] >> 16) & 0xFF; }
+        }
+        int prev = __shfl_up_sync(FULL, cur, 1);
+        bool head = lane == 0 || !uniform || prev != cur;
+        unsigned heads = __ballot_sync(FULL, head);
+        unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+        int seg_end = above ? lane + __ffs(above) - 1 : 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned c2 = __shfl_down_sync(FULL, cnt, o);
+            unsigned b2 = __shfl_down_sync(FULL, b, o);
+            unsigned g2 = __shfl_down_sync(FULL, g, o);
+            unsigned r2 = __shfl_down_sync(FULL, r, o);
+            if (lane + o <= seg_end) { cnt += c2; b += b2; g += g2; r += r2; }
+        }
+        if (head && cur > 0) stats_flush(t, cur, cnt, b, g, r);
+        // ---- adjacency pairs
+        int pl = __shfl_up_sync(FULL, lab[3], 1), pd = __shfl_up_sync(FULL, dn[3], 1);   // pixel left of my first one
+        if (lane == 0) { pl = 0; pd = 0; }
+        int rn[4] = {lab[1], lab[2], lab[3], nx};
+        bool er[4], ed[4];
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            er[k] = lab[k] > 0 && rn[k] > 0 && rn[k] != lab[k] && !(up[k] == lab[k] && up[k + 1] == rn[k]);
+            int ll = k ? lab[k - 1] : pl, ld = k ? dn[k - 1] : pd;
+            ed[k] = lab[k] > 0 && dn[k] > 0 && dn[k] != lab[k] && !(ll == lab[k] && ld == dn[k]);
+            mine += (int)er[k] + (int)ed[k];
+        }
+        if (__any_sync(FULL, mine)) {
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int tot = __shfl_sync(FULL, incl, 31);
+            long long pos = 0;
+            if (lane == 0) pos = (long long)atomicAdd(A.npairs, tot);
+            pos = __shfl_sync(FULL, pos, 0) + incl - mine;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (er[k]) { if (pos < A.pair_cap) A.pairs[pos] = make_int2(lab[k], rn[k]); pos++; }
+                if (ed[k]) { if (pos < A.pair_cap) A.pairs[pos] = make_int2(lab[k], dn[k]); pos++; }
+            }
+        }
     }
 }
 
@@ -88,6 +213,7 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
     const int cpr = (w + 31) / 32;                      // 32-pixel chunks per row
     const long long nchunks = (long long)cpr * h;
     merge_tables t = A.t;
+    MERGE_TRACE(0);
 
     // ---- init tables
     for (long long i = gtid; i < nl; i += nthreads) {
@@ -99,56 +225,60 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
     grid.sync();
 
     // ---- statistics from pixels, once (warp-level run aggregation)
-    for (long long c = gwarp; c < nchunks; c += nwarps) {
-        int y = (int)(c / cpr), x = (int)(c % cpr) * 32 + lane;
-        int lab = 0;
-        unsigned cnt = 0, b = 0, g = 0, r = 0;
-        if (x < w) {
-            lab = A.labels[(size_t)y * w + x];
-            if (lab > nin) lab = 0;
-            if (lab > 0) {
-                uint32_t col = __ldg(A.plane + (size_t)y * A.pitch + x);
-                cnt = 1; b = col & 0xFF; g = (col >> 8) & 0xFF; r = (col >> 16) & 0xFF;
+    if (A.vec) stats_pass_vec4(A, t, nin, lane, gwarp, nwarps);
+    else {
+        for (long long c = gwarp; c < nchunks; c += nwarps) {
+            int y = (int)(c / cpr), x = (int)(c % cpr) * 32 + lane;
+            int lab = 0;
+            unsigned cnt = 0, b = 0, g = 0, r = 0;
+            if (x < w) {
+                lab = A.labels[(size_t)y * w + x];
+                if (lab > nin) lab = 0;
+                if (lab > 0) {
+                    uint32_t col = __ldg(A.plane + (size_t)y * A.pitch + x);
+                    cnt = 1; b = col & 0xFF; g = (col >> 8) & 0xFF; r = (col >> 16) & 0xFF;
+                }
             }
-        }
-        int prev = __shfl_up_sync(0xffffffffu, lab, 1);
-        bool head = lane == 0 || prev != lab;
-        unsigned heads = __ballot_sync(0xffffffffu, head);
-        unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
-        int seg_end = above ? lane + __ffs(above) - 1 : 31;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned c2 = __shfl_down_sync(0xffffffffu, cnt, o);
-            unsigned b2 = __shfl_down_sync(0xffffffffu, b, o);
-            unsigned g2 = __shfl_down_sync(0xffffffffu, g, o);
-            unsigned r2 = __shfl_down_sync(0xffffffffu, r, o);
-            if (lane + o <= seg_end) { cnt += c2; b += b2; g += g2; r += r2; }
-        }
-        if (head && lab > 0) {
-            atomicAdd(t.area + lab, cnt);
-            atomicAdd(t.sum + 3 * (size_t)lab, (unsigned long long)b);
-            atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
-            atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
-        }
-        // region adjacency list: every 4-adjacent pixel pair with two different positive labels, found once here; the
-        // rounds then iterate over this list (a few % of the pixels) instead of over the image
-        int lr = 0, ld = 0;
-        if (lab > 0) {
-            if (x + 1 < w) { lr = A.labels[(size_t)y * w + x + 1]; if (lr > nin || lr == lab) lr = 0; }
-            if (y + 1 < h) { ld = A.labels[(size_t)(y + 1) * w + x]; if (ld > nin || ld == lab) ld = 0; }
-        }
-        unsigned mr = __ballot_sync(0xffffffffu, lr > 0), md = __ballot_sync(0xffffffffu, ld > 0);
-        int tot = __popc(mr) + __popc(md);
-        if (tot) {
-            long long pos = 0;
-            if (lane == 0) pos = (long long)atomicAdd(A.npairs, tot);
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            unsigned lt = (1u << lane) - 1;
-            if (lr > 0) { long long k = pos + __popc(mr & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, lr); }
-            if (ld > 0) { long long k = pos + __popc(mr) + __popc(md & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, ld); }
+            int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+            bool head = lane == 0 || prev != lab;
+            unsigned heads = __ballot_sync(0xffffffffu, head);
+            unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+            int seg_end = above ? lane + __ffs(above) - 1 : 31;
+    #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned c2 = __shfl_down_sync(0xffffffffu, cnt, o);
+                unsigned b2 = __shfl_down_sync(0xffffffffu, b, o);
+                unsigned g2 = __shfl_down_sync(0xffffffffu, g, o);
+                unsigned r2 = __shfl_down_sync(0xffffffffu, r, o);
+                if (lane + o <= seg_end) { cnt += c2; b += b2; g += g2; r += r2; }
+            }
+            if (head && lab > 0) {
+                atomicAdd(t.area + lab, cnt);
+                atomicAdd(t.sum + 3 * (size_t)lab, (unsigned long long)b);
+                atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
+                atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
+            }
+            // region adjacency list: every 4-adjacent pixel pair with two different positive labels, found once here; the
+            // rounds then iterate over this list (a few % of the pixels) instead of over the image
+            int lr = 0, ld = 0;
+            if (lab > 0) {
+                if (x + 1 < w) { lr = A.labels[(size_t)y * w + x + 1]; if (lr > nin || lr == lab) lr = 0; }
+                if (y + 1 < h) { ld = A.labels[(size_t)(y + 1) * w + x]; if (ld > nin || ld == lab) ld = 0; }
+            }
+            unsigned mr = __ballot_sync(0xffffffffu, lr > 0), md = __ballot_sync(0xffffffffu, ld > 0);
+            int tot = __popc(mr) + __popc(md);
+            if (tot) {
+                long long pos = 0;
+                if (lane == 0) pos = (long long)atomicAdd(A.npairs, tot);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                unsigned lt = (1u << lane) - 1;
+                if (lr > 0) { long long k = pos + __popc(mr & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, lr); }
+                if (ld > 0) { long long k = pos + __popc(mr) + __popc(md & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, ld); }
+            }
         }
     }
     grid.sync();
+    MERGE_TRACE(1);
     long long npairs = *((volatile int32_t*)A.npairs);
     if (npairs > A.pair_cap) npairs = A.pair_cap;
 
@@ -217,6 +347,7 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
         }
     }
 
+    MERGE_TRACE(2);
     // ---- dense renumbering of the surviving roots (ascending label == ascending first pixel)
     const int per = (nl + gridDim.x - 1) / gridDim.x;          // labels per block
     {
@@ -261,13 +392,43 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
         *A.rounds_out = rounds;
     }
     grid.sync();
-    // ---- rewrite the pixels
-    for (long long p = gtid; p < (long long)w * h; p += nthreads) {
+    MERGE_TRACE(3);
+    // ---- final id of every input label (one gather per pixel below instead of three); t.mean is free by now
+    int32_t* fin = reinterpret_cast<int32_t*>(t.mean);
+    for (long long i = gtid; i < nl; i += nthreads) {
+        int r = __ldcg(t.par + i);
+        fin[i] = i > 0 ? A.newid[r] + A.bsum[r / per] + 1 : 0;
+    }
+    grid.sync();
+    // ---- rewrite the pixels (labels outside 1..nin are left as they are)
+    const long long n = (long long)w * h;
+    long long done = 0;
+    if ((reinterpret_cast<uintptr_t>(A.labels) & 15) == 0) {
+        int4* L4 = reinterpret_cast<int4*>(A.labels);
+        const long long n4 = n >> 2;
+        auto map4 = [&](int4 v) {
+            int4 o = v;
+            if (v.x > 0 && v.x <= nin) o.x = __ldg(fin + v.x);
+            if (v.y > 0 && v.y <= nin) o.y = v.y == v.x ? o.x : __ldg(fin + v.y);
+            if (v.z > 0 && v.z <= nin) o.z = v.z == v.y ? o.y : __ldg(fin + v.z);
+            if (v.w > 0 && v.w <= nin) o.w = v.w == v.z ? o.z : __ldg(fin + v.w);
+            return o;
+        };
+        long long i = gtid;
+        for (; i + nthreads < n4; i += 2 * nthreads) {        // two independent 16-byte loads in flight per thread
+            int4 a = L4[i], b2 = L4[i + nthreads];
+            L4[i] = map4(a);
+            L4[i + nthreads] = map4(b2);
+        }
+        if (i < n4) L4[i] = map4(L4[i]);
+        done = n4 << 2;
+    }
+    for (long long p = done + gtid; p < n; p += nthreads) {
         int l0 = A.labels[p];
         if (l0 <= 0 || l0 > nin) continue;
-        int r = __ldcg(t.par + l0);
-        A.labels[p] = A.newid[r] + A.bsum[r / per] + 1;
+        A.labels[p] = fin[l0];
     }
+    if (A.trace) { grid.sync(); MERGE_TRACE(4); if (gtid == 0) { A.trace[5] = (unsigned long long)npairs; A.trace[6] = (unsigned long long)rounds; A.trace[7] = (unsigned long long)nin; } }
 }
 
 __global__ void __launch_bounds__(MT) render_kernel(const int32_t* __restrict__ L, size_t lstep, uint8_t* __restrict__ dst,
@@ -311,7 +472,7 @@ static int merge_persistent(msg_ctx* ctx, const uint32_t* d_plane, int pitch, in
     int grid = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
     size_t nl = (size_t)cap + 1;
     size_t pair_cap = 2 * n;                        // every pixel has at most a right and a down neighbour
-    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256 + pair_cap * sizeof(int2);
+    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 512 + pair_cap * sizeof(int2);
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));
     char* base = (char*)ctx->d_ovf;
     merge_persist_args A;
@@ -322,6 +483,9 @@ static int merge_persistent(msg_ctx* ctx, const uint32_t* d_plane, int pitch, in
     A.t.par = (int32_t*)base;              base += nl * 4;
     A.newid = (int32_t*)base;              base += nl * 4;
     A.bsum = (int32_t*)base;               base += ((size_t)(grid + 1) * 4 + 15) / 16 * 16;
+    const bool trace = getenv("MSG_MERGE_TRACE") != nullptr;
+    A.trace = trace ? (unsigned long long*)base : nullptr;
+    base += 256;
     A.pairs = (int2*)base;
     A.pair_cap = (long long)pair_cap;
     A.npairs = ctx->d_counters + 13;
@@ -331,9 +495,18 @@ static int merge_persistent(msg_ctx* ctx, const uint32_t* d_plane, int pitch, in
     A.rounds_out = ctx->d_counters + 10;
     A.n_out = d_n_out ? d_n_out : ctx->d_counters + 11;
     A.min_size = min_size; A.color_dist = color_dist;
+    A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !getenv("MSG_MERGE_SCALAR")) ? 1 : 0;
     void* args[] = {&A};
     MSG_CUDA(ctx, cudaLaunchCooperativeKernel((void*)merge_persistent_kernel, dim3(grid), dim3(MT), args, 0, ctx->stream));
     MSG_LAUNCHED(ctx);
+    if (trace) {                                     // diagnostics only: phase durations of this launch on stderr
+        unsigned long long t[8];
+        MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        MSG_CUDA(ctx, cudaMemcpy(t, A.trace, sizeof(t), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[merge trace] %dx%d labels=%llu pairs=%llu rounds=%llu grid=%d: init+stats %.1f us, rounds %.1f us, renumber %.1f us, "
+                "rewrite %.1f us\n", w, h, t[7], t[5], t[6], grid, (t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3,
+                (t[4] - t[3]) / 1e3);
+    }
     return MSG_OK;
 }
 
