@@ -5,8 +5,16 @@
 // smallest (dist2 of rounded mean colours, label) key, accepted selections are united
 // simultaneously (union by smallest label); phase A = colour fuse, phase B = min-size prune.
 // K2c = PictureService.colorByIndexes (PictureService.java:913-936).
+//
+// Launch sequence of one merge (the label count lives on the device, so both round kernels are always launched and the
+// one whose regime does not apply returns at once):
+//   merge_init_kernel          tables of the n_in labels
+//   merge_stats_kernel         one pass over the pixels: area + colour sums per label, list of adjacent label pairs
+//   merge_rounds_small_kernel  <= 4095 labels (a 1080p / 4K frame): ONE CTA, every table in shared memory, __syncthreads
+//                              between the passes of a round, then the dense renumbering
+//   merge_rounds_large_kernel  more labels: cooperative grid, tables in L2/HBM, grid-wide barriers, same passes
+//   merge_rewrite_kernel       one pass over the pixels: label -> final id
 #include <cooperative_groups.h>
-#include <stdio.h>
 #include <stdlib.h>
 
 #include "msg_internal.h"
@@ -17,11 +25,14 @@ namespace {
 
 constexpr int MT = 256;
 constexpr int MERGE_MAX_ROUNDS = 64;
+constexpr int SMALL_MAX_LABELS = 4095;          // small path: labels 1..4095 -> 12-bit label field in the 32-bit selection key
+constexpr long long SMALL_MAX_PIXELS = 1ll << 24;   // small path: colour sums of a region fit 32 bits (255 * 2^24 < 2^32)
+constexpr int ST = 1024;                        // threads of the small-path CTA
 
 struct merge_tables {
     unsigned int* area;            // [nl]
     unsigned long long* sum;       // [3*nl]  B,G,R
-    uint32_t* mean;                // [nl]   packed B | G<<8 | R<<16
+    uint32_t* mean;                // [nl]   packed B | G<<8 | R<<16; reused as the final-id table after the rounds
     unsigned long long* best;      // [nl]   (dist2 << 32) | neighbour label
     int32_t* par;                  // [nl]
 };
@@ -42,18 +53,15 @@ __device__ __forceinline__ int pf_find(const int32_t* P, int a)
     return a;
 }
 
-// ---------------------------------------------------------------- persistent merge (one cooperative launch)
-// All rounds of both phases inside one kernel with grid-wide barriers: no host round trip, no per-round pixel
-// passes for statistics (per-label sums are folded into the surviving roots) and the final renumbering is a scan
-// over the label table (valid because input labels are numbered by first pixel and unions keep the smallest label).
 struct merge_persist_args {
     const uint32_t* plane; int pitch;
     int32_t* labels; int w, h;
-    const int32_t* n_in;      // device: number of input labels (labels are 1..*n_in)
+    const int32_t* n_in;      // device: number of input labels (labels are 1..*n_in, numbered by first pixel)
+    int32_t* n_saved;         // device: copy of *n_in taken by the init kernel (n_out may alias n_in)
     int cap;                  // table capacity in labels
     merge_tables t;
     int32_t* newid;           // [cap+1]
-    int32_t* bsum;            // [gridDim.x + 1]
+    int32_t* bsum;            // [gridDim.x + 1] of the large-path kernel
     int32_t* accepted;        // device counter
     int32_t* n_out;           // device: number of regions after the merge
     int32_t* rounds_out;      // device: rounds executed (statistics)
@@ -61,17 +69,14 @@ struct merge_persist_args {
     int32_t* npairs;          // device counter
     long long pair_cap;
     int min_size, color_dist;
-    int vec;                     // 1: w % 4 == 0 and labels 16-byte aligned -> 16-byte loads in the pixel passes
-    unsigned long long* trace;   // [32] globaltimer at phase boundaries, or NULL (MSG_MERGE_TRACE=1 diagnostics)
+    int vec;                  // 1: w % 4 == 0 and labels 16-byte aligned -> 16-byte loads in the statistics pass
+    int small_max;            // labels up to which the single-CTA rounds kernel is used (0 forces the large path)
 };
 
-__device__ __forceinline__ unsigned long long global_ns()
+__device__ __forceinline__ bool merge_is_small(const merge_persist_args& A, int nin)
 {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
+    return nin <= A.small_max && (long long)A.w * A.h <= SMALL_MAX_PIXELS;
 }
-#define MERGE_TRACE(slot) do { if (A.trace && gtid == 0 && (slot) < 32) A.trace[(slot)] = global_ns(); } while (0)
 
 __device__ __forceinline__ void persist_union(int32_t* par, int a, int b)
 {
@@ -86,7 +91,22 @@ __device__ __forceinline__ void persist_union(int32_t* par, int a, int b)
     }
 }
 
+// ---------------------------------------------------------------- init
+__global__ void __launch_bounds__(MT) merge_init_kernel(merge_persist_args A)
+{
+    int nin = *A.n_in;
+    if (nin > A.cap) nin = A.cap;
+    const int nl = nin + 1;
+    const long long gtid = (long long)blockIdx.x * MT + threadIdx.x, nthreads = (long long)gridDim.x * MT;
+    for (long long i = gtid; i < nl; i += nthreads) {
+        A.t.area[i] = 0;
+        A.t.sum[3 * i] = 0; A.t.sum[3 * i + 1] = 0; A.t.sum[3 * i + 2] = 0;
+        A.t.par[i] = (int)i;
+    }
+    if (gtid == 0) { *A.accepted = 0; *A.rounds_out = 0; *A.npairs = 0; *A.n_saved = nin; }
+}
 
+// ---------------------------------------------------------------- statistics + adjacency pairs (one pass over the pixels)
 // add one run (label, pixel count, colour sums) to the tables
 __device__ __forceinline__ void stats_flush(const merge_tables& t, int lab, unsigned cnt, unsigned b, unsigned g, unsigned r)
 {
@@ -199,87 +219,233 @@ __device__ __forceinline__ void stats_pass_vec4(const merge_persist_args& A, con
     }
 }
 
-__global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args A)
+
+__global__ void __launch_bounds__(MT) merge_stats_kernel(merge_persist_args A)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gtid = (long long)blockIdx.x * MT + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * MT;
+    const long long gwarp = gtid >> 5, nwarps = nthreads >> 5;
+    int nin = *A.n_saved;
+    if (nin > A.cap) nin = A.cap;
+    const int w = A.w, h = A.h;
+    const merge_tables t = A.t;
+    if (A.vec) { stats_pass_vec4(A, t, nin, lane, gwarp, nwarps); return; }
+    const int cpr = (w + 31) / 32;                      // 32-pixel chunks per row
+    const long long nchunks = (long long)cpr * h;
+    for (long long c = gwarp; c < nchunks; c += nwarps) {
+        int y = (int)(c / cpr), x = (int)(c % cpr) * 32 + lane;
+        int lab = 0;
+        unsigned cnt = 0, b = 0, g = 0, r = 0;
+        if (x < w) {
+            lab = A.labels[(size_t)y * w + x];
+            if (lab > nin) lab = 0;
+            if (lab > 0) {
+                uint32_t col = __ldg(A.plane + (size_t)y * A.pitch + x);
+                cnt = 1; b = col & 0xFF; g = (col >> 8) & 0xFF; r = (col >> 16) & 0xFF;
+            }
+        }
+        int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+        bool head = lane == 0 || prev != lab;
+        unsigned heads = __ballot_sync(0xffffffffu, head);
+        unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+        int seg_end = above ? lane + __ffs(above) - 1 : 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned c2 = __shfl_down_sync(0xffffffffu, cnt, o);
+            unsigned b2 = __shfl_down_sync(0xffffffffu, b, o);
+            unsigned g2 = __shfl_down_sync(0xffffffffu, g, o);
+            unsigned r2 = __shfl_down_sync(0xffffffffu, r, o);
+            if (lane + o <= seg_end) { cnt += c2; b += b2; g += g2; r += r2; }
+        }
+        if (head && lab > 0) {
+            atomicAdd(t.area + lab, cnt);
+            atomicAdd(t.sum + 3 * (size_t)lab, (unsigned long long)b);
+            atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
+            atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
+        }
+        // region adjacency list: every 4-adjacent pixel pair with two different positive labels, found once here; the
+        // rounds then iterate over this list (a few % of the pixels) instead of over the image
+        int lr = 0, ld = 0;
+        if (lab > 0) {
+            if (x + 1 < w) { lr = A.labels[(size_t)y * w + x + 1]; if (lr > nin || lr == lab) lr = 0; }
+            if (y + 1 < h) { ld = A.labels[(size_t)(y + 1) * w + x]; if (ld > nin || ld == lab) ld = 0; }
+        }
+        unsigned mr = __ballot_sync(0xffffffffu, lr > 0), md = __ballot_sync(0xffffffffu, ld > 0);
+        int tot = __popc(mr) + __popc(md);
+        if (tot) {
+            long long pos = 0;
+            if (lane == 0) pos = (long long)atomicAdd(A.npairs, tot);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            unsigned lt = (1u << lane) - 1;
+            if (lr > 0) { long long k = pos + __popc(mr & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, lr); }
+            if (ld > 0) { long long k = pos + __popc(mr) + __popc(md & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, ld); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- rounds, small path (one CTA, tables in shared memory)
+// Selection key: (dist2 << 12) | neighbour label -- dist2 <= 3 * 255^2 < 2^18 and labels < 2^12, so 32 bits are enough
+// and shared-memory atomicMin is native.  Colour sums fit 32 bits because the image has at most 2^24 pixels.
+__device__ __forceinline__ int sm_find(volatile int* par, int a)
+{
+    int p = par[a];
+    while (p != a) { a = p; p = par[a]; }
+    return a;
+}
+
+__device__ __forceinline__ void sm_union(int* par, int a, int b)
+{
+    for (;;) {
+        a = sm_find(par, a);
+        b = sm_find(par, b);
+        if (a == b) return;
+        if (a < b) { int s = a; a = b; b = s; }
+        int old = atomicMin(par + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist_args A)
+{
+    extern __shared__ uint32_t sm_tab[];
+    constexpr int NS = SMALL_MAX_LABELS + 1;
+    int* par = reinterpret_cast<int*>(sm_tab);
+    uint32_t* area = sm_tab + NS;
+    uint32_t* mean = sm_tab + 2 * NS;
+    uint32_t* best = sm_tab + 3 * NS;          // reused for the dense ids after the rounds
+    uint32_t* sum0 = sm_tab + 4 * NS;
+    uint32_t* sum1 = sm_tab + 5 * NS;
+    uint32_t* sum2 = sm_tab + 6 * NS;
+    __shared__ int s_accepted;
+    __shared__ int s_wsum[ST / 32];
+    int nin = *A.n_saved;
+    if (nin > A.cap) nin = A.cap;
+    if (!merge_is_small(A, nin)) return;
+    const int nl = nin + 1;
+    const int tid = threadIdx.x, lane = tid & 31;
+    long long npairs = *A.npairs;
+    if (npairs > A.pair_cap) npairs = A.pair_cap;
+    for (int i = tid; i < nl; i += ST) {
+        par[i] = i;
+        area[i] = A.t.area[i];
+        sum0[i] = (uint32_t)A.t.sum[3 * (size_t)i];
+        sum1[i] = (uint32_t)A.t.sum[3 * (size_t)i + 1];
+        sum2[i] = (uint32_t)A.t.sum[3 * (size_t)i + 2];
+    }
+    __syncthreads();
+    int rounds = 0;
+    for (int phase = 0; phase < 2; phase++) {
+        uint32_t size_thr, dist_limit;
+        if (phase == 0) { if (A.color_dist <= 0) continue; size_thr = 0xffffffffu; dist_limit = (uint32_t)min((long long)A.color_dist * A.color_dist, 1ll << 19); }
+        else { if (A.min_size <= 0) continue; size_thr = (uint32_t)A.min_size; dist_limit = 0xffffffffu; }
+        for (int round = 0; round < MERGE_MAX_ROUNDS; round++) {
+            for (int i = tid; i < nl; i += ST) {          // rounded means of the live roots: floor(s / a + 1/2)
+                uint32_t a = area[i], m = 0;
+                if (i > 0 && a) {
+                    uint32_t q0 = sum0[i] / a, q1 = sum1[i] / a, q2 = sum2[i] / a;
+                    q0 += 2 * (sum0[i] - q0 * a) >= a;
+                    q1 += 2 * (sum1[i] - q1 * a) >= a;
+                    q2 += 2 * (sum2[i] - q2 * a) >= a;
+                    m = q0 | (q1 << 8) | (q2 << 16);
+                }
+                mean[i] = m;
+                best[i] = 0xffffffffu;
+            }
+            if (tid == 0) s_accepted = 0;
+            __syncthreads();
+            for (long long k = tid; k < npairs; k += ST) {
+                int2 pr = A.pairs[k];
+                int ra = par[pr.x], rb = par[pr.y];
+                if (ra == rb) continue;
+                bool pa = area[ra] < size_thr, pb = area[rb] < size_thr;
+                if (!pa && !pb) continue;
+                uint32_t e = __vabsdiffu4(mean[ra], mean[rb]);
+                uint32_t d2 = __dp4a(e, e, 0u) << 12;
+                if (pa) atomicMin(best + ra, d2 | (uint32_t)rb);
+                if (pb) atomicMin(best + rb, d2 | (uint32_t)ra);
+            }
+            __syncthreads();
+            for (int i = tid; i < nl; i += ST) {
+                if (i == 0) continue;
+                uint32_t k = best[i];
+                if (k == 0xffffffffu || (k >> 12) > dist_limit) continue;
+                sm_union(par, i, (int)(k & 0xfffu));
+                atomicAdd(&s_accepted, 1);
+            }
+            __syncthreads();
+            rounds++;
+            if (s_accepted == 0) break;                    // uniform; it is reset only after the barrier below
+            for (int i = tid; i < nl; i += ST) {           // fold: flatten, move the statistics of absorbed labels to their roots
+                if (i == 0) continue;
+                int r = sm_find(par, i);
+                if (r != i) {
+                    par[i] = r;
+                    uint32_t a = area[i];
+                    if (a) {
+                        atomicAdd(area + r, a);
+                        atomicAdd(sum0 + r, sum0[i]); atomicAdd(sum1 + r, sum1[i]); atomicAdd(sum2 + r, sum2[i]);
+                        area[i] = 0;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // dense renumbering of the surviving roots (ascending label == ascending first pixel); 4 consecutive labels per thread
+    constexpr int PER = NS / ST;
+    int alive[PER], cnt = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        int i = tid * PER + k;
+        alive[k] = (i > 0 && i < nl && par[i] == i && area[i] > 0) ? 1 : 0;
+        cnt += alive[k];
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[tid >> 5] = incl;
+    __syncthreads();                                       // also: every read of best[] as a key is done
+    int ws = s_wsum[lane], wincl = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += v;
+    }
+    int run = __shfl_sync(0xffffffffu, wincl - ws, tid >> 5) + incl - cnt;
+    const int total = __shfl_sync(0xffffffffu, wincl, 31);
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        int i = tid * PER + k;
+        if (i < nl) best[i] = (uint32_t)run;
+        run += alive[k];
+    }
+    __syncthreads();
+    int32_t* fin = reinterpret_cast<int32_t*>(A.t.mean);
+    for (int i = tid; i < nl; i += ST) fin[i] = i > 0 ? (int)best[par[i]] + 1 : 0;
+    if (tid == 0) { *A.n_out = total; *A.rounds_out = rounds; }
+}
+
+// ---------------------------------------------------------------- rounds, large path (cooperative grid)
+// All rounds of both phases inside one kernel with grid-wide barriers: no host round trip, no per-round pixel
+// passes for statistics (per-label sums are folded into the surviving roots) and the final renumbering is a scan
+// over the label table (valid because input labels are numbered by first pixel and unions keep the smallest label).
+__global__ void __launch_bounds__(MT) merge_rounds_large_kernel(merge_persist_args A)
 {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
     const long long gtid = (long long)blockIdx.x * MT + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * MT;
-    const long long gwarp = gtid >> 5, nwarps = nthreads >> 5;
-    int nin = *A.n_in;
+    int nin = *A.n_saved;
     if (nin > A.cap) nin = A.cap;
+    if (merge_is_small(A, nin)) return;                  // uniform over the grid: the small-path kernel did the work
     const int nl = nin + 1;
-    const int w = A.w, h = A.h;
-    const int cpr = (w + 31) / 32;                      // 32-pixel chunks per row
-    const long long nchunks = (long long)cpr * h;
     merge_tables t = A.t;
-    MERGE_TRACE(0);
-
-    // ---- init tables
-    for (long long i = gtid; i < nl; i += nthreads) {
-        t.area[i] = 0;
-        t.sum[3 * i] = 0; t.sum[3 * i + 1] = 0; t.sum[3 * i + 2] = 0;
-        t.par[i] = (int)i;
-    }
-    if (gtid == 0) { *A.accepted = 0; *A.rounds_out = 0; *A.npairs = 0; }
-    grid.sync();
-
-    // ---- statistics from pixels, once (warp-level run aggregation)
-    if (A.vec) stats_pass_vec4(A, t, nin, lane, gwarp, nwarps);
-    else {
-        for (long long c = gwarp; c < nchunks; c += nwarps) {
-            int y = (int)(c / cpr), x = (int)(c % cpr) * 32 + lane;
-            int lab = 0;
-            unsigned cnt = 0, b = 0, g = 0, r = 0;
-            if (x < w) {
-                lab = A.labels[(size_t)y * w + x];
-                if (lab > nin) lab = 0;
-                if (lab > 0) {
-                    uint32_t col = __ldg(A.plane + (size_t)y * A.pitch + x);
-                    cnt = 1; b = col & 0xFF; g = (col >> 8) & 0xFF; r = (col >> 16) & 0xFF;
-                }
-            }
-            int prev = __shfl_up_sync(0xffffffffu, lab, 1);
-            bool head = lane == 0 || prev != lab;
-            unsigned heads = __ballot_sync(0xffffffffu, head);
-            unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
-            int seg_end = above ? lane + __ffs(above) - 1 : 31;
-    #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned c2 = __shfl_down_sync(0xffffffffu, cnt, o);
-                unsigned b2 = __shfl_down_sync(0xffffffffu, b, o);
-                unsigned g2 = __shfl_down_sync(0xffffffffu, g, o);
-                unsigned r2 = __shfl_down_sync(0xffffffffu, r, o);
-                if (lane + o <= seg_end) { cnt += c2; b += b2; g += g2; r += r2; }
-            }
-            if (head && lab > 0) {
-                atomicAdd(t.area + lab, cnt);
-                atomicAdd(t.sum + 3 * (size_t)lab, (unsigned long long)b);
-                atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
-                atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
-            }
-            // region adjacency list: every 4-adjacent pixel pair with two different positive labels, found once here; the
-            // rounds then iterate over this list (a few % of the pixels) instead of over the image
-            int lr = 0, ld = 0;
-            if (lab > 0) {
-                if (x + 1 < w) { lr = A.labels[(size_t)y * w + x + 1]; if (lr > nin || lr == lab) lr = 0; }
-                if (y + 1 < h) { ld = A.labels[(size_t)(y + 1) * w + x]; if (ld > nin || ld == lab) ld = 0; }
-            }
-            unsigned mr = __ballot_sync(0xffffffffu, lr > 0), md = __ballot_sync(0xffffffffu, ld > 0);
-            int tot = __popc(mr) + __popc(md);
-            if (tot) {
-                long long pos = 0;
-                if (lane == 0) pos = (long long)atomicAdd(A.npairs, tot);
-                pos = __shfl_sync(0xffffffffu, pos, 0);
-                unsigned lt = (1u << lane) - 1;
-                if (lr > 0) { long long k = pos + __popc(mr & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, lr); }
-                if (ld > 0) { long long k = pos + __popc(mr) + __popc(md & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, ld); }
-            }
-        }
-    }
-    grid.sync();
-    MERGE_TRACE(1);
-    long long npairs = *((volatile int32_t*)A.npairs);
+    long long npairs = *A.npairs;
     if (npairs > A.pair_cap) npairs = A.pair_cap;
 
     const long long INF = 1ll << 40;
@@ -347,7 +513,6 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
         }
     }
 
-    MERGE_TRACE(2);
     // ---- dense renumbering of the surviving roots (ascending label == ascending first pixel)
     const int per = (nl + gridDim.x - 1) / gridDim.x;          // labels per block
     {
@@ -392,16 +557,23 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
         *A.rounds_out = rounds;
     }
     grid.sync();
-    MERGE_TRACE(3);
-    // ---- final id of every input label (one gather per pixel below instead of three); t.mean is free by now
+    // ---- final id of every input label (one gather per pixel in the rewrite pass); t.mean is free by now
     int32_t* fin = reinterpret_cast<int32_t*>(t.mean);
     for (long long i = gtid; i < nl; i += nthreads) {
         int r = __ldcg(t.par + i);
         fin[i] = i > 0 ? A.newid[r] + A.bsum[r / per] + 1 : 0;
     }
-    grid.sync();
-    // ---- rewrite the pixels (labels outside 1..nin are left as they are)
-    const long long n = (long long)w * h;
+}
+
+// ---------------------------------------------------------------- rewrite the pixels: label -> final id
+// Labels outside 1..n_in are left as they are.  16-byte loads, two in flight per thread, when the buffer is aligned.
+__global__ void __launch_bounds__(MT) merge_rewrite_kernel(merge_persist_args A)
+{
+    int nin = *A.n_saved;
+    if (nin > A.cap) nin = A.cap;
+    const int32_t* __restrict__ fin = reinterpret_cast<const int32_t*>(A.t.mean);
+    const long long gtid = (long long)blockIdx.x * MT + threadIdx.x, nthreads = (long long)gridDim.x * MT;
+    const long long n = (long long)A.w * A.h;
     long long done = 0;
     if ((reinterpret_cast<uintptr_t>(A.labels) & 15) == 0) {
         int4* L4 = reinterpret_cast<int4*>(A.labels);
@@ -415,7 +587,7 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
             return o;
         };
         long long i = gtid;
-        for (; i + nthreads < n4; i += 2 * nthreads) {        // two independent 16-byte loads in flight per thread
+        for (; i + nthreads < n4; i += 2 * nthreads) {
             int4 a = L4[i], b2 = L4[i + nthreads];
             L4[i] = map4(a);
             L4[i + nthreads] = map4(b2);
@@ -428,7 +600,6 @@ __global__ void __launch_bounds__(MT) merge_persistent_kernel(merge_persist_args
         if (l0 <= 0 || l0 > nin) continue;
         A.labels[p] = fin[l0];
     }
-    if (A.trace) { grid.sync(); MERGE_TRACE(4); if (gtid == 0) { A.trace[5] = (unsigned long long)npairs; A.trace[6] = (unsigned long long)rounds; A.trace[7] = (unsigned long long)nin; } }
 }
 
 __global__ void __launch_bounds__(MT) render_kernel(const int32_t* __restrict__ L, size_t lstep, uint8_t* __restrict__ dst,
@@ -460,19 +631,19 @@ int k_render(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, uint8_t* d_dst
 }
 
 // d_n_in: device count of input labels, which must be canonical (1..n by first pixel).
-// d_counters: [8] max label, [9] accepted, [10] rounds, [11] spare n_out
-static int merge_persistent(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels, int w, int h, int min_size,
-                       int color_dist, const int32_t* d_n_in, int32_t* d_n_out)
+// d_counters: [8] max label, [9] accepted, [10] rounds, [11] spare n_out, [13] pair count, [14] saved n_in
+static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels, int w, int h, int min_size,
+                        int color_dist, const int32_t* d_n_in, int32_t* d_n_out)
 {
     size_t n = (size_t)w * h;
     int cap = (int)n;                                 // worst case: every pixel its own region
     int blocks_per_sm = 0;
-    MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_persistent_kernel, MT, 0));
+    MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
     int grid = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
     size_t nl = (size_t)cap + 1;
     size_t pair_cap = 2 * n;                        // every pixel has at most a right and a down neighbour
-    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 512 + pair_cap * sizeof(int2);
+    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256 + pair_cap * sizeof(int2);
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));
     char* base = (char*)ctx->d_ovf;
     merge_persist_args A;
@@ -483,30 +654,38 @@ static int merge_persistent(msg_ctx* ctx, const uint32_t* d_plane, int pitch, in
     A.t.par = (int32_t*)base;              base += nl * 4;
     A.newid = (int32_t*)base;              base += nl * 4;
     A.bsum = (int32_t*)base;               base += ((size_t)(grid + 1) * 4 + 15) / 16 * 16;
-    const bool trace = getenv("MSG_MERGE_TRACE") != nullptr;
-    A.trace = trace ? (unsigned long long*)base : nullptr;
-    base += 256;
     A.pairs = (int2*)base;
     A.pair_cap = (long long)pair_cap;
     A.npairs = ctx->d_counters + 13;
     A.plane = d_plane; A.pitch = pitch; A.labels = d_labels; A.w = w; A.h = h;
     A.n_in = d_n_in; A.cap = cap;
+    A.n_saved = ctx->d_counters + 14;
     A.accepted = ctx->d_counters + 9;
     A.rounds_out = ctx->d_counters + 10;
     A.n_out = d_n_out ? d_n_out : ctx->d_counters + 11;
     A.min_size = min_size; A.color_dist = color_dist;
     A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !getenv("MSG_MERGE_SCALAR")) ? 1 : 0;
-    void* args[] = {&A};
-    MSG_CUDA(ctx, cudaLaunchCooperativeKernel((void*)merge_persistent_kernel, dim3(grid), dim3(MT), args, 0, ctx->stream));
+    const char* sm_env = getenv("MSG_MERGE_SMALL_MAX");            // test hook: 0 forces the cooperative path
+    A.small_max = sm_env ? atoi(sm_env) : SMALL_MAX_LABELS;
+    if (A.small_max > SMALL_MAX_LABELS) A.small_max = SMALL_MAX_LABELS;
+    cudaStream_t st = ctx->stream;
+    const int wide = ctx->sm_count * 8;                              // CTAs of the streaming kernels (grid-stride)
+    auto blocks_for = [&](size_t items) { size_t b = (items + MT - 1) / MT; return (int)(b < 1 ? 1 : (b > (size_t)wide ? (size_t)wide : b)); };
+    merge_init_kernel<<<blocks_for(n < 65536 ? n : 65536), MT, 0, st>>>(A);
     MSG_LAUNCHED(ctx);
-    if (trace) {                                     // diagnostics only: phase durations of this launch on stderr
-        unsigned long long t[8];
-        MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        MSG_CUDA(ctx, cudaMemcpy(t, A.trace, sizeof(t), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[merge trace] %dx%d labels=%llu pairs=%llu rounds=%llu grid=%d: init+stats %.1f us, rounds %.1f us, renumber %.1f us, "
-                "rewrite %.1f us\n", w, h, t[7], t[5], t[6], grid, (t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3,
-                (t[4] - t[3]) / 1e3);
-    }
+    size_t stat_threads = A.vec ? ((n + 127) / 128) * 32 : ((size_t)((w + 31) / 32) * h) * 32;   // one warp per chunk
+    merge_stats_kernel<<<blocks_for(stat_threads), MT, 0, st>>>(A);
+    MSG_LAUNCHED(ctx);
+    const size_t small_smem = (size_t)(SMALL_MAX_LABELS + 1) * 7 * sizeof(uint32_t);
+    MSG_CUDA(ctx, cudaFuncSetAttribute(merge_rounds_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+    merge_rounds_small_kernel<<<1, ST, small_smem, st>>>(A);
+    MSG_LAUNCHED(ctx);
+    void* args[] = {&A};
+    MSG_CUDA(ctx, cudaLaunchCooperativeKernel((void*)merge_rounds_large_kernel, dim3(grid), dim3(MT), args, 0, st));
+    MSG_LAUNCHED(ctx);
+    merge_rewrite_kernel<<<blocks_for((n / 4 + 1) / 2 + 1), MT, 0, st>>>(A);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;
 }
 
@@ -535,7 +714,7 @@ int k_merge(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels,
             MSG_CUDA(ctx, cudaMemcpyAsync(d_n_out, d_n_in, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
         return MSG_OK;
     }
-    MSG_TRY(merge_persistent(ctx, d_plane, pitch, d_labels, w, h, min_size, color_dist, d_n_in, d_n_out));
+    MSG_TRY(merge_launch(ctx, d_plane, pitch, d_labels, w, h, min_size, color_dist, d_n_in, d_n_out));
     MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 10, ctx->d_counters + 10, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return MSG_OK;
 }
