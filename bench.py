@@ -12,7 +12,8 @@ independent: weak scaling, no data-path collective.
 
   value     : frames resident in HBM, device-resident C-ABI calls (msg_segment_dev), CUDA-event timed, max over ranks.
   e2e       : same frames from pinned HOST buffers through msg_submit_segment / msg_wait (H2D and D2H copies of the
-              filtered image and the label map inside the timed region).
+              filtered image and the label map inside the timed region); one host thread per context keeps two frames in
+              flight, the library overlaps upload / kernels / download and replays the kernel sequence as a CUDA graph.
   roofline  : dominant kernel = level-0 mean-shift tile kernel; achieved = algorithmic int-ops (9 T + 5 Hit, counted on
               the device exactly as the CPU oracle counts them) / its CUDA-event duration; peak = INT issue rate measured
               on this GPU by tools/int_peak (MEASURED_PEAKS.json has no integer figure).
@@ -314,22 +315,25 @@ def run_ours(args):
     ctypes.memmove(h_src, src_host.ctypes.data, B * frame_bytes)
     del src_host
 
-    def _e2e_worker(k):
+    def _e2e_worker(k, steps):
+        # one host thread per context, as a frame server would run it: frames k, k+N, ... of every step, at most 2
+        # submissions in flight; consecutive steps are pipelined (no drain between them), every result is waited for
+        # (msg_wait = the device->host copies of that frame have landed) before its host buffers are reused
         tickets = []
-        for i in range(k, B, N_STREAMS):
-            if len(tickets) >= 2:                      # at most 2 submissions in flight per context
-                dev.wait(ctxs[k], tickets.pop(0))
-            tickets.append(dev.submit_segment(ctxs[k], h_src + i * frame_bytes, 3 * W, W, H, prm,
-                                              h_filt + i * frame_bytes, 3 * W, h_lab + i * lab_bytes, 4 * W))
+        for _ in range(steps):
+            for i in range(k, B, N_STREAMS):
+                if len(tickets) >= 2:
+                    dev.wait(ctxs[k], tickets.pop(0))
+                tickets.append(dev.submit_segment(ctxs[k], h_src + i * frame_bytes, 3 * W, W, H, prm,
+                                                  h_filt + i * frame_bytes, 3 * W, h_lab + i * lab_bytes, 4 * W))
         for t in tickets:
             dev.wait(ctxs[k], t)
 
-    def step_e2e():
-        list(pool.map(_e2e_worker, range(N_STREAMS)))
+    def run_e2e(steps):
+        list(pool.map(lambda k: _e2e_worker(k, steps), range(N_STREAMS)))
 
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    run_e2e(max(1, args.warmup // 2))
+    ms_e2e = timed(lambda: run_e2e(args.steps), 1)
     e2e_value = mpix_step * args.steps / (ms_e2e / 1e3)
     clocks = sampler.stop() if rank == 0 else None
 

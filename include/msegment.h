@@ -167,7 +167,9 @@ MSG_API int msg_segment(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, i
 
 /* ---- asynchronous batch interface (stream ordered within a context) ----------------------- */
 /* Buffers must stay valid until msg_wait(ticket); host buffers from msg_alloc_pinned make the
- * copies truly asynchronous.  Up to MSG_MAX_INFLIGHT submissions may be pending per context. */
+ * copies truly asynchronous.  Up to MSG_MAX_INFLIGHT submissions may be pending per context; consecutive submissions are
+ * pipelined (upload, kernels and downloads run on three streams, each in-flight frame owns its device buffers), so the
+ * upload of frame i+1 and the download of frame i-1 overlap the kernels of frame i. */
 #define MSG_MAX_INFLIGHT 4
 MSG_API int msg_submit_segment(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, int width, int height,
                        const msg_segment_params* params, uint8_t* filtered_bgr, size_t filtered_step,

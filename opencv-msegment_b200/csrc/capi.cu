@@ -3,6 +3,7 @@
 // ends in the CUDA kernels of k_*.cu or fails.
 #include <math.h>
 #include <stdarg.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "msg_internal.h"
@@ -27,6 +28,7 @@ int msg_reserve(msg_ctx* ctx, void** p, size_t* cap, size_t bytes)
         *p = nullptr;
         *cap = 0;
     }
+    ctx->ws_epoch++;
     size_t want = bytes + bytes / 8 + 256;  // head-room against ping-pong regrowth
     cudaError_t e = cudaMalloc(p, want);
     if (e != cudaSuccess) {
@@ -131,8 +133,12 @@ int msg_create(int device, msg_ctx** out)
         for (int k = 0; k < 3; k++) CR(cudaEventCreate(&ctx->prof_ev[l][k]));
     for (int i = 0; i < MSG_MAX_INFLIGHT; i++) {
         CR(cudaEventCreateWithFlags(&ctx->pend[i].done, cudaEventDisableTiming));
+        CR(cudaEventCreateWithFlags(&ctx->pend[i].ev_in, cudaEventDisableTiming));
+        CR(cudaEventCreateWithFlags(&ctx->pend[i].ev_core, cudaEventDisableTiming));
         ctx->pend[i].n_regions_host = ctx->h_counters + 32 + i;
     }
+    CR(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CR(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
 #undef CR
     *out = ctx;
     return MSG_OK;
@@ -143,6 +149,14 @@ void msg_destroy(msg_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->h2d_stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
+    for (int i = 0; i < MSG_MAX_INFLIGHT; i++) {
+        cudaFree(ctx->pend[i].d_in); cudaFree(ctx->pend[i].d_filt); cudaFree(ctx->pend[i].d_ren); cudaFree(ctx->pend[i].d_lab);
+        cudaEventDestroy(ctx->pend[i].ev_in); cudaEventDestroy(ctx->pend[i].ev_core);
+        if (ctx->pend[i].g_exec) cudaGraphExecDestroy(ctx->pend[i].g_exec);
+    }
+    cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_out2); cudaFree(ctx->d_labels);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_ovf); cudaFree(ctx->d_scratch); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_colors); cudaFree(ctx->d_work); cudaFree(ctx->d_cells); cudaFree(ctx->d_aux);
@@ -168,7 +182,9 @@ int msg_set_stream(msg_ctx* ctx, void* cuda_stream)
 int msg_synchronize(msg_ctx* ctx)
 {
     CTX_ENTER(ctx);
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->h2d_stream));
     MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     return MSG_OK;
 }
 
@@ -306,19 +322,36 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
-static int copy_in(msg_ctx* ctx, const void* host, size_t hstep, size_t row_bytes, int rows, uint8_t** d, size_t* dcap)
+static int copy_in_on(msg_ctx* ctx, cudaStream_t st, const void* host, size_t hstep, size_t row_bytes, int rows, uint8_t** d,
+                      size_t* dcap)
 {
     MSG_TRY(msg_reserve(ctx, (void**)d, dcap, row_bytes * (size_t)rows));
-    MSG_CUDA(ctx, cudaMemcpy2DAsync(*d, row_bytes, host, hstep, row_bytes, rows, cudaMemcpyHostToDevice, ctx->stream));
+    if (hstep == row_bytes)      // continuous Mat: one linear copy (the 2-D form is issued row by row by the copy engine)
+        MSG_CUDA(ctx, cudaMemcpyAsync(*d, host, row_bytes * (size_t)rows, cudaMemcpyHostToDevice, st));
+    else
+        MSG_CUDA(ctx, cudaMemcpy2DAsync(*d, row_bytes, host, hstep, row_bytes, rows, cudaMemcpyHostToDevice, st));
     ctx->st.h2d_bytes += row_bytes * (size_t)rows;
     return MSG_OK;
 }
 
-static int copy_out(msg_ctx* ctx, void* host, size_t hstep, const void* d, size_t row_bytes, int rows)
+static int copy_out_on(msg_ctx* ctx, cudaStream_t st, void* host, size_t hstep, const void* d, size_t row_bytes, int rows)
 {
-    MSG_CUDA(ctx, cudaMemcpy2DAsync(host, hstep, d, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hstep == row_bytes)
+        MSG_CUDA(ctx, cudaMemcpyAsync(host, d, row_bytes * (size_t)rows, cudaMemcpyDeviceToHost, st));
+    else
+        MSG_CUDA(ctx, cudaMemcpy2DAsync(host, hstep, d, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, st));
     ctx->st.d2h_bytes += row_bytes * (size_t)rows;
     return MSG_OK;
+}
+
+static int copy_in(msg_ctx* ctx, const void* host, size_t hstep, size_t row_bytes, int rows, uint8_t** d, size_t* dcap)
+{
+    return copy_in_on(ctx, ctx->stream, host, hstep, row_bytes, rows, d, dcap);
+}
+
+static int copy_out(msg_ctx* ctx, void* host, size_t hstep, const void* d, size_t row_bytes, int rows)
+{
+    return copy_out_on(ctx, ctx->stream, host, hstep, d, row_bytes, rows);
 }
 
 static int check_img(msg_ctx* ctx, const void* p, size_t step, int w, int h, int elem, const char* what)
@@ -621,10 +654,10 @@ static int segment_core_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, in
     const bool do_render = do_label && p->render_depth >= 0 && d_rendered;
     cudaStream_t st = ctx->stream;
     if (d_labels && lstep % 4) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of 4");
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     MSG_TRY(ms_run(ctx, d_src, sstep, w, h, 0, h, cfg));
     if (d_filtered) MSG_TRY(k_plane_to_bgr(ctx, ctx->D[0], 0, h, d_filtered, fstep));
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     int32_t* n_dev = d_n ? d_n : ctx->d_counters + 17;
     int32_t* work = nullptr;
     const bool dense = d_labels && lstep == (size_t)w * 4;
@@ -639,15 +672,30 @@ static int segment_core_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, in
     } else if (d_n) {
         MSG_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int32_t), st));
     }
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     if (do_merge) MSG_TRY(k_merge(ctx, ctx->D[0].p, ctx->D[0].pitch, work, w, h, p->min_size, p->color_dist, n_dev, n_dev));
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     if (do_label && d_labels && !dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
     if (do_render) {
         int depth = p->render_depth > 0 ? p->render_depth : 0x7fffffff;   // 0: every region renders
         MSG_TRY(k_render(ctx, work, (size_t)w * 4, d_rendered, rstep, w, h, depth, nullptr));
     }
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    return MSG_OK;
+}
+
+static int segment_validate(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
+                            uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered, size_t rstep,
+                            ms_config* cfg)
+{
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "segment src"));
+    if (!p) return msg_fail(ctx, MSG_EINVAL, "segment: params is NULL");
+    if (filtered) MSG_TRY(check_img(ctx, filtered, fstep, w, h, 3, "segment filtered"));
+    if (labels) MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "segment labels"));
+    if (rendered) MSG_TRY(check_img(ctx, rendered, rstep, w, h, 3, "segment rendered"));
+    MSG_TRY(ms_validate(ctx, w, h, p->sp, p->sr, p->max_level, p->term_type, p->max_count, p->eps, cfg));
+    if (p->min_size < 0 || p->color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
+    if (p->connectivity != 0 && p->connectivity != 4 && p->connectivity != 8) return msg_fail(ctx, MSG_EINVAL, "connectivity must be 4 or 8");
     return MSG_OK;
 }
 
@@ -655,15 +703,8 @@ static int segment_enqueue(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w
                            uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered,
                            size_t rstep, int32_t* h_n_slot)
 {
-    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "segment src"));
-    if (!p) return msg_fail(ctx, MSG_EINVAL, "segment: params is NULL");
-    if (filtered) MSG_TRY(check_img(ctx, filtered, fstep, w, h, 3, "segment filtered"));
-    if (labels) MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "segment labels"));
-    if (rendered) MSG_TRY(check_img(ctx, rendered, rstep, w, h, 3, "segment rendered"));
     ms_config cfg;
-    MSG_TRY(ms_validate(ctx, w, h, p->sp, p->sr, p->max_level, p->term_type, p->max_count, p->eps, &cfg));
-    if (p->min_size < 0 || p->color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
-    if (p->connectivity != 0 && p->connectivity != 4 && p->connectivity != 8) return msg_fail(ctx, MSG_EINVAL, "connectivity must be 4 or 8");
+    MSG_TRY(segment_validate(ctx, src, sstep, w, h, p, filtered, fstep, labels, lstep, rendered, rstep, &cfg));
     const bool do_label = p->lo_diff >= 0;
     const bool do_render = do_label && p->render_depth >= 0 && rendered;
     size_t rb = (size_t)w * 3;
@@ -732,9 +773,91 @@ int msg_submit_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, in
     for (int i = 0; i < MSG_MAX_INFLIGHT; i++)
         if (!ctx->pend[i].used) { slot = i; break; }
     if (slot < 0) return msg_fail(ctx, MSG_ESTATE, "submit: %d submissions already in flight; call msg_wait", MSG_MAX_INFLIGHT);
-    MSG_TRY(segment_enqueue(ctx, src, sstep, w, h, p, filtered, fstep, labels, lstep, rendered, rstep,
-                            ctx->pend[slot].n_regions_host));
-    MSG_CUDA(ctx, cudaEventRecord(ctx->pend[slot].done, ctx->stream));
+    // three-stage pipeline over consecutive submissions: upload on h2d_stream, kernels on the context stream, downloads
+    // on d2h_stream, chained by events; the frame owns its device buffers until msg_wait returns
+    ms_config cfg;
+    MSG_TRY(segment_validate(ctx, src, sstep, w, h, p, filtered, fstep, labels, lstep, rendered, rstep, &cfg));
+    msg_ctx::pending& q = ctx->pend[slot];
+    const bool do_label = p->lo_diff >= 0;
+    const bool do_render = do_label && p->render_depth >= 0 && rendered;
+    const size_t rb = (size_t)w * 3;
+    MSG_TRY(copy_in_on(ctx, ctx->h2d_stream, src, sstep, rb, h, &q.d_in, &q.d_in_cap));
+    MSG_CUDA(ctx, cudaEventRecord(q.ev_in, ctx->h2d_stream));
+    if (filtered) MSG_TRY(msg_reserve(ctx, (void**)&q.d_filt, &q.d_filt_cap, rb * h));
+    if (do_label) MSG_TRY(msg_reserve(ctx, (void**)&q.d_lab, &q.d_lab_cap, (size_t)w * h * 4));
+    if (do_render) MSG_TRY(msg_reserve(ctx, (void**)&q.d_ren, &q.d_ren_cap, rb * h));
+    int32_t* d_n = ctx->d_counters + 40 + slot;
+    MSG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, q.ev_in, 0));
+    // The kernel sequence of a frame is fixed by (geometry, parameters, buffers): replay it as a CUDA graph.  The first
+    // submission of a configuration runs eagerly (it sizes the workspace), the second is captured, later ones replay.
+    unsigned char key[sizeof(q.g_key)];
+    memset(key, 0, sizeof(key));
+    {
+        size_t o = 0;
+        auto put = [&](const void* v, size_t nbytes) { memcpy(key + o, v, nbytes); o += nbytes; };
+        const void* ptrs[6] = {q.d_in, filtered ? q.d_filt : nullptr, do_label ? q.d_lab : nullptr, do_render ? q.d_ren : nullptr,
+                               (void*)ctx->stream, d_n};
+        const double dv[3] = {p->sp, p->sr, p->eps};
+        const int iv[10] = {w, h, p->max_level, p->term_type, p->max_count, p->lo_diff, p->min_size, p->color_dist,
+                            p->render_depth, p->connectivity};
+        put(dv, sizeof(dv)); put(iv, sizeof(iv)); put(ptrs, sizeof(ptrs));     // field by field: no struct padding in the key
+        static_assert(sizeof(dv) + sizeof(iv) + sizeof(ptrs) <= sizeof(q.g_key), "graph key too small");
+    }
+    static const bool graphs_off = getenv("MSG_NO_GRAPH") != nullptr;
+    const bool same = q.g_state > 0 && memcmp(key, q.g_key, sizeof(key)) == 0 && q.g_epoch == ctx->ws_epoch;
+    auto run_core = [&]() {
+        return segment_core_dev(ctx, q.d_in, rb, w, h, p, cfg, filtered ? q.d_filt : nullptr, rb, do_label ? q.d_lab : nullptr,
+                                (size_t)w * 4, do_render ? q.d_ren : nullptr, rb, d_n);
+    };
+    ctx->no_events = 1;
+    int rc = MSG_OK;
+    if (graphs_off || ctx->profiling || q.g_state < 0 || !same) {
+        if (q.g_state == 2) { cudaGraphExecDestroy(q.g_exec); q.g_exec = nullptr; }
+        rc = run_core();
+        if (q.g_state >= 0) { q.g_state = (rc == MSG_OK && !graphs_off && !ctx->profiling) ? 1 : 0; }
+        memcpy(q.g_key, key, sizeof(key));
+        q.g_epoch = ctx->ws_epoch;                   // after the run: it may have grown the workspace
+    } else {
+        if (q.g_state == 1) {
+            cudaGraph_t graph = nullptr;
+            const uint64_t l0 = ctx->st.kernel_launches;
+            cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+            int crc = e == cudaSuccess ? run_core() : MSG_ECUDA;
+            cudaError_t e2 = e == cudaSuccess ? cudaStreamEndCapture(ctx->stream, &graph) : e;
+            if (crc == MSG_OK && e2 == cudaSuccess && graph && cudaGraphInstantiate(&q.g_exec, graph, 0) == cudaSuccess) {
+                q.g_state = 2;
+                q.g_launches = ctx->st.kernel_launches - l0;
+                ctx->st.kernel_launches = l0;        // counted again below, when the graph is launched
+            } else {                                 // capture not possible here: stay on the eager path for this slot
+                if (getenv("MSG_GRAPH_DEBUG"))
+                    fprintf(stderr, "[msegment] graph capture failed: begin=%s core=%d end=%s\n", cudaGetErrorString(e), crc,
+                            cudaGetErrorString(e2));
+                cudaGetLastError();
+                ctx->cuda_failed = 0;
+                ctx->st.kernel_launches = l0;
+                q.g_state = -1;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (q.g_state == 2) {
+            cudaError_t e = cudaGraphLaunch(q.g_exec, ctx->stream);
+            if (e != cudaSuccess) { ctx->no_events = 0; ctx->cuda_failed = 1; return msg_fail(ctx, MSG_ECUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); }
+            ctx->st.kernel_launches += q.g_launches;
+        } else {
+            rc = run_core();
+        }
+    }
+    ctx->no_events = 0;
+    if (rc != MSG_OK) return rc;
+    MSG_CUDA(ctx, cudaEventRecord(q.ev_core, ctx->stream));
+    cudaStream_t ds = ctx->d2h_stream;
+    MSG_CUDA(ctx, cudaStreamWaitEvent(ds, q.ev_core, 0));
+    if (filtered) MSG_TRY(copy_out_on(ctx, ds, filtered, fstep, q.d_filt, rb, h));
+    if (do_label && labels) MSG_TRY(copy_out_on(ctx, ds, labels, lstep, q.d_lab, (size_t)w * 4, h));
+    if (do_render) MSG_TRY(copy_out_on(ctx, ds, rendered, rstep, q.d_ren, rb, h));
+    MSG_CUDA(ctx, cudaMemcpyAsync(q.n_regions_host, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, ds));
+    MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ds));
+    MSG_CUDA(ctx, cudaEventRecord(q.done, ds));
     ctx->pend[slot].used = 1;
     *ticket = slot;
     return MSG_OK;

@@ -68,6 +68,9 @@ struct msg_ctx {
     // pinned host staging for pageable caller buffers
     uint8_t* h_stage; size_t h_stage_cap;
 
+    uint64_t ws_epoch;        // bumped by every (re)allocation of a workspace buffer: invalidates captured graphs
+    int no_events;            // 1 while enqueueing for the asynchronous path: no timing events (not meaningful there)
+
     msg_plane S[MSG_MAX_LEVELS], D[MSG_MAX_LEVELS];
     int last_levels;
 
@@ -81,10 +84,24 @@ struct msg_ctx {
     int prof_pending[MSG_MAX_LEVELS];
     msg_kernel_profile prof;
 
+    // asynchronous submissions (msg_submit_segment): upload, kernels and download of consecutive frames overlap on three
+    // streams; every in-flight frame owns its device input / output buffers
+    cudaStream_t h2d_stream, d2h_stream;
     struct pending {
         int used;
         int32_t* n_regions_host;  // pinned slot
-        cudaEvent_t done;
+        cudaEvent_t done;         // all downloads of the frame have landed
+        cudaEvent_t ev_in, ev_core;   // upload finished / kernels finished
+        uint8_t* d_in;   size_t d_in_cap;
+        uint8_t* d_filt; size_t d_filt_cap;
+        uint8_t* d_ren;  size_t d_ren_cap;
+        int32_t* d_lab;  size_t d_lab_cap;
+        // CUDA graph of the frame's kernel sequence (one launch call per frame instead of ~35); re-captured whenever
+        // the geometry, the parameters, a buffer or the stream changes
+        cudaGraphExec_t g_exec;
+        int g_state;              // 0 nothing, 1 the configuration ran eagerly once (buffers sized), 2 g_exec valid, -1 disabled
+        uint64_t g_epoch, g_launches;
+        unsigned char g_key[160];
         // deferred host copies (pageable destinations) are not supported asynchronously:
         // submit requires pinned or registered memory, otherwise it degrades to synchronous.
     } pend[MSG_MAX_INFLIGHT];

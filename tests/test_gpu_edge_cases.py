@@ -120,6 +120,45 @@ def test_async_submit_wait_pinned(ctx):
             dev.free_pinned(p)
 
 
+def test_async_pipeline_graph_replay_matches_blocking_calls(ctx):
+    """msg_submit_segment replays the frame's kernel sequence as a CUDA graph from the third use of a slot on: many
+    different frames through the same slots, with a geometry change and a parameter change in between (re-capture),
+    must give exactly what the blocking msg_segment call gives (itself checked against the oracle elsewhere)."""
+    dev = mseg.device
+    rng = np.random.default_rng(11)
+    plan = [((320, 240), dict(sp=6, sr=12, lo_diff=2, min_size=20, color_dist=6), 14),
+            ((200, 333), dict(sp=6, sr=12, lo_diff=2, min_size=20, color_dist=6), 9),     # geometry change
+            ((200, 333), dict(sp=4, sr=20, lo_diff=3, min_size=0, color_dist=9), 9),      # parameter change
+            ((320, 240), dict(sp=6, sr=12, lo_diff=2, min_size=20, color_dist=6), 6)]     # back to the first one
+    with mseg.Context(0) as ref_ctx:
+        ref = mseg.GpuImgproc(ref_ctx)
+        for (w, h), kw, count in plan:
+            nb, nl = w * h * 3, w * h * 4
+            hs, hf, hl = dev.alloc_pinned(count * nb), dev.alloc_pinned(count * nb), dev.alloc_pinned(count * nl)
+            try:
+                frames = [orc.synth_bgr(w, h, 300 + i) if i % 3 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+                          for i in range(count)]
+                for i, f in enumerate(frames):
+                    C.memmove(hs + i * nb, f.ctypes.data, nb)
+                prm = dev.params(render_depth=-1, **kw)
+                tickets, out_n = [], []
+                for i in range(count):
+                    if len(tickets) == 2:
+                        out_n.append(dev.wait(ctx, tickets.pop(0)))
+                    tickets.append(dev.submit_segment(ctx, hs + i * nb, 3 * w, w, h, prm, hf + i * nb, 3 * w, hl + i * nl, 4 * w))
+                out_n += [dev.wait(ctx, t) for t in tickets]
+                for i, f in enumerate(frames):
+                    want = ref.segment(f, sp=kw["sp"], sr=kw["sr"], loDiff=kw["lo_diff"], minSize=kw["min_size"],
+                                       colorDist=kw["color_dist"], renderDepth=-1, want=("filtered", "labels"))
+                    got_f = np.ctypeslib.as_array((C.c_uint8 * nb).from_address(hf + i * nb)).reshape(h, w, 3)
+                    got_l = np.ctypeslib.as_array((C.c_int32 * (w * h)).from_address(hl + i * nl)).reshape(h, w)
+                    assert np.array_equal(got_f, want["filtered"]), (w, h, i)
+                    assert np.array_equal(got_l, want["labels"]) and out_n[i] == want["n_regions"], (w, h, i)
+            finally:
+                for ptr in (hs, hf, hl):
+                    dev.free_pinned(ptr)
+
+
 def test_device_entry_points_with_torch():
     torch = pytest.importorskip("torch")
     dev = mseg.device
