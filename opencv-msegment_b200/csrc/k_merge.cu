@@ -28,6 +28,7 @@ constexpr int MERGE_MAX_ROUNDS = 64;
 constexpr int SMALL_MAX_LABELS = 4095;          // small path: labels 1..4095 -> 12-bit label field in the 32-bit selection key
 constexpr long long SMALL_MAX_PIXELS = 1ll << 24;   // small path: colour sums of a region fit 32 bits (255 * 2^24 < 2^32)
 constexpr int ST = 1024;                        // threads of the small-path CTA
+constexpr int SMALL_HSET_BITS = 14, SMALL_HSET = 1 << SMALL_HSET_BITS;   // slots of its adjacent-pair set
 
 struct merge_tables {
     unsigned int* area;            // [nl]
@@ -318,7 +319,8 @@ __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist
     uint32_t* sum0 = sm_tab + 4 * NS;
     uint32_t* sum1 = sm_tab + 5 * NS;
     uint32_t* sum2 = sm_tab + 6 * NS;
-    __shared__ int s_accepted;
+    uint32_t* hset = sm_tab + 7 * NS;          // set of adjacent label pairs
+    __shared__ int s_accepted, s_overflow;
     __shared__ int s_wsum[ST / 32];
     int nin = *A.n_saved;
     if (nin > A.cap) nin = A.cap;
@@ -334,7 +336,46 @@ __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist
         sum1[i] = (uint32_t)A.t.sum[3 * (size_t)i + 1];
         sum2[i] = (uint32_t)A.t.sum[3 * (size_t)i + 2];
     }
+    // The pair list holds one entry per boundary corner; the rounds only need every adjacent (label, label) pair once.
+    // Build that set in shared memory (open addressing, key = min << 12 | max): a region adjacency graph of 4095 regions
+    // has at most ~12k edges when it is planar; if the table ever fills up the rounds walk the list in global memory.
+    for (int i = tid; i < SMALL_HSET; i += ST) hset[i] = 0;
+    if (tid == 0) s_overflow = 0;
     __syncthreads();
+    for (long long base = 0; base < npairs; base += (long long)ST * 8) {
+        int2 pr[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {                      // 8 independent loads in flight per thread
+            long long k = base + (long long)u * ST + tid;
+            pr[u] = k < npairs ? A.pairs[k] : make_int2(0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (pr[u].x <= 0) continue;
+            uint32_t a = (uint32_t)min(pr[u].x, pr[u].y), b = (uint32_t)max(pr[u].x, pr[u].y);
+            uint32_t key = (a << 12) | b;
+            uint32_t slot = (key * 2654435761u) >> (32 - SMALL_HSET_BITS);
+            int probes = 0;
+            for (; probes < 128; probes++) {
+                uint32_t old = atomicCAS(hset + slot, 0u, key);
+                if (old == 0u || old == key) break;
+                slot = (slot + 1) & (SMALL_HSET - 1);
+            }
+            if (probes == 128) s_overflow = 1;
+        }
+    }
+    __syncthreads();
+    const bool use_set = s_overflow == 0;
+    auto edge = [&](int la, int lb, uint32_t size_thr) {    // both ends of an adjacent pair bid for each other
+        int ra = par[la], rb = par[lb];
+        if (ra == rb) return;
+        bool pa = area[ra] < size_thr, pb = area[rb] < size_thr;
+        if (!pa && !pb) return;
+        uint32_t e = __vabsdiffu4(mean[ra], mean[rb]);
+        uint32_t d2 = __dp4a(e, e, 0u) << 12;
+        if (pa) atomicMin(best + ra, d2 | (uint32_t)rb);
+        if (pb) atomicMin(best + rb, d2 | (uint32_t)ra);
+    };
     int rounds = 0;
     for (int phase = 0; phase < 2; phase++) {
         uint32_t size_thr, dist_limit;
@@ -355,16 +396,16 @@ __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist
             }
             if (tid == 0) s_accepted = 0;
             __syncthreads();
-            for (long long k = tid; k < npairs; k += ST) {
-                int2 pr = A.pairs[k];
-                int ra = par[pr.x], rb = par[pr.y];
-                if (ra == rb) continue;
-                bool pa = area[ra] < size_thr, pb = area[rb] < size_thr;
-                if (!pa && !pb) continue;
-                uint32_t e = __vabsdiffu4(mean[ra], mean[rb]);
-                uint32_t d2 = __dp4a(e, e, 0u) << 12;
-                if (pa) atomicMin(best + ra, d2 | (uint32_t)rb);
-                if (pb) atomicMin(best + rb, d2 | (uint32_t)ra);
+            if (use_set) {
+                for (int i = tid; i < SMALL_HSET; i += ST) {
+                    uint32_t key = hset[i];
+                    if (key) edge((int)(key >> 12), (int)(key & 0xfffu), size_thr);
+                }
+            } else {
+                for (long long k = tid; k < npairs; k += ST) {
+                    int2 pr = A.pairs[k];
+                    edge(pr.x, pr.y, size_thr);
+                }
             }
             __syncthreads();
             for (int i = tid; i < nl; i += ST) {
@@ -676,7 +717,7 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     size_t stat_threads = A.vec ? ((n + 127) / 128) * 32 : ((size_t)((w + 31) / 32) * h) * 32;   // one warp per chunk
     merge_stats_kernel<<<blocks_for(stat_threads), MT, 0, st>>>(A);
     MSG_LAUNCHED(ctx);
-    const size_t small_smem = (size_t)(SMALL_MAX_LABELS + 1) * 7 * sizeof(uint32_t);
+    const size_t small_smem = ((size_t)(SMALL_MAX_LABELS + 1) * 7 + SMALL_HSET) * sizeof(uint32_t);
     MSG_CUDA(ctx, cudaFuncSetAttribute(merge_rounds_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
     merge_rounds_small_kernel<<<1, ST, small_smem, st>>>(A);
     MSG_LAUNCHED(ctx);
