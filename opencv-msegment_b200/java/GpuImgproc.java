@@ -92,6 +92,47 @@ public final class GpuImgproc {
 		out.copyTo(dst);
 	}
 
+	/** Imgproc.Canny(image, edges, threshold1, threshold2) (PictureService.java:416). */
+	public static void Canny(Mat image, Mat edges, double threshold1, double threshold2) {
+		require(image.type() == CvType.CV_8UC1, "image must be CV_8UC1");
+		Mat out = new Mat(image.size(), CvType.CV_8UC1);
+		status(nCanny(CTX.get(), image.dataAddr(), image.step1(), out.dataAddr(), out.step1(), image.cols(), image.rows(),
+			threshold1, threshold2));
+		out.copyTo(edges);
+	}
+
+	/** Imgproc.dilate(src, dst, Mat.ones(krows, kcols, type)) (PictureService.java:428-429). */
+	public static void dilate(Mat src, Mat dst, int krows, int kcols) {
+		require(src.type() == CvType.CV_8UC1, "src must be CV_8UC1");
+		Mat out = new Mat(src.size(), CvType.CV_8UC1);
+		status(nDilate(CTX.get(), src.dataAddr(), src.step1(), out.dataAddr(), out.step1(), src.cols(), src.rows(), kcols, krows));
+		out.copyTo(dst);
+	}
+
+	/** Core.subtract(src1, src2, dst) on CV_8UC1 (PictureService.java:430). */
+	public static void subtract(Mat src1, Mat src2, Mat dst) {
+		require(src1.type() == CvType.CV_8UC1 && src2.type() == CvType.CV_8UC1 && src1.size().equals(src2.size()),
+			"subtract: CV_8UC1 of equal size");
+		Mat out = new Mat(src1.size(), CvType.CV_8UC1);
+		status(nSubtract(CTX.get(), src1.dataAddr(), src1.step1(), src2.dataAddr(), src2.step1(), out.dataAddr(), out.step1(),
+			src1.cols(), src1.rows()));
+		out.copyTo(dst);
+	}
+
+	/**
+	 * Marker half of PictureService.shapeAutoMarkerWatershed (PictureService.java:404-442) as one call, intermediates on
+	 * the device: gray, medianBlur(medianKsize), Canny(low, low * ratio), dilate 3x3, dilate 5x5, subtract, medianBlur 3,
+	 * connectedComponents(8).  Returns the label count, background included.
+	 */
+	public static int shapeSeeds(Mat src, Mat markers, int medianKsize, double lowThreshold, double ratio) {
+		require(src.type() == CvType.CV_8UC3, "src must be CV_8UC3");
+		markers.create(src.size(), CvType.CV_32SC1);
+		int[] n = new int[1];
+		status(nShapeSeeds(CTX.get(), src.dataAddr(), src.step1(), src.cols(), src.rows(), medianKsize, lowThreshold,
+			lowThreshold * ratio, markers.dataAddr(), markers.step1() * 4, n));
+		return n[0];
+	}
+
 	private static void require(boolean ok, String msg) {
 		if (!ok) {
 			throw new CvException(msg);
@@ -125,6 +166,11 @@ public final class GpuImgproc {
 		int krows, int kcols);
 	private static native int nGray(long ctx, long src, long sstep, long dst, long dstep, int w, int h);
 	private static native int nMedian(long ctx, long src, long sstep, long dst, long dstep, int w, int h, int ksize);
+	private static native int nCanny(long ctx, long src, long sstep, long dst, long dstep, int w, int h, double t1, double t2);
+	private static native int nDilate(long ctx, long src, long sstep, long dst, long dstep, int w, int h, int kw, int kh);
+	private static native int nSubtract(long ctx, long a, long astep, long b, long bstep, long dst, long dstep, int w, int h);
+	private static native int nShapeSeeds(long ctx, long src, long sstep, int w, int h, int ksize, double t1, double t2,
+		long markers, long mstep, int[] n);
 	private static native int nRender(long ctx, long labels, long lstep, long dst, long dstep, int w, int h, int depth,
 		byte[] colors);
 }

@@ -92,3 +92,32 @@ JNIEXPORT jint JNICALL J(nMedian)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlo
 {
     return msg_median_blur((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h, ksize);
 }
+
+JNIEXPORT jint JNICALL J(nCanny)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h,
+                                 jdouble t1, jdouble t2)
+{
+    return msg_canny((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h, t1, t2);
+}
+
+JNIEXPORT jint JNICALL J(nDilate)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h,
+                                  jint kw, jint kh)
+{
+    return msg_dilate((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h, kw, kh);
+}
+
+JNIEXPORT jint JNICALL J(nSubtract)(JNIEnv* e, jclass c, jlong ctx, jlong a, jlong astep, jlong b, jlong bstep, jlong dst,
+                                    jlong dstep, jint w, jint h)
+{
+    return msg_subtract((msg_ctx*)P(ctx), (const uint8_t*)P(a), (size_t)astep, (const uint8_t*)P(b), (size_t)bstep,
+                        (uint8_t*)P(dst), (size_t)dstep, w, h);
+}
+
+JNIEXPORT jint JNICALL J(nShapeSeeds)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jint w, jint h, jint ksize,
+                                      jdouble t1, jdouble t2, jlong markers, jlong mstep, jintArray n)
+{
+    int32_t count = 0;
+    int rc = msg_shape_seeds((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, w, h, ksize, t1, t2, (int32_t*)P(markers),
+                             (size_t)mstep, &count, NULL, 0);
+    if (rc == 0 && n) { jint v = count; (*e)->SetIntArrayRegion(e, n, 0, 1, &v); }
+    return rc;
+}
