@@ -121,7 +121,35 @@ __device__ __forceinline__ void window_scan(const uint32_t* __restrict__ base, i
         } else {
             uint32_t lo = 0, hi = 0;
             int sx = 0;
-            if (NX > 0) {
+            if (NX > 0 && NX <= 41) {
+                // Issue-slot and pipe balance: a hit costs PRMT (B,0,R,0) + three plain adds -- `lo` (16-bit lanes B, R),
+                // `st` (the whole packed word: B + G<<8 + R<<16 + flag<<24 with flag = 1, no carry out of 32 bits for
+                // rows of <= 41 pixels) and `cx` (count << 16 | sum of xx).  G is recovered at the row flush from
+                // st - B - (R << 16) - (count << 24).  Plain adds can issue on either integer pipe, so the 8 slots per
+                // test split 4 : 4 between the ALU pipe (VABSDIFF4, ISETP, PRMT, one add) and the FMA pipe (IDP4A,
+                // two adds as IMAD) instead of 5 : 3 with two PRMTs.
+                uint32_t st = 0, cx = 0;
+#pragma unroll
+                for (int xx = 0; xx < (NX > 0 ? NX : 1); ++xx) {
+                    uint32_t t = row[xx];
+                    uint32_t e = __vabsdiffu4(t, c);
+                    const uint32_t x = __byte_perm(t, 0u, 0x4240);     // (B, 0, R, 0), unconditional
+                    // one predicate, three predicated adds -- spelled in PTX so that they stay predicated adds
+                    asm("{\n\t"
+                        ".reg .pred p;\n\t"
+                        "setp.le.s32 p, %3, %4;\n\t"
+                        "@p add.u32 %0, %0, %5;\n\t"
+                        "@p add.u32 %1, %1, %6;\n\t"
+                        "@p add.u32 %2, %2, %7;\n\t"
+                        "}"
+                        : "+r"(lo), "+r"(st), "+r"(cx)
+                        : "r"(dp4a_u(e, e, 0u)), "r"(isr2), "r"(x), "r"(t), "r"(0x10000u + (uint32_t)xx));
+                }
+                const uint32_t rcn = cx >> 16;
+                sx = (int)(cx & 0xFFFFu);
+                const uint32_t g = (st - (lo & 0xFFFFu) - (lo & 0xFFFF0000u) - (rcn << 24)) >> 8;
+                hi = g | (rcn << 16);
+            } else if (NX > 0) {
 #pragma unroll
                 for (int xx = 0; xx < (NX > 0 ? NX : 1); ++xx) {
                     uint32_t t = row[xx];
