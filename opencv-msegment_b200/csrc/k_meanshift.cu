@@ -267,22 +267,45 @@ __global__ void __launch_bounds__(TW * 4, 3) meanshift_tile_kernel(msg_plane S, 
     }
     __syncthreads();
 
-    // ---- initial queue: active pixels of the tile, in raster order within each warp chunk
-    for (int base = (tid / 32) * 32; base < NPIX; base += NT) {
-        int p = base + lane;
-        int ty = p / TW, tx = p % TW;
-        int gx = tx0 + tx, gy = ty0 + ty;
-        int r = gy - S.y0;
-        bool act = (gx < S.w) && (gy < S.hfull) && (r < S.rows);
-        if (act && prm.use_mask) act = (D.p[(size_t)r * D.pitch + gx] >> 24) != 0;
-        unsigned m = __ballot_sync(0xffffffffu, act);
-        int pos = 0;
-        if (lane == 0 && m) pos = atomicAdd(&qn[0], __popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (act) {
-            int slot = pos + __popc(m & ((1u << lane) - 1));
-            uint32_t w0 = (uint32_t)p | ((uint32_t)(tx + g.halo) << 12) | ((uint32_t)(ty + g.halo) << 21);
-            q0[slot] = make_uint2(w0, stage[(ty + g.halo) * g.swp + tx + g.halo]);
+    // ---- initial queue: active pixels of the tile.  A warp queues a block of RPW consecutive rows of one 32-pixel-wide
+    //      column of the tile (one slot allocation per block), so 32 consecutive queue items come from few rows of one 32-column
+    //      band: pixels of one row fall in distinct shared-memory banks, and the row pitch residue spreads consecutive rows
+    //      (fewer bank conflicts among the 32 windows a warp reads at a time than with half-rows in arrival order).
+    {
+        constexpr int NW = NT / 32, RPW = TH / NW;             // 8 warps x 4 rows (TW = 64) or 4 warps x 8 rows (TW = 32)
+        const int wq = tid / 32;
+        for (int half = 0; half < TW / 32; ++half) {
+            const int tx = half * 32 + lane;
+            const int gx = tx0 + tx;
+            unsigned actbits = 0;
+            int total = 0;
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) {
+                const int ty = wq * RPW + k;
+                const int gy = ty0 + ty, r = gy - S.y0;
+                bool act = (gx < S.w) && (gy < S.hfull) && (r < S.rows);
+                if (act && prm.use_mask) act = (D.p[(size_t)r * D.pitch + gx] >> 24) != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, act);
+                if (act) actbits |= 1u << k;
+                total += __popc(m);
+            }
+            int pos = 0;
+            if (lane == 0 && total) pos = atomicAdd(&qn[0], total);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            int run = 0;
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) {
+                const bool act = (actbits >> k) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, act);
+                if (act) {
+                    const int ty = wq * RPW + k;
+                    const int p = ty * TW + tx;
+                    const int slot = pos + run + __popc(m & ((1u << lane) - 1));
+                    uint32_t w0 = (uint32_t)p | ((uint32_t)(tx + g.halo) << 12) | ((uint32_t)(ty + g.halo) << 21);
+                    q0[slot] = make_uint2(w0, stage[(ty + g.halo) * g.swp + tx + g.halo]);
+                }
+                run += __popc(m);
+            }
         }
     }
     __syncthreads();
@@ -568,9 +591,15 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
             g.sw = TWsel + 2 * g.halo;
             g.sh = TH + 2 * g.halo;
             // row pitch: a multiple of 4 words (TMA bulk copies need 16-byte aligned destinations) whose residue mod 32 banks
-            // keeps runs of active pixels on neighbouring rows apart (measured: residues 12..24 give the fewest conflicts)
+            // is +-8: the queue holds blocks of 4..8 consecutive rows of a 32-column band, so runs of active pixels on
+            // neighbouring rows land 8 banks apart (measured at 1080p, sp = 10: residue 8 / 24: 0.342 ms, 16: 0.359, 0: 0.425)
             g.swp = g.sw;
-            while (g.swp % 32 < 12 || g.swp % 32 > 24) g.swp += 4;
+            while (g.swp % 32 != 8 && g.swp % 32 != 24) g.swp += 4;
+            if (const char* e = getenv("MSG_PITCH_RES")) {     // experiment switch: force the pitch residue mod 32 banks
+                const int want = atoi(e) & 28;
+                g.swp = g.sw;
+                while (g.swp % 32 != want) g.swp += 4;
+            }
             smem = ((size_t)((g.sh * g.swp + 1) & ~1) + 4 * (size_t)(TWsel * TH)) * sizeof(uint32_t);
             if (smem <= (size_t)ctx->max_smem_optin - 1024 && g.sw < 512 && g.sh < 512) break;
             if (drift == 0) { tile_ok = false; break; }
