@@ -145,6 +145,68 @@ MSG_API int msg_shape_seeds_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step,
                         double threshold1, double threshold2, int32_t* d_markers, size_t markers_step, int32_t* d_n_labels,
                         uint8_t* d_stages);
 
+/* ---- colour-method marker generator (PictureService.java:309-366, :938-943, :1018-1023) -- */
+/* The Java loop of PictureService.java:309-318: pixels equal to (255,255,255) become (0,0,0). */
+MSG_API int msg_white_to_black(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, uint8_t* dst_bgr, size_t dst_step,
+                       int width, int height);
+/* Imgproc.threshold(src 8UC1, dst, thresh, maxval, type) (PictureService.java:941) for type = THRESH_BINARY (0), optionally
+ * | THRESH_OTSU (8): dst = src > t ? maxval : 0 with t = floor(thresh), or the Otsu threshold (getThreshVal_Otsu_8u: the
+ * sequential double-precision scan over the 256 bins).  *used_thresh (may be NULL) receives t, the value cv::threshold returns. */
+#define MSG_THRESH_BINARY 0
+#define MSG_THRESH_OTSU 8
+MSG_API int msg_threshold(msg_ctx* ctx, const uint8_t* src_gray, size_t src_step, uint8_t* dst, size_t dst_step, int width,
+                  int height, double thresh, double maxval, int type, double* used_thresh);
+/* Imgproc.distanceTransform(src 8UC1, dst 32FC1, CV_DIST_L2, 5) (PictureService.java:1020): two-pass 5x5 chamfer with the
+ * metrics 1 / 1.4 / 2.1969 accumulated in float32 (the arithmetic of the IPP-backed cv2 build the oracle is pinned on; see
+ * DESIGN.md for the 1-ulp corner where that build deviates from the plain two-pass order).  Only (dist_type 2, mask 5).
+ * A source without zero pixels gives FLT_MAX everywhere, as cv2 does.  Rows up to msg_distance_transform_max_width(). */
+MSG_API int msg_distance_transform(msg_ctx* ctx, const uint8_t* src, size_t src_step, float* dst, size_t dst_step, int width,
+                           int height, int dist_type, int mask_size);
+MSG_API int msg_distance_transform_max_width(msg_ctx* ctx);
+/* Core.normalize(src 32FC1, dst, alpha, beta, NORM_MINMAX) (PictureService.java:1021): scale / shift in double, applied in
+ * float with one fused multiply-add; a constant image maps to min(alpha, beta). */
+MSG_API int msg_normalize_minmax(msg_ctx* ctx, const float* src, size_t src_step, float* dst, size_t dst_step, int width,
+                         int height, double alpha, double beta);
+/* Imgproc.threshold on 32FC1, THRESH_BINARY (PictureService.java:348): dst = src > (float)thresh ? (float)maxval : 0. */
+MSG_API int msg_threshold_f32(msg_ctx* ctx, const float* src, size_t src_step, float* dst, size_t dst_step, int width, int height,
+                      double thresh, double maxval);
+/* Imgproc.dilate(src 32FC1, dst, Mat.ones(kh, kw)) (PictureService.java:349-350). */
+MSG_API int msg_dilate_f32(msg_ctx* ctx, const float* src, size_t src_step, float* dst, size_t dst_step, int width, int height,
+                   int kw, int kh);
+/* Mat.convertTo(dst, CV_8U) from 32FC1 (PictureService.java:355-356): saturate_cast<uchar>(cvRound(v)). */
+MSG_API int msg_convert_f32_to_u8(msg_ctx* ctx, const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int width,
+                          int height);
+/* findContours(mask, contours, hierarchy, RETR_CCOMP, CHAIN_APPROX_NONE) followed by
+ * for (i = 0; i < contours.size(); i++) drawContours(markers, contours, i, Scalar.all(i + 1), -1, 8, hierarchy, INT_MAX, Point())
+ * (PictureService.java:360-364, also :272-278) in one call, without tracing: markers (32SC1) is written completely (0 where
+ * nothing is painted), *n_contours = contours.size() (the reference's `depth`, :365).  Equivalent rule: DESIGN.md section K3. */
+MSG_API int msg_contour_markers(msg_ctx* ctx, const uint8_t* mask, size_t mask_step, int32_t* markers, size_t markers_step,
+                        int width, int height, int32_t* n_contours);
+/* Imgproc.circle(img 32SC1, (cx,cy), radius, Scalar(value), FILLED) (PictureService.java:366), in place. */
+MSG_API int msg_circle_filled(msg_ctx* ctx, int32_t* img, size_t step, int width, int height, int cx, int cy, int radius,
+                      int32_t value);
+/* The whole generator, intermediates in HBM (PictureService.java:309-366): white->black, Laplacian sharpen (taps as in
+ * msg_laplacian_sharpen), cvtColor(BGR2GRAY), threshold(40, 255, BINARY | OTSU), distanceTransform(L2, 5), normalize(0, 1,
+ * MINMAX), threshold(peak_thresh, 1, BINARY), dilate 3x3, convertTo 8U, findContours / drawContours labelling,
+ * circle((5,5), 3, 255, FILLED).  markers: 32SC1; *n_contours = contours.size().  Optional stage outputs (NULL to skip):
+ * sharp (8UC3, sharp_step) = "laplassian_sharp", bw (8UC1) = "bw", dist (32FC1, normalised) = "distance_transform",
+ * peaks (8UC1, 0/1) = "distance_peaks". */
+MSG_API int msg_color_seeds(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, int width, int height, const int8_t* taps,
+                    int krows, int kcols, double peak_thresh, int32_t* markers, size_t markers_step, int32_t* n_contours,
+                    uint8_t* sharp_bgr, size_t sharp_step, uint8_t* bw, size_t bw_step, float* dist, size_t dist_step,
+                    uint8_t* peaks, size_t peaks_step);
+/* Device-resident form: every pointer is device memory on ctx's device; the optional stage planes are dense (width*3,
+ * width, width*4, width bytes per row).  *n_contours is a HOST int (the labelling reads its list sizes back). */
+MSG_API int msg_color_seeds_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int width, int height, const int8_t* taps,
+                        int krows, int kcols, double peak_thresh, int32_t* d_markers, size_t markers_step,
+                        int32_t* n_contours, uint8_t* d_sharp, uint8_t* d_bw, float* d_dist, uint8_t* d_peaks);
+
+/* Imgproc.bilateralFilter(src, dst, d, sigmaColor, sigmaSpace) on 8UC1 / 8UC3 (PictureService.java:490),
+ * BORDER_REFLECT_101: OpenCV's scalar loop (float accumulation in window order).  Floating point: equal to the oracle bit for
+ * bit, within 1 LSB of cv2 (whose vector path fuses the multiply-adds).  channels = 1 or 3; window radius <= 32. */
+MSG_API int msg_bilateral_filter(msg_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step, int width,
+                         int height, int channels, int d, double sigma_color, double sigma_space);
+
 /* ---- fused pipeline: filter -> label -> merge -> render, intermediates stay in HBM -------- */
 typedef struct msg_segment_params {
     double sp, sr;

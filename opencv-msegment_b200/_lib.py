@@ -55,6 +55,20 @@ SIGNATURES = {
     "msg_subtract": (_I, [_P, _P, _SZ, _P, _SZ, _P, _SZ, _I, _I]),
     "msg_shape_seeds": (_I, [_P, _P, _SZ, _I, _I, _I, _D, _D, _P, _SZ, _P, _P, _SZ]),
     "msg_shape_seeds_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _D, _D, _P, _SZ, _P, _P]),
+    "msg_white_to_black": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I]),
+    "msg_threshold": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _D, _D, _I, C.POINTER(_D)]),
+    "msg_distance_transform": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I]),
+    "msg_distance_transform_max_width": (_I, [_P]),
+    "msg_normalize_minmax": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _D, _D]),
+    "msg_threshold_f32": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _D, _D]),
+    "msg_dilate_f32": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I]),
+    "msg_convert_f32_to_u8": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I]),
+    "msg_contour_markers": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, C.POINTER(C.c_int32)]),
+    "msg_circle_filled": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _I, C.c_int32]),
+    "msg_color_seeds": (_I, [_P, _P, _SZ, _I, _I, _P, _I, _I, _D, _P, _SZ, C.POINTER(C.c_int32), _P, _SZ, _P, _SZ, _P, _SZ,
+                             _P, _SZ]),
+    "msg_color_seeds_dev": (_I, [_P, _P, _SZ, _I, _I, _P, _I, _I, _D, _P, _SZ, C.POINTER(C.c_int32), _P, _P, _P, _P]),
+    "msg_bilateral_filter": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, _D, _D]),
     "msg_segment_params_default": (None, [C.POINTER(SegmentParams)]),
     "msg_segment": (_I, [_P, _P, _SZ, _I, _I, C.POINTER(SegmentParams), _P, _SZ, _P, _SZ, _P, _SZ, C.POINTER(C.c_int32)]),
     "msg_submit_segment": (_I, [_P, _P, _SZ, _I, _I, C.POINTER(SegmentParams), _P, _SZ, _P, _SZ, _P, _SZ, C.POINTER(_I)]),

@@ -159,7 +159,7 @@ void msg_destroy(msg_ctx* ctx)
     cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_out2); cudaFree(ctx->d_labels);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_ovf); cudaFree(ctx->d_scratch); cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_colors); cudaFree(ctx->d_work); cudaFree(ctx->d_cells); cudaFree(ctx->d_aux);
+    cudaFree(ctx->d_colors); cudaFree(ctx->d_work); cudaFree(ctx->d_cells); cudaFree(ctx->d_aux); cudaFree(ctx->d_small);
     for (int l = 0; l < MSG_MAX_LEVELS; l++)
         for (int k = 0; k < 3; k++) cudaEventDestroy(ctx->prof_ev[l][k]);
     cudaFreeHost(ctx->h_counters);
@@ -1204,6 +1204,306 @@ int msg_shape_seeds(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h
         for (int k = 0; k < 4; k++)
             MSG_TRY(copy_out(ctx, stages + (size_t)k * stage_step * h, stage_step, ctx->d_out + (size_t)k * n, (size_t)w, h));
     return finish_count(ctx, n_labels);
+}
+
+// ============================================================================ colour-method seeds (8(f3), rows a6 / a4)
+
+// small device tables live in d_small: [0,1024) histogram, [1024, 1024+64) scalars (Otsu threshold, max, min/max pair),
+// [2048, ...) circle spans / bilateral tables
+static int small_reserve(msg_ctx* ctx, size_t extra)
+{
+    return msg_reserve(ctx, (void**)&ctx->d_small, &ctx->d_small_cap, 2048 + extra);
+}
+#define SMALL_HIST(ctx) ((unsigned*)(ctx)->d_small)
+#define SMALL_THRESH(ctx) ((int32_t*)((ctx)->d_small + 1024))
+#define SMALL_MAX(ctx) ((float*)((ctx)->d_small + 1024 + 8))
+#define SMALL_MM(ctx) ((float*)((ctx)->d_small + 1024 + 16))
+#define SMALL_TABLES(ctx) ((ctx)->d_small + 2048)
+
+int msg_white_to_black(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "white_to_black src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 3, "white_to_black dst"));
+    size_t rb = (size_t)w * 3;
+    MSG_TRY(copy_in(ctx, src, sstep, rb, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rb * h));
+    MSG_TRY(k_white_to_black(ctx, ctx->d_in, rb, ctx->d_out, rb, w, h));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, rb, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+static int clamp_to_u8_range(double v) { return (int)floor(fmin(fmax(v, -1.0), 256.0)); }
+
+int msg_threshold(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, double thresh,
+                  double maxval, int type, double* used)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 1, "threshold src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 1, "threshold dst"));
+    if (type != MSG_THRESH_BINARY && type != (MSG_THRESH_BINARY | MSG_THRESH_OTSU))
+        return msg_fail(ctx, MSG_EINVAL, "threshold: only THRESH_BINARY, optionally | THRESH_OTSU (got type %d)", type);
+    if (!(thresh == thresh) || !(maxval == maxval)) return msg_fail(ctx, MSG_EINVAL, "threshold: thresh / maxval must be numbers");
+    int imax = (int)lrint(fmin(fmax(maxval, 0.0), 255.0));          // saturate_cast<uchar>(cvRound(maxval))
+    MSG_TRY(small_reserve(ctx, 0));
+    MSG_TRY(copy_in(ctx, src, sstep, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, (size_t)w * h));
+    int t = clamp_to_u8_range(thresh);
+    if (type & MSG_THRESH_OTSU) {
+        MSG_TRY(k_otsu(ctx, ctx->d_in, (size_t)w, w, h, SMALL_HIST(ctx), SMALL_THRESH(ctx)));
+        MSG_TRY(k_threshold_u8(ctx, ctx->d_in, (size_t)w, ctx->d_out, (size_t)w, w, h, SMALL_THRESH(ctx), 0, imax));
+        MSG_CUDA(ctx, cudaMemcpyAsync(&t, SMALL_THRESH(ctx), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        MSG_TRY(k_threshold_u8(ctx, ctx->d_in, (size_t)w, ctx->d_out, (size_t)w, w, h, nullptr, t, imax));
+    }
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (used) *used = (double)t;
+    return MSG_OK;
+}
+
+int msg_distance_transform_max_width(msg_ctx* ctx) { return ctx ? k_distance_transform_max_width(ctx) : 0; }
+
+int msg_distance_transform(msg_ctx* ctx, const uint8_t* src, size_t sstep, float* dst, size_t dstep, int w, int h, int dist_type,
+                           int mask_size)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 1, "distanceTransform src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 4, "distanceTransform dst"));
+    if (dist_type != 2 || mask_size != 5)
+        return msg_fail(ctx, MSG_EINVAL, "distanceTransform: only CV_DIST_L2 (2) with mask size 5 (got %d, %d)", dist_type, mask_size);
+    MSG_TRY(small_reserve(ctx, 0));
+    MSG_TRY(copy_in(ctx, src, sstep, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, (size_t)w * h * 4));
+    MSG_TRY(k_distance_transform(ctx, ctx->d_in, (size_t)w, (float*)ctx->d_out, w, h, SMALL_MAX(ctx)));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w * 4, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+// 32F plane in, 32F plane out through d_in / d_out (which: 0 normalise, 1 threshold, 2 dilate)
+static int f32_host(msg_ctx* ctx, const float* src, size_t sstep, float* dst, size_t dstep, int w, int h, int which, double a,
+                    double b, int kw, int kh)
+{
+    size_t rb = (size_t)w * 4;
+    MSG_TRY(small_reserve(ctx, 0));
+    MSG_TRY(copy_in(ctx, src, sstep, rb, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rb * h));
+    if (which == 0) MSG_TRY(k_normalize_minmax_f32(ctx, (const float*)ctx->d_in, (float*)ctx->d_out, w, h, a, b, SMALL_MM(ctx)));
+    else if (which == 1) MSG_TRY(k_threshold_f32(ctx, (const float*)ctx->d_in, (float*)ctx->d_out, w, h, (float)a, (float)b));
+    else MSG_TRY(k_dilate_f32(ctx, (const float*)ctx->d_in, (float*)ctx->d_out, w, h, kw, kh));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, rb, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+int msg_normalize_minmax(msg_ctx* ctx, const float* src, size_t sstep, float* dst, size_t dstep, int w, int h, double alpha,
+                         double beta)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 4, "normalize src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 4, "normalize dst"));
+    if (!(alpha == alpha) || !(beta == beta)) return msg_fail(ctx, MSG_EINVAL, "normalize: alpha / beta must be numbers");
+    return f32_host(ctx, src, sstep, dst, dstep, w, h, 0, alpha, beta, 0, 0);
+}
+
+int msg_threshold_f32(msg_ctx* ctx, const float* src, size_t sstep, float* dst, size_t dstep, int w, int h, double thresh,
+                      double maxval)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 4, "threshold src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 4, "threshold dst"));
+    if (!(thresh == thresh) || !(maxval == maxval)) return msg_fail(ctx, MSG_EINVAL, "threshold: thresh / maxval must be numbers");
+    return f32_host(ctx, src, sstep, dst, dstep, w, h, 1, thresh, maxval, 0, 0);
+}
+
+int msg_dilate_f32(msg_ctx* ctx, const float* src, size_t sstep, float* dst, size_t dstep, int w, int h, int kw, int kh)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 4, "dilate src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 4, "dilate dst"));
+    if (kw < 1 || kh < 1 || kw > 63 || kh > 63) return msg_fail(ctx, MSG_EINVAL, "dilate: kernel must be 1..63 x 1..63 (got %dx%d)", kw, kh);
+    return f32_host(ctx, src, sstep, dst, dstep, w, h, 2, 0, 0, kw, kh);
+}
+
+int msg_convert_f32_to_u8(msg_ctx* ctx, const float* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 4, "convertTo src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 1, "convertTo dst"));
+    MSG_TRY(copy_in(ctx, src, sstep, (size_t)w * 4, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, (size_t)w * h));
+    MSG_TRY(k_f32_to_u8(ctx, (const float*)ctx->d_in, ctx->d_out, (size_t)w, w, h));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+int msg_contour_markers(msg_ctx* ctx, const uint8_t* mask, size_t step, int32_t* markers, size_t mstep, int w, int h,
+                        int32_t* n_contours)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, mask, step, w, h, 1, "findContours image"));
+    MSG_TRY(check_img(ctx, markers, mstep, w, h, 4, "markers"));
+    MSG_TRY(copy_in(ctx, mask, step, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out2, &ctx->d_out2_cap, (size_t)w * h * 4));
+    int32_t n = 0;
+    MSG_TRY(k_contour_markers(ctx, ctx->d_in, (size_t)w, w, h, (int32_t*)ctx->d_out2, (size_t)w * 4, &n));
+    MSG_TRY(copy_out(ctx, markers, mstep, ctx->d_out2, (size_t)w * 4, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_contours) *n_contours = n;
+    return MSG_OK;
+}
+
+static int circle_dev(msg_ctx* ctx, int32_t* d_img, size_t step, int w, int h, int cx, int cy, int radius, int32_t value)
+{
+    if (radius < 0 || radius > 16384) return msg_fail(ctx, MSG_EINVAL, "circle: radius must be in [0, 16384] (got %d)", radius);
+    size_t ints = (size_t)12 * (radius + 2);
+    MSG_TRY(small_reserve(ctx, ints * sizeof(int)));
+    int* h_spans = (int*)malloc(ints * sizeof(int));
+    if (!h_spans) return msg_fail(ctx, MSG_ENOMEM, "circle: out of host memory");
+    int rc = k_circle_filled_i32(ctx, d_img, step, w, h, cx, cy, radius, value, (int*)SMALL_TABLES(ctx), h_spans);
+    if (rc == MSG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = msg_fail(ctx, MSG_ECUDA, "circle: stream sync failed");
+    free(h_spans);
+    return rc;
+}
+
+int msg_circle_filled(msg_ctx* ctx, int32_t* img, size_t step, int w, int h, int cx, int cy, int radius, int32_t value)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, img, step, w, h, 4, "circle img"));
+    MSG_TRY(copy_in(ctx, img, step, (size_t)w * 4, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(circle_dev(ctx, (int32_t*)ctx->d_in, (size_t)w * 4, w, h, cx, cy, radius, value));
+    MSG_TRY(copy_out(ctx, img, step, ctx->d_in, (size_t)w * 4, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+int msg_color_seeds_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int w, int h, const int8_t* taps, int krows, int kcols,
+                        double peak_thresh, int32_t* d_markers, size_t mstep, int32_t* n_contours, uint8_t* d_sharp, uint8_t* d_bw,
+                        float* d_dist, uint8_t* d_peaks)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_bgr, step, w, h, 3, "colour seeds src"));
+    MSG_TRY(check_img(ctx, d_markers, mstep, w, h, 4, "markers"));
+    if (!taps || krows < 1 || kcols < 1 || !(krows & 1) || !(kcols & 1) || krows * kcols > 1024)
+        return msg_fail(ctx, MSG_EINVAL, "colour seeds: sharpen kernel must be odd x odd with at most 1024 taps");
+    if (!(peak_thresh == peak_thresh)) return msg_fail(ctx, MSG_EINVAL, "colour seeds: peak threshold must be a number");
+    if (!n_contours) return msg_fail(ctx, MSG_EINVAL, "colour seeds: null count pointer");
+    const size_t n = (size_t)w * h;
+    MSG_TRY(small_reserve(ctx, 256));
+    // d_aux: [black 3n][sharp 3n][gray n][bw n][peaks n][pad][dist 4n][tmpA 4n][tmpB 4n]
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_aux, &ctx->d_aux_cap, 21 * n + 64));
+    uint8_t* a = ctx->d_aux;
+    uint8_t* black = a;
+    uint8_t* sharp = d_sharp ? d_sharp : a + 3 * n;
+    uint8_t* gray = a + 6 * n;
+    uint8_t* bw = d_bw ? d_bw : a + 7 * n;
+    uint8_t* peaks = d_peaks ? d_peaks : a + 8 * n;
+    float* f0 = (float*)(a + ((9 * n + 15) & ~(size_t)15));
+    float* dist = d_dist ? d_dist : f0;
+    float* tmpA = f0 + n;
+    float* tmpB = f0 + 2 * n;
+    const size_t rb3 = (size_t)w * 3;
+    MSG_TRY(k_white_to_black(ctx, d_bgr, step, black, rb3, w, h));                                   // PictureService.java:309-318
+    MSG_TRY(k_sharpen(ctx, black, rb3, sharp, rb3, w, h, taps, krows, kcols));                        // :323-333
+    MSG_TRY(k_gray(ctx, sharp, rb3, gray, (size_t)w, w, h));                                          // :940
+    MSG_TRY(k_otsu(ctx, gray, (size_t)w, w, h, SMALL_HIST(ctx), SMALL_THRESH(ctx)));                  // :941
+    MSG_TRY(k_threshold_u8(ctx, gray, (size_t)w, bw, (size_t)w, w, h, SMALL_THRESH(ctx), 0, 255));
+    MSG_TRY(k_distance_transform(ctx, bw, (size_t)w, tmpA, w, h, SMALL_MAX(ctx)));                    // :1020
+    MSG_TRY(k_normalize_minmax_f32(ctx, tmpA, dist, w, h, 0., 1., SMALL_MM(ctx)));                    // :1021
+    MSG_TRY(k_threshold_f32(ctx, dist, tmpA, w, h, (float)peak_thresh, 1.f));                         // :348 (raw distances are dead)
+    MSG_TRY(k_dilate_f32(ctx, tmpA, tmpB, w, h, 3, 3));                                               // :349-350
+    MSG_TRY(k_f32_to_u8(ctx, tmpB, peaks, (size_t)w, w, h));                                          // :355-356
+    MSG_TRY(k_contour_markers(ctx, peaks, (size_t)w, w, h, d_markers, mstep, n_contours));            // :360-365
+    return circle_dev(ctx, d_markers, mstep, w, h, 5, 5, 3, 255);                                     // :366
+}
+
+int msg_color_seeds(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const int8_t* taps, int krows, int kcols,
+                    double peak_thresh, int32_t* markers, size_t mstep, int32_t* n_contours, uint8_t* sharp, size_t sharp_step,
+                    uint8_t* bw, size_t bw_step, float* dist, size_t dist_step, uint8_t* peaks, size_t peaks_step)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "colour seeds src"));
+    MSG_TRY(check_img(ctx, markers, mstep, w, h, 4, "markers"));
+    if (sharp) MSG_TRY(check_img(ctx, sharp, sharp_step, w, h, 3, "colour seeds sharp"));
+    if (bw) MSG_TRY(check_img(ctx, bw, bw_step, w, h, 1, "colour seeds bw"));
+    if (dist) MSG_TRY(check_img(ctx, dist, dist_step, w, h, 4, "colour seeds dist"));
+    if (peaks) MSG_TRY(check_img(ctx, peaks, peaks_step, w, h, 1, "colour seeds peaks"));
+    const size_t n = (size_t)w * h;
+    MSG_TRY(copy_in(ctx, src, sstep, (size_t)w * 3, h, &ctx->d_in, &ctx->d_in_cap));
+    // d_out: [sharp 3n][bw n][peaks n][pad][dist 4n];  d_out2: markers
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, 9 * n + 64));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out2, &ctx->d_out2_cap, 4 * n));
+    uint8_t* d_sharp = ctx->d_out;
+    uint8_t* d_bw = ctx->d_out + 3 * n;
+    uint8_t* d_peaks = ctx->d_out + 4 * n;
+    float* d_dist = (float*)(ctx->d_out + (((5 * n) + 15) & ~(size_t)15));
+    int32_t cnt = 0;
+    MSG_TRY(msg_color_seeds_dev(ctx, ctx->d_in, (size_t)w * 3, w, h, taps, krows, kcols, peak_thresh, (int32_t*)ctx->d_out2,
+                                (size_t)w * 4, &cnt, d_sharp, d_bw, d_dist, d_peaks));
+    MSG_TRY(copy_out(ctx, markers, mstep, ctx->d_out2, (size_t)w * 4, h));
+    if (sharp) MSG_TRY(copy_out(ctx, sharp, sharp_step, d_sharp, (size_t)w * 3, h));
+    if (bw) MSG_TRY(copy_out(ctx, bw, bw_step, d_bw, (size_t)w, h));
+    if (dist) MSG_TRY(copy_out(ctx, dist, dist_step, d_dist, (size_t)w * 4, h));
+    if (peaks) MSG_TRY(copy_out(ctx, peaks, peaks_step, d_peaks, (size_t)w, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_contours) *n_contours = cnt;
+    return MSG_OK;
+}
+
+// ============================================================================ bilateral filter (8(f2), row a5)
+
+int msg_bilateral_filter(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, int cn, int d,
+                         double sigma_color, double sigma_space)
+{
+    CTX_ENTER(ctx);
+    if (cn != 1 && cn != 3) return msg_fail(ctx, MSG_EINVAL, "bilateralFilter: 1 or 3 channels (got %d)", cn);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, cn, "bilateralFilter src"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, cn, "bilateralFilter dst"));
+    if (!(sigma_color == sigma_color) || !(sigma_space == sigma_space))
+        return msg_fail(ctx, MSG_EINVAL, "bilateralFilter: sigmas must be numbers");
+    if (sigma_color <= 0) sigma_color = 1;
+    if (sigma_space <= 0) sigma_space = 1;
+    const double gc = -0.5 / (sigma_color * sigma_color), gs = -0.5 / (sigma_space * sigma_space);
+    int radius = d <= 0 ? (int)lrint(sigma_space * 1.5) : d / 2;
+    if (radius < 1) radius = 1;
+    if (radius > 32) return msg_fail(ctx, MSG_EINVAL, "bilateralFilter: window radius %d > 32", radius);
+    const int dd = 2 * radius + 1;
+    // tables exactly as cv::bilateralFilter builds them (double exp, rounded to float)
+    size_t tbytes = (size_t)dd * dd * (sizeof(float) + 2 * sizeof(short)) + (size_t)256 * cn * sizeof(float);
+    uint8_t* host = (uint8_t*)malloc(tbytes);
+    if (!host) return msg_fail(ctx, MSG_ENOMEM, "bilateralFilter: out of host memory");
+    float* sw = (float*)host;
+    float* cw = sw + dd * dd;
+    short* ofs = (short*)(cw + 256 * cn);
+    for (int i = 0; i < 256 * cn; i++) cw[i] = (float)exp(i * i * gc);
+    int maxk = 0;
+    for (int i = -radius; i <= radius; i++)
+        for (int j = -radius; j <= radius; j++) {
+            double r = sqrt((double)i * i + (double)j * j);
+            if (r > radius) continue;
+            sw[maxk] = (float)exp(r * r * gs);
+            ofs[2 * maxk] = (short)j; ofs[2 * maxk + 1] = (short)i;
+            maxk++;
+        }
+    int rc = small_reserve(ctx, tbytes);
+    if (rc == MSG_OK && cudaMemcpyAsync(SMALL_TABLES(ctx), host, tbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        rc = msg_fail(ctx, MSG_ECUDA, "bilateralFilter: table upload failed");
+    if (rc == MSG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = msg_fail(ctx, MSG_ECUDA, "bilateralFilter: sync failed");
+    free(host);
+    MSG_TRY(rc);
+    const float* d_sw = (const float*)SMALL_TABLES(ctx);
+    const float* d_cw = d_sw + dd * dd;
+    const short* d_ofs = (const short*)(d_cw + 256 * cn);
+    size_t rb = (size_t)w * cn;
+    MSG_TRY(copy_in(ctx, src, sstep, rb, h, &ctx->d_in, &ctx->d_in_cap));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rb * h));
+    MSG_TRY(k_bilateral(ctx, ctx->d_in, rb, ctx->d_out, rb, w, h, cn, radius, maxk, d_sw, d_ofs, d_cw));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, rb, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
 }
 
 }  // extern "C"

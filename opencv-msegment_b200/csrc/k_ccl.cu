@@ -648,6 +648,15 @@ int k_ccl_binary(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h,
     return MSG_OK;
 }
 
+// union-find parents -> roots (label = linear index of the component's first pixel, background stays negative)
+int k_ccl_flatten(msg_ctx* ctx, int32_t* d_labels, size_t n)
+{
+    ccl_flatten_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, ctx->stream>>>(d_labels, n);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
 int k_copy_labels_2d(msg_ctx* ctx, const int32_t* src, size_t sstep, int32_t* dst, size_t dstep, int w, int h)
 {
     dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);

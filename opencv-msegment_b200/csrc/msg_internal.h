@@ -63,6 +63,7 @@ struct msg_ctx {
     int32_t* h_counters;                     // pinned mirror
     uint8_t* d_colors; size_t d_colors_cap;
     uint8_t* d_aux;    size_t d_aux_cap;     // 8-bit planes of the seed generator (gray, blurred, classes, edges, ...)
+    uint8_t* d_small;  size_t d_small_cap;   // small tables of the colour-seed generator / bilateral filter (histogram, spans, weights)
     int32_t* d_cells;  size_t d_cells_cap;   // active pixels per 32x32 cell of the current level + tile order (K1 scheduling)
 
     // pinned host staging for pageable caller buffers
@@ -173,6 +174,25 @@ int k_hysteresis(msg_ctx* ctx, const uint8_t* d_cls, int w, int h, int32_t* d_la
 int k_dilate(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, int kw, int kh);
 int k_subtract(msg_ctx* ctx, const uint8_t* d_a, size_t astep, const uint8_t* d_b, size_t bstep, uint8_t* d_dst, size_t dstep,
                int w, int h);
+
+// k_colorseeds.cu / k_contours.cu: colour-method marker generator (8(f3), rows a6 / a4) and the bilateral pre-filter (a5)
+int k_ccl_flatten(msg_ctx* ctx, int32_t* d_labels, size_t n);
+int k_white_to_black(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h);
+int k_otsu(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, int w, int h, unsigned* d_hist, int32_t* d_thresh);
+int k_threshold_u8(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h,
+                   const int32_t* d_thresh, int thresh, int maxval);
+int k_distance_transform_max_width(msg_ctx* ctx);
+int k_distance_transform(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, float* d_dist, int w, int h, float* d_max);
+int k_normalize_minmax_f32(msg_ctx* ctx, const float* d_src, float* d_dst, int w, int h, double alpha, double beta, float* d_mm);
+int k_threshold_f32(msg_ctx* ctx, const float* d_src, float* d_dst, int w, int h, float thresh, float maxval);
+int k_dilate_f32(msg_ctx* ctx, const float* d_src, float* d_dst, int w, int h, int kw, int kh);
+int k_f32_to_u8(msg_ctx* ctx, const float* d_src, uint8_t* d_dst, size_t dstep, int w, int h);
+int k_circle_filled_i32(msg_ctx* ctx, int32_t* d_img, size_t step, int w, int h, int cx, int cy, int radius, int32_t value,
+                        int* d_spans, int* h_spans);
+int k_bilateral(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, int cn, int radius,
+                int maxk, const float* d_space_w, const short* d_space_ofs, const float* d_color_w);
+int k_contour_markers(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int32_t* d_markers, size_t mstep,
+                      int32_t* n_contours_host);
 
 #define MSG_LAUNCHED(ctx) ((ctx)->st.kernel_launches++)
 #define MSG_CHECK_LAUNCH(ctx) MSG_CUDA(ctx, cudaGetLastError())

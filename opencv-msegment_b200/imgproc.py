@@ -291,6 +291,138 @@ class GpuImgproc:
             return n.value, markers, {"blurred": st[0], "edges": st[1], "dde": st[2], "dde3": st[3], "k": k}
         return n.value, markers
 
+    # ---- colour-method marker generator (PictureService.java:309-366)
+    THRESH_BINARY, THRESH_OTSU, CV_DIST_L2, NORM_MINMAX = 0, 8, 2, 32
+    SHARPEN_KERNEL = ((1,), (1,), (1,), (1,), (-8,), (1,), (1,), (1,), (1,))   # new MatOfFloat(1,1,1,1,-8,1,1,1,1): 9 x 1
+
+    def _f32(self, a, what):
+        a = np.asarray(a)
+        if a.dtype != np.float32 or a.ndim != 2:
+            raise CvException(L.MSG_EINVAL, "%s: CV_32FC1 only" % what)
+        return a if a.strides[1] == 4 else np.ascontiguousarray(a)
+
+    # the Java loop of PictureService.java:309-318
+    def whiteToBlack(self, src):
+        src = _mat8uc3(src, "src")
+        h, w = src.shape[:2]
+        dst = np.empty_like(src)
+        self.ctx.check(self._lib.msg_white_to_black(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h))
+        return dst
+
+    # Imgproc.threshold(src, dst, thresh, maxval, type) -> (computed threshold, dst); 8UC1 (BINARY [| OTSU]) or 32FC1 (BINARY)
+    def threshold(self, src, thresh, maxval, type=0):
+        src = np.asarray(src)
+        if src.dtype == np.float32:
+            src = self._f32(src, "threshold")
+            if type != self.THRESH_BINARY:
+                raise CvException(L.MSG_EINVAL, "threshold: CV_32F supports THRESH_BINARY only")
+            h, w = src.shape
+            dst = np.empty((h, w), np.float32)
+            self.ctx.check(self._lib.msg_threshold_f32(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0],
+                                                       w, h, float(thresh), float(maxval)))
+            return float(thresh), dst
+        src = self._gray(src, "threshold")
+        h, w = src.shape
+        dst = np.empty((h, w), np.uint8)
+        used = C.c_double(0)
+        self.ctx.check(self._lib.msg_threshold(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h,
+                                               float(thresh), float(maxval), int(type), C.byref(used)))
+        return used.value, dst
+
+    # Imgproc.distanceTransform(src, dst, Imgproc.CV_DIST_L2, 5)
+    def distanceTransform(self, src, distanceType=2, maskSize=5):
+        src = self._gray(src, "distanceTransform")
+        h, w = src.shape
+        dst = np.empty((h, w), np.float32)
+        self.ctx.check(self._lib.msg_distance_transform(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0],
+                                                        w, h, int(distanceType), int(maskSize)))
+        return dst
+
+    # Core.normalize(src, dst, alpha, beta, Core.NORM_MINMAX)
+    def normalize(self, src, alpha=0.0, beta=1.0, norm_type=32):
+        if norm_type != self.NORM_MINMAX:
+            raise CvException(L.MSG_EINVAL, "normalize: NORM_MINMAX only")
+        src = self._f32(src, "normalize")
+        h, w = src.shape
+        dst = np.empty((h, w), np.float32)
+        self.ctx.check(self._lib.msg_normalize_minmax(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0],
+                                                      w, h, float(alpha), float(beta)))
+        return dst
+
+    # Imgproc.dilate on CV_32FC1 (PictureService.java:349-350)
+    def dilateF32(self, src, kernel_shape):
+        src = self._f32(src, "dilate")
+        kh, kw = kernel_shape
+        h, w = src.shape
+        dst = np.empty((h, w), np.float32)
+        self.ctx.check(self._lib.msg_dilate_f32(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h,
+                                                int(kw), int(kh)))
+        return dst
+
+    # Mat.convertTo(dst, CvType.CV_8U) from CV_32FC1
+    def convertToU8(self, src):
+        src = self._f32(src, "convertTo")
+        h, w = src.shape
+        dst = np.empty((h, w), np.uint8)
+        self.ctx.check(self._lib.msg_convert_f32_to_u8(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h))
+        return dst
+
+    # findContours(RETR_CCOMP, CHAIN_APPROX_NONE) + the drawContours loop of PictureService.java:360-364 -> (contours.size(), markers)
+    def contourMarkers(self, image):
+        image = self._gray(image, "findContours")
+        h, w = image.shape
+        markers = np.empty((h, w), np.int32)
+        n = C.c_int32(0)
+        self.ctx.check(self._lib.msg_contour_markers(self.ctx._h, image.ctypes.data, image.strides[0], markers.ctypes.data,
+                                                     markers.strides[0], w, h, C.byref(n)))
+        return n.value, markers
+
+    # Imgproc.circle(img, center, radius, color, -1) on CV_32SC1, in place like OpenCV
+    def circle(self, img, center, radius, value):
+        if not (isinstance(img, np.ndarray) and img.dtype == np.int32 and img.ndim == 2 and img.strides[1] == 4):
+            raise CvException(L.MSG_EINVAL, "circle: CV_32SC1 ndarray only")
+        h, w = img.shape
+        self.ctx.check(self._lib.msg_circle_filled(self.ctx._h, img.ctypes.data, img.strides[0], w, h, int(center[0]), int(center[1]),
+                                                   int(radius), int(value)))
+        return img
+
+    # the marker half of PictureService.colorAutoMarkerWatershed (:309-366) as one call, intermediates on the device
+    def colorSeeds(self, src, kernel=None, peakThresh=0.4, stages=False):
+        src = _mat8uc3(src, "src")
+        taps = np.ascontiguousarray(self.SHARPEN_KERNEL if kernel is None else kernel, dtype=np.int8)
+        if taps.ndim != 2:
+            raise CvException(L.MSG_EINVAL, "kernel must be 2-D (MatOfFloat(...) is N x 1)")
+        h, w = src.shape[:2]
+        markers = np.empty((h, w), np.int32)
+        n = C.c_int32(0)
+        if stages:
+            sharp, bw = np.empty((h, w, 3), np.uint8), np.empty((h, w), np.uint8)
+            dist, peaks = np.empty((h, w), np.float32), np.empty((h, w), np.uint8)
+            args = (sharp.ctypes.data, sharp.strides[0], bw.ctypes.data, bw.strides[0], dist.ctypes.data, dist.strides[0],
+                    peaks.ctypes.data, peaks.strides[0])
+        else:
+            args = (None, 0, None, 0, None, 0, None, 0)
+        self.ctx.check(self._lib.msg_color_seeds(self.ctx._h, src.ctypes.data, src.strides[0], w, h, taps.ctypes.data, taps.shape[0],
+                                                 taps.shape[1], float(peakThresh), markers.ctypes.data, markers.strides[0],
+                                                 C.byref(n), *args))
+        if stages:
+            return n.value, markers, {"sharp": sharp, "bw": bw, "norm": dist, "peaks": peaks}
+        return n.value, markers
+
+    # Imgproc.bilateralFilter(src, dst, d, sigmaColor, sigmaSpace) on CV_8UC1 / CV_8UC3 (PictureService.java:490)
+    def bilateralFilter(self, src, d, sigmaColor, sigmaSpace):
+        src = np.asarray(src)
+        if src.dtype != np.uint8 or not (src.ndim == 2 or (src.ndim == 3 and src.shape[2] == 3)):
+            raise CvException(L.MSG_EINVAL, "bilateralFilter: CV_8UC1 or CV_8UC3 only")
+        cn = 1 if src.ndim == 2 else 3
+        if src.strides[-1] != 1 or (cn == 3 and src.strides[1] != 3):
+            src = np.ascontiguousarray(src)
+        h, w = src.shape[:2]
+        dst = np.empty_like(src)
+        self.ctx.check(self._lib.msg_bilateral_filter(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0],
+                                                      w, h, cn, int(d), float(sigmaColor), float(sigmaSpace)))
+        return dst
+
     # fused pipeline
     def segment(self, src, sp=10.0, sr=10.0, maxLevel=1, termcrit=DEFAULT_TERMCRIT, loDiff=2, minSize=0, colorDist=0,
                 renderDepth=0, want=("filtered", "labels", "rendered"), connectivity=4):

@@ -716,3 +716,305 @@ void orc_subtract_u8(const uint8_t* a, size_t astep, const uint8_t* b, size_t bs
             dst[(size_t)y * dstep + x] = (uint8_t)(v < 0 ? 0 : v);
         }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Colour-method seeds (PictureService.java:338-366, :938-943, :1018-1023): Otsu threshold,
+ * chamfer distance transform, min-max normalisation, peak threshold + dilate, contour labelling, background disc.
+ * Restated from the published OpenCV algorithms (imgproc thresh.cpp / distransform.cpp / contours / drawing.cpp
+ * semantics), pinned on cv2 4.13.0 by tests/golden/color_seeds.npz.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* cv::threshold(..., THRESH_OTSU) threshold selection on 8UC1 (getThreshVal_Otsu_8u): double arithmetic, sequential
+ * over the 256 bins; the order of the operations is part of the specification. */
+int orc_otsu_threshold(const uint8_t* src, size_t sstep, int w, int h)
+{
+    int hist[256];
+    memset(hist, 0, sizeof(hist));
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) hist[src[(size_t)y * sstep + x]]++;
+    double mu = 0, scale = 1. / ((double)w * h);
+    for (int i = 0; i < 256; i++) mu += i * (double)hist[i];
+    mu *= scale;
+    double mu1 = 0, q1 = 0, max_sigma = 0, max_val = 0;
+    for (int i = 0; i < 256; i++) {
+        double p_i = hist[i] * scale;
+        mu1 *= q1;
+        q1 += p_i;
+        double q2 = 1. - q1;
+        double lo = q1 < q2 ? q1 : q2, hi = q1 > q2 ? q1 : q2;
+        if (lo < 1.1920928955078125e-07 || hi > 1. - 1.1920928955078125e-07) continue;
+        mu1 = (mu1 + i * p_i) / q1;
+        double mu2 = (mu - q1 * mu1) / q2;
+        double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+        if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    return (int)max_val;
+}
+
+/* cv::threshold(src 8UC1, thresh, maxval, THRESH_BINARY): dst = src > thresh ? maxval : 0 */
+void orc_threshold_binary_u8(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, int thresh, int maxval)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) dst[(size_t)y * dstep + x] = (uint8_t)(src[(size_t)y * sstep + x] > thresh ? maxval : 0);
+}
+
+/* cv::distanceTransform(src 8UC1, dst 32F, DIST_L2, 5): two-pass 5x5 chamfer with the metrics a = 1, b = 1.4,
+ * c = 2.1969 accumulated in float32, frame of "infinite" (FLT_MAX) pixels.  This is the arithmetic of the IPP-backed cv2
+ * 4.13 build the oracle is pinned on (OpenCV's own fallback uses 16.16 fixed point instead and differs by ~4e-6 relative);
+ * cv2 == this function bit for bit except on an exact rounding tie of a horizontal step across 32.0 / 64.0 (1 ulp, rare:
+ * tests/golden/gen_color_seeds.py).  A source without zero pixels gives FLT_MAX everywhere, as cv2 does. */
+void orc_distance_transform_l2_5(const uint8_t* src, size_t sstep, float* dst, size_t dstep, int w, int h)
+{
+    const float A = 1.0f, B = 1.4f, C = 2.1969f, INF = 3.402823466e+38f;
+    const size_t tp = (size_t)w + 4;
+    float* t = (float*)malloc(tp * ((size_t)h + 4) * sizeof(float));
+    for (size_t i = 0; i < tp * ((size_t)h + 4); i++) t[i] = INF;
+#define T_(y, x) t[(size_t)((y) + 2) * tp + (size_t)((x) + 2)]
+#define MIN_(v) do { float q_ = (v); if (q_ < t0) t0 = q_; } while (0)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            if (!src[(size_t)y * sstep + x]) { T_(y, x) = 0; continue; }
+            float t0 = T_(y - 2, x - 1) + C;
+            MIN_(T_(y - 2, x + 1) + C);
+            MIN_(T_(y - 1, x - 2) + C);
+            MIN_(T_(y - 1, x - 1) + B);
+            MIN_(T_(y - 1, x) + A);
+            MIN_(T_(y - 1, x + 1) + B);
+            MIN_(T_(y - 1, x + 2) + C);
+            MIN_(T_(y, x - 1) + A);
+            T_(y, x) = t0;
+        }
+    for (int y = h - 1; y >= 0; y--)
+        for (int x = w - 1; x >= 0; x--) {
+            float t0 = T_(y, x);
+            if (t0 > A) {
+                MIN_(T_(y + 2, x + 1) + C);
+                MIN_(T_(y + 2, x - 1) + C);
+                MIN_(T_(y + 1, x + 2) + C);
+                MIN_(T_(y + 1, x + 1) + B);
+                MIN_(T_(y + 1, x) + A);
+                MIN_(T_(y + 1, x - 1) + B);
+                MIN_(T_(y + 1, x - 2) + C);
+                MIN_(T_(y, x + 1) + A);
+                T_(y, x) = t0;
+            }
+            *(float*)((uint8_t*)dst + (size_t)y * dstep + (size_t)x * 4) = t0;
+        }
+#undef T_
+#undef MIN_
+    free(t);
+}
+
+/* Core.normalize(src 32F, dst, 0, 1, NORM_MINMAX) (PictureService.java:1021): scale = 1 * (1 / (max - min)) in double,
+ * shift = 0 - min * scale; dst = src * (float)scale + (float)shift in float; a constant image becomes all zero. */
+void orc_normalize_minmax01_f32(const float* src, size_t sstep, float* dst, size_t dstep, int w, int h)
+{
+    double smin = INFINITY, smax = -INFINITY;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float v = *(const float*)((const uint8_t*)src + (size_t)y * sstep + (size_t)x * 4);
+            if (v < smin) smin = v;
+            if (v > smax) smax = v;
+        }
+    double scale = (1. - 0.) * (smax - smin > 2.220446049250313e-16 ? 1. / (smax - smin) : 0.);
+    double shift = 0. - smin * scale;
+    float a = (float)scale, b = (float)shift;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float v = *(const float*)((const uint8_t*)src + (size_t)y * sstep + (size_t)x * 4);
+            *(float*)((uint8_t*)dst + (size_t)y * dstep + (size_t)x * 4) = fmaf(v, a, b);   /* cv2's vector path fuses */
+        }
+}
+
+/* threshold(dist, .4, 1., THRESH_BINARY) + dilate(3x3 ones) + convertTo(CV_8U) (PictureService.java:348-356): 0 / 1 */
+void orc_peaks_u8(const float* nrm, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, double thresh)
+{
+    const float th = (float)thresh;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int on = 0;
+            for (int yy = y - 1; yy <= y + 1; yy++)
+                for (int xx = x - 1; xx <= x + 1; xx++)
+                    if (yy >= 0 && yy < h && xx >= 0 && xx < w &&
+                        *(const float*)((const uint8_t*)nrm + (size_t)yy * sstep + (size_t)xx * 4) > th) on = 1;
+            dst[(size_t)y * dstep + x] = (uint8_t)on;
+        }
+}
+
+/* findContours(mask, RETR_CCOMP, CHAIN_APPROX_NONE) followed by drawContours(markers, contours, i, i + 1, FILLED, 8,
+ * hierarchy, INT_MAX) for i = 0 .. n-1 (PictureService.java:360-364), restated without contour tracing:
+ *   - outer contours = 8-connected components of the non-zero pixels, holes = 4-connected components of the zero pixels
+ *     that do not touch the image border; a hole belongs to the component of the pixel left of its first (raster) pixel;
+ *   - contour index: components in REVERSE raster order of their first pixel, each followed by its holes in reverse
+ *     raster order of their first pixel;
+ *   - painting contour i (outer) covers the component's pixels; painting a hole covers the hole, everything enclosed
+ *     by it, and the component's pixels 4-adjacent to the hole; later (larger) indices overwrite earlier ones.
+ * Returns the number of contours. */
+static int32_t cc_generic(const uint8_t* mask, size_t step, int w, int h, int want_nonzero, int conn8, int32_t* par)
+{
+    const size_t n = (size_t)w * h;
+    for (size_t i = 0; i < n; i++) par[i] = (int32_t)i;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            if ((mask[(size_t)y * step + x] != 0) != want_nonzero) continue;
+            int32_t i = y * w + x;
+            if (x > 0 && (mask[(size_t)y * step + x - 1] != 0) == want_nonzero) uf_union(par, i, i - 1);
+            if (y > 0) {
+                const uint8_t* up = mask + (size_t)(y - 1) * step;
+                if ((up[x] != 0) == want_nonzero) uf_union(par, i, i - w);
+                if (conn8 && x > 0 && (up[x - 1] != 0) == want_nonzero) uf_union(par, i, i - w - 1);
+                if (conn8 && x + 1 < w && (up[x + 1] != 0) == want_nonzero) uf_union(par, i, i - w + 1);
+            }
+        }
+    for (size_t i = 0; i < n; i++) par[i] = uf_find(par, (int32_t)i);
+    return 0;
+}
+
+int32_t orc_contour_markers(const uint8_t* mask, size_t step, int32_t* markers, size_t mstep, int w, int h)
+{
+    const size_t n = (size_t)w * h;
+    int32_t* fg = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));    /* root = first pixel of the component */
+    int32_t* bg = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
+    uint8_t* open = (uint8_t*)calloc(n ? n : 1, 1);                     /* per bg root: touches the image border */
+    int32_t* nholes = (int32_t*)calloc(n ? n : 1, sizeof(int32_t));     /* per fg root */
+    int32_t* idx = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));     /* per root (fg or hole): contour index */
+    int32_t* seen = (int32_t*)calloc(n ? n : 1, sizeof(int32_t));
+    cc_generic(mask, step, w, h, 1, 1, fg);
+    cc_generic(mask, step, w, h, 0, 0, bg);
+#define ISFG(i) (mask[(size_t)((i) / w) * step + (size_t)((i) % w)] != 0)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            if ((y == 0 || y == h - 1 || x == 0 || x == w - 1) && !ISFG(y * w + x)) open[bg[y * w + x]] = 1;
+    int32_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (ISFG(i)) { if (fg[i] == (int32_t)i) total++; }
+        else if (bg[i] == (int32_t)i && !open[i]) { nholes[fg[i - 1]]++; total++; }
+    }
+    int32_t acc = 0;
+    for (size_t i = 0; i < n; i++)                       /* components in discovery order */
+        if (ISFG(i) && fg[i] == (int32_t)i) { acc += 1 + nholes[i]; idx[i] = total - acc; }
+    for (size_t i = 0; i < n; i++)                       /* holes in discovery order */
+        if (!ISFG(i) && bg[i] == (int32_t)i && !open[i]) {
+            int32_t c = fg[i - 1];
+            idx[i] = idx[c] + nholes[c] - seen[c];
+            seen[c]++;
+        }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int32_t i = y * w + x, out = 0;
+            /* walk outwards: the outermost enclosing hole wins */
+            int32_t hole = -1, cur = i;
+            int cur_fg = ISFG(i);
+            for (;;) {
+                if (cur_fg) {                              /* component -> the background region left of its first pixel */
+                    int32_t r = fg[cur];
+                    if (r % w == 0) break;
+                    int32_t b = bg[r - 1];
+                    if (open[b]) break;
+                    cur = b; cur_fg = 0;
+                } else {                                   /* hole (or open background) -> its component */
+                    int32_t b = bg[cur];
+                    if (open[b]) break;
+                    hole = b;
+                    cur = b - 1; cur_fg = 1;
+                }
+            }
+            if (hole >= 0) out = idx[hole] + 1;
+            else if (ISFG(i)) {
+                int32_t best = idx[fg[i]];
+                const int nx[4] = {x - 1, x + 1, x, x}, ny[4] = {y, y, y - 1, y + 1};
+                for (int k = 0; k < 4; k++)
+                    if (nx[k] >= 0 && nx[k] < w && ny[k] >= 0 && ny[k] < h && !ISFG(ny[k] * w + nx[k])) {
+                        int32_t b = bg[ny[k] * w + nx[k]];
+                        if (!open[b] && idx[b] > best) best = idx[b];
+                    }
+                out = best + 1;
+            }
+            *(int32_t*)((uint8_t*)markers + (size_t)y * mstep + (size_t)x * 4) = out;
+        }
+#undef ISFG
+    free(seen); free(idx); free(nholes); free(open); free(bg); free(fg);
+    return total;
+}
+
+/* Imgproc.circle(markers, centre, radius, value, FILLED) on 32SC1 (PictureService.java:366): OpenCV's midpoint circle,
+ * horizontal spans clipped to the image. */
+void orc_circle_filled_i32(int32_t* img, size_t step, int w, int h, int cx, int cy, int radius, int32_t value)
+{
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        int ys[4] = {cy - dy, cy + dy, cy - dx, cy + dx};
+        int xa[4] = {cx - dx, cx - dx, cx - dy, cx - dy}, xb[4] = {cx + dx, cx + dx, cx + dy, cx + dy};
+        for (int k = 0; k < 4; k++) {
+            if (ys[k] < 0 || ys[k] >= h) continue;
+            int a = xa[k] < 0 ? 0 : xa[k], b = xb[k] >= w ? w - 1 : xb[k];
+            for (int x = a; x <= b; x++) *(int32_t*)((uint8_t*)img + (size_t)ys[k] * step + (size_t)x * 4) = value;
+        }
+        dy++;
+        err += plus;
+        plus += 2;
+        int mask = (err <= 0) - 1;
+        err -= minus & mask;
+        dx += mask;
+        minus -= mask & 2;
+    }
+}
+
+/* The reference's first pipeline step (PictureService.java:309-318): pure white pixels become black. */
+void orc_white_to_black(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p = src + (size_t)y * sstep + 3 * x;
+            uint8_t* q = dst + (size_t)y * dstep + 3 * x;
+            int white = p[0] == 255 && p[1] == 255 && p[2] == 255;
+            q[0] = white ? 0 : p[0]; q[1] = white ? 0 : p[1]; q[2] = white ? 0 : p[2];
+        }
+}
+
+/* cv::bilateralFilter on 8UC1 / 8UC3 (PictureService.java:490; f2 row), BORDER_REFLECT_101: the scalar OpenCV loop
+ * (float accumulation in window order, colour weights (float)exp(i*i*coeff) by |delta| summed over channels, circular
+ * window r <= radius).  cv2's SIMD path fuses the multiply-adds, hence the +-1 LSB tolerance against cv2. */
+void orc_bilateral_filter(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h, int cn, int d,
+                          double sigma_color, double sigma_space)
+{
+    if (sigma_color <= 0) sigma_color = 1;
+    if (sigma_space <= 0) sigma_space = 1;
+    double gc = -0.5 / (sigma_color * sigma_color), gs = -0.5 / (sigma_space * sigma_space);
+    int radius = d <= 0 ? cv_round_d(sigma_space * 1.5) : d / 2;
+    if (radius < 1) radius = 1;
+    int dd = 2 * radius + 1, maxk = 0;
+    float* cw = (float*)malloc(sizeof(float) * 256 * cn);
+    float* sw = (float*)malloc(sizeof(float) * dd * dd);
+    int* oy = (int*)malloc(sizeof(int) * dd * dd);
+    int* ox = (int*)malloc(sizeof(int) * dd * dd);
+    for (int i = 0; i < 256 * cn; i++) cw[i] = (float)exp(i * i * gc);
+    for (int i = -radius; i <= radius; i++)
+        for (int j = -radius; j <= radius; j++) {
+            double r = sqrt((double)i * i + (double)j * j);
+            if (r > radius) continue;
+            sw[maxk] = (float)exp(r * r * gs);
+            oy[maxk] = i; ox[maxk] = j; maxk++;
+        }
+    uint8_t* out = (uint8_t*)malloc((size_t)w * h * cn);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p0 = src + (size_t)y * sstep + (size_t)x * cn;
+            float sum[3] = {0, 0, 0}, wsum = 0;
+            for (int k = 0; k < maxk; k++) {
+                const uint8_t* p = src + (size_t)reflect101(y + oy[k], h) * sstep + (size_t)reflect101(x + ox[k], w) * cn;
+                int diff = 0;
+                for (int c = 0; c < cn; c++) diff += abs((int)p[c] - (int)p0[c]);
+                float wgt = sw[k] * cw[diff];
+                for (int c = 0; c < cn; c++) sum[c] += p[c] * wgt;
+                wsum += wgt;
+            }
+            if (cn == 1) out[((size_t)y * w + x)] = (uint8_t)cv_round_f(sum[0] / wsum);
+            else {
+                float inv = 1.f / wsum;
+                for (int c = 0; c < cn; c++) out[((size_t)y * w + x) * cn + c] = (uint8_t)cv_round_f(sum[c] * inv);
+            }
+        }
+    for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * dstep, out + (size_t)y * w * cn, (size_t)w * cn);
+    free(out); free(ox); free(oy); free(sw); free(cw);
+}

@@ -63,6 +63,17 @@ def lib():
         L.orc_canny.argtypes = [u8p, sz, u8p, sz, i, i, d, d]
         L.orc_dilate_rect.argtypes = [u8p, sz, u8p, sz, i, i, i, i]
         L.orc_subtract_u8.argtypes = [u8p, sz, u8p, sz, u8p, sz, i, i]
+        L.orc_otsu_threshold.argtypes = [u8p, sz, i, i]
+        L.orc_otsu_threshold.restype = i
+        L.orc_threshold_binary_u8.argtypes = [u8p, sz, u8p, sz, i, i, i, i]
+        L.orc_distance_transform_l2_5.argtypes = [u8p, sz, C.c_void_p, sz, i, i]
+        L.orc_normalize_minmax01_f32.argtypes = [C.c_void_p, sz, C.c_void_p, sz, i, i]
+        L.orc_peaks_u8.argtypes = [C.c_void_p, sz, u8p, sz, i, i, d]
+        L.orc_contour_markers.argtypes = [u8p, sz, i32p, sz, i, i]
+        L.orc_contour_markers.restype = C.c_int32
+        L.orc_circle_filled_i32.argtypes = [i32p, sz, i, i, i, i, i, C.c_int32]
+        L.orc_white_to_black.argtypes = [u8p, sz, u8p, sz, i, i]
+        L.orc_bilateral_filter.argtypes = [u8p, sz, u8p, sz, i, i, i, i, d, d]
         _lib = L
     return _lib
 
@@ -254,3 +265,98 @@ def shape_seeds(bgr, low=5, high=50):
     dde3 = median_blur(dde, 3)
     n, markers = connected_components(dde3, 8)
     return n, markers, {"gray": g, "blurred": blurred, "edges": edges, "dde": dde, "dde3": dde3, "k": k}
+
+
+# ---------------------------------------------------------------- colour-method seeds (rows a6 / a4) and bilateral filter
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def otsu_threshold(gray):
+    gray = _u8(gray)
+    h, w = gray.shape
+    return int(lib().orc_otsu_threshold(gray.ctypes.data, gray.strides[0], w, h))
+
+
+def threshold_binary(gray, thresh, maxval=255):
+    gray = _u8(gray)
+    h, w = gray.shape
+    dst = np.empty_like(gray)
+    lib().orc_threshold_binary_u8(gray.ctypes.data, gray.strides[0], dst.ctypes.data, dst.strides[0], w, h, int(thresh), int(maxval))
+    return dst
+
+
+def distance_transform(mask):
+    mask = _u8(mask)
+    h, w = mask.shape
+    dst = np.empty((h, w), np.float32)
+    lib().orc_distance_transform_l2_5(mask.ctypes.data, mask.strides[0], dst.ctypes.data, dst.strides[0], w, h)
+    return dst
+
+
+def normalize_minmax01(dist):
+    dist = np.ascontiguousarray(dist, dtype=np.float32)
+    h, w = dist.shape
+    dst = np.empty_like(dist)
+    lib().orc_normalize_minmax01_f32(dist.ctypes.data, dist.strides[0], dst.ctypes.data, dst.strides[0], w, h)
+    return dst
+
+
+def peaks(nrm, thresh=0.4):
+    nrm = np.ascontiguousarray(nrm, dtype=np.float32)
+    h, w = nrm.shape
+    dst = np.empty((h, w), np.uint8)
+    lib().orc_peaks_u8(nrm.ctypes.data, nrm.strides[0], dst.ctypes.data, dst.strides[0], w, h, float(thresh))
+    return dst
+
+
+def contour_markers(mask):
+    mask = _u8(mask)
+    h, w = mask.shape
+    out = np.empty((h, w), np.int32)
+    n = lib().orc_contour_markers(mask.ctypes.data, mask.strides[0], out.ctypes.data, out.strides[0], w, h)
+    return int(n), out
+
+
+def circle_filled(markers, cx, cy, radius, value):
+    markers = np.ascontiguousarray(markers, dtype=np.int32).copy()
+    h, w = markers.shape
+    lib().orc_circle_filled_i32(markers.ctypes.data, markers.strides[0], w, h, int(cx), int(cy), int(radius), int(value))
+    return markers
+
+
+def white_to_black(bgr):
+    bgr = _img(bgr)
+    h, w = bgr.shape[:2]
+    dst = np.empty_like(bgr)
+    lib().orc_white_to_black(bgr.ctypes.data, bgr.strides[0], dst.ctypes.data, dst.strides[0], w, h)
+    return dst
+
+
+def bilateral_filter(img, d, sigma_color, sigma_space):
+    img = _u8(img)
+    h, w = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    dst = np.empty_like(img)
+    lib().orc_bilateral_filter(img.ctypes.data, img.strides[0], dst.ctypes.data, dst.strides[0], w, h, cn, int(d),
+                               float(sigma_color), float(sigma_space))
+    return dst
+
+
+SHARPEN_TAPS_9x1 = np.array([1, 1, 1, 1, -8, 1, 1, 1, 1], np.int8).reshape(9, 1)   # literal MatOfFloat reading (App. C#2)
+
+
+def color_seeds(bgr, taps=SHARPEN_TAPS_9x1, peak_thresh=0.4):
+    """Colour-method marker generator (PictureService.java:309-366): returns (n_contours, markers int32, stages dict)."""
+    black = white_to_black(bgr)
+    sharp = laplacian_sharpen(black, taps)
+    gray = bgr2gray(sharp)
+    t = otsu_threshold(gray)
+    bw = threshold_binary(gray, t, 255)
+    dist = distance_transform(bw)
+    nrm = normalize_minmax01(dist)
+    pk = peaks(nrm, peak_thresh)
+    n, markers = contour_markers(pk)
+    markers = circle_filled(markers, 5, 5, 3, 255)
+    return n, markers, {"black_bg": black, "sharp": sharp, "gray": gray, "otsu": t, "bw": bw, "dist": dist, "norm": nrm,
+                        "peaks": pk}
