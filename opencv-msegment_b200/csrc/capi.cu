@@ -1276,9 +1276,13 @@ int msg_distance_transform(msg_ctx* ctx, const uint8_t* src, size_t sstep, float
     MSG_TRY(small_reserve(ctx, 0));
     MSG_TRY(copy_in(ctx, src, sstep, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, (size_t)w * h * 4));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     MSG_TRY(k_distance_transform(ctx, ctx->d_in, (size_t)w, (float*)ctx->d_out, w, h, SMALL_MAX(ctx)));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w * 4, h));
     MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->tm.filter_ms = ev_ms(ctx->ev[0], ctx->ev[1]);          // the kernel alone (msg_get_timings)
     return MSG_OK;
 }
 

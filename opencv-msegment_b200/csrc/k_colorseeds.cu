@@ -86,175 +86,206 @@ __global__ void __launch_bounds__(256) threshold_u8_kernel(const uint8_t* __rest
 }
 
 // ---------------------------------------------------------------- chamfer distance transform (L2, 5x5, float metrics)
-constexpr int DT_THREADS = 1024;
+// The transform is a sequential recurrence: pixel (y, x) of a pass needs (y, x-1), (y-1, x-2 .. x+2) and (y-2, x-1), (y-2, x+1)
+// of the same pass, and the float additions do not associate, so the order of the published two-pass algorithm is kept and
+// only its wavefront parallelism is used.  Lane G of one CTA owns the P consecutive columns [G*P, (G+1)*P) and handles row r
+// at step s = 2r + G: then its left neighbour has just finished row r (the carry of the in-row recurrence) and its right
+// neighbour row r-1.  A lane keeps its last two rows in registers; the seven halo values it needs come from the neighbour
+// lanes by shuffles (from the neighbour warps through a double-buffered shared-memory slot), one __syncthreads per step.
+// Steps per pass: 2 * height + lanes in use.  The initial values of a lane's next row are loaded two steps ahead.
+constexpr int DT_THREADS = 256, DT_WARPS = DT_THREADS / 32, DT_PMAXMAX = 32;
 constexpr float DT_A = 1.0f, DT_B = 1.4f, DT_C = 2.1969f;
 
-// F^n(v), F(v) = fl(v + 1.0f), for v = 0 or v >= 1
-__device__ __forceinline__ float dt_advance(float v, int n)
+template <int P>
+__device__ __forceinline__ float dt_pick(const float (&row)[P], int k, float l0, float l1, float r0, float r1)
 {
-    while (n > 0) {
-        if (!(v < 16777216.f)) return v;                      // the "infinite" value (FLT_MAX): v + 1 rounds back to v
-        if (v < 1.f) { v = __fadd_rn(v, 1.f); n--; continue; }
-        int e = (__float_as_int(v) >> 23) - 127;              // v in [2^e, 2^(e+1))
-        float lim = __int_as_float((e + 128) << 23);
-        int k = (int)ceilf(__fsub_rn(lim, v)) - 1;            // additions that stay below lim are exact
-        if (n <= k) return __fadd_rn(v, (float)n);
-        v = __fadd_rn(v, (float)k);
-        v = __fadd_rn(v, 1.f);                                // the addition that enters the next binade rounds
-        n -= k + 1;
-    }
-    return v;
+    // k is a compile-time constant after unrolling: -2, -1 -> left halo; P, P+1 -> right halo
+    return k < 0 ? (k == -1 ? l1 : l0) : (k >= P ? (k == P ? r0 : r1) : row[k < 0 ? 0 : (k >= P ? P - 1 : k)]);
 }
 
-struct dt_sum { float c; int n; };
-__device__ __forceinline__ dt_sum dt_compose(dt_sum l, dt_sum r)
-{
-    dt_sum o;
-    o.c = fminf(r.c, dt_advance(l.c, r.n));
-    o.n = l.n + r.n;
-    return o;
-}
+struct dt_shared {
+    float4 right[2][DT_WARPS];    // lane 31 of each warp: A[P-1], B[P-2], B[P-1], Clast
+    float4 left[2][DT_WARPS];     // lane 0 of each warp: A[0], A[1], B[0]
+};
 
-// One pass over the rows.  DIR = +1: forward (top -> bottom, left -> right, init = 0 on zero pixels / infinite elsewhere),
-// DIR = -1: backward (bottom -> top, right -> left, init = forward value).  `dist` (dense w floats per row) receives the
-// forward values and is updated in place by the backward pass; the backward pass also reduces the maximum.
-template <int DIR>
-__device__ void dt_pass(const uint8_t* __restrict__ src, size_t sstep, float* __restrict__ dist, int w, int h, float* smem,
-                        float* s_scan_c, int* s_scan_n, float* d_max)
+// One pass.  DIR = +1: forward (top -> bottom, left -> right; initial value 0 on zero pixels of src, "infinite" elsewhere),
+// DIR = -1: backward (bottom -> top, right -> left; initial value = the forward result in dist).  Coordinates are in pass
+// order (mirrored for the backward pass).  Returns the lane's maximum of the values it stored.
+template <int V> struct dt_vec;
+template <> struct dt_vec<1> { typedef float type; };
+template <> struct dt_vec<2> { typedef float2 type; };
+template <> struct dt_vec<4> { typedef float4 type; };
+
+// V = floats per memory access of a lane's chunk (rows must then be a multiple of V floats wide: aligned chunks).  Every lane
+// works on a different row, so a warp-wide access touches up to 32 cache lines: wide accesses keep the load/store unit,
+// which is what bounds this kernel, four times less busy.
+template <int P, int DIR, int V>
+__device__ __forceinline__ float dt_wave_pass(float* __restrict__ dist, int w, int h, dt_shared& sh)
 {
-    const int pw = w + 4;                          // two "infinite" pixels on either side
-    float* ring = smem;                            // 3 rows of pw floats
-    float* init = smem + 3 * pw;                   // 2 rows of w floats (double buffer of the row's initial values)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int P = (w + DT_THREADS - 1) / DT_THREADS;
-    for (int i = tid; i < 3 * pw; i += DT_THREADS) ring[i] = FLT_MAX;
-    const int ystart = DIR > 0 ? 0 : h - 1;
-    // initial values of the first row
-    for (int x = tid; x < w; x += DT_THREADS)
-        init[x] = DIR > 0 ? (src[(size_t)ystart * sstep + x] ? FLT_MAX : 0.f) : dist[(size_t)ystart * w + x];
-    float vmax = 0.f;
-    __syncthreads();
-    for (int it = 0; it < h; it++) {
+    typedef typename dt_vec<V>::type vec_t;
+    const int G = threadIdx.x, lane = G & 31, warp = G >> 5;
+    const int m0 = G * P, cnt = max(0, min(w - m0, P));
+    const int NL = (w + P - 1) / P;            // lanes in use
+    const int nsteps = 2 * h + NL - 2;
+    // lowest image column of the chunk (the chunk is [m0, m0 + P) in pass order, mirrored for the backward pass)
+    const int xlo = DIR > 0 ? m0 : w - m0 - P;
+    const bool full = cnt == P;                // only the last lane in use can hold a partial chunk
+    // A = the lane's last finished row, B = the one before, Clast = last pixel of the one before that (pass order)
+    float A[P], B[P], Clast = FLT_MAX, vmax = 0.f;
+    // initial values of the lane's coming rows, loaded four steps (two rows) ahead.  The register set is chosen by the step
+    // number modulo 4 (uniform over the warp), so a set is not touched between its load and its use.
+    float q0[P], q1[P], q2[P], q3[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) { A[j] = FLT_MAX; B[j] = FLT_MAX; q0[j] = q1[j] = q2[j] = q3[j] = FLT_MAX; }
+    // element e (ascending image column xlo + e) of the chunk is pixel j = e (forward) or P - 1 - e (backward) in pass order
+    auto load_row = [&](int it, float (&pre)[P]) {            // only called with cnt > 0
         const int y = DIR > 0 ? it : h - 1 - it;
-        float* cur = ring + (it % 3) * pw + 2;
-        const float* r1 = ring + ((it + 2) % 3) * pw + 2;     // previous row of this pass
-        const float* r2 = ring + ((it + 1) % 3) * pw + 2;     // the row before it
-        const float* ini = init + (it & 1) * w;
-        float* ini_next = init + ((it + 1) & 1) * w;
-        // (a) store the previous row (final for this pass), prefetch the next row's initial values
-        if (it > 0) {
-            const int yp = y - DIR;
-            for (int x = tid; x < w; x += DT_THREADS) {
-                float v = r1[x];
-                dist[(size_t)yp * w + x] = v;
-                if (DIR < 0) vmax = fmaxf(vmax, v);
-            }
-        }
-        if (it + 1 < h) {
-            const int yn = y + DIR;
-            for (int x = tid; x < w; x += DT_THREADS)
-                ini_next[x] = DIR > 0 ? (src[(size_t)yn * sstep + x] ? FLT_MAX : 0.f) : dist[(size_t)yn * w + x];
-        }
-        // (b) the thread's chunk, sequentially, with an unknown ("infinite") carry
-        const int m0 = tid * P, m1 = min(w, m0 + P);           // chunk in pass order (mirrored for the backward pass)
-        float run = FLT_MAX;
-        for (int m = m0; m < m1; m++) {
-            const int x = DIR > 0 ? m : w - 1 - m;
-            float t = ini[x];
-            if (t > DT_A) {
-                t = fminf(t, __fadd_rn(r2[x - 1], DT_C));
-                t = fminf(t, __fadd_rn(r2[x + 1], DT_C));
-                t = fminf(t, __fadd_rn(r1[x - 2], DT_C));
-                t = fminf(t, __fadd_rn(r1[x - 1], DT_B));
-                t = fminf(t, __fadd_rn(r1[x], DT_A));
-                t = fminf(t, __fadd_rn(r1[x + 1], DT_B));
-                t = fminf(t, __fadd_rn(r1[x + 2], DT_C));
-                t = fminf(t, __fadd_rn(run, DT_A));
-            }
-            run = t;
-            cur[x] = t;
-        }
-        // (c) scan of the chunk summaries
-        dt_sum s;
-        s.c = m0 < m1 ? run : FLT_MAX;
-        s.n = max(m1 - m0, 0);
-        dt_sum inc = s;
+        const float* p = dist + (size_t)y * w + xlo;
+        if (full) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            dt_sum l;
-            l.c = __shfl_up_sync(0xffffffffu, inc.c, o);
-            l.n = __shfl_up_sync(0xffffffffu, inc.n, o);
-            if (lane >= o) inc = dt_compose(l, inc);
-        }
-        dt_sum exc;                                            // exclusive prefix inside the warp
-        exc.c = __shfl_up_sync(0xffffffffu, inc.c, 1);
-        exc.n = __shfl_up_sync(0xffffffffu, inc.n, 1);
-        if (lane == 0) { exc.c = FLT_MAX; exc.n = 0; }
-        if (lane == 31) { s_scan_c[warp] = inc.c; s_scan_n[warp] = inc.n; }
-        __syncthreads();
-        if (warp == 0) {
-            dt_sum v;
-            v.c = s_scan_c[lane]; v.n = s_scan_n[lane];
+            for (int e = 0; e < P; e += V) {
+                vec_t v = __ldcg((const vec_t*)(p + e));
+                const float* f = (const float*)&v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                dt_sum l;
-                l.c = __shfl_up_sync(0xffffffffu, v.c, o);
-                l.n = __shfl_up_sync(0xffffffffu, v.n, o);
-                if (lane >= o) v = dt_compose(l, v);
+                for (int i = 0; i < V; i++) pre[DIR > 0 ? e + i : P - 1 - (e + i)] = f[i];
             }
-            float ec = __shfl_up_sync(0xffffffffu, v.c, 1);    // exclusive: what enters warp `lane`
-            if (lane == 0) ec = FLT_MAX;
-            s_scan_c[32 + lane] = ec;
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const int jj = min(j, cnt - 1);               // clamped: always inside the row
+                float v = __ldcg(p + (DIR > 0 ? jj : P - 1 - jj));
+                pre[j] = j < cnt ? v : FLT_MAX;
+            }
         }
-        __syncthreads();
-        // (d) fold the carry into the chunk
-        {
-            float carry = fminf(exc.c, dt_advance(s_scan_c[32 + warp], exc.n));
-            if (carry < 16777216.f)
-                for (int m = m0; m < m1; m++) {
-                    const int x = DIR > 0 ? m : w - 1 - m;
-                    carry = __fadd_rn(carry, DT_A);
-                    if (carry < cur[x]) cur[x] = carry;
-                    else break;                                // monotone: the carry cannot matter further right
-                }
+    };
+    auto store_row = [&](int it, const float (&val)[P]) {
+        const int y = DIR > 0 ? it : h - 1 - it;
+        float* p = dist + (size_t)y * w + xlo;
+        if (full) {
+#pragma unroll
+            for (int e = 0; e < P; e += V) {
+                vec_t v;
+                float* f = (float*)&v;
+#pragma unroll
+                for (int i = 0; i < V; i++) f[i] = val[DIR > 0 ? e + i : P - 1 - (e + i)];
+                *(vec_t*)(p + e) = v;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; j++)
+                if (j < cnt) p[DIR > 0 ? j : P - 1 - j] = val[j];
         }
-        __syncthreads();
+    };
+    if (cnt > 0) {                                            // row 0 is used at step G, row 1 at step G + 2
+        if ((G & 3) == 0) { load_row(0, q0); if (h > 1) load_row(1, q2); }
+        if ((G & 3) == 1) { load_row(0, q1); if (h > 1) load_row(1, q3); }
+        if ((G & 3) == 2) { load_row(0, q2); if (h > 1) load_row(1, q0); }
+        if ((G & 3) == 3) { load_row(0, q3); if (h > 1) load_row(1, q1); }
     }
-    // the last row
-    {
-        const int y = DIR > 0 ? h - 1 : 0;
-        const float* last = ring + ((h - 1) % 3) * pw + 2;
-        for (int x = tid; x < w; x += DT_THREADS) {
-            float v = last[x];
-            dist[(size_t)y * w + x] = v;
-            if (DIR < 0) vmax = fmaxf(vmax, v);
-        }
-    }
-    if (DIR < 0) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        __syncthreads();
-        if (lane == 0) s_scan_c[warp] = vmax;
-        __syncthreads();
-        if (warp == 0) {
-            float v = s_scan_c[lane];
-#pragma unroll
-            for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if (lane == 0) *d_max = v;
-        }
+    if (G < 2 * DT_WARPS) {
+        const float4 inf = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+        (&sh.right[0][0])[G] = inf;
+        (&sh.left[0][0])[G] = inf;
     }
     __syncthreads();
+    auto step = [&](int s, float (&pre)[P]) {
+        const int d = s - G;
+        const bool active = cnt > 0 && d >= 0 && !(d & 1) && (d >> 1) < h;
+        // halo: left lane finished row r one step ago (A = row r, B = r-1, Clast = r-2), right lane row r-1 (A = r-1, B = r-2)
+        float Lc = __shfl_up_sync(0xffffffffu, A[P - 1], 1);
+        float Lb0 = __shfl_up_sync(0xffffffffu, B[P - 2], 1);
+        float Lb1 = __shfl_up_sync(0xffffffffu, B[P - 1], 1);
+        float Lcl = __shfl_up_sync(0xffffffffu, Clast, 1);
+        float Ra0 = __shfl_down_sync(0xffffffffu, A[0], 1);
+        float Ra1 = __shfl_down_sync(0xffffffffu, A[1], 1);
+        float Rb0 = __shfl_down_sync(0xffffffffu, B[0], 1);
+        if (lane == 0) {
+            float4 v = warp > 0 ? sh.right[(s + 1) & 1][warp - 1] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+            Lc = v.x; Lb0 = v.y; Lb1 = v.z; Lcl = v.w;
+        }
+        if (lane == 31) {
+            float4 v = warp + 1 < DT_WARPS ? sh.left[(s + 1) & 1][warp + 1] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+            Ra0 = v.x; Ra1 = v.y; Rb0 = v.z;
+        }
+        if (active) {
+            const int it = d >> 1;
+            float t[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) t[j] = pre[j];
+            if (it + 2 < h) load_row(it + 2, pre);            // consumed four steps later, from the same register set
+            // candidates that do not depend on the in-row recurrence: independent min trees (a pixel whose initial value is
+            // <= 1 keeps it: every candidate is >= 1; FLT_MAX + metric rounds back to FLT_MAX)
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float a0 = __fadd_rn(dt_pick<P>(B, j - 1, FLT_MAX, Lcl, Rb0, FLT_MAX), DT_C);
+                float a1 = __fadd_rn(dt_pick<P>(B, j + 1, FLT_MAX, Lcl, Rb0, FLT_MAX), DT_C);
+                float a2 = __fadd_rn(dt_pick<P>(A, j - 2, Lb0, Lb1, Ra0, Ra1), DT_C);
+                float a3 = __fadd_rn(dt_pick<P>(A, j - 1, Lb0, Lb1, Ra0, Ra1), DT_B);
+                float a4 = __fadd_rn(A[j], DT_A);
+                float a5 = __fadd_rn(dt_pick<P>(A, j + 1, Lb0, Lb1, Ra0, Ra1), DT_B);
+                float a6 = __fadd_rn(dt_pick<P>(A, j + 2, Lb0, Lb1, Ra0, Ra1), DT_C);
+                t[j] = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(fminf(a4, a5), fminf(a6, t[j])));
+            }
+            // the recurrence along the row: two dependent operations per pixel
+            float run = Lc;
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                run = fminf(t[j], __fadd_rn(run, DT_A));
+                t[j] = j < cnt ? run : FLT_MAX;               // outside the image
+                vmax = fmaxf(vmax, j < cnt ? run : 0.f);
+            }
+            store_row(it, t);
+            Clast = B[P - 1];
+#pragma unroll
+            for (int j = 0; j < P; j++) { B[j] = A[j]; A[j] = t[j]; }
+        }
+        if (lane == 31) sh.right[s & 1][warp] = make_float4(A[P - 1], B[P - 2], B[P - 1], Clast);
+        if (lane == 0) sh.left[s & 1][warp] = make_float4(A[0], A[1], B[0], 0.f);
+        __syncthreads();
+    };
+#pragma unroll 1
+    for (int s = 0; s < nsteps; s += 4) {                     // nsteps is uniform over the CTA: every thread meets every barrier
+        step(s, q0);
+        if (s + 1 < nsteps) step(s + 1, q1);
+        if (s + 2 < nsteps) step(s + 2, q2);
+        if (s + 3 < nsteps) step(s + 3, q3);
+    }
+    __syncthreads();                                          // the pass' values (global) are visible to the whole CTA
+    return vmax;
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 1) dt_kernel(const uint8_t* __restrict__ src, size_t sstep,
-                                                           float* __restrict__ dist, int w, int h, float* d_max)
+template <int P, int V>
+__global__ void __launch_bounds__(DT_THREADS, 1) dt_wave_kernel(float* __restrict__ dist, int w, int h, float* d_max)
 {
-    extern __shared__ float dt_smem[];
-    __shared__ float s_scan_c[64];
-    __shared__ int s_scan_n[32];
-    dt_pass<1>(src, sstep, dist, w, h, dt_smem, s_scan_c, s_scan_n, d_max);
-    __threadfence_block();
-    dt_pass<-1>(src, sstep, dist, w, h, dt_smem, s_scan_c, s_scan_n, d_max);
+    __shared__ dt_shared sh;
+    __shared__ float s_max[DT_WARPS];
+    dt_wave_pass<P, 1, V>(dist, w, h, sh);
+    float vmax = dt_wave_pass<P, -1, V>(dist, w, h, sh);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) s_max[warp] = vmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = s_max[0];
+        for (int i = 1; i < DT_WARPS; i++) v = fmaxf(v, s_max[i]);
+        *d_max = v;
+    }
+}
+
+// initial values of the forward pass: 0 on the zero pixels of the source, "infinite" elsewhere
+__global__ void __launch_bounds__(256) dt_init_kernel(const uint8_t* __restrict__ src, size_t sstep, float* __restrict__ dist, int w)
+{
+    int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x < w) dist[(size_t)y * w + x] = src[(size_t)y * sstep + x] ? FLT_MAX : 0.f;
+}
+
+template <int P>
+void dt_launch(cudaStream_t st, float* d_dist, int w, int h, float* d_max)
+{
+    constexpr int V = P < 4 ? P : 4;
+    if (w % V == 0 && ((uintptr_t)d_dist & 15) == 0) dt_wave_kernel<P, V><<<1, DT_THREADS, 0, st>>>(d_dist, w, h, d_max);
+    else dt_wave_kernel<P, 1><<<1, DT_THREADS, 0, st>>>(d_dist, w, h, d_max);
 }
 
 // ---------------------------------------------------------------- float planes: normalise, threshold, dilate, convert
@@ -428,16 +459,23 @@ int k_threshold_u8(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_
     return MSG_OK;
 }
 
-int k_distance_transform_max_width(msg_ctx* ctx) { return ((ctx->max_smem_optin - 1024) / 4 - 12) / 5; }
+int k_distance_transform_max_width(msg_ctx* ctx) { (void)ctx; return DT_THREADS * DT_PMAXMAX; }
 
 // d_dist: dense w*h floats; d_max (device float, may not be NULL): maximum of the result
 int k_distance_transform(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, float* d_dist, int w, int h, float* d_max)
 {
-    size_t smem = ((size_t)3 * (w + 4) + 2 * (size_t)w) * sizeof(float);
     if (w > k_distance_transform_max_width(ctx))
         return msg_fail(ctx, MSG_EINVAL, "distanceTransform supports rows up to %d pixels", k_distance_transform_max_width(ctx));
-    MSG_CUDA(ctx, cudaFuncSetAttribute(dt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dt_kernel<<<1, DT_THREADS, smem, ctx->stream>>>(d_src, sstep, d_dist, w, h, d_max);
+    int need = (w + DT_THREADS - 1) / DT_THREADS;
+    cudaStream_t st = ctx->stream;
+    dim3 grid((w + 255) / 256, h);
+    dt_init_kernel<<<grid, 256, 0, st>>>(d_src, sstep, d_dist, w);
+    MSG_LAUNCHED(ctx);
+    if (need <= 2) dt_launch<2>(st, d_dist, w, h, d_max);
+    else if (need <= 4) dt_launch<4>(st, d_dist, w, h, d_max);
+    else if (need <= 8) dt_launch<8>(st, d_dist, w, h, d_max);
+    else if (need <= 16) dt_launch<16>(st, d_dist, w, h, d_max);
+    else dt_launch<32>(st, d_dist, w, h, d_max);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;
