@@ -17,7 +17,7 @@
 
 namespace msegment {
 
-enum MatType { CV_8UC1 = 0, CV_8UC3 = 16, CV_32SC1 = 4 };   // OpenCV's CvType codes
+enum MatType { CV_8UC1 = 0, CV_8UC3 = 16, CV_32SC1 = 4, CV_32FC1 = 5 };   // OpenCV's CvType codes
 
 struct CvException : std::runtime_error {
     int status;
@@ -29,7 +29,7 @@ struct Mat {   // row-major, continuous (like every Mat the reference creates: i
     std::vector<uint8_t> buf;
     Mat() = default;
     Mat(int r, int c, int t) { create(r, c, t); }
-    static int elemSize(int t) { return t == CV_8UC3 ? 3 : (t == CV_32SC1 ? 4 : 1); }
+    static int elemSize(int t) { return t == CV_8UC3 ? 3 : (t == CV_32SC1 || t == CV_32FC1 ? 4 : 1); }
     void create(int r, int c, int t) { rows = r; cols = c; type = t; buf.assign((size_t)r * c * elemSize(t), 0); }
     size_t step() const { return (size_t)cols * elemSize(type); }
     uint8_t* data() { return buf.data(); }
@@ -184,6 +184,114 @@ public:
         check(msg_shape_seeds(ctx(), src.data(), src.step(), src.cols, src.rows, calculateSizeOfSquareBlurMask(src.cols, src.rows),
                               lowThreshold, lowThreshold * ratio, (int32_t*)markers.data(), markers.step(), &n, nullptr, 0));
         return n;
+    }
+
+    // ---- colour-method marker generator (PictureService.java:309-366, :938-943, :1018-1023)
+    enum { THRESH_BINARY = 0, THRESH_OTSU = 8, CV_DIST_L2 = 2, NORM_MINMAX = 32 };
+
+    // the Java loop of PictureService.java:309-318: (255,255,255) -> (0,0,0)
+    static void whiteToBlack(const Mat& src, Mat& dst)
+    {
+        require(src.type == CV_8UC3, "src must be CV_8UC3");
+        Mat out(src.rows, src.cols, CV_8UC3);
+        check(msg_white_to_black(ctx(), src.data(), src.step(), out.data(), out.step(), src.cols, src.rows));
+        dst = out;
+    }
+
+    // Imgproc.threshold(src, dst, thresh, maxval, type): CV_8UC1 (BINARY [| OTSU]) or CV_32FC1 (BINARY); returns the threshold used
+    static double threshold(const Mat& src, Mat& dst, double thresh, double maxval, int type)
+    {
+        require(src.type == CV_8UC1 || src.type == CV_32FC1, "src must be CV_8UC1 or CV_32FC1");
+        Mat out(src.rows, src.cols, src.type);
+        double used = thresh;
+        if (src.type == CV_8UC1)
+            check(msg_threshold(ctx(), src.data(), src.step(), out.data(), out.step(), src.cols, src.rows, thresh, maxval, type, &used));
+        else {
+            require(type == THRESH_BINARY, "CV_32FC1: THRESH_BINARY only");
+            check(msg_threshold_f32(ctx(), (const float*)src.data(), src.step(), (float*)out.data(), out.step(), src.cols, src.rows,
+                                    thresh, maxval));
+        }
+        dst = out;
+        return used;
+    }
+
+    // Imgproc.distanceTransform(src, dst, Imgproc.CV_DIST_L2, 5)
+    static void distanceTransform(const Mat& src, Mat& dst, int distanceType, int maskSize)
+    {
+        require(src.type == CV_8UC1, "src must be CV_8UC1");
+        Mat out(src.rows, src.cols, CV_32FC1);
+        check(msg_distance_transform(ctx(), src.data(), src.step(), (float*)out.data(), out.step(), src.cols, src.rows, distanceType,
+                                     maskSize));
+        dst = out;
+    }
+
+    // Core.normalize(src, dst, alpha, beta, Core.NORM_MINMAX)
+    static void normalize(const Mat& src, Mat& dst, double alpha, double beta, int normType)
+    {
+        require(src.type == CV_32FC1 && normType == NORM_MINMAX, "normalize: CV_32FC1, NORM_MINMAX");
+        Mat out(src.rows, src.cols, CV_32FC1);
+        check(msg_normalize_minmax(ctx(), (const float*)src.data(), src.step(), (float*)out.data(), out.step(), src.cols, src.rows,
+                                   alpha, beta));
+        dst = out;
+    }
+
+    // Imgproc.dilate on CV_32FC1 with Mat.ones(krows, kcols) (PictureService.java:349-350)
+    static void dilateF32(const Mat& src, Mat& dst, int krows, int kcols)
+    {
+        require(src.type == CV_32FC1, "src must be CV_32FC1");
+        Mat out(src.rows, src.cols, CV_32FC1);
+        check(msg_dilate_f32(ctx(), (const float*)src.data(), src.step(), (float*)out.data(), out.step(), src.cols, src.rows, kcols,
+                             krows));
+        dst = out;
+    }
+
+    // Mat.convertTo(dst, CvType.CV_8U) from CV_32FC1
+    static void convertToU8(const Mat& src, Mat& dst)
+    {
+        require(src.type == CV_32FC1, "src must be CV_32FC1");
+        Mat out(src.rows, src.cols, CV_8UC1);
+        check(msg_convert_f32_to_u8(ctx(), (const float*)src.data(), src.step(), out.data(), out.step(), src.cols, src.rows));
+        dst = out;
+    }
+
+    // findContours(RETR_CCOMP, CHAIN_APPROX_NONE) + the drawContours loop of PictureService.java:360-364; returns contours.size()
+    static int contourMarkers(const Mat& image, Mat& markers)
+    {
+        require(image.type == CV_8UC1, "image must be CV_8UC1");
+        markers.create(image.rows, image.cols, CV_32SC1);
+        int32_t n = 0;
+        check(msg_contour_markers(ctx(), image.data(), image.step(), (int32_t*)markers.data(), markers.step(), image.cols,
+                                  image.rows, &n));
+        return n;
+    }
+
+    // Imgproc.circle(img, center, radius, color, -1) on CV_32SC1
+    static void circle(Mat& img, int cx, int cy, int radius, int value)
+    {
+        require(img.type == CV_32SC1, "img must be CV_32SC1");
+        check(msg_circle_filled(ctx(), (int32_t*)img.data(), img.step(), img.cols, img.rows, cx, cy, radius, value));
+    }
+
+    // marker half of colorAutoMarkerWatershed (:309-366) with the reference's literal 9 x 1 sharpen kernel; returns contours.size()
+    static int colorSeeds(const Mat& src, Mat& markers, double peakThresh = 0.4)
+    {
+        require(src.type == CV_8UC3, "src must be CV_8UC3");
+        static const int8_t taps[9] = {1, 1, 1, 1, -8, 1, 1, 1, 1};
+        markers.create(src.rows, src.cols, CV_32SC1);
+        int32_t n = 0;
+        check(msg_color_seeds(ctx(), src.data(), src.step(), src.cols, src.rows, taps, 9, 1, peakThresh, (int32_t*)markers.data(),
+                              markers.step(), &n, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0));
+        return n;
+    }
+
+    // Imgproc.bilateralFilter(src, dst, d, sigmaColor, sigmaSpace) (PictureService.java:490)
+    static void bilateralFilter(const Mat& src, Mat& dst, int d, double sigmaColor, double sigmaSpace)
+    {
+        require(src.type == CV_8UC1 || src.type == CV_8UC3, "src must be CV_8UC1 or CV_8UC3");
+        Mat out(src.rows, src.cols, src.type);
+        check(msg_bilateral_filter(ctx(), src.data(), src.step(), out.data(), out.step(), src.cols, src.rows,
+                                   src.type == CV_8UC3 ? 3 : 1, d, sigmaColor, sigmaSpace));
+        dst = out;
     }
 
 private:

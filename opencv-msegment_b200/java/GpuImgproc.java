@@ -3,6 +3,8 @@ package ru.shayhulud.opencvcmsegment.gpu;
 import org.opencv.core.CvException;
 import org.opencv.core.CvType;
 import org.opencv.core.Mat;
+import org.opencv.core.Point;
+import org.opencv.core.Scalar;
 import org.opencv.core.TermCriteria;
 
 /**
@@ -133,6 +135,109 @@ public final class GpuImgproc {
 		return n[0];
 	}
 
+	/** The Java loop of PictureService.java:309-318 as one kernel: (255,255,255) becomes (0,0,0). */
+	public static void whiteToBlack(Mat src, Mat dst) {
+		require(src.type() == CvType.CV_8UC3, "src must be CV_8UC3");
+		Mat out = new Mat(src.size(), CvType.CV_8UC3);
+		status(nWhiteToBlack(CTX.get(), src.dataAddr(), src.step1(), out.dataAddr(), out.step1(), src.cols(), src.rows()));
+		out.copyTo(dst);
+	}
+
+	/** Imgproc.threshold(src, dst, thresh, maxval, type) (PictureService.java:941, :348): CV_8UC1 BINARY [| OTSU], CV_32FC1 BINARY. */
+	public static double threshold(Mat src, Mat dst, double thresh, double maxval, int type) {
+		require(src.type() == CvType.CV_8UC1 || src.type() == CvType.CV_32FC1, "src must be CV_8UC1 or CV_32FC1");
+		Mat out = new Mat(src.size(), src.type());
+		double[] used = new double[] {thresh};
+		if (src.type() == CvType.CV_8UC1) {
+			status(nThreshold(CTX.get(), src.dataAddr(), src.step1(), out.dataAddr(), out.step1(), src.cols(), src.rows(),
+				thresh, maxval, type, used));
+		} else {
+			require(type == 0, "CV_32FC1: THRESH_BINARY only");
+			status(nThresholdF32(CTX.get(), src.dataAddr(), src.step1() * 4, out.dataAddr(), out.step1() * 4, src.cols(),
+				src.rows(), thresh, maxval));
+		}
+		out.copyTo(dst);
+		return used[0];
+	}
+
+	/** Imgproc.distanceTransform(src, dst, Imgproc.CV_DIST_L2, 5) (PictureService.java:1020). */
+	public static void distanceTransform(Mat src, Mat dst, int distanceType, int maskSize) {
+		require(src.type() == CvType.CV_8UC1, "src must be CV_8UC1");
+		Mat out = new Mat(src.size(), CvType.CV_32FC1);
+		status(nDistanceTransform(CTX.get(), src.dataAddr(), src.step1(), out.dataAddr(), out.step1() * 4, src.cols(),
+			src.rows(), distanceType, maskSize));
+		out.copyTo(dst);
+	}
+
+	/** Core.normalize(src, dst, alpha, beta, Core.NORM_MINMAX) on CV_32FC1 (PictureService.java:1021). */
+	public static void normalize(Mat src, Mat dst, double alpha, double beta, int normType) {
+		require(src.type() == CvType.CV_32FC1 && normType == 32, "normalize: CV_32FC1, NORM_MINMAX");
+		Mat out = new Mat(src.size(), CvType.CV_32FC1);
+		status(nNormalize(CTX.get(), src.dataAddr(), src.step1() * 4, out.dataAddr(), out.step1() * 4, src.cols(), src.rows(),
+			alpha, beta));
+		out.copyTo(dst);
+	}
+
+	/** Imgproc.dilate on CV_32FC1 with Mat.ones(krows, kcols) (PictureService.java:349-350). */
+	public static void dilateF32(Mat src, Mat dst, int krows, int kcols) {
+		require(src.type() == CvType.CV_32FC1, "src must be CV_32FC1");
+		Mat out = new Mat(src.size(), CvType.CV_32FC1);
+		status(nDilateF32(CTX.get(), src.dataAddr(), src.step1() * 4, out.dataAddr(), out.step1() * 4, src.cols(), src.rows(),
+			kcols, krows));
+		out.copyTo(dst);
+	}
+
+	/** Mat.convertTo(dst, CvType.CV_8U) from CV_32FC1 (PictureService.java:355-356). */
+	public static void convertToU8(Mat src, Mat dst) {
+		require(src.type() == CvType.CV_32FC1, "src must be CV_32FC1");
+		Mat out = new Mat(src.size(), CvType.CV_8UC1);
+		status(nConvertU8(CTX.get(), src.dataAddr(), src.step1() * 4, out.dataAddr(), out.step1(), src.cols(), src.rows()));
+		out.copyTo(dst);
+	}
+
+	/**
+	 * findContours(image, contours, hierarchy, RETR_CCOMP, CHAIN_APPROX_NONE) and the drawContours(markers, contours, i,
+	 * Scalar.all(i + 1), -1, 8, hierarchy, Integer.MAX_VALUE, new Point()) loop of PictureService.java:360-364 in one call.
+	 * Returns contours.size() (the reference's depth, :365).
+	 */
+	public static int contourMarkers(Mat image, Mat markers) {
+		require(image.type() == CvType.CV_8UC1, "image must be CV_8UC1");
+		markers.create(image.size(), CvType.CV_32SC1);
+		int[] n = new int[1];
+		status(nContourMarkers(CTX.get(), image.dataAddr(), image.step1(), markers.dataAddr(), markers.step1() * 4,
+			image.cols(), image.rows(), n));
+		return n[0];
+	}
+
+	/** Imgproc.circle(img, center, radius, color, -1) on CV_32SC1 (PictureService.java:366). */
+	public static void circle(Mat img, Point center, int radius, Scalar color) {
+		require(img.type() == CvType.CV_32SC1, "img must be CV_32SC1");
+		status(nCircle(CTX.get(), img.dataAddr(), img.step1() * 4, img.cols(), img.rows(), (int) center.x, (int) center.y,
+			radius, (int) color.val[0]));
+	}
+
+	/**
+	 * Marker half of PictureService.colorAutoMarkerWatershed (PictureService.java:309-366) as one call, intermediates on the
+	 * device; kernel = the sharpen taps (the reference's MatOfFloat(1,1,1,1,-8,1,1,1,1) is 9 x 1).  Returns contours.size().
+	 */
+	public static int colorSeeds(Mat src, Mat markers, byte[] taps, int krows, int kcols, double peakThresh) {
+		require(src.type() == CvType.CV_8UC3, "src must be CV_8UC3");
+		markers.create(src.size(), CvType.CV_32SC1);
+		int[] n = new int[1];
+		status(nColorSeeds(CTX.get(), src.dataAddr(), src.step1(), src.cols(), src.rows(), taps, krows, kcols, peakThresh,
+			markers.dataAddr(), markers.step1() * 4, n));
+		return n[0];
+	}
+
+	/** Imgproc.bilateralFilter(src, dst, d, sigmaColor, sigmaSpace) on CV_8UC1 / CV_8UC3 (PictureService.java:490). */
+	public static void bilateralFilter(Mat src, Mat dst, int d, double sigmaColor, double sigmaSpace) {
+		require(src.type() == CvType.CV_8UC1 || src.type() == CvType.CV_8UC3, "src must be CV_8UC1 or CV_8UC3");
+		Mat out = new Mat(src.size(), src.type());
+		status(nBilateral(CTX.get(), src.dataAddr(), src.step1(), out.dataAddr(), out.step1(), src.cols(), src.rows(),
+			src.channels(), d, sigmaColor, sigmaSpace));
+		out.copyTo(dst);
+	}
+
 	private static void require(boolean ok, String msg) {
 		if (!ok) {
 			throw new CvException(msg);
@@ -171,6 +276,23 @@ public final class GpuImgproc {
 	private static native int nSubtract(long ctx, long a, long astep, long b, long bstep, long dst, long dstep, int w, int h);
 	private static native int nShapeSeeds(long ctx, long src, long sstep, int w, int h, int ksize, double t1, double t2,
 		long markers, long mstep, int[] n);
+	private static native int nWhiteToBlack(long ctx, long src, long sstep, long dst, long dstep, int w, int h);
+	private static native int nThreshold(long ctx, long src, long sstep, long dst, long dstep, int w, int h, double thresh,
+		double maxval, int type, double[] used);
+	private static native int nThresholdF32(long ctx, long src, long sstep, long dst, long dstep, int w, int h, double thresh,
+		double maxval);
+	private static native int nDistanceTransform(long ctx, long src, long sstep, long dst, long dstep, int w, int h,
+		int distType, int maskSize);
+	private static native int nNormalize(long ctx, long src, long sstep, long dst, long dstep, int w, int h, double alpha,
+		double beta);
+	private static native int nDilateF32(long ctx, long src, long sstep, long dst, long dstep, int w, int h, int kw, int kh);
+	private static native int nConvertU8(long ctx, long src, long sstep, long dst, long dstep, int w, int h);
+	private static native int nContourMarkers(long ctx, long img, long step, long markers, long mstep, int w, int h, int[] n);
+	private static native int nCircle(long ctx, long img, long step, int w, int h, int cx, int cy, int radius, int value);
+	private static native int nColorSeeds(long ctx, long src, long sstep, int w, int h, byte[] taps, int krows, int kcols,
+		double peakThresh, long markers, long mstep, int[] n);
+	private static native int nBilateral(long ctx, long src, long sstep, long dst, long dstep, int w, int h, int channels,
+		int d, double sigmaColor, double sigmaSpace);
 	private static native int nRender(long ctx, long labels, long lstep, long dst, long dstep, int w, int h, int depth,
 		byte[] colors);
 }

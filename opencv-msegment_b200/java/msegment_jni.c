@@ -121,3 +121,84 @@ JNIEXPORT jint JNICALL J(nShapeSeeds)(JNIEnv* e, jclass c, jlong ctx, jlong src,
     if (rc == 0 && n) { jint v = count; (*e)->SetIntArrayRegion(e, n, 0, 1, &v); }
     return rc;
 }
+
+/* ---- colour-method marker generator and bilateral filter ---- */
+JNIEXPORT jint JNICALL J(nWhiteToBlack)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h)
+{
+    return msg_white_to_black((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h);
+}
+
+JNIEXPORT jint JNICALL J(nThreshold)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h,
+                                     jdouble thresh, jdouble maxval, jint type, jdoubleArray used)
+{
+    double u = 0;
+    int rc = msg_threshold((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h, thresh,
+                           maxval, type, &u);
+    if (rc == 0 && used) { jdouble v = u; (*e)->SetDoubleArrayRegion(e, used, 0, 1, &v); }
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nThresholdF32)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w,
+                                        jint h, jdouble thresh, jdouble maxval)
+{
+    return msg_threshold_f32((msg_ctx*)P(ctx), (const float*)P(src), (size_t)sstep, (float*)P(dst), (size_t)dstep, w, h, thresh, maxval);
+}
+
+JNIEXPORT jint JNICALL J(nDistanceTransform)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w,
+                                             jint h, jint dist_type, jint mask_size)
+{
+    return msg_distance_transform((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (float*)P(dst), (size_t)dstep, w, h,
+                                  dist_type, mask_size);
+}
+
+JNIEXPORT jint JNICALL J(nNormalize)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h,
+                                     jdouble alpha, jdouble beta)
+{
+    return msg_normalize_minmax((msg_ctx*)P(ctx), (const float*)P(src), (size_t)sstep, (float*)P(dst), (size_t)dstep, w, h, alpha, beta);
+}
+
+JNIEXPORT jint JNICALL J(nDilateF32)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h,
+                                     jint kw, jint kh)
+{
+    return msg_dilate_f32((msg_ctx*)P(ctx), (const float*)P(src), (size_t)sstep, (float*)P(dst), (size_t)dstep, w, h, kw, kh);
+}
+
+JNIEXPORT jint JNICALL J(nConvertU8)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h)
+{
+    return msg_convert_f32_to_u8((msg_ctx*)P(ctx), (const float*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h);
+}
+
+JNIEXPORT jint JNICALL J(nContourMarkers)(JNIEnv* e, jclass c, jlong ctx, jlong img, jlong step, jlong markers, jlong mstep, jint w,
+                                          jint h, jintArray n)
+{
+    int32_t count = 0;
+    int rc = msg_contour_markers((msg_ctx*)P(ctx), (const uint8_t*)P(img), (size_t)step, (int32_t*)P(markers), (size_t)mstep, w, h,
+                                 &count);
+    if (rc == 0 && n) { jint v = count; (*e)->SetIntArrayRegion(e, n, 0, 1, &v); }
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nCircle)(JNIEnv* e, jclass c, jlong ctx, jlong img, jlong step, jint w, jint h, jint cx, jint cy, jint radius,
+                                  jint value)
+{
+    return msg_circle_filled((msg_ctx*)P(ctx), (int32_t*)P(img), (size_t)step, w, h, cx, cy, radius, value);
+}
+
+JNIEXPORT jint JNICALL J(nColorSeeds)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jint w, jint h, jbyteArray taps,
+                                      jint krows, jint kcols, jdouble peak, jlong markers, jlong mstep, jintArray n)
+{
+    int32_t count = 0;
+    jbyte* t = (*e)->GetByteArrayElements(e, taps, NULL);
+    int rc = msg_color_seeds((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, w, h, (const int8_t*)t, krows, kcols, peak,
+                             (int32_t*)P(markers), (size_t)mstep, &count, NULL, 0, NULL, 0, NULL, 0, NULL, 0);
+    (*e)->ReleaseByteArrayElements(e, taps, t, JNI_ABORT);
+    if (rc == 0 && n) { jint v = count; (*e)->SetIntArrayRegion(e, n, 0, 1, &v); }
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nBilateral)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong dst, jlong dstep, jint w, jint h,
+                                     jint channels, jint d, jdouble sigma_color, jdouble sigma_space)
+{
+    return msg_bilateral_filter((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h,
+                                channels, d, sigma_color, sigma_space);
+}
