@@ -12,6 +12,7 @@
 // MSG_COLOR_DIST, MSG_OUT_FORMAT.
 #include <sys/stat.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
@@ -76,6 +77,18 @@ static std::vector<uint8_t> labels_to_gray(const Mat& m, int multiplier)
     return g;
 }
 
+// Core.multiply(m, Scalar(multiplier)) followed by imwrite's conversion to 8 bit (saturate_cast<uchar>(cvRound(v)))
+static std::vector<uint8_t> float_to_gray(const Mat& m, int multiplier)
+{
+    const float* p = (const float*)m.data();
+    std::vector<uint8_t> g((size_t)m.rows * m.cols);
+    for (size_t i = 0; i < g.size(); i++) {
+        double v = std::nearbyint((double)p[i] * multiplier);
+        g[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+    return g;
+}
+
 static void write_png(const std::string& path, const Mat& m, int multiplier)
 {
     bool ok;
@@ -85,8 +98,8 @@ static void write_png(const std::string& path, const Mat& m, int multiplier)
             rgb[3 * i] = m.buf[3 * i + 2]; rgb[3 * i + 1] = m.buf[3 * i + 1]; rgb[3 * i + 2] = m.buf[3 * i];
         }
         ok = png::write(path, rgb.data(), (size_t)m.cols * 3, m.cols, m.rows, 3);
-    } else if (m.type == CV_32SC1) {
-        std::vector<uint8_t> g = labels_to_gray(m, multiplier);
+    } else if (m.type == CV_32SC1 || m.type == CV_32FC1) {
+        std::vector<uint8_t> g = m.type == CV_32SC1 ? labels_to_gray(m, multiplier) : float_to_gray(m, multiplier);
         ok = png::write(path, g.data(), (size_t)m.cols, m.cols, m.rows, 1);
     } else {
         ok = png::write(path, m.data(), (size_t)m.cols, m.cols, m.rows, 1);
@@ -104,9 +117,9 @@ static void write_pnm(const std::string& path, const Mat& m, int multiplier)
             rgb[3 * i] = m.buf[3 * i + 2]; rgb[3 * i + 1] = m.buf[3 * i + 1]; rgb[3 * i + 2] = m.buf[3 * i];
         }
         f.write((const char*)rgb.data(), (std::streamsize)rgb.size());
-    } else if (m.type == CV_32SC1) {                // Core.multiply(m, multiplier) then saturate to 8 bit, as imwrite would
+    } else if (m.type == CV_32SC1 || m.type == CV_32FC1) {   // Core.multiply(m, multiplier) then saturate to 8 bit, as imwrite would
         f << "P5\n" << m.cols << " " << m.rows << "\n255\n";
-        std::vector<uint8_t> g = labels_to_gray(m, multiplier);
+        std::vector<uint8_t> g = m.type == CV_32SC1 ? labels_to_gray(m, multiplier) : float_to_gray(m, multiplier);
         f.write((const char*)g.data(), (std::streamsize)g.size());
     } else {
         f << "P5\n" << m.cols << " " << m.rows << "\n255\n";
@@ -139,10 +152,11 @@ int main(int argc, char** argv)
     mkdir(odir.c_str(), 0755);
     const char* fmt = getenv("MSG_OUT_FORMAT");
     const bool pnm = fmt && std::string(fmt) == "pnm";
-    auto save = [&](int step, const char* step_name, const Mat& m, int multiplier) {
+    std::string method = "MEANSHIFT_METHOD";
+    auto save = [&](int step, const std::string& step_name, const Mat& m, int multiplier) {
         char b[64];
         snprintf(b, sizeof(b), "%05d", step);
-        const std::string stem = odir + "/MEANSHIFT_METHOD_" + name + "_" + b + "_" + step_name;
+        const std::string stem = odir + "/" + method + "_" + name + "_" + b + "_" + step_name;
         if (pnm) write_pnm(stem + (m.type == CV_8UC3 ? ".ppm" : ".pgm"), m, multiplier);
         else write_png(stem + ".png", m, multiplier);
     };
@@ -161,6 +175,52 @@ int main(int argc, char** argv)
         std::cout << "regions after merge: " << n << std::endl;
         Mat result = GpuImgproc::colorByIndexes(labels, n);           // colored=false -> white (CLI path, PictureService.java:293)
         save(++step, "result", result, 1);
+        if (env_or("MSG_REFERENCE_MARKERS", 1) != 0) {
+            // The marker halves of the reference's two pipelines, step names and multipliers as it saves them
+            // (PictureService.java:320-369 and :410-444); their last two steps ("result", "bw_result") need Imgproc.watershed,
+            // which has no exact parallel form and is not produced here.
+            method = "COLOR_METHOD";                                  // SegMethod.COLOR_METHOD
+            step = 0;
+            Mat black, sharp, gray, bw, dist, peaks, peaks8, markers;
+            GpuImgproc::whiteToBlack(src, black);
+            save(++step, "black_bg", black, 1);
+            static const int8_t taps[9] = {1, 1, 1, 1, -8, 1, 1, 1, 1};
+            GpuImgproc::sharpenLaplacian(black, sharp, taps, 9, 1);
+            save(++step, "laplassian_sharp", sharp, 1);
+            GpuImgproc::cvtColorBGR2GRAY(sharp, gray);
+            GpuImgproc::threshold(gray, bw, 40, 255, GpuImgproc::THRESH_BINARY | GpuImgproc::THRESH_OTSU);
+            save(++step, "bw", bw, 1);
+            GpuImgproc::distanceTransform(bw, dist, GpuImgproc::CV_DIST_L2, 5);
+            GpuImgproc::normalize(dist, dist, 0, 1., GpuImgproc::NORM_MINMAX);
+            save(++step, "distance_transform", dist, 1000);
+            GpuImgproc::threshold(dist, peaks, .4, 1., GpuImgproc::THRESH_BINARY);
+            GpuImgproc::dilateF32(peaks, peaks, 3, 3);
+            save(++step, "distance_peaks", peaks, 1000);
+            GpuImgproc::convertToU8(peaks, peaks8);
+            int depth = GpuImgproc::contourMarkers(peaks8, markers);
+            GpuImgproc::circle(markers, 5, 5, 3, 255);
+            save(++step, "markers", markers, 10000);
+            std::cout << "colour-method contours: " << depth << std::endl;
+            method = "SHAPE_METHOD";                                  // SegMethod.SHAPE_METHOD
+            step = 0;
+            Mat sgray, edges, d3, d5, dde, dde3, smarkers;
+            const int k = GpuImgproc::calculateSizeOfSquareBlurMask(src.cols, src.rows);
+            GpuImgproc::cvtColorBGR2GRAY(src, sgray);
+            GpuImgproc::medianBlur(sgray, sgray, k);
+            save(++step, "blured_by_" + std::to_string(k) + "x" + std::to_string(k), sgray, 1);
+            GpuImgproc::Canny(sgray, edges, 5, 50);
+            ++step;                                                   // "borders" (src.copyTo(dst, mask)) is a display step, not computed
+            save(++step, "gray_borders", edges, 1);
+            GpuImgproc::dilate(edges, d3, 3, 3);
+            GpuImgproc::dilate(d3, d5, 5, 5);
+            GpuImgproc::subtract(d5, d3, dde);
+            save(++step, "dde_step", dde, 1);
+            GpuImgproc::medianBlur(dde, dde3, 3);
+            save(++step, "dde_step_blurred_3x3", dde3, 1);
+            int nlab = GpuImgproc::connectedComponents(dde3, smarkers, 8);
+            save(++step, "markers", smarkers, 10000);
+            std::cout << "shape-method labels: " << nlab << std::endl;
+        }
         std::cout << "results written to " << odir << std::endl;
     } catch (const CvException& e) {                // the reference lets CvException propagate: uncaught -> non-zero exit
         std::cerr << "CvException: " << e.what() << std::endl;

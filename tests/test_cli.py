@@ -153,8 +153,33 @@ def test_cli_batch_matches_oracle(tmp_path):
     stamp = sorted(os.listdir(outdir))[0]
     files = sorted(os.listdir(outdir / stamp))
     # same naming scheme and file type as PictureService.saveResultsToFS (PictureService.java:209-216)
-    assert files == ["MEANSHIFT_METHOD_input_00001_meanshift_filtered.png", "MEANSHIFT_METHOD_input_00002_markers.png",
-                     "MEANSHIFT_METHOD_input_00003_merged_markers.png", "MEANSHIFT_METHOD_input_00004_result.png"]
+    ms = [f for f in files if f.startswith("MEANSHIFT_METHOD_")]
+    assert ms == ["MEANSHIFT_METHOD_input_00001_meanshift_filtered.png", "MEANSHIFT_METHOD_input_00002_markers.png",
+                  "MEANSHIFT_METHOD_input_00003_merged_markers.png", "MEANSHIFT_METHOD_input_00004_result.png"]
+    # the marker halves of the reference's two pipelines under its own step names (PictureService.java:320-369, :410-444)
+    assert [f for f in files if f.startswith("COLOR_METHOD_")] == [
+        "COLOR_METHOD_input_00001_black_bg.png", "COLOR_METHOD_input_00002_laplassian_sharp.png", "COLOR_METHOD_input_00003_bw.png",
+        "COLOR_METHOD_input_00004_distance_transform.png", "COLOR_METHOD_input_00005_distance_peaks.png",
+        "COLOR_METHOD_input_00006_markers.png"]
+    assert [f for f in files if f.startswith("SHAPE_METHOD_")] == [
+        "SHAPE_METHOD_input_00001_blured_by_%dx%d.png" % ((orc.blur_mask_size(200, 150),) * 2), "SHAPE_METHOD_input_00003_gray_borders.png",
+        "SHAPE_METHOD_input_00004_dde_step.png", "SHAPE_METHOD_input_00005_dde_step_blurred_3x3.png",
+        "SHAPE_METHOD_input_00006_markers.png"]
+    cn, cm, cst = orc.color_seeds(im)
+    rd = lambda name: _read_png(str(outdir / stamp / name))
+    assert np.array_equal(rd("COLOR_METHOD_input_00002_laplassian_sharp.png"), cst["sharp"])
+    assert np.array_equal(rd("COLOR_METHOD_input_00003_bw.png"), cst["bw"])
+    assert np.array_equal(rd("COLOR_METHOD_input_00004_distance_transform.png"),
+                          np.clip(np.rint(cst["norm"].astype(np.float64) * 1000), 0, 255).astype(np.uint8))
+    assert np.array_equal(rd("COLOR_METHOD_input_00005_distance_peaks.png"), cst["peaks"] * 255)
+    assert np.array_equal(rd("COLOR_METHOD_input_00006_markers.png"), np.clip(cm.astype(np.int64) * 10000, 0, 255).astype(np.uint8))
+    assert "colour-method contours: %d" % cn in r.stdout
+    sn, sm, sst = orc.shape_seeds(im)
+    assert np.array_equal(rd("SHAPE_METHOD_input_00003_gray_borders.png"), sst["edges"])
+    assert np.array_equal(rd("SHAPE_METHOD_input_00005_dde_step_blurred_3x3.png"), sst["dde3"])
+    assert np.array_equal(rd("SHAPE_METHOD_input_00006_markers.png"), np.clip(sm.astype(np.int64) * 10000, 0, 255).astype(np.uint8))
+    assert "shape-method labels: %d" % sn in r.stdout
+    files = ms
     f = orc.meanshift_filter(im, 10, 10, 1)
     assert np.array_equal(_read_png(str(outdir / stamp / files[0])), f)
     n0, l0 = orc.label_regions(f, 2)
