@@ -38,6 +38,37 @@ __global__ void __launch_bounds__(256) plane_to_bgr_kernel(const uint32_t* __res
     p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16);
 }
 
+// Four pixels per thread: 12 bytes of BGR as three 32-bit words against one 16-byte access of packed words (rows whose width
+// is a multiple of 4 and whose BGR side is 4-byte aligned; everything else takes the one-pixel kernels above).
+__global__ void __launch_bounds__(256) bgr_to_plane_v4_kernel(const uint8_t* __restrict__ src, size_t step,
+                                                              uint32_t* __restrict__ dst, int w4, int rows, int pitch)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (q >= w4 || y >= rows) return;
+    const uint32_t* p = (const uint32_t*)(src + (size_t)y * step) + 3 * (size_t)q;
+    uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    uint4 o;
+    o.x = (w0 & 0x00FFFFFFu) | 0x01000000u;
+    o.y = (w0 >> 24) | ((w1 & 0xFFFFu) << 8) | 0x01000000u;
+    o.z = (w1 >> 16) | ((w2 & 0xFFu) << 16) | 0x01000000u;
+    o.w = (w2 >> 8) | 0x01000000u;
+    *(uint4*)(dst + (size_t)y * pitch + 4 * (size_t)q) = o;
+}
+
+__global__ void __launch_bounds__(256) plane_to_bgr_v4_kernel(const uint32_t* __restrict__ src, int pitch, int w4, int nrows,
+                                                              uint8_t* __restrict__ dst, size_t step)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (q >= w4 || y >= nrows) return;
+    uint4 c = *(const uint4*)(src + (size_t)y * pitch + 4 * (size_t)q);
+    uint32_t* p = (uint32_t*)(dst + (size_t)y * step) + 3 * (size_t)q;
+    p[0] = (c.x & 0x00FFFFFFu) | (c.y << 24);
+    p[1] = ((c.y >> 8) & 0xFFFFu) | (c.z << 16);
+    p[2] = ((c.z >> 16) & 0xFFu) | (c.w << 8);
+}
+
 // ------------------------------------------------------------------ pyrDown: 5x5 [1 4 6 4 1]^2, (acc+128)>>8
 __global__ void __launch_bounds__(256) pyr_down_kernel(msg_plane s, msg_plane d)
 {
@@ -215,6 +246,13 @@ uint64_t host_splitmix64(uint64_t z)
 
 int k_bgr_to_plane(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, msg_plane dst)
 {
+    if (dst.w % 4 == 0 && step % 4 == 0 && ((uintptr_t)d_bgr & 3) == 0 && ((uintptr_t)dst.p & 15) == 0 && dst.pitch % 4 == 0) {
+        dim3 grid4((dst.w / 4 + 255) / 256, dst.rows);
+        bgr_to_plane_v4_kernel<<<grid4, 256, 0, ctx->stream>>>(d_bgr, step, dst.p, dst.w / 4, dst.rows, dst.pitch);
+        MSG_LAUNCHED(ctx);
+        MSG_CHECK_LAUNCH(ctx);
+        return MSG_OK;
+    }
     dim3 grid((dst.w + 255) / 256, dst.rows);
     bgr_to_plane_kernel<<<grid, 256, 0, ctx->stream>>>(d_bgr, step, dst.p, dst.w, dst.rows, dst.pitch);
     MSG_LAUNCHED(ctx);
@@ -224,6 +262,14 @@ int k_bgr_to_plane(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, msg_plane ds
 
 int k_plane_to_bgr(msg_ctx* ctx, msg_plane src, int row_first, int nrows, uint8_t* d_bgr, size_t step)
 {
+    if (src.w % 4 == 0 && step % 4 == 0 && ((uintptr_t)d_bgr & 3) == 0 && ((uintptr_t)src.p & 15) == 0 && src.pitch % 4 == 0) {
+        dim3 grid4((src.w / 4 + 255) / 256, nrows);
+        plane_to_bgr_v4_kernel<<<grid4, 256, 0, ctx->stream>>>(src.p + (size_t)row_first * src.pitch, src.pitch, src.w / 4, nrows,
+                                                              d_bgr, step);
+        MSG_LAUNCHED(ctx);
+        MSG_CHECK_LAUNCH(ctx);
+        return MSG_OK;
+    }
     dim3 grid((src.w + 255) / 256, nrows);
     plane_to_bgr_kernel<<<grid, 256, 0, ctx->stream>>>(src.p + (size_t)row_first * src.pitch, src.pitch, src.w, nrows,
                                                       d_bgr, step);

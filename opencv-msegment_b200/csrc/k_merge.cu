@@ -659,11 +659,45 @@ __global__ void __launch_bounds__(MT) render_kernel(const int32_t* __restrict__ 
     p[0] = c0; p[1] = c1; p[2] = c2;
 }
 
+// four labels per thread: one 16-byte load, 12 bytes of BGR as three 32-bit words
+__global__ void __launch_bounds__(MT) render_v4_kernel(const int32_t* __restrict__ L, size_t lstep, uint8_t* __restrict__ dst,
+                                                       size_t dstep, int w4, int depth, const uint8_t* __restrict__ colors)
+{
+    int q = blockIdx.x * MT + threadIdx.x;
+    int y = blockIdx.y;
+    if (q >= w4) return;
+    int4 v = *(const int4*)((const char*)L + (size_t)y * lstep + 16 * (size_t)q);
+    const int lab[4] = {v.x, v.y, v.z, v.w};
+    uint32_t c[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t col = 0;
+        if (lab[i] > 0 && lab[i] <= depth) {
+            if (colors) {
+                const uint8_t* t = colors + 3 * (size_t)(lab[i] - 1);
+                col = (uint32_t)__ldg(t) | ((uint32_t)__ldg(t + 1) << 8) | ((uint32_t)__ldg(t + 2) << 16);
+            } else col = 0x00FFFFFFu;
+        }
+        c[i] = col;
+    }
+    uint32_t* p = (uint32_t*)(dst + (size_t)y * dstep) + 3 * (size_t)q;
+    p[0] = c[0] | (c[1] << 24);
+    p[1] = (c[1] >> 8) | (c[2] << 16);
+    p[2] = (c[2] >> 16) | (c[3] << 8);
+}
+
 }  // namespace
 
 int k_render(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, uint8_t* d_dst, size_t dstep, int w, int h, int depth,
              const uint8_t* d_colors)
 {
+    if (w % 4 == 0 && lstep % 16 == 0 && dstep % 4 == 0 && ((uintptr_t)d_labels & 15) == 0 && ((uintptr_t)d_dst & 3) == 0) {
+        dim3 grid4((w / 4 + MT - 1) / MT, h);
+        render_v4_kernel<<<grid4, MT, 0, ctx->stream>>>(d_labels, lstep, d_dst, dstep, w / 4, depth, d_colors);
+        MSG_LAUNCHED(ctx);
+        MSG_CHECK_LAUNCH(ctx);
+        return MSG_OK;
+    }
     dim3 grid((w + MT - 1) / MT, h);
     render_kernel<<<grid, MT, 0, ctx->stream>>>(d_labels, lstep, d_dst, dstep, w, depth, d_colors);
     MSG_LAUNCHED(ctx);
