@@ -309,6 +309,23 @@ MSG_API int msg_strip_apply_dense_dev(msg_ctx* ctx, int32_t* d_labels, size_t la
                               int full_width, int offset, const int32_t* d_remote_labels_sorted,
                               const int32_t* d_remote_dense, int n_remote);
 
+/* Single-exchange form of the seam resolution + dense numbering (one boundary-row transfer and ONE all-gather per image):
+ *  (1) msg_strip_rank_dev on the PROVISIONAL strip labels (right after msg_label_strip_dev): *d_count = roots of the strip;
+ *  (2) the rank above sends its last row of colours, labels and msg_strip_query_dense_dev(labels of that row, offset 0) =
+ *      rank + 1 of every label's root; msg_seam_quads_dev emits one quad (A, B, rankA + 1, rankB + 1) per equivalence
+ *      (up to `width` quads, count to d_count); B's rank comes from this context's tables of step (1);
+ *  (3) the ranks all-gather (quad count, root count, quads); every rank resolves the equivalences (union-find over the quads)
+ *      and derives, identically, the sorted list d_frm of labels that merge into a smaller one, the dense id d_dense[j] of the
+ *      class frm[j] joins, this strip's offset (surviving roots of the strips above) and frm_lo (index of the first entry of
+ *      d_frm that lies in this strip) -- opencv-msegment_b200/sharded.py:resolve_dense;
+ *  (4) msg_strip_finalize_dense_dev rewrites the strip in one pass.  Result: identical to the unsharded call's labels. */
+MSG_API int msg_seam_quads_dev(msg_ctx* ctx, const uint8_t* d_upper_row_bgr, const int32_t* d_upper_row_labels,
+                       const int32_t* d_upper_row_rank1, const uint8_t* d_lower_row_bgr, const int32_t* d_lower_row_labels,
+                       int width, int lo_diff, int rows, int row0, int full_width, int32_t* d_quads, int32_t* d_count);
+MSG_API int msg_strip_finalize_dense_dev(msg_ctx* ctx, int32_t* d_labels, size_t labels_step, int width, int rows, int row0,
+                                 int full_width, int offset, const int32_t* d_frm_sorted, const int32_t* d_dense, int n_map,
+                                 int frm_lo);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 typedef struct msg_timings { /* milliseconds of the last host-buffer call, CUDA events */
     float h2d_ms, filter_ms, label_ms, merge_ms, render_ms, d2h_ms, total_ms;

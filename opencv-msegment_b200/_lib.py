@@ -93,6 +93,8 @@ SIGNATURES = {
     "msg_strip_rank_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _P]),
     "msg_strip_query_dense_dev": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "msg_strip_apply_dense_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _I, _P, _P, _I]),
+    "msg_seam_quads_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "msg_strip_finalize_dense_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _I, _P, _P, _I, _I]),
     "msg_get_timings": (_I, [_P, C.POINTER(Timings)]),
     "msg_get_stats": (_I, [_P, C.POINTER(Stats)]),
     "msg_debug_get_plane": (_I, [_P, _I, _I, _P, _SZ, C.POINTER(_I), C.POINTER(_I)]),

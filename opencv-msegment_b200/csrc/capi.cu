@@ -1040,6 +1040,28 @@ int msg_strip_apply_dense_dev(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int
     return k_strip_apply_dense(ctx, d_labels, lstep, w, rows, (long long)row0 * full_w, offset, d_rlab, d_rdense, nr);
 }
 
+int msg_seam_quads_dev(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const int32_t* up_rank1, const uint8_t* lo_bgr,
+                       const int32_t* lo_lab, int w, int lo_diff, int rows, int row0, int full_w, int32_t* d_quads, int32_t* d_count)
+{
+    CTX_ENTER(ctx);
+    if (!up_bgr || !up_lab || !up_rank1 || !lo_bgr || !lo_lab || !d_quads || !d_count || w <= 0 || lo_diff < 0 || rows <= 0 ||
+        row0 < 0 || full_w != w)
+        return msg_fail(ctx, MSG_EINVAL, "seam_quads: bad argument");
+    if (!ctx->d_scratch) return msg_fail(ctx, MSG_ESTATE, "seam_quads: call msg_strip_rank_dev first");
+    return k_seam_quads(ctx, up_bgr, up_lab, up_rank1, lo_bgr, lo_lab, w, lo_diff, rows, (long long)row0 * full_w, d_quads, d_count);
+}
+
+int msg_strip_finalize_dense_dev(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, int row0, int full_w, int offset,
+                                 const int32_t* d_frm, const int32_t* d_dense, int n_map, int frm_lo)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, rows, 4, "labels"));
+    if (n_map < 0 || (n_map > 0 && (!d_frm || !d_dense)) || frm_lo < 0 || frm_lo > n_map || full_w != w || lstep % 4)
+        return msg_fail(ctx, MSG_EINVAL, "strip_finalize_dense: bad argument");
+    if (!ctx->d_scratch) return msg_fail(ctx, MSG_ESTATE, "strip_finalize_dense: call msg_strip_rank_dev first");
+    return k_strip_finalize(ctx, d_labels, lstep, w, rows, (long long)row0 * full_w, offset, d_frm, d_dense, n_map, frm_lo);
+}
+
 // ============================================================================ pre-filters (8(f2))
 
 static int filter_host(msg_ctx* ctx, const uint8_t* src, size_t sstep, int in_ch, uint8_t* dst, size_t dstep, int out_ch, int w,

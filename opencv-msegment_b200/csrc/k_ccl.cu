@@ -527,6 +527,60 @@ __global__ void __launch_bounds__(CCL_THREADS) strip_apply_dense_kernel(int32_t*
     }
 }
 
+
+// Seam equivalences with the strip-local ranks of both roots (single-exchange sharding): quads (A, B, rankA + 1, rankB + 1).
+// up_rank1: rank + 1 of the upper labels' roots inside the upper strip (the rank above sends it with its boundary row);
+// the lower labels are this strip's own: their ranks come from the tables msg_strip_rank_dev left in the workspace.
+__global__ void __launch_bounds__(CCL_THREADS) seam_quads_kernel(const uint8_t* __restrict__ up_bgr, const int32_t* __restrict__ up_lab,
+                                                                 const int32_t* __restrict__ up_rank1, const uint8_t* __restrict__ lo_bgr,
+                                                                 const int32_t* __restrict__ lo_lab, int w, int d, long long base, size_t n,
+                                                                 const int32_t* __restrict__ block_offs, const int32_t* __restrict__ lrank,
+                                                                 int32_t* __restrict__ quads, int32_t* __restrict__ count)
+{
+    int x = blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (x >= w) return;
+    auto close = [&](const uint8_t* a, const uint8_t* b) {
+        return abs((int)a[0] - (int)b[0]) <= d && abs((int)a[1] - (int)b[1]) <= d && abs((int)a[2] - (int)b[2]) <= d;
+    };
+    if (!close(up_bgr + 3 * x, lo_bgr + 3 * x)) return;
+    int a = up_lab[x], b = lo_lab[x];
+    if (a == b) return;
+    if (x > 0 && up_lab[x - 1] == a && lo_lab[x - 1] == b && close(up_bgr + 3 * (x - 1), lo_bgr + 3 * (x - 1))) return;
+    long long loc = (long long)b - 1 - base;
+    int rb = (loc >= 0 && loc < (long long)n) ? block_offs[loc / SCAN_CHUNK] + lrank[loc] + 1 : 0;
+    int slot = atomicAdd(count, 1);
+    quads[4 * slot] = a;
+    quads[4 * slot + 1] = b;
+    quads[4 * slot + 2] = up_rank1[x];
+    quads[4 * slot + 3] = rb;
+}
+
+// Single pass from provisional strip labels (1 + global index of the strip-local root) to the dense global numbering:
+// a label listed in `frm` (sorted; the labels that seam resolution merges into a smaller one) takes dense[j]; every other
+// label is a surviving root of this strip: offset + its local rank - the number of removed roots of this strip before it.
+__global__ void __launch_bounds__(CCL_THREADS) strip_finalize_kernel(int32_t* __restrict__ L, size_t lstep_words, int w, size_t n,
+                                                                     long long base, int offset,
+                                                                     const int32_t* __restrict__ block_offs,
+                                                                     const int32_t* __restrict__ lrank,
+                                                                     const int32_t* __restrict__ frm,
+                                                                     const int32_t* __restrict__ dense, int nmap, int frm_lo)
+{
+    size_t i = (size_t)blockIdx.x * CCL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int32_t* p = L + (i / w) * lstep_words + (i % w);
+    int v = *p;
+    if (v <= 0) return;
+    int lo = 0, hi = nmap;                       // lower bound of v in frm
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(frm + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    if (lo < nmap && __ldg(frm + lo) == v) { *p = __ldg(dense + lo); return; }
+    long long loc = (long long)v - 1 - base;
+    if (loc < 0 || loc >= (long long)n) return;   // not a label of this strip: left untouched (caller error)
+    *p = offset + block_offs[loc / SCAN_CHUNK] + lrank[loc] - (lo - frm_lo) + 1;
+}
+
 inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 // ---------------------------------------------------------------- Canny hysteresis on top of the binary union-find
@@ -722,6 +776,31 @@ int k_strip_apply_dense(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, in
     int32_t* lrank = (int32_t*)ctx->d_scratch;
     strip_apply_dense_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, ctx->stream>>>(d_labels, lstep / 4, w, n, base, offset,
                                                                                           lrank + n, lrank, d_rlab, d_rdense, nr);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_seam_quads(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const int32_t* up_rank1, const uint8_t* lo_bgr,
+                 const int32_t* lo_lab, int w, int d, int rows, long long base, int32_t* quads, int32_t* count)
+{
+    size_t n = (size_t)w * rows;
+    int32_t* lrank = (int32_t*)ctx->d_scratch;
+    MSG_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t), ctx->stream));
+    seam_quads_kernel<<<blocks_for((size_t)w, CCL_THREADS), CCL_THREADS, 0, ctx->stream>>>(up_bgr, up_lab, up_rank1, lo_bgr, lo_lab, w, d,
+                                                                                          base, n, lrank + n, lrank, quads, count);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_strip_finalize(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, long long base, int offset,
+                     const int32_t* d_frm, const int32_t* d_dense, int nmap, int frm_lo)
+{
+    size_t n = (size_t)w * rows;
+    int32_t* lrank = (int32_t*)ctx->d_scratch;
+    strip_finalize_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, ctx->stream>>>(d_labels, lstep / 4, w, n, base, offset, lrank + n,
+                                                                                       lrank, d_frm, d_dense, nmap, frm_lo);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;

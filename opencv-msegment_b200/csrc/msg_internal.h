@@ -162,6 +162,11 @@ int k_strip_query(msg_ctx* ctx, const int32_t* d_q, int nq, int w, int rows, lon
 int k_strip_apply_dense(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, long long base, int offset,
                         const int32_t* d_rlab, const int32_t* d_rdense, int nr);
 
+int k_seam_quads(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const int32_t* up_rank1, const uint8_t* lo_bgr,
+                 const int32_t* lo_lab, int w, int d, int rows, long long base, int32_t* quads, int32_t* count);
+int k_strip_finalize(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, long long base, int offset,
+                     const int32_t* d_frm, const int32_t* d_dense, int nmap, int frm_lo);
+
 // pre-filters (k_filters.cu)
 int k_sharpen(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, const int8_t* taps,
               int krows, int kcols);

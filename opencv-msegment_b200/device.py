@@ -79,6 +79,16 @@ def strip_apply_dense(ctx, d_labels, lstep, w, rows, row0, full_w, offset, d_rla
                                                  _p(d_rdense), int(nr)))
 
 
+def seam_quads(ctx, d_up_bgr, d_up_lab, d_up_rank1, d_lo_bgr, d_lo_lab, w, lo_diff, rows, row0, full_w, d_quads, d_count):
+    ctx.check(ctx._lib.msg_seam_quads_dev(ctx._h, _p(d_up_bgr), _p(d_up_lab), _p(d_up_rank1), _p(d_lo_bgr), _p(d_lo_lab), w,
+                                          int(lo_diff), rows, row0, full_w, _p(d_quads), _p(d_count)))
+
+
+def strip_finalize_dense(ctx, d_labels, lstep, w, rows, row0, full_w, offset, d_frm, d_dense, n_map, frm_lo):
+    ctx.check(ctx._lib.msg_strip_finalize_dense_dev(ctx._h, _p(d_labels), lstep, w, rows, row0, full_w, int(offset), _p(d_frm),
+                                                    _p(d_dense), int(n_map), int(frm_lo)))
+
+
 def connected_components(ctx, d_mask, step, d_labels, lstep, w, h, connectivity=8, d_n=0):
     ctx.check(ctx._lib.msg_connected_components_dev(ctx._h, _p(d_mask), step, _p(d_labels), lstep, w, h, int(connectivity),
                                                     _p(d_n)))

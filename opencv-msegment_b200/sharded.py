@@ -74,6 +74,40 @@ def resolve_pairs(pairs):
     return labels[changed].astype(np.int32), labels[roots[changed]].astype(np.int32)
 
 
+def resolve_dense(quads, n_roots, strips, width):
+    """Single-exchange seam resolution + dense numbering tables (msg_seam_quads_dev / msg_strip_finalize_dense_dev).
+
+    quads   : int array (m,4): (A, B, rankA + 1, rankB + 1) over all seams -- provisional labels (1 + global index of the
+              strip-local root) of two equivalent regions and the ranks of their roots inside their strips
+    n_roots : roots per strip before resolution (msg_strip_rank_dev on the provisional labels)
+    strips  : [(row0,row1), ...];  width: image width
+    Returns (frm, dense, offsets, frm_lo, total): frm = sorted labels that merge into a smaller label, dense[j] = dense id
+    (1..total in raster order of first pixel) of the class frm[j] joins, offsets[s] = surviving roots of the strips above s,
+    frm_lo[s] = index of the first entry of frm inside strip s, total = regions of the whole image.
+    Deterministic: every rank derives the same tables from the same gathered quads."""
+    quads = np.asarray(quads, dtype=np.int64).reshape(-1, 4)
+    n_roots = np.asarray(n_roots, dtype=np.int64)
+    starts = np.array([r0 * width + 1 for r0, _ in strips], np.int64)          # first label value of every strip
+    frm, to = resolve_pairs(quads[:, :2])
+    frm64, to64 = frm.astype(np.int64), to.astype(np.int64)
+    frm_lo = np.searchsorted(frm64, starts)                                     # entries of frm before each strip
+    removed = np.diff(np.concatenate([frm_lo, [len(frm64)]]))
+    surviving = n_roots - removed
+    offsets = np.concatenate([[0], np.cumsum(surviving)[:-1]])
+    if len(frm64) == 0:
+        return frm, np.zeros(0, np.int32), offsets.astype(np.int64), frm_lo.astype(np.int64), int(surviving.sum())
+    # strip-local rank of every label that occurs in a quad
+    labs = np.concatenate([quads[:, 0], quads[:, 1]])
+    rks = np.concatenate([quads[:, 2], quads[:, 3]]) - 1
+    ulab, first = np.unique(labs, return_index=True)
+    urank = rks[first]
+    t_rank = urank[np.searchsorted(ulab, to64)]
+    t_strip = np.searchsorted(starts, to64, side="right") - 1
+    t_removed_before = np.searchsorted(frm64, to64) - frm_lo[t_strip]          # removed roots of that strip before `to`
+    dense = offsets[t_strip] + t_rank - t_removed_before + 1
+    return frm, dense.astype(np.int32), offsets.astype(np.int64), frm_lo.astype(np.int64), int(surviving.sum())
+
+
 def first_pixel_labels(dense_labels):
     """Converts dense canonical labels (1..n in raster order of first pixel) to the sharded representation
     (1 + linear index of the region's first pixel); used to compare sharded and unsharded results."""

@@ -97,6 +97,58 @@ def test_strips_bit_identical(w, h, n, sp, sr, ml):
     ctx.close()
 
 
+@pytest.mark.parametrize("w,h,n,sp,sr,ml", [(600, 518, 3, 10, 10, 1), (333, 400, 4, 6, 15, 2), (420, 300, 5, 10, 10, 1),
+                                           (512, 96, 6, 4, 30, 0)])
+def test_strips_single_exchange_dense(w, h, n, sp, sr, ml):
+    """The single-exchange form (msg_strip_rank_dev on provisional labels, msg_seam_quads_dev, one gather,
+    sharded.resolve_dense, msg_strip_finalize_dense_dev): labels identical to the unsharded call's, integer for integer."""
+    im = orc.synth_bgr(w, h, 23)
+    src = torch.from_numpy(im).cuda()
+    ctx = mseg.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    full = torch.empty_like(src)
+    dev.meanshift(ctx, src.data_ptr(), 3 * w, full.data_ptr(), 3 * w, w, h, sp, sr, ml)
+    lab_full = torch.empty((h, w), dtype=torch.int32, device="cuda")
+    dev.label_regions(ctx, full.data_ptr(), 3 * w, lab_full.data_ptr(), 4 * w, w, h, 2)
+    ctx.synchronize()
+    strips = sh.plan_strips(h, n, ml)
+    ctxs = [mseg.Context(0) for _ in strips]                  # one context per simulated rank (keeps the rank tables)
+    for c in ctxs:
+        c.set_stream(torch.cuda.current_stream().cuda_stream)
+    labs, cnt = [], torch.zeros(len(strips), dtype=torch.int32, device="cuda")
+    for k, (r0, r1) in enumerate(strips):
+        rows = full[r0:r1].contiguous()
+        l = torch.empty((r1 - r0, w), dtype=torch.int32, device="cuda")
+        dev.label_strip(ctxs[k], rows.data_ptr(), 3 * w, l.data_ptr(), 4 * w, w, r1 - r0, r0, w, 2)
+        dev.strip_rank(ctxs[k], l.data_ptr(), 4 * w, w, r1 - r0, r0, w, cnt[k:].data_ptr())
+        labs.append(l)
+    quads_all = []
+    for k in range(1, len(strips)):
+        (u0, u1), (r0, r1) = strips[k - 1], strips[k]
+        up_lab = labs[k - 1][-1].contiguous()
+        up_rank1 = torch.zeros(w, dtype=torch.int32, device="cuda")           # what the rank above sends with its last row
+        dev.strip_query_dense(ctxs[k - 1], up_lab.data_ptr(), w, w, u1 - u0, u0, w, 0, up_rank1.data_ptr())
+        quads = torch.zeros((w, 4), dtype=torch.int32, device="cuda")
+        qn = torch.zeros(1, dtype=torch.int32, device="cuda")
+        dev.seam_quads(ctxs[k], full[r0 - 1].data_ptr(), up_lab.data_ptr(), up_rank1.data_ptr(), full[r0].data_ptr(),
+                       labs[k][0].data_ptr(), w, 2, r1 - r0, r0, w, quads.data_ptr(), qn.data_ptr())
+        torch.cuda.synchronize()
+        quads_all.append(quads[:int(qn.item())].cpu().numpy().copy())
+    frm, dense, offsets, frm_lo, total = sh.resolve_dense(np.concatenate(quads_all), cnt.cpu().numpy(), strips, w)
+    d_frm = torch.from_numpy(np.ascontiguousarray(frm)).cuda() if len(frm) else torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_dense = torch.from_numpy(np.ascontiguousarray(dense)).cuda() if len(frm) else torch.zeros(1, dtype=torch.int32, device="cuda")
+    for k, (r0, r1) in enumerate(strips):
+        dev.strip_finalize_dense(ctxs[k], labs[k].data_ptr(), 4 * w, w, r1 - r0, r0, w, int(offsets[k]), d_frm.data_ptr(),
+                                 d_dense.data_ptr(), len(frm), int(frm_lo[k]))
+    torch.cuda.synchronize()
+    got = torch.cat(labs)
+    assert total == int(lab_full.max().item())
+    assert torch.equal(got, lab_full), int((got != lab_full).sum().item())
+    for c in ctxs:
+        c.close()
+    ctx.close()
+
+
 def test_synth_rows_matches_full():
     ctx = mseg.Context(0)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)

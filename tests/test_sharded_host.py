@@ -118,3 +118,51 @@ def test_two_rank_gloo_seam_resolution():
         p.join(timeout=180)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def _strip_local(colors, r0, r1, d):
+    """Provisional strip labels as msg_label_strip_dev writes them: 1 + GLOBAL index of the strip-local region's first pixel."""
+    h, w = colors.shape[:2]
+    n, lab = orc.label_regions(np.ascontiguousarray(colors[r0:r1]), d)        # canonical 1..n inside the strip
+    flat = lab.ravel()
+    first = np.full(n + 1, -1, np.int64)
+    idx = np.arange(flat.size)
+    first[flat[::-1]] = idx[::-1]                                               # smallest index wins
+    return n, (first[flat] + r0 * w + 1).reshape(lab.shape).astype(np.int32)
+
+
+@pytest.mark.parametrize("w,h,n_strips,seed", [(64, 96, 3, 1), (37, 120, 5, 2), (90, 40, 2, 3), (50, 50, 4, 4)])
+def test_resolve_dense_single_exchange(w, h, n_strips, seed):
+    """Host logic of the single-exchange strip finalisation (sharded.resolve_dense) against the unsharded labelling."""
+    sh = _sharded()
+    rng = np.random.default_rng(seed)
+    # a few flat colours in blobs: many regions cross the seams, some span several strips
+    base = rng.integers(0, 3, (h // 4 + 1, w // 4 + 1))
+    colors = (np.kron(base, np.ones((4, 4), np.int64))[:h, :w, None] * np.array([70, 40, 90])).astype(np.uint8)
+    colors[rng.random((h, w)) < 0.05] = 255                                     # speckles: small regions
+    d = 2
+    want_n, want = orc.label_regions(np.ascontiguousarray(colors), d)
+    strips = sh.plan_strips(h, n_strips, 0)
+    prov, n_roots, ranks = [], [], []
+    for (r0, r1) in strips:
+        n, lab = _strip_local(colors, r0, r1, d)
+        roots = np.unique(lab)                                                  # ascending label = ascending first pixel
+        prov.append(lab); n_roots.append(n); ranks.append(roots)
+    quads = []
+    for s in range(1, len(strips)):
+        up_c, lo_c = colors[strips[s][0] - 1].astype(int), colors[strips[s][0]].astype(int)
+        close = (np.abs(up_c - lo_c) <= d).all(axis=1)
+        a, b = prov[s - 1][-1][close], prov[s][0][close]
+        ra = np.searchsorted(ranks[s - 1], a) + 1
+        rb = np.searchsorted(ranks[s], b) + 1
+        quads.append(np.stack([a, b, ra, rb], axis=1))
+    frm, dense, offsets, frm_lo, total = sh.resolve_dense(np.concatenate(quads), n_roots, strips, w)
+    assert total == want_n
+    got = np.zeros((h, w), np.int32)
+    for s, (r0, r1) in enumerate(strips):
+        v = prov[s].astype(np.int64)
+        j = np.searchsorted(frm, v)
+        hit = (j < len(frm)) & (frm[np.minimum(j, max(len(frm) - 1, 0))] == v) if len(frm) else np.zeros(v.shape, bool)
+        own = offsets[s] + np.searchsorted(ranks[s], v) - (j - frm_lo[s]) + 1
+        got[r0:r1] = np.where(hit, dense[np.minimum(j, max(len(dense) - 1, 0))] if len(dense) else 0, own)
+    assert np.array_equal(got, want)

@@ -102,50 +102,46 @@ def main():
         dev.label_strip(ctx, filt.data_ptr(), 3 * w, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, args.lo)
         ev[3].record()
 
-        # ---- seam: my first row against the last row of the rank above
+        # ---- seams + dense global numbering, single exchange: one boundary-row transfer, ONE all-gather, one host sync.
+        # The rank above sends its last row of colours, provisional labels and the strip-local rank of every label's root; the
+        # seam kernel emits (A, B, rankA + 1, rankB + 1); the gathered quads + root counts let every rank derive the same tables
+        # (sharded.resolve_dense) and rewrite its strip in one pass (1..N in raster order of first pixel, as the unsharded call).
+        rows = r1 - r0
+        cnt_d = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        dev.strip_rank(ctx, lab.data_ptr(), 4 * w, w, rows, r0, w, cnt_d.data_ptr())
+        my_last_lab = lab[-1].contiguous()
+        my_last_rank1 = torch.zeros((w,), dtype=torch.int32, device="cuda")
+        if rank + 1 < world:
+            dev.strip_query_dense(ctx, my_last_lab.data_ptr(), w, w, rows, r0, w, 0, my_last_rank1.data_ptr())
         up_bgr = torch.empty((w, 3), dtype=torch.uint8, device="cuda")
-        up_lab = torch.empty((w,), dtype=torch.int32, device="cuda")
+        up_lr = torch.empty((2, w), dtype=torch.int32, device="cuda")           # labels, rank + 1
         ops = []
         if rank + 1 < world:
-            ops += [dist.P2POp(dist.isend, filt[-1].contiguous(), rank + 1), dist.P2POp(dist.isend, lab[-1].contiguous(), rank + 1)]
+            ops += [dist.P2POp(dist.isend, filt[-1].contiguous(), rank + 1),
+                    dist.P2POp(dist.isend, torch.stack([my_last_lab, my_last_rank1]), rank + 1)]
         if rank > 0:
-            ops += [dist.P2POp(dist.irecv, up_bgr, rank - 1), dist.P2POp(dist.irecv, up_lab, rank - 1)]
+            ops += [dist.P2POp(dist.irecv, up_bgr, rank - 1), dist.P2POp(dist.irecv, up_lr, rank - 1)]
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        pairs = torch.zeros((w, 2), dtype=torch.int32, device="cuda")
-        cnt = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        payload = torch.zeros((w + 1, 4), dtype=torch.int32, device="cuda")      # row 0: (quad count, root count, 0, 0)
         if rank > 0:
-            dev.seam_pairs(ctx, up_bgr.data_ptr(), up_lab.data_ptr(), filt[0].data_ptr(), lab[0].data_ptr(), w, args.lo,
-                           pairs.data_ptr(), cnt.data_ptr())
-        torch.cuda.synchronize()
-        mine = pairs[:int(cnt.item())].cpu().numpy()
-        allp = sh.allgather_pairs(dist, mine, device="cuda", cap=w)
-        frm, to = sh.resolve_pairs(allp)
+            dev.seam_quads(ctx, up_bgr.data_ptr(), up_lr[0].data_ptr(), up_lr[1].data_ptr(), filt[0].data_ptr(), lab[0].data_ptr(),
+                           w, args.lo, rows, r0, w, payload[1:].data_ptr(), payload[0, 0:].data_ptr())
+        payload[0, 1:2].copy_(cnt_d)
+        gathered = torch.empty((world, w + 1, 4), dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(gathered, payload)
+        host = gathered.cpu().numpy()                                            # the one host synchronisation
+        counts = host[:, 0, 1].astype(np.int64)
+        allp = np.concatenate([host[r, 1:1 + int(host[r, 0, 0])] for r in range(world)], axis=0)
+        frm, dense, offsets, frm_lo, total = sh.resolve_dense(allp, counts, strips, w)
         if len(frm):
-            d_from, d_to = torch.from_numpy(frm).cuda(), torch.from_numpy(to).cuda()
-            dev.apply_label_map(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, d_from.data_ptr(), d_to.data_ptr(), len(frm))
-        # ---- dense global numbering (1..N in raster order of first pixel, as the unsharded call numbers regions)
-        cnt_d = torch.zeros((1,), dtype=torch.int32, device="cuda")
-        dev.strip_rank(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, cnt_d.data_ptr())
-        counts = [torch.zeros_like(cnt_d) for _ in range(world)]
-        dist.all_gather(counts, cnt_d)
-        counts = [int(c.item()) for c in counts]
-        offset = sum(counts[:rank])
-        uniq_to = np.unique(to).astype(np.int32) if len(frm) else np.zeros(0, np.int32)
-        own = np.flatnonzero((uniq_to > r0 * w) & (uniq_to <= r1 * w))
-        mine_tab = np.zeros((len(own), 2), np.int32)
-        if len(own):
-            q = torch.from_numpy(uniq_to[own]).cuda()
-            o = torch.zeros(len(own), dtype=torch.int32, device="cuda")
-            dev.strip_query_dense(ctx, q.data_ptr(), len(own), w, r1 - r0, r0, w, offset, o.data_ptr())
-            mine_tab[:, 0] = uniq_to[own]
-            mine_tab[:, 1] = o.cpu().numpy()
-        tab = sh.allgather_pairs(dist, mine_tab, device="cuda", cap=max(1, len(uniq_to)))
-        tab = tab[np.argsort(tab[:, 0], kind="stable")] if len(tab) else tab
-        d_rl = torch.from_numpy(np.ascontiguousarray(tab[:, 0])).cuda() if len(tab) else torch.zeros(1, dtype=torch.int32, device="cuda")
-        d_rd = torch.from_numpy(np.ascontiguousarray(tab[:, 1])).cuda() if len(tab) else torch.zeros(1, dtype=torch.int32, device="cuda")
-        dev.strip_apply_dense(ctx, lab.data_ptr(), 4 * w, w, r1 - r0, r0, w, offset, d_rl.data_ptr(), d_rd.data_ptr(), len(tab))
+            tab = torch.from_numpy(np.stack([frm, dense])).cuda()
+        else:
+            tab = torch.zeros((2, 1), dtype=torch.int32, device="cuda")
+        dev.strip_finalize_dense(ctx, lab.data_ptr(), 4 * w, w, rows, r0, w, int(offsets[rank]), tab[0].data_ptr(), tab[1].data_ptr(),
+                                 len(frm), int(frm_lo[rank]))
+        counts = [int(total)]
         ev[4].record()
         torch.cuda.synchronize()
         dist.barrier()
