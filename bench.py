@@ -228,6 +228,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
+    host = bind_to_gpu_cpus(local)          # before any pinned allocation: first-touch puts the staging buffers on the GPU's node
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -421,7 +422,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(), "frames_per_step_per_gpu": B, "streams_per_gpu": N_STREAMS,
-                       "flush": "per-step input 199 MB per GPU > 126 MB L2 (no explicit flush)", "parallelism": "frames x%d" % world},
+                       "flush": "per-step input 199 MB per GPU > 126 MB L2 (no explicit flush)", "parallelism": "frames x%d" % world,
+                       "host": host},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes,
                     "d2h_bytes_per_step": B * (frame_bytes + lab_bytes), "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
@@ -429,6 +431,28 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line))
     return 0
+
+
+def bind_to_gpu_cpus(local):
+    """One process per GPU: run on the CPUs NVML reports as local to that GPU (same socket / NUMA node), so that the pinned
+    staging buffers of the end-to-end path are allocated next to the GPU's PCIe root.  Best effort: without NVML, or when the
+    local CPUs are not in this process' allowed set, the affinity is left alone.  Returns what was done (goes into `config`)."""
+    info = {"cpus_allowed": len(os.sched_getaffinity(0)), "affinity": "unchanged"}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        mine = cpus & os.sched_getaffinity(0)
+        info["gpu_local_cpus"] = len(cpus)
+        if mine and mine != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, mine)
+            info["affinity"] = "nvml local cpus (%d)" % len(mine)
+        pynvml.nvmlShutdown()
+    except Exception as e:   # noqa: BLE001  (diagnostic only)
+        info["affinity"] = "unchanged (%s)" % type(e).__name__
+    return info
 
 
 def measure_int_peak():

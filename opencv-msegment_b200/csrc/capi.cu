@@ -132,7 +132,9 @@ int msg_create(int device, msg_ctx** out)
     for (int l = 0; l < MSG_MAX_LEVELS; l++)
         for (int k = 0; k < 3; k++) CR(cudaEventCreate(&ctx->prof_ev[l][k]));
     for (int i = 0; i < MSG_MAX_INFLIGHT; i++) {
-        CR(cudaEventCreateWithFlags(&ctx->pend[i].done, cudaEventDisableTiming));
+        // msg_wait blocks on this event: a sleeping wait (not a spin) keeps the host cores free for the submitting threads when
+        // many contexts share few cores (8 GPUs x 6 contexts on a 16-core host)
+        CR(cudaEventCreateWithFlags(&ctx->pend[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
         CR(cudaEventCreateWithFlags(&ctx->pend[i].ev_in, cudaEventDisableTiming));
         CR(cudaEventCreateWithFlags(&ctx->pend[i].ev_core, cudaEventDisableTiming));
         ctx->pend[i].n_regions_host = ctx->h_counters + 32 + i;
