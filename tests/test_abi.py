@@ -82,3 +82,17 @@ def test_only_allowed_files_touch_the_oracle():
             for f in files:
                 if f.endswith(".py"):
                     assert not bad.search(open(os.path.join(dirpath, f)).read()), (dirpath, f)
+
+
+def test_bench_cpu_binding_is_best_effort():
+    """bench.bind_to_gpu_cpus never raises (no NVML / no GPU here) and leaves the allowed CPU set non-empty."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    before = os.sched_getaffinity(0)
+    info = bench.bind_to_gpu_cpus(0)
+    assert info["cpus_allowed"] == len(before) and "affinity" in info
+    assert os.sched_getaffinity(0) and os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
