@@ -4,7 +4,7 @@ findContours(RETR_CCOMP, CHAIN_APPROX_NONE) + the drawContours loop of PictureSe
 (noise at several densities, smooth blobs, circles / rings with punched holes, rectangles + lines, 3x3 block noise, diagonal
 stripes + speckle), sizes 1x1 .. 160x160.  Result when run for round 1: 0 mismatches of 1500 masks (up to 9713 contours)."""
 import numpy as np, cv2, sys, time
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from oracle import oracle as orc
 rng = np.random.default_rng(77)
 def ref(mask):
