@@ -7,8 +7,8 @@
 //   <imageDir>/<name>_output/<yyyyMMdd'T'HHmmss>/<SegMethod>_<name>_<step %05d>_<stepName>.png
 // This program runs the mean-shift segmentation pass named by BASELINE.json (filter -> label -> merge -> render) and writes
 // that batch with the same naming scheme and file type (.png, written by the small codec in png_io.hpp; MSG_OUT_FORMAT=pnm
-// switches to binary P6/P5).  Inputs: PNG (non-interlaced, 8 bit or palette) or binary PPM; JPEG decoding is not provided
-// (no codec in the image, and decoding is outside the hot path).  Optional environment: MSG_SP, MSG_SR, MSG_MIN_SIZE,
+// switches to binary P6/P5).  Inputs: PNG (non-interlaced, 8 bit or palette), baseline JPEG (jpeg_io.hpp: the reference's own
+// sample images are baseline 4:2:0 files; pixels equal imread's) or binary PPM.  Optional environment: MSG_SP, MSG_SR, MSG_MIN_SIZE,
 // MSG_COLOR_DIST, MSG_OUT_FORMAT.
 #include <sys/stat.h>
 
@@ -21,6 +21,7 @@
 #include <sstream>
 
 #include "GpuImgproc.hpp"
+#include "jpeg_io.hpp"
 #include "png_io.hpp"
 
 using namespace msegment;
@@ -59,7 +60,7 @@ static bool read_image(const std::string& path, Mat& img)
     if (read_ppm(path, img)) return true;
     std::vector<uint8_t> bgr;
     int w = 0, h = 0;
-    if (!png::read_bgr(path, bgr, w, h)) return false;
+    if (!png::read_bgr(path, bgr, w, h) && !jpeg::read_bgr(path, bgr, w, h)) return false;
     img.create(h, w, CV_8UC3);
     img.buf = bgr;
     return true;
@@ -140,7 +141,7 @@ int main(int argc, char** argv)
     (void)out_root;                                 // dead in the reference too (PictureService.java:118, :130)
     Mat src;
     if (!read_image(dir + "/" + file, src)) {         // readPicture: dataAddr()==0 -> IOException -> logged, pipeline returns null
-        std::cerr << "There is an error with file stream processing: cannot read PNG / binary PPM " << dir << "/" << file << std::endl;
+        std::cerr << "There is an error with file stream processing: cannot read PNG / baseline JPEG / binary PPM " << dir << "/" << file << std::endl;
         return 0;
     }
     const std::string name = file.substr(0, file.find('.'));   // ImageInfo: text before the first '.'

@@ -11,6 +11,7 @@ import msegment_b200 as mseg
 from oracle import oracle as orc
 
 CLI = os.path.join(mseg.PKG_DIR, "host", "msegment_cli")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _write_ppm(path, bgr):
@@ -124,6 +125,43 @@ def test_png_codec_roundtrip(tmp_path, kind):
     assert subprocess.run([rt, str(tmp_path / "missing.png"), dst]).returncode == 2
 
 
+def _decode_with_cli_reader(path, tmp_path):
+    rt = os.path.join(mseg.PKG_DIR, "host", "png_roundtrip")
+    dst = str(tmp_path / "decoded.png")
+    r = subprocess.run([rt, path, dst])
+    return r.returncode, (_read_png(dst) if r.returncode == 0 else None)
+
+
+def test_jpeg_reader_matches_imread_fixtures(tmp_path):
+    """host/jpeg_io.hpp against cv2.imread (libjpeg-turbo) on the committed baseline fixtures: sizes that are not MCU multiples,
+    4:2:0 / 4:2:2 / 4:4:0 / 4:4:4, gray, optimised Huffman tables, restart intervals (tests/golden/gen_jpeg.py)."""
+    d = os.path.join(ROOT, "tests", "golden", "jpeg")
+    exp = np.load(os.path.join(d, "expected.npz"))
+    assert len(exp.files) >= 10
+    for name in exp.files:
+        rc, got = _decode_with_cli_reader(os.path.join(d, name + ".jpg"), tmp_path)
+        assert rc == 0, name
+        assert np.array_equal(got, exp[name]), name
+    rc, _ = _decode_with_cli_reader(os.path.join(d, "expected.npz"), tmp_path)      # not an image: unreadable, no crash
+    assert rc == 2
+
+
+def test_jpeg_reader_on_the_reference_images(tmp_path):
+    """The reference's own sample inputs (baseline 4:2:0 JPEGs) decode to the pixels cv2.imread gives (hashes recorded by
+    tests/golden/gen_jpeg.py).  Only where /root/reference exists (the build container)."""
+    import hashlib
+    import json
+    d = "/root/reference/src/main/resources/images"
+    if not os.path.isdir(d):
+        pytest.skip("/root/reference is not available here")
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "jpeg", "reference_images.json")))
+    assert set(want) == {"album.jpg", "haha.jpg", "hkp.jpg"}
+    for f, meta in want.items():
+        rc, got = _decode_with_cli_reader(os.path.join(d, f), tmp_path)
+        assert rc == 0 and list(got.shape) == meta["shape"], f
+        assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == meta["sha256"], f
+
+
 def test_cli_argument_contract():
     assert os.path.exists(CLI), "run `python __graft_entry__.py` first"
     r = subprocess.run([CLI, "only", "two"], capture_output=True, text=True)
@@ -195,3 +233,15 @@ def test_cli_batch_matches_oracle(tmp_path):
     outdir = tmp_path / "second_output"
     stamp = sorted(os.listdir(outdir))[0]
     assert np.array_equal(_read_pnm(str(outdir / stamp / "MEANSHIFT_METHOD_second_00001_meanshift_filtered.ppm")), f)
+    # JPEG input (the reference's sample images are baseline JPEGs): decoded as imread decodes it, then the same pipeline
+    import shutil
+    jdir = os.path.join(ROOT, "tests", "golden", "jpeg")
+    shutil.copy(os.path.join(jdir, "synth_128x96_q75_420.jpg"), str(tmp_path / "third.jpg"))
+    r = subprocess.run([CLI, str(tmp_path), "unused_out_root", "third.jpg"], capture_output=True, text=True,
+                       env=dict(os.environ, MSG_OUT_FORMAT="pnm", MSG_REFERENCE_MARKERS="0"))
+    assert r.returncode == 0, r.stderr
+    decoded = np.load(os.path.join(jdir, "expected.npz"))["synth_128x96_q75_420"]
+    outdir = tmp_path / "third_output"
+    stamp = sorted(os.listdir(outdir))[0]
+    assert np.array_equal(_read_pnm(str(outdir / stamp / "MEANSHIFT_METHOD_third_00001_meanshift_filtered.ppm")),
+                          orc.meanshift_filter(decoded, 10, 10, 1))
