@@ -96,3 +96,25 @@ def test_bench_cpu_binding_is_best_effort():
     assert info["cpus_allowed"] == len(before) and "affinity" in info
     assert os.sched_getaffinity(0) and os.sched_getaffinity(0) <= before
     os.sched_setaffinity(0, before)
+
+
+def test_java_natives_match_jni_glue():
+    """No JDK here, so the Java shim cannot be compiled: check at least that every `native` method of GpuImgproc.java has a JNI
+    function of the same name and arity in msegment_jni.c (JNIEnv*, jclass + the Java parameters), and vice versa, and that
+    every msg_* function the glue calls is declared in include/msegment.h."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    java = open(os.path.join(root, "opencv-msegment_b200", "java", "GpuImgproc.java")).read()
+    glue = open(os.path.join(root, "opencv-msegment_b200", "java", "msegment_jni.c")).read()
+    header = open(os.path.join(root, "include", "msegment.h")).read()
+    natives = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+               for m in re.finditer(r"private static native \w+(?:\[\])? (\w+)\(([^)]*)\)", java, re.S)}
+    jni = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()]) - 2
+           for m in re.finditer(r"JNICALL J\((\w+)\)\(([^)]*)\)", glue, re.S)}
+    assert len(natives) >= 25
+    assert natives == jni, (sorted(set(natives.items()) ^ set(jni.items())))
+    declared = set(re.findall(r"\b(msg_\w+)\s*\(", header))
+    called = set(re.findall(r"\b(msg_\w+)\s*\(", glue))
+    assert called <= declared, sorted(called - declared)
+    # every public method of the shim that forwards to a native uses one that exists
+    used = set(re.findall(r"\b(n[A-Z]\w+)\(", java)) - {"new"}
+    assert used <= set(natives), sorted(used - set(natives))
