@@ -157,8 +157,8 @@ MSG_API int msg_white_to_black(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_
 MSG_API int msg_threshold(msg_ctx* ctx, const uint8_t* src_gray, size_t src_step, uint8_t* dst, size_t dst_step, int width,
                   int height, double thresh, double maxval, int type, double* used_thresh);
 /* Imgproc.distanceTransform(src 8UC1, dst 32FC1, CV_DIST_L2, 5) (PictureService.java:1020): two-pass 5x5 chamfer with the
- * metrics 1 / 1.4 / 2.1969 accumulated in float32 (the arithmetic of the IPP-backed cv2 build the oracle is pinned on; see
- * DESIGN.md for the 1-ulp corner where that build deviates from the plain two-pass order).  Only (dist_type 2, mask 5).
+ * metrics 1 / 1.4 / 2.1969 accumulated in float32 exactly as the IPP-backed cv2 build the oracle is pinned on does it (forward
+ * pass: running value unrounded inside aligned groups of four columns).  Only (dist_type 2, mask 5).
  * A source without zero pixels gives FLT_MAX everywhere, as cv2 does.  Rows up to msg_distance_transform_max_width().
  * msg_get_timings().filter_ms holds the kernel time of the last call (CUDA events). */
 MSG_API int msg_distance_transform(msg_ctx* ctx, const uint8_t* src, size_t src_step, float* dst, size_t dst_step, int width,

@@ -92,7 +92,9 @@ __global__ void __launch_bounds__(256) threshold_u8_kernel(const uint8_t* __rest
 // at step s = 2r + G: then its left neighbour has just finished row r (the carry of the in-row recurrence) and its right
 // neighbour row r-1.  A lane keeps its last two rows in registers; the seven halo values it needs come from the neighbour
 // lanes by shuffles (from the neighbour warps through a double-buffered shared-memory slot), one __syncthreads per step.
-// Steps per pass: 2 * height + lanes in use.  The initial values of a lane's next row are loaded two steps ahead.
+// Steps per pass: 2 * height + lanes in use.  The initial values of a lane's coming rows are loaded four steps ahead.
+// Arithmetic: the backward pass is the plain float recurrence; the forward pass keeps the running value unrounded inside
+// aligned groups of four columns (dt_wave_pass), which is what the IPP-backed cv2 build computes.
 constexpr int DT_THREADS = 256, DT_WARPS = DT_THREADS / 32, DT_PMAXMAX = 32;
 constexpr float DT_A = 1.0f, DT_B = 1.4f, DT_C = 2.1969f;
 
@@ -213,26 +215,55 @@ __device__ __forceinline__ float dt_wave_pass(float* __restrict__ dist, int w, i
 #pragma unroll
             for (int j = 0; j < P; j++) t[j] = pre[j];
             if (it + 2 < h) load_row(it + 2, pre);            // consumed four steps later, from the same register set
-            // candidates that do not depend on the in-row recurrence: independent min trees (a pixel whose initial value is
-            // <= 1 keeps it: every candidate is >= 1; FLT_MAX + metric rounds back to FLT_MAX)
+            if constexpr (DIR > 0) {
+                // Forward pass.  Inside aligned groups of four columns (x < lim) the running value of the in-row recurrence is
+                // NOT rounded to float between pixels: the candidates are exact float + float sums, the running value carries
+                // that exact sum through up to three additions of 1, and only the stored pixel is rounded.  A group starts
+                // (x % 4 == 0) from the stored, rounded left neighbour; the last columns (x >= lim) round at every pixel.
+                // Exact sums fit a double.  (This is what the IPP-backed cv2 build computes: see the oracle.)
+                double tu[P];
 #pragma unroll
-            for (int j = 0; j < P; j++) {
-                float a0 = __fadd_rn(dt_pick<P>(B, j - 1, FLT_MAX, Lcl, Rb0, FLT_MAX), DT_C);
-                float a1 = __fadd_rn(dt_pick<P>(B, j + 1, FLT_MAX, Lcl, Rb0, FLT_MAX), DT_C);
-                float a2 = __fadd_rn(dt_pick<P>(A, j - 2, Lb0, Lb1, Ra0, Ra1), DT_C);
-                float a3 = __fadd_rn(dt_pick<P>(A, j - 1, Lb0, Lb1, Ra0, Ra1), DT_B);
-                float a4 = __fadd_rn(A[j], DT_A);
-                float a5 = __fadd_rn(dt_pick<P>(A, j + 1, Lb0, Lb1, Ra0, Ra1), DT_B);
-                float a6 = __fadd_rn(dt_pick<P>(A, j + 2, Lb0, Lb1, Ra0, Ra1), DT_C);
-                t[j] = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(fminf(a4, a5), fminf(a6, t[j])));
-            }
-            // the recurrence along the row: two dependent operations per pixel
-            float run = Lc;
+                for (int j = 0; j < P; j++) {
+                    double a0 = (double)dt_pick<P>(B, j - 1, FLT_MAX, Lcl, Rb0, FLT_MAX) + (double)DT_C;
+                    double a1 = (double)dt_pick<P>(B, j + 1, FLT_MAX, Lcl, Rb0, FLT_MAX) + (double)DT_C;
+                    double a2 = (double)dt_pick<P>(A, j - 2, Lb0, Lb1, Ra0, Ra1) + (double)DT_C;
+                    double a3 = (double)dt_pick<P>(A, j - 1, Lb0, Lb1, Ra0, Ra1) + (double)DT_B;
+                    double a4 = (double)A[j] + (double)DT_A;
+                    double a5 = (double)dt_pick<P>(A, j + 1, Lb0, Lb1, Ra0, Ra1) + (double)DT_B;
+                    double a6 = (double)dt_pick<P>(A, j + 2, Lb0, Lb1, Ra0, Ra1) + (double)DT_C;
+                    tu[j] = fmin(fmin(fmin(a0, a1), fmin(a2, a3)), fmin(fmin(a4, a5), fmin(a6, (double)t[j])));
+                }
+                const int lim = ((w - 2) / 4) * 4;
+                double runv = (double)Lc;
 #pragma unroll
-            for (int j = 0; j < P; j++) {
-                run = fminf(t[j], __fadd_rn(run, DT_A));
-                t[j] = j < cnt ? run : FLT_MAX;               // outside the image
-                vmax = fmaxf(vmax, j < cnt ? run : 0.f);
+                for (int j = 0; j < P; j++) {
+                    const int x = m0 + j;
+                    const double rin = ((x & 3) == 0 || x >= lim) ? (double)__double2float_rn(runv) : runv;
+                    runv = fmin(tu[j], rin + 1.0);
+                    t[j] = j < cnt ? __double2float_rn(runv) : FLT_MAX;     // outside the image: "infinite"
+                }
+            } else {
+                // Backward pass: plain float.  Candidates that do not depend on the in-row recurrence are independent min trees
+                // (a pixel whose value is <= 1 keeps it: every candidate is >= 1; FLT_MAX + metric rounds back to FLT_MAX)
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    float a0 = __fadd_rn(dt_pick<P>(B, j - 1, FLT_MAX, Lcl, Rb0, FLT_MAX), DT_C);
+                    float a1 = __fadd_rn(dt_pick<P>(B, j + 1, FLT_MAX, Lcl, Rb0, FLT_MAX), DT_C);
+                    float a2 = __fadd_rn(dt_pick<P>(A, j - 2, Lb0, Lb1, Ra0, Ra1), DT_C);
+                    float a3 = __fadd_rn(dt_pick<P>(A, j - 1, Lb0, Lb1, Ra0, Ra1), DT_B);
+                    float a4 = __fadd_rn(A[j], DT_A);
+                    float a5 = __fadd_rn(dt_pick<P>(A, j + 1, Lb0, Lb1, Ra0, Ra1), DT_B);
+                    float a6 = __fadd_rn(dt_pick<P>(A, j + 2, Lb0, Lb1, Ra0, Ra1), DT_C);
+                    t[j] = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(fminf(a4, a5), fminf(a6, t[j])));
+                }
+                // the recurrence along the row: two dependent operations per pixel
+                float run = Lc;
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    run = fminf(t[j], __fadd_rn(run, DT_A));
+                    t[j] = j < cnt ? run : FLT_MAX;           // outside the image
+                    vmax = fmaxf(vmax, j < cnt ? run : 0.f);
+                }
             }
             store_row(it, t);
             Clast = B[P - 1];
@@ -471,8 +502,7 @@ int k_distance_transform(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, float
     dim3 grid((w + 255) / 256, h);
     dt_init_kernel<<<grid, 256, 0, st>>>(d_src, sstep, d_dist, w);
     MSG_LAUNCHED(ctx);
-    if (need <= 2) dt_launch<2>(st, d_dist, w, h, d_max);
-    else if (need <= 4) dt_launch<4>(st, d_dist, w, h, d_max);
+    if (need <= 4) dt_launch<4>(st, d_dist, w, h, d_max);           // a lane's chunk is a whole number of 4-column groups
     else if (need <= 8) dt_launch<8>(st, d_dist, w, h, d_max);
     else if (need <= 16) dt_launch<16>(st, d_dist, w, h, d_max);
     else dt_launch<32>(st, d_dist, w, h, d_max);

@@ -7,9 +7,9 @@ Run from the repo root IN THE BUILD CONTAINER (needs cv2 and, for the two real-i
 stored with the outputs so the tests never need cv2 or /root/reference.
 
 Distance transform: this cv2 build dispatches distanceTransform(DIST_L2, 5) to IPP, which accumulates the float metrics
-1 / 1.4 / 2.1969 in float32.  The oracle restates that as the plain two-pass float recurrence; on 400 random images up to
-200 x 200 it equals cv2 bit for bit except where a horizontal step crosses 32.0 on an exact rounding tie (10 images, <= 12
-pixels each, 1 ulp).  Every vector stored here was checked to be free of that corner (asserted below)."""
+1 / 1.4 / 2.1969 in float32 with an unrounded running value inside aligned groups of four columns of the forward pass; the
+oracle restates exactly that (oracle/msg_oracle.c: orc_distance_transform_l2_5) and equals cv2 bit for bit on every image tried
+(asserted below for the stored vectors)."""
 import os
 import sys
 
