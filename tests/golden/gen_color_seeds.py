@@ -88,6 +88,14 @@ def main():
         cv2.circle(c, (cx, cy), r, (77, 77, 77), -1)
         out["mask_circle/%d" % k] = c
         out["mask_circle_args/%d" % k] = np.array([cx, cy, r, 77], np.int32)
+    # distance transform where the unrounded running value of the forward pass matters: a horizontal step crosses 32 / 64 on an
+    # exact rounding tie (single zero pixels far away), at several group phases (x % 4) and row tails (w % 4)
+    for k, (w, h, zy, zx) in enumerate([(140, 40, 0, 0), (141, 40, 0, 1), (139, 36, 0, 2), (123, 120, 119, 122), (75, 70, 0, 3),
+                                        (130, 33, 2, 5)]):
+        m = np.full((h, w), 1, np.uint8)
+        m[zy, zx] = 0
+        out["dt_tie_mask/%d" % k] = m
+        out["dt_tie/%d" % k] = cv2.distanceTransform(m * 255, cv2.DIST_L2, 5)
     # bilateral filter (d = mask, sigmas = 2 * mask as PictureService.java:490 calls it)
     for name in ("synth96x80", "noise41x47", "hkp_crop96", "row50", "col50"):
         if name not in ins:
@@ -104,6 +112,8 @@ def main():
             assert np.array_equal(orc.distance_transform(out["bw/" + key[5:]]), out[key]), key
         if key.startswith("mask_dist/"):
             assert np.array_equal(orc.distance_transform(out["mask/" + key[10:]] * 255), out[key]), key
+        if key.startswith("dt_tie/"):
+            assert np.array_equal(orc.distance_transform(out["dt_tie_mask/" + key[7:]] * 255), out[key]), key
     np.savez_compressed(os.path.join(HERE, "color_seeds.npz"), **out)
     with open(os.path.join(HERE, "PROVENANCE.txt"), "a") as f:
         f.write("color_seeds.npz generated by tests/golden/gen_color_seeds.py with cv2 %s, numpy %s\n" % (cv2.__version__, np.__version__))

@@ -57,6 +57,43 @@ def test_oracle_contours_dist_circle_golden(golden_dir):
         assert np.array_equal(orc.circle_filled(lab, cx, cy, r, v), g["mask_circle/%d" % k]), k
 
 
+def test_oracle_distance_transform_tie_cases_golden(golden_dir):
+    """cv2 vectors where the forward pass' unrounded running value inside aligned groups of four columns decides the result
+    (a horizontal step crosses 32 / 64 on an exact rounding tie); plain float rounding everywhere fails these by 1 ulp."""
+    g = _golden(golden_dir)
+    ks = sorted(int(k[7:]) for k in g.files if k.startswith("dt_tie/"))
+    assert len(ks) >= 6
+    plain_differs = 0
+    for k in ks:
+        m = g["dt_tie_mask/%d" % k] * 255
+        want = g["dt_tie/%d" % k]
+        assert np.array_equal(orc.distance_transform(m), want), k
+        # the plain two-pass float recurrence (numpy, row by row) is NOT what cv2 computes on these
+        plain_differs += int(not np.array_equal(_plain_float_chamfer(m), want))
+    assert plain_differs >= 3
+
+
+def _plain_float_chamfer(mask):
+    """Two-pass 5x5 chamfer with every addition rounded to float32 (the textbook order)."""
+    f = np.float32
+    h, w = mask.shape
+    a, b, c, inf = f(1.0), f(1.4), f(2.1969), np.finfo(np.float32).max
+    t = np.full((h + 4, w + 4), inf, np.float32)
+    fw = ((-2, -1, c), (-2, 1, c), (-1, -2, c), (-1, -1, b), (-1, 0, a), (-1, 1, b), (-1, 2, c), (0, -1, a))
+    with np.errstate(over="ignore"):
+        for y in range(h):
+            for x in range(w):
+                if mask[y, x] == 0:
+                    t[y + 2, x + 2] = 0
+                    continue
+                t[y + 2, x + 2] = min(min(f(t[y + 2 + dy, x + 2 + dx] + m), inf) for dy, dx, m in fw)
+        for y in range(h - 1, -1, -1):
+            for x in range(w - 1, -1, -1):
+                v = t[y + 2, x + 2]
+                t[y + 2, x + 2] = min(v, min(min(f(t[y + 2 - dy, x + 2 - dx] + m), inf) for dy, dx, m in fw))
+    return t[2:-2, 2:-2].copy()
+
+
 def test_oracle_bilateral_golden(golden_dir):
     g = _golden(golden_dir)
     keys = [k for k in g.files if k.startswith("bil_")]
