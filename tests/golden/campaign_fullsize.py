@@ -56,6 +56,17 @@ for (w,h,seed) in [(1920,1080,2),(3840,2160,3)]:
     if w==1920:
         f=cv2.pyrMeanShiftFiltering(im,10,10,maxLevel=1,termcrit=(3,5,1.0))
         res['meanshift']=np.array_equal(f,orc.meanshift_filter(im,10,10,1))
+        # the floodFill region-growing loop (samples/cpp/meanshift_segmentation.cpp) on the filtered frame vs the oracle's labels
+        fmask=np.zeros((h+2,w+2),np.uint8); flab=np.zeros((h,w),np.int32); nreg=0; inner=fmask[1:-1,1:-1]; fimg=f.copy()
+        for yy in range(h):
+            while True:
+                xs=np.flatnonzero(inner[yy]==0)
+                if len(xs)==0: break
+                nreg+=1
+                cv2.floodFill(fimg,fmask,(int(xs[0]),yy),(0,0,0),(2,2,2),(2,2,2),4|cv2.FLOODFILL_MASK_ONLY|(2<<8))
+                new=(inner==2); flab[new]=nreg; inner[new]=1
+        on2,ol2=orc.label_regions(f,2)
+        res['floodfill_labels']=(nreg==on2) and np.array_equal(flab,ol2)
         b1=cv2.bilateralFilter(g,11,22,22); o1=orc.bilateral_filter(g,11,22,22)
         res['bilateral_maxdiff']=int(np.abs(b1.astype(int)-o1.astype(int)).max())
     print((w,h),'%.0f s'%(time.time()-t0),res)
