@@ -4,20 +4,26 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[1] -- 1920x1080 synthetic frames, pyrMeanShiftFiltering
-(sp=10, sr=10, maxLevel=1, termcrit (COUNT+EPS,5,1)) + floodFill-style labelling (lo=up=2, 4-conn) + region merge
-(minSize=50, colorDist=10).  One step = one pass over a batch of FRAMES_PER_STEP distinct frames per GPU
-(199 MB of input per GPU > the 126 MB L2, so no frame is L2-resident between steps).  Frames and ranks are
-independent: weak scaling, no data-path collective.
+Workload (config.workload): BASELINE.json configs[3] on one GPU per rank, i.e. the frames of config 3/4 -- 3840x2160 synthetic
+frames (seeds 1000..1255), pyrMeanShiftFiltering(sp=10, sr=10, maxLevel=1, termcrit (COUNT+EPS,5,1)) +
+floodFill-style labelling (lo=up=2, 4-conn) + region merge (minSize=50, colorDist=10): the configuration the north-star target
+("4K frames") is stated on and the largest one that fits a single GPU.  One step = one pass over FRAMES_PER_STEP distinct frames
+per GPU (299 MB of input per GPU > the 126 MB L2: no frame is L2-resident between steps).  Frames and ranks are independent:
+weak scaling, no data-path collective.
 
-  value     : frames resident in HBM, device-resident C-ABI calls (msg_segment_dev), CUDA-event timed, max over ranks.
-  e2e       : same frames from pinned HOST buffers through msg_submit_segment / msg_wait (H2D and D2H copies of the
-              filtered image and the label map inside the timed region); one host thread per context keeps two frames in
-              flight, the library overlaps upload / kernels / download and replays the kernel sequence as a CUDA graph.
-  roofline  : dominant kernel = level-0 mean-shift tile kernel; achieved = algorithmic int-ops (9 T + 5 Hit, counted on
-              the device exactly as the CPU oracle counts them) / its CUDA-event duration; peak = INT issue rate measured
-              on this GPU by tools/int_peak (MEASURED_PEAKS.json has no integer figure).
-  cpu_baseline / --impl reference : OpenCV's own CPU implementation (cv2) or the oracle port, timed on the host cores.
+  value        : frames resident in HBM, device-resident C-ABI calls (msg_segment_dev), CUDA-event timed, max over ranks.
+  e2e          : the same frames from PINNED host buffers through msg_submit_segment / msg_wait, host->device copy of the
+                 frame (3 B/pixel) and device->host copy of the result -- the region label map as CV_16U (2 B/pixel, every
+                 frame here has < 65536 regions; MSG_ERANGE otherwise) plus the region count -- inside the timed region.
+  e2e_full     : same, downloading the filtered image and the CV_32S label map as well (10 B/pixel, round 1's figure).
+  e2e_pageable : as e2e but from / to plain malloc'ed (pageable) numpy buffers, the memory a Java Mat hands over: the library
+                 stages them through its pinned ring / per-frame output staging.
+  roofline     : dominant kernel = level-0 mean-shift tile kernel; achieved = algorithmic int-ops (9 T + 5 Hit, counted on
+                 the device exactly as the CPU oracle counts them) / its CUDA-event duration; peak = INT issue rate measured
+                 on this GPU by tools/int_peak (MEASURED_PEAKS.json has no integer figure).
+  cpu_baseline / --impl reference : OpenCV's own CPU implementation (cv2) or the oracle port, timed on the host cores on
+                 WHOLE frames of the same size (reference arm: each frame split into row strips + halo over 8 cores).
+  secondary_1080p : the round-1 workload (configs[1], 1920x1080 x32 frames per step), short run, for continuity.
 """
 import argparse
 import json
@@ -30,18 +36,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 1920, 1080
-FRAMES_PER_STEP = 32
-SEED0 = 2          # config 2 -> seed 2 (frame i of rank r uses seed 2 + 1000*r + i)
+W, H = 3840, 2160
+FRAMES_PER_STEP = int(os.environ.get("BENCH_FRAMES", "12"))
+SEED0 = 1000       # config 4 -> seeds 1000..1255 (frame i of rank r uses 1000 + (r * FRAMES_PER_STEP + i) % 256)
 PARAMS = dict(sp=10.0, sr=10.0, max_level=1, termcrit=(3, 5, 1.0), lo_diff=2, min_size=50, color_dist=10)
 METRIC = "segmented_mpix_per_s"
 UNIT = "Mpix/s"
-N_STREAMS = int(os.environ.get("BENCH_STREAMS", "6"))   # contexts (stream + workspace + host thread) per GPU; frames dealt round-robin
+N_STREAMS = int(os.environ.get("BENCH_STREAMS", "4"))   # contexts (stream + workspace + host thread) per GPU; frames dealt round-robin
+REF_CORES_PER_FRAME = 8     # reference arm: row strips per frame
+REF_HALO = 64               # rows of halo on each side of a strip (even; >= the 58-row dependency bound of SURVEY 8(e))
 
 
-def workload_name():
-    return ("1920x1080 synthetic frames x%d per GPU per step; meanshift(sp=10,sr=10,maxLevel=1,termcrit=(3,5,1)) + "
-            "label(lo=up=2,4-conn) + merge(minSize=50,colorDist=10)" % FRAMES_PER_STEP)
+def frame_seed(rank, i, frames=None):
+    return SEED0 + (rank * (frames or FRAMES_PER_STEP) + i) % 256
+
+
+def workload_name(w=W, h=H, frames=None):
+    return ("%dx%d synthetic frames (seeds 1000..) x%d per GPU per step; meanshift(sp=10,sr=10,maxLevel=1,termcrit=(3,5,1)) + "
+            "label(lo=up=2,4-conn) + merge(minSize=50,colorDist=10)" % (w, h, frames or FRAMES_PER_STEP))
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -101,19 +113,15 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- CPU legs
 
-def _cv2_segment(im):
-    """OpenCV CPU path for one frame: pyrMeanShiftFiltering + the floodFill region-growing loop of OpenCV's
-    meanshift_segmentation sample (merge has no OpenCV counterpart and is left out: the CPU figure is an upper bound)."""
+def _cv2_floodfill_labels(f):
+    """The floodFill region-growing loop of OpenCV's meanshift_segmentation sample: one floodFill per yet-unlabelled pixel in
+    raster order (numpy finds the next unmasked pixel of a row).  Returns the number of regions."""
     import cv2
     import numpy as np
-    cv2.setNumThreads(1)
-    f = cv2.pyrMeanShiftFiltering(im, PARAMS["sp"], PARAMS["sr"], maxLevel=PARAMS["max_level"],
-                                  termcrit=(3, 5, 1.0))
     h, w = f.shape[:2]
     mask = np.zeros((h + 2, w + 2), np.uint8)
     d = (PARAMS["lo_diff"],) * 3
     n = 0
-    # one floodFill per yet-unlabelled pixel in raster order (numpy finds the next unmasked pixel of a row)
     for y in range(h):
         row = mask[y + 1, 1:-1]
         x = 0
@@ -128,24 +136,46 @@ def _cv2_segment(im):
     return n
 
 
-def _oracle_segment(im):
+def _ref_strip_job(args):
+    """One row strip of a frame (+ halo rows) through the reference's CPU implementation; returns the strip's filtered rows.
+    This spreads ONE frame over several cores although cv2.pyrMeanShiftFiltering itself is single-threaded.  With an even
+    start row and a >= 58-row halo the oracle port (absolute coordinates) reproduces the whole-frame rows exactly; cv2
+    evaluates the position means in strip-local coordinates, so isolated pixels (< 0.1 %) differ from its own whole-frame call
+    (tests/test_reference_arm.py) -- the same amount of arithmetic, which is all a TIMING baseline needs
+    (parity is pinned by the oracle on whole frames, never by this arm)."""
+    kind, strip, lo, hi, top, full_h = args   # strip = rows [top, ...) of the frame incl. halo; wanted rows [lo, hi)
+    if kind == "reference":
+        import cv2
+        cv2.setNumThreads(1)
+        f = cv2.pyrMeanShiftFiltering(strip, PARAMS["sp"], PARAMS["sr"], maxLevel=PARAMS["max_level"], termcrit=(3, 5, 1.0))
+    else:
+        from oracle import oracle as orc
+        f = orc.meanshift_filter_roi(strip, 0, top, strip.shape[1], full_h, PARAMS["sp"], PARAMS["sr"], PARAMS["max_level"],
+                                     PARAMS["termcrit"])
+    return f[lo - top:hi - top]
+
+
+def _ref_label_job(args):
+    kind, f = args
+    if kind == "reference":
+        import cv2
+        cv2.setNumThreads(1)
+        return _cv2_floodfill_labels(f)
     from oracle import oracle as orc
-    f = orc.meanshift_filter(im, PARAMS["sp"], PARAMS["sr"], PARAMS["max_level"], PARAMS["termcrit"])
     n, lab = orc.label_regions(f, PARAMS["lo_diff"])
     n, lab = orc.merge_regions(f, lab, PARAMS["min_size"], PARAMS["color_dist"])
     return n
 
 
-def _ref_worker(args):
-    kind, seed, w, h = args
-    from oracle import oracle as orc   # synthetic generator only (+ the port when cv2 is absent)
-    im = orc.synth_bgr(w, h, seed)
-    t0 = time.perf_counter()
-    if kind == "reference":
-        _cv2_segment(im)
-    else:
-        _oracle_segment(im)
-    return time.perf_counter() - t0
+def strip_plan(h, parts, halo):
+    """Row strips [lo, hi) with even starts and their halo ranges [top, bot)."""
+    base = (h // parts) & ~1
+    plan = []
+    for k in range(parts):
+        lo = k * base
+        hi = h if k == parts - 1 else (k + 1) * base
+        plan.append((lo, hi, max(0, lo - halo), min(h, hi + halo)))
+    return plan
 
 
 def _have_cv2():
@@ -157,71 +187,177 @@ def _have_cv2():
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path on all host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores (rank 0 only), WHOLE frames of the
+    bench size: every frame is cut into REF_CORES_PER_FRAME row strips (+ halo) so that a step stays a few seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
+
+    import numpy as np
+
+    from oracle import oracle as orc   # synthetic generator (+ the port when cv2 is absent)
     kind = "reference" if _have_cv2() else "port"
     cores = os.cpu_count() or 1
-    sw, sh = W // 2, H // 2     # bounded sample: one quarter-frame tile per core per step
+    parts = min(REF_CORES_PER_FRAME, cores)
+    frames_per_step = max(1, cores // parts)
+    plan = strip_plan(H, parts, REF_HALO)
+    overhead = sum(b - t for (_, _, t, b) in plan) / float(H)
     ctx = mp.get_context("spawn")
+    # frames are generated outside the timed region (the GPU arm's inputs are resident before its timed region, too)
+    n_distinct = min(4, frames_per_step * 2)
+    frames = [orc.synth_bgr(W, H, frame_seed(0, i)) for i in range(n_distinct)]
     with ctx.Pool(cores) as pool:
         def step(k):
-            jobs = [(kind, SEED0 + 7919 * k + i, sw, sh) for i in range(cores)]
+            chosen = [frames[(k * frames_per_step + j) % n_distinct] for j in range(frames_per_step)]
             t0 = time.perf_counter()
-            pool.map(_ref_worker, jobs)
+            jobs = [(kind, im[t:b], lo, hi, t, H) for im in chosen for (lo, hi, t, b) in plan]
+            strips = pool.map(_ref_strip_job, jobs, chunksize=1)
+            filt = [np.concatenate(strips[j * parts:(j + 1) * parts], axis=0) for j in range(frames_per_step)]
+            pool.map(_ref_label_job, [(kind, f) for f in filt], chunksize=1)
             return time.perf_counter() - t0
         for k in range(args.warmup):
-            step(-1 - k)
-        t = sum(step(k) for k in range(args.steps))
-    mpix = args.steps * cores * sw * sh / 1e6
+            step(k)
+        t = sum(step(args.warmup + k) for k in range(args.steps))
+    mpix = args.steps * frames_per_step * W * H / 1e6
     value = mpix / t
-    sample = ("%d x %dx%d tiles (quarter 1080p frames) per step, one per worker process; " % (cores, sw, sh) +
-              ("cv2 %s pyrMeanShiftFiltering + floodFill loop (OpenCV natives; the Java reference binds OpenCV 3.4.2, "
-               "unavailable offline); merge stage has no OpenCV counterpart and is not included" % __import__("cv2").__version__
-               if kind == "reference" else "oracle C port: meanshift + label + merge"))
+    what = ("cv2 %s pyrMeanShiftFiltering + floodFill labelling loop (OpenCV natives; the Java reference binds OpenCV 3.4.2, "
+            "unavailable offline); the merge stage has no OpenCV counterpart and is not included (CPU figure = upper bound)"
+            % __import__("cv2").__version__ if kind == "reference" else "oracle C port: meanshift + label + merge")
+    sample = ("%d whole %dx%d frame(s) per step on %d cores: each frame = %d row strips + %d halo rows per side, one strip per "
+              "worker process (same arithmetic as the whole-frame call; halo overhead x%.2f of the mean-shift work), then the "
+              "labelling loop per frame; %s" % (frames_per_step, W, H, cores, parts, REF_HALO, overhead, what))
     line = {"metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 * t / args.steps, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(), "flush": "inputs differ every step"},
-            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "config": {"workload": workload_name(), "flush": "frames alternate every step; 24.9 MB per frame",
+                       "frames_per_step": frames_per_step, "merge_stage": "not included: no CPU/OpenCV counterpart exists"},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "halo_overhead": round(overhead, 3)},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
 
-def cpu_baseline_leg(want_counters=True):
-    """Rank 0, N=1: the oracle port (1 core) on ONE frame of the workload, which also yields the exact algorithmic
-    work counters (T, Hit) the roofline uses as a cross-check of the device counters; cv2 timed beside it."""
+def cpu_baseline_leg():
+    """Rank 0, N=1: the oracle port (1 core) on ONE whole frame of the workload, which also yields the exact algorithmic
+    work counters (T, Hit) the roofline uses as a cross-check of the device counters; cv2 timed beside it on a second core."""
     from oracle import oracle as orc
-    im = orc.synth_bgr(W, H, SEED0)
+    im = orc.synth_bgr(W, H, frame_seed(0, 0))
+    cv_out = {}
+
+    def cv_leg():
+        import cv2
+        cv2.setNumThreads(1)
+        t0 = time.perf_counter()
+        cv2.pyrMeanShiftFiltering(im, PARAMS["sp"], PARAMS["sr"], maxLevel=PARAMS["max_level"], termcrit=(3, 5, 1.0))
+        cv_out["t"] = time.perf_counter() - t0
+        cv_out["v"] = cv2.__version__
+    th = None
+    if _have_cv2():
+        th = threading.Thread(target=cv_leg)
+        th.start()
     t0 = time.perf_counter()
     f, ct = orc.meanshift_filter(im, PARAMS["sp"], PARAMS["sr"], PARAMS["max_level"], PARAMS["termcrit"], counters=True)
     n, lab = orc.label_regions(f, PARAMS["lo_diff"])
     n, lab = orc.merge_regions(f, lab, PARAMS["min_size"], PARAMS["color_dist"])
     t_port = time.perf_counter() - t0
     out = {"value": round(W * H / 1e6 / t_port, 4), "unit": UNIT, "cores": 1, "kind": "port",
-           "sample": "1 frame 1920x1080 (seed %d) through the oracle C port: meanshift+label+merge, %.1f s" % (SEED0, t_port),
+           "sample": "1 whole frame %dx%d (seed %d) through the oracle C port: meanshift+label+merge, %.1f s" % (W, H, frame_seed(0, 0), t_port),
            "oracle_counters": ct}
-    if _have_cv2():
-        import cv2
-        cv2.setNumThreads(1)
-        t0 = time.perf_counter()
-        cv2.pyrMeanShiftFiltering(im, PARAMS["sp"], PARAMS["sr"], maxLevel=PARAMS["max_level"], termcrit=(3, 5, 1.0))
-        t_cv = time.perf_counter() - t0
-        out["opencv_cv2"] = {"value": round(W * H / 1e6 / t_cv, 4), "unit": UNIT, "cores": 1,
-                             "what": "cv2 %s pyrMeanShiftFiltering only, same frame, %.1f s" % (cv2.__version__, t_cv)}
+    if th is not None:
+        th.join()
+        out["opencv_cv2"] = {"value": round(W * H / 1e6 / cv_out["t"], 4), "unit": UNIT, "cores": 1,
+                             "what": "cv2 %s pyrMeanShiftFiltering only, same frame, %.1f s (run concurrently on a second core)" % (cv_out["v"], cv_out["t"])}
     return out, (f, n, lab)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 
+class Workload:
+    """B frames of w x h resident in HBM + the three end-to-end legs, on N_STREAMS contexts of one GPU."""
+
+    def __init__(self, torch, mseg, local, rank, w, h, frames, n_streams):
+        self.torch, self.mseg, self.dev = torch, mseg, mseg.device
+        self.w, self.h, self.B, self.ns = w, h, frames, n_streams
+        self.rank = rank
+        self.streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        self.ctxs = [mseg.Context(local) for _ in range(n_streams)]
+        for c, s in zip(self.ctxs, self.streams):
+            c.set_stream(s.cuda_stream)
+        dev = self.dev
+        self.prm = dev.params(**PARAMS, render_depth=-1)
+        self.prm16 = dev.params(**PARAMS, render_depth=-1, labels_type=1)
+        # inputs resident in HBM (generated on the device, bit-identical to the oracle's generator)
+        self.src = torch.empty((frames, h, w, 3), dtype=torch.uint8, device="cuda")
+        for i in range(frames):
+            dev.synth(self.ctxs[0], self.src[i].data_ptr(), 3 * w, w, h, frame_seed(rank, i, frames))
+        self.ctxs[0].synchronize()
+        self.filt = [torch.empty((h, w, 3), dtype=torch.uint8, device="cuda") for _ in range(n_streams)]
+        self.labs = [torch.empty((h, w), dtype=torch.int32, device="cuda") for _ in range(n_streams)]
+        self.nreg = torch.zeros((frames,), dtype=torch.int32, device="cuda")
+        from concurrent.futures import ThreadPoolExecutor
+        # one host thread per context: ctypes releases the GIL for the duration of every C-ABI call
+        self.pool = ThreadPoolExecutor(max_workers=n_streams)
+        self.pinned = []
+
+    def close(self):
+        self.pool.shutdown()
+        for p in self.pinned:
+            self.dev.free_pinned(p)
+        for c in self.ctxs:
+            c.close()
+
+    # ---- device-resident step
+    def _device_worker(self, k):
+        w, h = self.w, self.h
+        for i in range(k, self.B, self.ns):
+            self.dev.segment(self.ctxs[k], self.src[i].data_ptr(), 3 * w, w, h, self.prm, self.filt[k].data_ptr(), 3 * w,
+                             self.labs[k].data_ptr(), 4 * w, 0, 0, self.nreg[i:].data_ptr())
+
+    def step_device(self):
+        list(self.pool.map(self._device_worker, range(self.ns)))
+
+    # ---- end to end: host buffers through the asynchronous C-ABI calls
+    def host_inputs(self):
+        """(pinned pointer, pageable numpy array) holding the B frames."""
+        import ctypes
+        nb = self.B * self.w * self.h * 3
+        p = self.dev.alloc_pinned(nb)
+        self.pinned.append(p)
+        self.torch.cuda.synchronize()
+        host = self.src.cpu().numpy()
+        ctypes.memmove(p, host.ctypes.data, nb)
+        return p, host
+
+    def e2e_runner(self, src_ptr, filt_ptr, lab_ptr, lab_bytes_px, prm):
+        """One host thread per context, as a frame server would run it: frames k, k+N, ... of every step, at most 2 submissions
+        in flight; consecutive steps are pipelined (no drain between them), every result is waited for (msg_wait = the
+        device->host copies of that frame have landed, staged copies included) before its host buffers are reused."""
+        dev, w, h, B, ns = self.dev, self.w, self.h, self.B, self.ns
+        fb, lb = w * h * 3, w * h * lab_bytes_px
+
+        def worker(k, steps):
+            tickets = []
+            for _ in range(steps):
+                for i in range(k, B, ns):
+                    if len(tickets) >= 2:
+                        dev.wait(self.ctxs[k], tickets.pop(0))
+                    tickets.append(dev.submit_segment(self.ctxs[k], src_ptr + i * fb, 3 * w, w, h, prm,
+                                                      filt_ptr + i * fb if filt_ptr else 0, 3 * w,
+                                                      lab_ptr + i * lb, w * lab_bytes_px))
+            for t in tickets:
+                dev.wait(self.ctxs[k], t)
+
+        return lambda steps: list(self.pool.map(lambda k: worker(k, steps), range(ns)))
+
+
 def run_ours(args):
     import torch
     import msegment_b200 as mseg
-    dev = mseg.device
+    import numpy as np
+    import ctypes
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,51 +371,21 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    B = FRAMES_PER_STEP
-    streams = [torch.cuda.Stream() for _ in range(N_STREAMS)]
-    ctxs = [mseg.Context(local) for _ in range(N_STREAMS)]
-    for c, s in zip(ctxs, streams):
-        c.set_stream(s.cuda_stream)
-    prm = dev.params(**PARAMS, render_depth=-1)
-
-    # ---- inputs resident in HBM (generated on the device, bit-identical to the oracle's generator)
-    src = torch.empty((B, H, W, 3), dtype=torch.uint8, device="cuda")
-    for i in range(B):
-        dev.synth(ctxs[0], src[i].data_ptr(), 3 * W, W, H, SEED0 + 1000 * rank + i)
-    ctxs[0].synchronize()
-    filt = [torch.empty((H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(N_STREAMS)]
-    labs = [torch.empty((H, W), dtype=torch.int32, device="cuda") for _ in range(N_STREAMS)]
-    nreg = torch.zeros((B,), dtype=torch.int32, device="cuda")
-
-    # one host thread per context: msg_segment_dev blocks its caller while the merge stage iterates to a fixed point
-    # (one stream sync per round), so contexts must be driven concurrently for their streams to overlap on the GPU.
-    # ctypes releases the GIL for the duration of every C-ABI call.
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=N_STREAMS)
-
-    def _device_worker(k):
-        for i in range(k, B, N_STREAMS):
-            dev.segment(ctxs[k], src[i].data_ptr(), 3 * W, W, H, prm, filt[k].data_ptr(), 3 * W, labs[k].data_ptr(), 4 * W,
-                        0, 0, nreg[i:].data_ptr())
-
-    def step_device():
-        list(pool.map(_device_worker, range(N_STREAMS)))
-
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
-        """CUDA-event time of `steps` steps across all streams of this rank."""
+    def timed(wl, step_fn, steps):
+        """CUDA-event time of `steps` steps across all streams of this rank, max over ranks."""
         barrier()
+        streams = wl.streams
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(streams[0])
         for s in streams[1:]:
             s.wait_event(e0)
-        for _ in range(steps):
-            step_fn()
+        step_fn(steps)
         for s in streams[1:]:
             done = torch.cuda.Event()
             done.record(s)
@@ -293,85 +399,103 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(args.warmup):
-        step_device()
-    launches0 = sum(c.stats()["kernel_launches"] for c in ctxs)
+    def measure(wl, steps, warmup, legs):
+        """value + the end-to-end legs of one workload.  Returns a dict of figures."""
+        w, h, B = wl.w, wl.h, wl.B
+        out = {}
+        for _ in range(warmup):
+            wl.step_device()
+        l0 = sum(c.stats()["kernel_launches"] for c in wl.ctxs)
+        ms = timed(wl, lambda k: [wl.step_device() for _ in range(k)], steps)
+        out["launches"] = sum(c.stats()["kernel_launches"] for c in wl.ctxs) - l0
+        mpix_step = world * B * w * h / 1e6
+        out["ms_per_step"] = ms / steps
+        out["value"] = mpix_step * steps / (ms / 1e3)
+        fb = w * h * 3
+        h_src, src_np = wl.host_inputs()
+        res = {}
+        if "e2e" in legs:
+            h_lab16 = wl.dev.alloc_pinned(B * w * h * 2)
+            wl.pinned.append(h_lab16)
+            run = wl.e2e_runner(h_src, 0, h_lab16, 2, wl.prm16)
+            run(max(1, warmup // 2))
+            t = timed(wl, run, steps)
+            res["e2e"] = {"value": round(mpix_step * steps / (t / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": B * fb,
+                          "d2h_bytes_per_step": B * (w * h * 2 + 4), "ms_per_step": round(t / steps, 3),
+                          "bytes_per_pixel": {"h2d": 3, "d2h": 2},
+                          "result": "region label map CV_16U + region count (labels_type = MSG_LABELS_16U); pinned host buffers"}
+            out["lab16_frame0"] = np.ctypeslib.as_array((ctypes.c_uint16 * (w * h)).from_address(h_lab16)).reshape(h, w).copy()
+        if "e2e_full" in legs:
+            h_filt = wl.dev.alloc_pinned(B * fb)
+            h_lab = wl.dev.alloc_pinned(B * w * h * 4)
+            wl.pinned += [h_filt, h_lab]
+            run = wl.e2e_runner(h_src, h_filt, h_lab, 4, wl.prm)
+            run(max(1, warmup // 2))
+            t = timed(wl, run, steps)
+            res["e2e_full"] = {"value": round(mpix_step * steps / (t / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": B * fb,
+                               "d2h_bytes_per_step": B * (fb + w * h * 4 + 4), "ms_per_step": round(t / steps, 3),
+                               "bytes_per_pixel": {"h2d": 3, "d2h": 7},
+                               "result": "filtered image 8UC3 + label map CV_32S + region count; pinned host buffers"}
+            out["filt_frame0"] = np.ctypeslib.as_array((ctypes.c_uint8 * fb).from_address(h_filt)).reshape(h, w, 3).copy()
+            out["lab_frame0"] = np.ctypeslib.as_array((ctypes.c_int32 * (w * h)).from_address(h_lab)).reshape(h, w).copy()
+        if "e2e_pageable" in legs:
+            lab_pg = np.zeros((B, h, w), np.uint16)          # plain malloc'ed memory, first-touched here
+            staged0 = sum(c.stats()["staged_bytes"] for c in wl.ctxs)
+            run = wl.e2e_runner(src_np.ctypes.data, 0, lab_pg.ctypes.data, 2, wl.prm16)
+            run(max(1, warmup // 2))
+            t = timed(wl, run, steps)
+            staged = sum(c.stats()["staged_bytes"] for c in wl.ctxs) - staged0
+            res["e2e_pageable"] = {"value": round(mpix_step * steps / (t / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": B * fb,
+                                   "d2h_bytes_per_step": B * (w * h * 2 + 4), "ms_per_step": round(t / steps, 3),
+                                   "staged_bytes_per_step": int(staged // (steps + max(1, warmup // 2))),
+                                   "result": "as e2e, from / to pageable (malloc) buffers through the library's pinned staging"}
+            out["lab16_pageable_frame0"] = lab_pg[0].copy()
+        out["legs"] = res
+        return out
+
+    B = FRAMES_PER_STEP
+    wl = Workload(torch, mseg, local, rank, W, H, B, N_STREAMS)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(step_device, args.steps)
-    launches = sum(c.stats()["kernel_launches"] for c in ctxs) - launches0
-    mpix_step = world * B * W * H / 1e6
-    value = mpix_step * args.steps / (ms / 1e3)
-
-    # ---- end to end: pinned host buffers through the asynchronous C-ABI calls
-    import ctypes
-    import numpy as np
-    frame_bytes, lab_bytes = W * H * 3, W * H * 4
-    h_src = dev.alloc_pinned(B * frame_bytes)
-    h_filt = dev.alloc_pinned(B * frame_bytes)
-    h_lab = dev.alloc_pinned(B * lab_bytes)
-    torch.cuda.synchronize()
-    src_host = src.cpu().numpy()            # keep the array alive across the memmove
-    ctypes.memmove(h_src, src_host.ctypes.data, B * frame_bytes)
-    del src_host
-
-    def _e2e_worker(k, steps):
-        # one host thread per context, as a frame server would run it: frames k, k+N, ... of every step, at most 2
-        # submissions in flight; consecutive steps are pipelined (no drain between them), every result is waited for
-        # (msg_wait = the device->host copies of that frame have landed) before its host buffers are reused
-        tickets = []
-        for _ in range(steps):
-            for i in range(k, B, N_STREAMS):
-                if len(tickets) >= 2:
-                    dev.wait(ctxs[k], tickets.pop(0))
-                tickets.append(dev.submit_segment(ctxs[k], h_src + i * frame_bytes, 3 * W, W, H, prm,
-                                                  h_filt + i * frame_bytes, 3 * W, h_lab + i * lab_bytes, 4 * W))
-        for t in tickets:
-            dev.wait(ctxs[k], t)
-
-    def run_e2e(steps):
-        list(pool.map(lambda k: _e2e_worker(k, steps), range(N_STREAMS)))
-
-    run_e2e(max(1, args.warmup // 2))
-    ms_e2e = timed(lambda: run_e2e(args.steps), 1)
-    e2e_value = mpix_step * args.steps / (ms_e2e / 1e3)
+    m = measure(wl, args.steps, args.warmup, ("e2e", "e2e_full", "e2e_pageable"))
     clocks = sampler.stop() if rank == 0 else None
-
-    # ---- parity spot check of what was just timed (frame 0 of rank 0 vs the CPU oracle, done in the cpu_baseline leg)
-    gpu_f0 = np.ctypeslib.as_array((ctypes.c_uint8 * frame_bytes).from_address(h_filt)).reshape(H, W, 3).copy()
-    gpu_l0 = np.ctypeslib.as_array((ctypes.c_int32 * (W * H)).from_address(h_lab)).reshape(H, W).copy()
 
     # ---- roofline of the dominant kernel (profiling pass: per-kernel CUDA events + device work counters)
     roof = None
     cpu_base = None
+    dev = mseg.device
     if rank == 0:
-        c = ctxs[0]
+        c = wl.ctxs[0]
         c.set_profiling(True)
         for i in range(B):
-            dev.segment(c, src[i].data_ptr(), 3 * W, W, H, prm, filt[0].data_ptr(), 3 * W, labs[0].data_ptr(), 4 * W)
+            dev.segment(c, wl.src[i].data_ptr(), 3 * W, W, H, wl.prm, wl.filt[0].data_ptr(), 3 * W, wl.labs[0].data_ptr(), 4 * W)
         prof = c.kernel_profile()
         c.set_profiling(False)
         peak = measure_int_peak()
-        ops0 = 9 * prof["tile_tests"][0] + 5 * prof["tile_hits"][0]
+        T0, Hit0 = prof["tile_tests"][0], prof["tile_hits"][0]
+        ops0 = 9 * T0 + 5 * Hit0
         t0_ms = prof["tile_ms"][0]
         achieved = ops0 / (t0_ms * 1e-3) / 1e12 if t0_ms > 0 else 0.0
         all_ms = sum(prof["tile_ms"]) + sum(prof["overflow_ms"])
         traffic, traffic_src = None, None
         try:   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (not measurable live)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_k1_traffic_4k.json")))
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
             traffic_src = tj["source"]
         except Exception:
             pass
-        roof = {"bound": "int_alu", "kernel": "meanshift_tile_kernel<21,64,0> (level 0, sp=10)",
+        npx = B * W * H
+        roof = {"bound": "int_alu", "kernel": "meanshift_tile_kernel<21,64,0> (level 0 of a 3840x2160 frame, sp=10)",
                 "achieved": round(achieved, 3), "peak": peak["tiops"], "unit": "Tiop/s",
                 "frac": round(achieved / peak["tiops"], 4) if peak["tiops"] else None, "traffic": traffic,
-                "traffic_unit": "bytes/launch (algorithmic HBM bytes: 8.3 MB, one pass over the 1080p source plane)",
+                "traffic_unit": "bytes/launch (algorithmic HBM bytes: 33.2 MB, one pass over the 4K source plane)",
                 "traffic_source": traffic_src,
                 "peak_source": peak["source"], "ops_model": "9*T + 5*Hit int-ops (SURVEY 8(d)); T, Hit counted on device",
+                "T_window_tests_per_launch": int(T0 // max(1, prof["launches"][0])),
+                "Hit_in_range_per_launch": int(Hit0 // max(1, prof["launches"][0])),
+                "T_per_pixel_L0": round(T0 / npx, 2), "Hit_per_pixel_L0": round(Hit0 / npx, 2),
                 "launches": prof["launches"][0], "avg_launch_ms": round(t0_ms / max(1, prof["launches"][0]), 4),
-                "tests_per_pixel_L0": round(prof["tile_tests"][0] / (B * W * H), 2),
                 "share_of_meanshift_time": round(t0_ms / all_ms, 4) if all_ms else None,
                 "level1_tile_ms_avg": round(prof["tile_ms"][1] / max(1, prof["launches"][1]), 4),
                 "overflow_ms_avg": round(sum(prof["overflow_ms"]) / max(1, prof["launches"][0]), 4),
@@ -381,12 +505,12 @@ def run_ours(args):
         # with the CUDA events of the synchronous host call (msg_get_timings), against the measured copy bandwidth
         try:
             gi = mseg.GpuImgproc(c)
-            host_frames = [src[i].cpu().numpy().reshape(H, W, 3) for i in range(min(4, B))]
+            host_frames = [wl.src[i].cpu().numpy().reshape(H, W, 3) for i in range(min(3, B))]
             acc = {"label_ms": [], "merge_ms": [], "render_ms": [], "filter_ms": []}
             for rep in range(2):
                 for fr in host_frames:
-                    gi.segment(fr, sp=prm.sp, sr=prm.sr, maxLevel=prm.max_level, loDiff=prm.lo_diff, minSize=prm.min_size,
-                               colorDist=prm.color_dist, renderDepth=0)
+                    gi.segment(fr, sp=wl.prm.sp, sr=wl.prm.sr, maxLevel=wl.prm.max_level, loDiff=wl.prm.lo_diff,
+                               minSize=wl.prm.min_size, colorDist=wl.prm.color_dist, renderDepth=0)
                     if rep:
                         t = c.timings()
                         for k in acc:
@@ -396,7 +520,7 @@ def run_ours(args):
                 hbm_src = "MEASURED_PEAKS.json"
             except Exception:
                 hbm, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
-            stages = {"peak_gbs": hbm, "peak_source": hbm_src, "how": "one 1080p frame at a time on an idle GPU, mean of %d" % len(acc["label_ms"])}
+            stages = {"peak_gbs": hbm, "peak_source": hbm_src, "how": "one 4K frame at a time on an idle GPU, mean of %d" % len(acc["label_ms"])}
             for k, bpp in (("label_ms", 7), ("merge_ms", 11), ("render_ms", 7)):
                 msv = float(np.mean(acc[k]))
                 gbs = bpp * W * H / (msv * 1e-3) / 1e9 if msv > 0 else 0.0
@@ -409,24 +533,46 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cpu_base, (f0, n0, l0) = cpu_baseline_leg()
             ct = cpu_base["oracle_counters"]
-            cpu_base["parity_frame0"] = {"filtered_bit_exact": bool(np.array_equal(gpu_f0, f0)),
-                                         "labels_bit_exact": bool(np.array_equal(gpu_l0, l0))}
+            cpu_base["parity_frame0"] = {
+                "filtered_bit_exact": bool(np.array_equal(m["filt_frame0"], f0)),
+                "labels_bit_exact": bool(np.array_equal(m["lab_frame0"], l0)),
+                "labels_u16_bit_exact": bool(np.array_equal(m["lab16_frame0"].astype(np.int32), l0)),
+                "labels_u16_pageable_bit_exact": bool(np.array_equal(m["lab16_pageable_frame0"].astype(np.int32), l0)),
+                "what": "frame 0 of rank 0 as the three end-to-end legs delivered it vs the CPU oracle on the whole 4K frame"}
             roof["oracle_tests_per_pixel_all_levels"] = round(ct["window_tests"] / (W * H), 2)
+    wl.close()
+    del wl
+    torch.cuda.empty_cache()
+
+    # ---- secondary: the round-1 workload (1920x1080 x32 frames, 6 contexts), short run
+    secondary = None
+    if not args.no_secondary:
+        try:
+            wl2 = Workload(torch, mseg, local, rank, 1920, 1080, 32, 6)
+            m2 = measure(wl2, max(2, args.steps // 2), 3, ("e2e", "e2e_full"))
+            secondary = {"workload": workload_name(1920, 1080, 32), "value": round(m2["value"], 2), "unit": UNIT,
+                         "ms_per_step": round(m2["ms_per_step"], 3), "streams_per_gpu": 6,
+                         "e2e": m2["legs"]["e2e"], "e2e_full": m2["legs"]["e2e_full"]}
+            wl2.close()
+        except Exception as e:   # noqa: BLE001
+            secondary = {"error": str(e)}
 
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
-    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+    line = {"metric": METRIC, "value": round(m["value"], 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(m["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(), "frames_per_step_per_gpu": B, "streams_per_gpu": N_STREAMS,
-                       "flush": "per-step input 199 MB per GPU > 126 MB L2 (no explicit flush)", "parallelism": "frames x%d" % world,
-                       "host": host},
-            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes,
-                    "d2h_bytes_per_step": B * (frame_bytes + lab_bytes), "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+                       "flush": "per-step input %d MB per GPU > 126 MB L2 (no explicit flush)" % (B * W * H * 3 // 1000000),
+                       "parallelism": "frames x%d" % world, "host": host,
+                       "e2e_bytes_per_pixel": {"h2d": 3, "d2h": 2, "full": {"h2d": 3, "d2h": 7}}},
+            "e2e": m["legs"]["e2e"], "e2e_full": m["legs"]["e2e_full"], "e2e_pageable": m["legs"]["e2e_pageable"],
+            "gpu_launches": int(m["launches"]), "clocks": clocks, "roofline": roof}
+    if secondary is not None:
+        line["secondary_1080p"] = secondary
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line))
@@ -477,6 +623,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the 1080p secondary workload")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSG_VERSION 100 /* 0.1.0 */
+#define MSG_VERSION 200 /* 0.2.0: msg_segment_params.labels_type, options, host registration, watershed, sharding plan */
 
 #if defined(__GNUC__)
 #define MSG_API __attribute__((visibility("default")))
@@ -52,7 +52,8 @@ typedef enum msg_status {
     MSG_EINVAL = -1,  /* bad argument (mirrors OpenCV's CV_Assert failures -> CvException) */
     MSG_ECUDA = -2,   /* CUDA runtime / driver error (sticky per context) */
     MSG_ENOMEM = -3,  /* host or device allocation failed */
-    MSG_ESTATE = -4   /* call sequence error (bad ticket, ...) */
+    MSG_ESTATE = -4,  /* call sequence error (bad ticket, ...) */
+    MSG_ERANGE = -5   /* result does not fit the requested output type (more than 65535 regions for 16-bit labels) */
 } msg_status;
 
 /* cv::TermCriteria type bits */
@@ -71,6 +72,28 @@ MSG_API const char* msg_last_error(const msg_ctx* ctx);   /* ctx may be NULL: la
  * pass cudaStreamLegacy, (void*)1, for the legacy default stream). */
 MSG_API int msg_set_stream(msg_ctx* ctx, void* cuda_stream);
 MSG_API int msg_synchronize(msg_ctx* ctx);
+
+/* Per-context options (integers).  Every option is initialised once in msg_create from the environment variable MSG_<NAME>
+ * (upper case) when that is set; nothing on the launch path reads the environment.
+ *   "gray_compat"     0 (default): cvtColor(BGR2GRAY) with the OpenCV 4.x coefficients (3735, 19235, 9798) >> 15 -- what the
+ *                     cv2 4.13 oracle is pinned on; 1: the OpenCV 3.4.2 ones (1868, 9617, 4899) >> 14 -- the version the
+ *                     reference binds (pom.xml:39-43); differs by 1 LSB on 0.26 % of colours (INTEGRATION.md "version skew")
+ *   "dt_fixed"        0 (default): distanceTransform(L2, 5) in the float arithmetic of the IPP-backed cv2 4.13 build;
+ *                     1: OpenCV's own 16.16 fixed-point chamfer (what a non-IPP build, e.g. the openpnp 3.4.2 natives, runs)
+ *   "staging"         1 (default): pageable caller buffers are staged through the context's pinned ring; 0: handed to
+ *                     cudaMemcpyAsync as they are (driver staging, serialises the asynchronous path)
+ *   "merge_small_max", "tile_w", "acc", "pitch_res", "tma", "no_order", "merge_scalar", "no_graph", "ccl_legacy":
+ *                     tuning / test hooks */
+MSG_API int msg_set_option(msg_ctx* ctx, const char* name, int value);
+MSG_API int msg_get_option(msg_ctx* ctx, const char* name, int* value);
+
+/* Page-lock a caller-owned host range (a long-lived Mat: cv::Mat data is pageable fastMalloc memory) so that every later call
+ * that passes a buffer inside it copies straight from / to it asynchronously (no staging copy).  The caller MUST unregister
+ * before freeing the memory.  Up to 16 ranges per context.  Unregistered pageable buffers are always legal: they go through the
+ * context's pinned staging ring (uploads: chunked memcpy + DMA overlapped; msg_submit_segment downloads: DMA into pinned staging,
+ * copied to the caller's buffer inside msg_wait). */
+MSG_API int msg_register_host(msg_ctx* ctx, void* ptr, size_t bytes);
+MSG_API int msg_unregister_host(msg_ctx* ctx, void* ptr);
 
 /* ---- drop-in operators on HOST buffers (synchronous; staging + H2D/D2H inside) ---------- */
 
@@ -106,6 +129,22 @@ MSG_API int msg_connected_components(msg_ctx* ctx, const uint8_t* mask, size_t s
 MSG_API int msg_render_labels(msg_ctx* ctx, const int32_t* labels, size_t labels_step, uint8_t* dst_bgr,
                       size_t dst_step, int width, int height, int depth, const uint8_t* colors_bgr);
 
+/* Imgproc.watershed(image 8UC3, markers 32SC1 in/out) -- PictureService.java:908-911 (call sites :284, :372, :457, :852): the
+ * reference's region-growing step.  EXACT emulation of cv::watershed: the border and every pixel where two
+ * basins meet become -1, positive seeds flood the zero pixels in priority order of the max-channel difference to the pushing
+ * neighbour, FIFO inside a level; unreachable pixels stay 0.  The flood is inherently sequential, so one image runs on one warp
+ * (about the speed of one CPU core); msg_watershed_batch_dev floods `count` images of one geometry concurrently, which is where
+ * the GPU pays (DESIGN.md "K4").  msg_get_timings().filter_ms = kernel time of the last msg_watershed call. */
+MSG_API int msg_watershed(msg_ctx* ctx, const uint8_t* image_bgr, size_t step, int32_t* markers, size_t markers_step, int width,
+                  int height);
+MSG_API int msg_watershed_dev(msg_ctx* ctx, const uint8_t* d_image_bgr, size_t step, int32_t* d_markers, size_t markers_step,
+                      int width, int height);
+/* image k at d_images_bgr + k * image_stride bytes, its markers at d_markers + k * markers_stride bytes.  d_pops (device
+ * uint64, may be NULL) receives the total number of queue pops = the length of the sequential chains. */
+MSG_API int msg_watershed_batch_dev(msg_ctx* ctx, const uint8_t* d_images_bgr, size_t step, size_t image_stride, int32_t* d_markers,
+                            size_t markers_step, size_t markers_stride, int width, int height, int count,
+                            unsigned long long* d_pops);
+
 /* ---- pre-filters the reference calls around its segmentation stage (exact integer forms) ------------- */
 /* Laplacian sharpen chain of PictureService.java:323-333: filter2D(src, lap, CV_32F, K); src.convertTo(CV_32F);
  * subtract; convertTo(CV_8UC3)  ==  dst = saturate_u8(src - sum_K taps * src), BORDER_REFLECT_101, anchor at the kernel centre.
@@ -132,6 +171,9 @@ MSG_API int msg_dilate(msg_ctx* ctx, const uint8_t* src, size_t src_step, uint8_
 /* Core.subtract(a, b, dst) on 8UC1 (PictureService.java:430): saturating. */
 MSG_API int msg_subtract(msg_ctx* ctx, const uint8_t* a, size_t a_step, const uint8_t* b, size_t b_step, uint8_t* dst,
                  size_t dst_step, int width, int height);
+/* src.copyTo(dst, mask) onto Mat.zeros (PictureService.java:417-418, the "borders" Result): dst = mask != 0 ? src : 0. */
+MSG_API int msg_copy_masked(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, const uint8_t* mask, size_t mask_step,
+                    uint8_t* dst_bgr, size_t dst_step, int width, int height);
 /* The whole generator, intermediates in HBM: cvtColor(BGR2GRAY) -> medianBlur(median_ksize) -> Canny(t1, t2) -> dilate 3x3 ->
  * dilate 5x5 -> subtract -> medianBlur 3 -> connectedComponents(8, CV_32S).  markers: 0 background, 1..n-1 in raster order of
  * first pixel; *n_labels counts the background like OpenCV.  stages (optional, NULL to skip): 4 planes of `height` rows of
@@ -218,14 +260,20 @@ typedef struct msg_segment_params {
     int color_dist;
     int render_depth; /* > 0: render with that depth; 0: depth = n_regions; < 0: skip */
     int connectivity; /* label stage: 4 (default, also for 0) or 8 */
+    int labels_type;  /* MSG_LABELS_32S (0, CV_32SC1, what the reference's Mat expects) or MSG_LABELS_16U (CV_16UC1: the labels
+                         pointer is a uint16_t buffer, 2 bytes per pixel over PCIe instead of 4; more than 65535 regions ->
+                         MSG_ERANGE from msg_segment / msg_wait, pixels saturate at 65535) */
 } msg_segment_params;
+#define MSG_LABELS_32S 0
+#define MSG_LABELS_16U 1
 
 MSG_API void msg_segment_params_default(msg_segment_params* p); /* sp=sr=10, L1, (3,5,1), lo=2, no merge */
 
-/* Any output pointer may be NULL (that product is then not downloaded). */
+/* Any output pointer may be NULL: that product is then neither converted nor downloaded (the download mask of the call).
+ * labels is int32_t* or, with labels_type = MSG_LABELS_16U, uint16_t* (labels_step in bytes either way). */
 MSG_API int msg_segment(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, int width, int height,
                 const msg_segment_params* params, uint8_t* filtered_bgr, size_t filtered_step,
-                int32_t* labels, size_t labels_step, uint8_t* rendered_bgr, size_t rendered_step,
+                void* labels, size_t labels_step, uint8_t* rendered_bgr, size_t rendered_step,
                 int32_t* n_regions);
 
 /* ---- asynchronous batch interface (stream ordered within a context) ----------------------- */
@@ -236,7 +284,7 @@ MSG_API int msg_segment(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, i
 #define MSG_MAX_INFLIGHT 4
 MSG_API int msg_submit_segment(msg_ctx* ctx, const uint8_t* src_bgr, size_t src_step, int width, int height,
                        const msg_segment_params* params, uint8_t* filtered_bgr, size_t filtered_step,
-                       int32_t* labels, size_t labels_step, uint8_t* rendered_bgr, size_t rendered_step,
+                       void* labels, size_t labels_step, uint8_t* rendered_bgr, size_t rendered_step,
                        int* ticket);
 MSG_API int msg_wait(msg_ctx* ctx, int ticket, int32_t* n_regions);
 
@@ -248,7 +296,7 @@ MSG_API void msg_free_pinned(void* p);
 /* msg_segment on device buffers (any output may be NULL); d_n_regions: device int32 or NULL. */
 MSG_API int msg_segment_dev(msg_ctx* ctx, const uint8_t* d_src_bgr, size_t src_step, int width, int height,
                     const msg_segment_params* params, uint8_t* d_filtered_bgr, size_t filtered_step,
-                    int32_t* d_labels, size_t labels_step, uint8_t* d_rendered_bgr, size_t rendered_step,
+                    void* d_labels, size_t labels_step, uint8_t* d_rendered_bgr, size_t rendered_step,
                     int32_t* d_n_regions);
 MSG_API int msg_meanshift_filter_dev(msg_ctx* ctx, const uint8_t* d_src_bgr, size_t src_step, uint8_t* d_dst_bgr,
                              size_t dst_step, int width, int height, double sp, double sr, int max_level,
@@ -339,6 +387,7 @@ typedef struct msg_stats {
     uint64_t ms_active_items;     /* mean-shift pixels processed (all levels), last call */
     uint64_t merge_rounds;        /* rounds of the last merge call */
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied by host-buffer calls so far */
+    uint64_t staged_bytes;        /* of those, bytes that went through pinned staging because the caller's buffer was pageable */
 } msg_stats;
 MSG_API int msg_get_stats(msg_ctx* ctx, msg_stats* out);
 

@@ -6,7 +6,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmsegment_b200.so")
 
-MSG_OK, MSG_EINVAL, MSG_ECUDA, MSG_ENOMEM, MSG_ESTATE = 0, -1, -2, -3, -4
+MSG_OK, MSG_EINVAL, MSG_ECUDA, MSG_ENOMEM, MSG_ESTATE, MSG_ERANGE = 0, -1, -2, -3, -4, -5
+LABELS_32S, LABELS_16U = 0, 1
 TERM_COUNT, TERM_EPS = 1, 2
 MAX_INFLIGHT = 4
 
@@ -14,7 +15,7 @@ MAX_INFLIGHT = 4
 class SegmentParams(C.Structure):
     _fields_ = [("sp", C.c_double), ("sr", C.c_double), ("max_level", C.c_int), ("term_type", C.c_int),
                 ("max_count", C.c_int), ("eps", C.c_double), ("lo_diff", C.c_int), ("min_size", C.c_int),
-                ("color_dist", C.c_int), ("render_depth", C.c_int), ("connectivity", C.c_int)]
+                ("color_dist", C.c_int), ("render_depth", C.c_int), ("connectivity", C.c_int), ("labels_type", C.c_int)]
 
 
 class Timings(C.Structure):
@@ -23,7 +24,7 @@ class Timings(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "ms_overflow_items", "ms_active_items", "merge_rounds",
-                                           "h2d_bytes", "d2h_bytes")]
+                                           "h2d_bytes", "d2h_bytes", "staged_bytes")]
 
 
 class KernelProfile(C.Structure):
@@ -42,17 +43,25 @@ SIGNATURES = {
     "msg_last_error": (C.c_char_p, [_P]),
     "msg_set_stream": (_I, [_P, _P]),
     "msg_synchronize": (_I, [_P]),
+    "msg_set_option": (_I, [_P, C.c_char_p, _I]),
+    "msg_get_option": (_I, [_P, C.c_char_p, C.POINTER(_I)]),
+    "msg_register_host": (_I, [_P, _P, _SZ]),
+    "msg_unregister_host": (_I, [_P, _P]),
     "msg_meanshift_filter": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _D, _D, _I, _I, _I, _D]),
     "msg_label_regions": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, _I, C.POINTER(C.c_int32)]),
     "msg_merge_regions": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I, C.POINTER(C.c_int32)]),
     "msg_connected_components": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, C.POINTER(C.c_int32)]),
     "msg_render_labels": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _P]),
+    "msg_watershed": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I]),
+    "msg_watershed_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I]),
+    "msg_watershed_batch_dev": (_I, [_P, _P, _SZ, _SZ, _P, _SZ, _SZ, _I, _I, _I, _P]),
     "msg_laplacian_sharpen": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _P, _I, _I]),
     "msg_bgr2gray": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I]),
     "msg_median_blur": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I]),
     "msg_canny": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _D, _D]),
     "msg_dilate": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _I, _I]),
     "msg_subtract": (_I, [_P, _P, _SZ, _P, _SZ, _P, _SZ, _I, _I]),
+    "msg_copy_masked": (_I, [_P, _P, _SZ, _P, _SZ, _P, _SZ, _I, _I]),
     "msg_shape_seeds": (_I, [_P, _P, _SZ, _I, _I, _I, _D, _D, _P, _SZ, _P, _P, _SZ]),
     "msg_shape_seeds_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _D, _D, _P, _SZ, _P, _P]),
     "msg_white_to_black": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I]),

@@ -40,6 +40,49 @@ int msg_reserve(msg_ctx* ctx, void** p, size_t* cap, size_t bytes)
     return MSG_OK;
 }
 
+int msg_func_smem(msg_ctx* ctx, const void* func, size_t smem)
+{
+    for (int i = 0; i < ctx->n_attr; i++)
+        if (ctx->attr_cache[i].func == func) {
+            if (ctx->attr_cache[i].smem >= smem) return MSG_OK;
+            MSG_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->attr_cache[i].smem = smem;
+            return MSG_OK;
+        }
+    MSG_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->n_attr < 64) {
+        ctx->attr_cache[ctx->n_attr].func = func;
+        ctx->attr_cache[ctx->n_attr].smem = smem;
+        ctx->n_attr++;
+    }
+    return MSG_OK;
+}
+
+// ---- options: one table maps names to msg_tuning fields; msg_create seeds them from MSG_<NAME> once
+struct opt_entry { const char* name; size_t off; int dflt; };
+#define OPT(n, f, d) {n, offsetof(msg_tuning, f), d}
+static const opt_entry g_opts[] = {
+    OPT("tile_w", tile_w, 0),           OPT("acc", acc, -1),           OPT("pitch_res", pitch_res, -1),
+    OPT("tma", use_tma, 1),             OPT("no_order", no_order, 0),  OPT("merge_scalar", merge_scalar, 0),
+    OPT("merge_small_max", merge_small_max, -1), OPT("no_graph", no_graph, 0), OPT("graph_debug", graph_debug, 0),
+    OPT("ccl_legacy", ccl_legacy, 0),   OPT("gray_compat", gray_compat, 0), OPT("dt_fixed", dt_fixed, 0),
+    OPT("staging", staging, 1),
+};
+#undef OPT
+static int* opt_field(msg_tuning* t, const opt_entry& e) { return (int*)((char*)t + e.off); }
+
+static void tuning_from_env(msg_tuning* t)
+{
+    for (const opt_entry& e : g_opts) {
+        *opt_field(t, e) = e.dflt;
+        char env[64] = "MSG_";
+        size_t k = 4;
+        for (const char* c = e.name; *c && k < sizeof(env) - 1; c++) env[k++] = (char)((*c >= 'a' && *c <= 'z') ? *c - 32 : *c);
+        env[k] = 0;
+        if (const char* v = getenv(env)) *opt_field(t, e) = *v ? atoi(v) : 1;     // MSG_NO_GRAPH= (empty) counts as set
+    }
+}
+
 static void prof_fold(msg_ctx* ctx, int level)
 {
     if (!ctx->prof_pending[level]) return;
@@ -105,7 +148,7 @@ int msg_create(int device, msg_ctx** out)
         cudaError_t e2 = (call);                                                                  \
         if (e2 != cudaSuccess) {                                                                  \
             msg_fail(nullptr, MSG_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e2));         \
-            free(ctx);                                                                            \
+            msg_destroy(ctx);   /* frees whatever was created so far (streams, events, allocations) */ \
             return MSG_ECUDA;                                                                     \
         }                                                                                         \
     } while (0)
@@ -118,6 +161,7 @@ int msg_create(int device, msg_ctx** out)
         free(ctx);
         return MSG_ECUDA;
     }
+    tuning_from_env(&ctx->tune);
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     CR(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
@@ -138,7 +182,13 @@ int msg_create(int device, msg_ctx** out)
         CR(cudaEventCreateWithFlags(&ctx->pend[i].ev_in, cudaEventDisableTiming));
         CR(cudaEventCreateWithFlags(&ctx->pend[i].ev_core, cudaEventDisableTiming));
         ctx->pend[i].n_regions_host = ctx->h_counters + 32 + i;
+        // every in-flight frame owns its counters (region count, mean-shift statistics) and their pinned mirror
+        CR(cudaMalloc((void**)&ctx->pend[i].d_cnt, 16 * sizeof(int32_t)));
+        CR(cudaMemset(ctx->pend[i].d_cnt, 0, 16 * sizeof(int32_t)));
+        CR(cudaMallocHost((void**)&ctx->pend[i].h_cnt, 16 * sizeof(int32_t)));
+        memset(ctx->pend[i].h_cnt, 0, 16 * sizeof(int32_t));
     }
+    for (int i = 0; i < MSG_RING_CHUNKS; i++) CR(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
     CR(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     CR(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
 #undef CR
@@ -148,27 +198,39 @@ int msg_create(int device, msg_ctx** out)
 
 void msg_destroy(msg_ctx* ctx)
 {
+    // also the cleanup path of a failed msg_create: every member may still be null
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->h2d_stream);
-    cudaStreamSynchronize(ctx->d2h_stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+    for (int i = 0; i < ctx->n_reg; i++) cudaHostUnregister((void*)ctx->reg[i].base);
     for (int i = 0; i < MSG_MAX_INFLIGHT; i++) {
-        cudaFree(ctx->pend[i].d_in); cudaFree(ctx->pend[i].d_filt); cudaFree(ctx->pend[i].d_ren); cudaFree(ctx->pend[i].d_lab);
-        cudaEventDestroy(ctx->pend[i].ev_in); cudaEventDestroy(ctx->pend[i].ev_core);
-        if (ctx->pend[i].g_exec) cudaGraphExecDestroy(ctx->pend[i].g_exec);
+        msg_ctx::pending& q = ctx->pend[i];
+        cudaFree(q.d_in); cudaFree(q.d_filt); cudaFree(q.d_ren); cudaFree(q.d_lab); cudaFree(q.d_lab16); cudaFree(q.d_cnt);
+        if (q.h_cnt) cudaFreeHost(q.h_cnt);
+        if (q.h_out) cudaFreeHost(q.h_out);
+        if (q.ev_in) cudaEventDestroy(q.ev_in);
+        if (q.ev_core) cudaEventDestroy(q.ev_core);
+        if (q.done) cudaEventDestroy(q.done);
+        if (q.g_exec) cudaGraphExecDestroy(q.g_exec);
     }
-    cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_out2); cudaFree(ctx->d_labels);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_ovf); cudaFree(ctx->d_scratch); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_colors); cudaFree(ctx->d_work); cudaFree(ctx->d_cells); cudaFree(ctx->d_aux); cudaFree(ctx->d_small);
+    cudaFree(ctx->d_ws);
     for (int l = 0; l < MSG_MAX_LEVELS; l++)
-        for (int k = 0; k < 3; k++) cudaEventDestroy(ctx->prof_ev[l][k]);
-    cudaFreeHost(ctx->h_counters);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < MSG_MAX_INFLIGHT; i++) cudaEventDestroy(ctx->pend[i].done);
-    cudaStreamDestroy(ctx->own_stream);
+        for (int k = 0; k < 3; k++)
+            if (ctx->prof_ev[l][k]) cudaEventDestroy(ctx->prof_ev[l][k]);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+    for (int i = 0; i < MSG_RING_CHUNKS; i++)
+        if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
+    for (int i = 0; i < 8; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     cudaGetLastError();
     free(ctx);
 }
@@ -190,6 +252,56 @@ int msg_synchronize(msg_ctx* ctx)
     return MSG_OK;
 }
 
+int msg_set_option(msg_ctx* ctx, const char* name, int value)
+{
+    if (!ctx || !name) return MSG_EINVAL;
+    for (const opt_entry& e : g_opts)
+        if (!strcmp(e.name, name)) {
+            if (*opt_field(&ctx->tune, e) != value) ctx->ws_epoch++;     // captured graphs must not outlive an option change
+            *opt_field(&ctx->tune, e) = value;
+            return MSG_OK;
+        }
+    return msg_fail(ctx, MSG_EINVAL, "unknown option '%s'", name);
+}
+
+int msg_get_option(msg_ctx* ctx, const char* name, int* value)
+{
+    if (!ctx || !name || !value) return MSG_EINVAL;
+    for (const opt_entry& e : g_opts)
+        if (!strcmp(e.name, name)) { *value = *opt_field(&ctx->tune, e); return MSG_OK; }
+    return msg_fail(ctx, MSG_EINVAL, "unknown option '%s'", name);
+}
+
+int msg_register_host(msg_ctx* ctx, void* ptr, size_t bytes)
+{
+    CTX_ENTER(ctx);
+    if (!ptr || !bytes) return msg_fail(ctx, MSG_EINVAL, "register_host: null range");
+    if (ctx->n_reg >= 16) return msg_fail(ctx, MSG_ESTATE, "register_host: 16 ranges already registered");
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return msg_fail(ctx, MSG_ENOMEM, "cudaHostRegister(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->reg[ctx->n_reg].base = (const uint8_t*)ptr;
+    ctx->reg[ctx->n_reg].bytes = bytes;
+    ctx->n_reg++;
+    return MSG_OK;
+}
+
+int msg_unregister_host(msg_ctx* ctx, void* ptr)
+{
+    CTX_ENTER(ctx);
+    for (int i = 0; i < ctx->n_reg; i++)
+        if (ctx->reg[i].base == (const uint8_t*)ptr) {
+            MSG_TRY(msg_synchronize(ctx));                       // no copy of ours may still be using the range
+            cudaHostUnregister(ptr);
+            cudaGetLastError();
+            ctx->reg[i] = ctx->reg[--ctx->n_reg];
+            return MSG_OK;
+        }
+    return msg_fail(ctx, MSG_ESTATE, "unregister_host: range was not registered with this context");
+}
+
 void* msg_alloc_pinned(size_t bytes)
 {
     void* p = nullptr;
@@ -208,6 +320,7 @@ void msg_segment_params_default(msg_segment_params* p)
     p->sp = 10.0; p->sr = 10.0; p->max_level = 1;
     p->term_type = MSG_TERM_COUNT | MSG_TERM_EPS; p->max_count = 5; p->eps = 1.0;
     p->lo_diff = 2; p->min_size = 0; p->color_dist = 0; p->render_depth = 0; p->connectivity = 4;
+    p->labels_type = MSG_LABELS_32S;
 }
 
 int msg_get_timings(msg_ctx* ctx, msg_timings* out)
@@ -324,25 +437,133 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
+// ---- host buffers.  cv::Mat storage is pageable (fastMalloc); handing it to cudaMemcpyAsync makes the driver stage it
+// synchronously, which serialises the asynchronous path.  Pageable buffers therefore go through the context's pinned ring
+// (uploads, synchronous downloads) or through the frame's pinned output staging (msg_submit_segment); pinned memory
+// (msg_alloc_pinned, cudaHostAlloc, cudaHostRegister, msg_register_host) is used in place.
+static bool host_is_pinned(msg_ctx* ctx, const void* p)
+{
+    if (!ctx->tune.staging) return true;          // option staging = 0: behave as round 1 (driver staging)
+    const uint8_t* b = (const uint8_t*)p;
+    for (int i = 0; i < ctx->n_reg; i++)
+        if (b >= ctx->reg[i].base && b < ctx->reg[i].base + ctx->reg[i].bytes) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeDevice;
+}
+
+static int ring_acquire(msg_ctx* ctx, int* idx)
+{
+    if (!ctx->h_ring) {
+        cudaError_t e = cudaMallocHost((void**)&ctx->h_ring, MSG_RING_CHUNKS * MSG_RING_CHUNK_BYTES);
+        if (e != cudaSuccess) { cudaGetLastError(); ctx->h_ring = nullptr; return msg_fail(ctx, MSG_ENOMEM, "pinned staging ring: %s", cudaGetErrorString(e)); }
+    }
+    const int i = ctx->ring_next;
+    ctx->ring_next = (i + 1) % MSG_RING_CHUNKS;
+    if (ctx->ring_busy[i]) {
+        MSG_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[i]));
+        ctx->ring_busy[i] = 0;
+    }
+    *idx = i;
+    return MSG_OK;
+}
+
+// bytes [off, off + n) of the dense row-major image <-> the strided host image
+static void host_gather(uint8_t* dst, const uint8_t* host, size_t hstep, size_t row_bytes, size_t off, size_t n)
+{
+    if (hstep == row_bytes) { memcpy(dst, host + off, n); return; }
+    size_t r = off / row_bytes, c = off % row_bytes;
+    while (n) {
+        size_t k = row_bytes - c < n ? row_bytes - c : n;
+        memcpy(dst, host + r * hstep + c, k);
+        dst += k; n -= k; r++; c = 0;
+    }
+}
+
+static void host_scatter(uint8_t* host, size_t hstep, size_t row_bytes, size_t off, const uint8_t* src, size_t n)
+{
+    if (hstep == row_bytes) { memcpy(host + off, src, n); return; }
+    size_t r = off / row_bytes, c = off % row_bytes;
+    while (n) {
+        size_t k = row_bytes - c < n ? row_bytes - c : n;
+        memcpy(host + r * hstep + c, src, k);
+        src += k; n -= k; r++; c = 0;
+    }
+}
+
+// upload into an already reserved dense device buffer
+static int upload_on(msg_ctx* ctx, cudaStream_t st, const void* host, size_t hstep, size_t row_bytes, int rows, uint8_t* d)
+{
+    const size_t total = row_bytes * (size_t)rows;
+    if (host_is_pinned(ctx, host)) {
+        if (hstep == row_bytes)      // continuous Mat: one linear copy (the 2-D form is issued row by row by the copy engine)
+            MSG_CUDA(ctx, cudaMemcpyAsync(d, host, total, cudaMemcpyHostToDevice, st));
+        else
+            MSG_CUDA(ctx, cudaMemcpy2DAsync(d, row_bytes, host, hstep, row_bytes, rows, cudaMemcpyHostToDevice, st));
+    } else {
+        // pageable: chunks are copied into the pinned ring by this thread while the DMA of the previous chunks runs
+        for (size_t off = 0; off < total; off += MSG_RING_CHUNK_BYTES) {
+            const size_t n = total - off < MSG_RING_CHUNK_BYTES ? total - off : MSG_RING_CHUNK_BYTES;
+            int i;
+            MSG_TRY(ring_acquire(ctx, &i));
+            uint8_t* chunk = ctx->h_ring + (size_t)i * MSG_RING_CHUNK_BYTES;
+            host_gather(chunk, (const uint8_t*)host, hstep, row_bytes, off, n);
+            MSG_CUDA(ctx, cudaMemcpyAsync(d + off, chunk, n, cudaMemcpyHostToDevice, st));
+            MSG_CUDA(ctx, cudaEventRecord(ctx->ring_ev[i], st));
+            ctx->ring_busy[i] = 1;
+        }
+        ctx->st.staged_bytes += total;
+    }
+    ctx->st.h2d_bytes += total;
+    return MSG_OK;
+}
+
 static int copy_in_on(msg_ctx* ctx, cudaStream_t st, const void* host, size_t hstep, size_t row_bytes, int rows, uint8_t** d,
                       size_t* dcap)
 {
     MSG_TRY(msg_reserve(ctx, (void**)d, dcap, row_bytes * (size_t)rows));
-    if (hstep == row_bytes)      // continuous Mat: one linear copy (the 2-D form is issued row by row by the copy engine)
-        MSG_CUDA(ctx, cudaMemcpyAsync(*d, host, row_bytes * (size_t)rows, cudaMemcpyHostToDevice, st));
-    else
-        MSG_CUDA(ctx, cudaMemcpy2DAsync(*d, row_bytes, host, hstep, row_bytes, rows, cudaMemcpyHostToDevice, st));
-    ctx->st.h2d_bytes += row_bytes * (size_t)rows;
-    return MSG_OK;
+    return upload_on(ctx, st, host, hstep, row_bytes, rows, *d);
 }
 
+// Download on `st`.  Pinned destination: asynchronous.  Pageable destination: chunks are DMA'd into the pinned ring and copied
+// out by this thread as they land -- the call returns when the host buffer is complete (the synchronous entry points
+// synchronise right after it anyway; msg_submit_segment uses the frame's own output staging instead, see there).
 static int copy_out_on(msg_ctx* ctx, cudaStream_t st, void* host, size_t hstep, const void* d, size_t row_bytes, int rows)
 {
-    if (hstep == row_bytes)
-        MSG_CUDA(ctx, cudaMemcpyAsync(host, d, row_bytes * (size_t)rows, cudaMemcpyDeviceToHost, st));
-    else
-        MSG_CUDA(ctx, cudaMemcpy2DAsync(host, hstep, d, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, st));
-    ctx->st.d2h_bytes += row_bytes * (size_t)rows;
+    const size_t total = row_bytes * (size_t)rows;
+    ctx->st.d2h_bytes += total;
+    if (host_is_pinned(ctx, host)) {
+        if (hstep == row_bytes)
+            MSG_CUDA(ctx, cudaMemcpyAsync(host, d, total, cudaMemcpyDeviceToHost, st));
+        else
+            MSG_CUDA(ctx, cudaMemcpy2DAsync(host, hstep, d, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, st));
+        return MSG_OK;
+    }
+    struct { int slot; size_t off, n; } fifo[MSG_RING_CHUNKS];
+    int head = 0, cnt = 0;
+    auto retire = [&]() -> int {
+        MSG_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[fifo[head].slot]));
+        ctx->ring_busy[fifo[head].slot] = 0;
+        host_scatter((uint8_t*)host, hstep, row_bytes, fifo[head].off, ctx->h_ring + (size_t)fifo[head].slot * MSG_RING_CHUNK_BYTES,
+                     fifo[head].n);
+        head = (head + 1) % MSG_RING_CHUNKS;
+        cnt--;
+        return MSG_OK;
+    };
+    for (size_t off = 0; off < total; off += MSG_RING_CHUNK_BYTES) {
+        const size_t n = total - off < MSG_RING_CHUNK_BYTES ? total - off : MSG_RING_CHUNK_BYTES;
+        if (cnt == MSG_RING_CHUNKS) MSG_TRY(retire());
+        int i;
+        MSG_TRY(ring_acquire(ctx, &i));
+        MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + (size_t)i * MSG_RING_CHUNK_BYTES, (const uint8_t*)d + off, n, cudaMemcpyDeviceToHost, st));
+        MSG_CUDA(ctx, cudaEventRecord(ctx->ring_ev[i], st));
+        ctx->ring_busy[i] = 1;
+        const int tail = (head + cnt) % MSG_RING_CHUNKS;
+        fifo[tail].slot = i; fifo[tail].off = off; fifo[tail].n = n;
+        cnt++;
+    }
+    while (cnt) MSG_TRY(retire());
+    ctx->st.staged_bytes += total;
     return MSG_OK;
 }
 
@@ -362,6 +583,7 @@ static int check_img(msg_ctx* ctx, const void* p, size_t step, int w, int h, int
     if (!p) return msg_fail(ctx, MSG_EINVAL, "%s: null pointer", what);
     if (step < (size_t)w * elem) return msg_fail(ctx, MSG_EINVAL, "%s: step %zu < row bytes %zu", what, step, (size_t)w * elem);
     if ((long long)w * h > 0x7fffffffLL - 1) return msg_fail(ctx, MSG_EINVAL, "%s: more than 2^31-2 pixels", what);
+    if (h > 65535) return msg_fail(ctx, MSG_EINVAL, "%s: more than 65535 rows (image rows map to gridDim.y)", what);
     return MSG_OK;
 }
 
@@ -588,8 +810,7 @@ int msg_merge_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* la
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     MSG_TRY(copy_in(ctx, bgr, step, rb, h, &ctx->d_in, &ctx->d_in_cap));
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
-    MSG_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_labels, (size_t)w * 4, labels, lstep, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->st.h2d_bytes += (size_t)w * 4 * h;
+    MSG_TRY(upload_on(ctx, ctx->stream, labels, lstep, (size_t)w * 4, h, (uint8_t*)ctx->d_labels));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     msg_plane s;
     s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
@@ -620,8 +841,7 @@ int msg_render_labels(msg_ctx* ctx, const int32_t* labels, size_t lstep, uint8_t
     size_t rb = (size_t)w * 3;
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
-    MSG_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_labels, (size_t)w * 4, labels, lstep, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->st.h2d_bytes += (size_t)w * 4 * h;
+    MSG_TRY(upload_on(ctx, ctx->stream, labels, lstep, (size_t)w * 4, h, (uint8_t*)ctx->d_labels));
     const uint8_t* d_colors = nullptr;
     if (colors && depth > 0) {
         MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_colors, &ctx->d_colors_cap, (size_t)depth * 3));
@@ -645,39 +865,44 @@ int msg_render_labels(msg_ctx* ctx, const int32_t* labels, size_t lstep, uint8_t
 
 // ============================================================================ fused pipeline
 
-// Device core of the fused pipeline.  All pointers are device pointers; any output may be NULL.
+// Device core of the fused pipeline.  All pointers are device pointers; any output may be NULL.  d_labels is int32_t* or,
+// with labels_type = MSG_LABELS_16U, uint16_t* (lstep in bytes).  d_stats (optional): 4 int32 receiving the mean-shift
+// statistics of THIS frame (active items u64, overflow items u64) in stream order, so that pipelined frames do not read each
+// other's counters.
 // Events: ev[1] start, ev[2] after filter, ev[3] after label, ev[4] after merge, ev[5] after render.
 static int segment_core_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, int w, int h, const msg_segment_params* p,
-                            const ms_config& cfg, uint8_t* d_filtered, size_t fstep, int32_t* d_labels, size_t lstep,
-                            uint8_t* d_rendered, size_t rstep, int32_t* d_n)
+                            const ms_config& cfg, uint8_t* d_filtered, size_t fstep, void* d_labels, size_t lstep,
+                            uint8_t* d_rendered, size_t rstep, int32_t* d_n, int32_t* d_stats)
 {
+    const bool l16 = p->labels_type == MSG_LABELS_16U;
     const bool do_label = p->lo_diff >= 0 && (d_labels || d_rendered || d_n);
     const bool do_merge = do_label && (p->min_size > 0 || p->color_dist > 0);
     const bool do_render = do_label && p->render_depth >= 0 && d_rendered;
     cudaStream_t st = ctx->stream;
-    if (d_labels && lstep % 4) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of 4");
+    if (d_labels && lstep % (l16 ? 2 : 4)) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of the label size");
     if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     MSG_TRY(ms_run(ctx, d_src, sstep, w, h, 0, h, cfg));
+    if (d_stats) MSG_CUDA(ctx, cudaMemcpyAsync(d_stats, ctx->d_counters + 2, 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (d_filtered) MSG_TRY(k_plane_to_bgr(ctx, ctx->D[0], 0, h, d_filtered, fstep));
     if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     int32_t* n_dev = d_n ? d_n : ctx->d_counters + 17;
     int32_t* work = nullptr;
-    const bool dense = d_labels && lstep == (size_t)w * 4;
+    const bool dense = d_labels && !l16 && lstep == (size_t)w * 4;
     if (do_label) {
-        work = d_labels;
+        work = (int32_t*)d_labels;
         if (!dense) {
             MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
             work = ctx->d_labels;
         }
-        MSG_TRY(k_ccl_color(ctx, ctx->D[0].p, ctx->D[0].pitch, w, h, p->lo_diff, p->connectivity == 8 ? 8 : 4, work, -1, w));
-        MSG_TRY(k_relabel_canonical(ctx, work, w, h, 1, n_dev, 0));
+        MSG_TRY(k_label_canonical(ctx, ctx->D[0].p, ctx->D[0].pitch, w, h, p->lo_diff, p->connectivity == 8 ? 8 : 4, work, n_dev));
     } else if (d_n) {
         MSG_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int32_t), st));
     }
     if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     if (do_merge) MSG_TRY(k_merge(ctx, ctx->D[0].p, ctx->D[0].pitch, work, w, h, p->min_size, p->color_dist, n_dev, n_dev));
     if (!ctx->no_events) MSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    if (do_label && d_labels && !dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
+    if (do_label && d_labels && l16) MSG_TRY(k_labels_to_u16(ctx, work, w, h, (uint16_t*)d_labels, lstep));
+    else if (do_label && d_labels && !dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, (int32_t*)d_labels, lstep, w, h));
     if (do_render) {
         int depth = p->render_depth > 0 ? p->render_depth : 0x7fffffff;   // 0: every region renders
         MSG_TRY(k_render(ctx, work, (size_t)w * 4, d_rendered, rstep, w, h, depth, nullptr));
@@ -687,13 +912,15 @@ static int segment_core_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, in
 }
 
 static int segment_validate(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
-                            uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered, size_t rstep,
+                            uint8_t* filtered, size_t fstep, void* labels, size_t lstep, uint8_t* rendered, size_t rstep,
                             ms_config* cfg)
 {
     MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "segment src"));
     if (!p) return msg_fail(ctx, MSG_EINVAL, "segment: params is NULL");
+    if (p->labels_type != MSG_LABELS_32S && p->labels_type != MSG_LABELS_16U)
+        return msg_fail(ctx, MSG_EINVAL, "segment: labels_type must be MSG_LABELS_32S or MSG_LABELS_16U");
     if (filtered) MSG_TRY(check_img(ctx, filtered, fstep, w, h, 3, "segment filtered"));
-    if (labels) MSG_TRY(check_img(ctx, labels, lstep, w, h, 4, "segment labels"));
+    if (labels) MSG_TRY(check_img(ctx, labels, lstep, w, h, p->labels_type == MSG_LABELS_16U ? 2 : 4, "segment labels"));
     if (rendered) MSG_TRY(check_img(ctx, rendered, rstep, w, h, 3, "segment rendered"));
     MSG_TRY(ms_validate(ctx, w, h, p->sp, p->sr, p->max_level, p->term_type, p->max_count, p->eps, cfg));
     if (p->min_size < 0 || p->color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
@@ -702,26 +929,32 @@ static int segment_validate(msg_ctx* ctx, const uint8_t* src, size_t sstep, int 
 }
 
 static int segment_enqueue(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
-                           uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered,
+                           uint8_t* filtered, size_t fstep, void* labels, size_t lstep, uint8_t* rendered,
                            size_t rstep, int32_t* h_n_slot)
 {
     ms_config cfg;
     MSG_TRY(segment_validate(ctx, src, sstep, w, h, p, filtered, fstep, labels, lstep, rendered, rstep, &cfg));
     const bool do_label = p->lo_diff >= 0;
     const bool do_render = do_label && p->render_depth >= 0 && rendered;
-    size_t rb = (size_t)w * 3;
+    const bool l16 = p->labels_type == MSG_LABELS_16U;
+    const size_t rb = (size_t)w * 3, lb = (size_t)w * (l16 ? 2 : 4);
     cudaStream_t st = ctx->stream;
-    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    MSG_TRY(copy_in(ctx, src, sstep, rb, h, &ctx->d_in, &ctx->d_in_cap));
+    // every allocation before the first enqueue: a failed reservation must not leave a DMA reading the caller's buffer
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, rb * h));
     if (filtered) MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, rb * h));
     if (do_label) MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
+    if (do_label && labels && l16) MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_aux, &ctx->d_aux_cap, lb * h));
     if (do_render) MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out2, &ctx->d_out2_cap, rb * h));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    MSG_TRY(upload_on(ctx, st, src, sstep, rb, h, ctx->d_in));
     int32_t* d_n = ctx->d_counters + 16;
-    MSG_TRY(segment_core_dev(ctx, ctx->d_in, rb, w, h, p, cfg, filtered ? ctx->d_out : nullptr, rb,
-                             do_label ? ctx->d_labels : nullptr, (size_t)w * 4, do_render ? ctx->d_out2 : nullptr, rb, d_n));
+    void* d_lab_out = !do_label ? nullptr : (l16 ? (labels ? (void*)ctx->d_aux : nullptr) : (void*)ctx->d_labels);
+    int rc = segment_core_dev(ctx, ctx->d_in, rb, w, h, p, cfg, filtered ? ctx->d_out : nullptr, rb, d_lab_out, lb,
+                              do_render ? ctx->d_out2 : nullptr, rb, d_n, nullptr);
+    if (rc != MSG_OK) { cudaStreamSynchronize(st); return rc; }      // the upload may still be reading the caller's buffer
     // all downloads last, so the stage timings are clean
     if (filtered) MSG_TRY(copy_out(ctx, filtered, fstep, ctx->d_out, rb, h));
-    if (do_label && labels) MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
+    if (do_label && labels) MSG_TRY(copy_out(ctx, labels, lstep, d_lab_out, lb, h));
     if (do_render) MSG_TRY(copy_out(ctx, rendered, rstep, ctx->d_out2, rb, h));
     MSG_CUDA(ctx, cudaMemcpyAsync(h_n_slot, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MSG_TRY(fetch_ms_stats(ctx));
@@ -730,23 +963,17 @@ static int segment_enqueue(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w
 }
 
 int msg_segment_dev(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, int w, int h, const msg_segment_params* p,
-                    uint8_t* d_filtered, size_t fstep, int32_t* d_labels, size_t lstep, uint8_t* d_rendered, size_t rstep,
+                    uint8_t* d_filtered, size_t fstep, void* d_labels, size_t lstep, uint8_t* d_rendered, size_t rstep,
                     int32_t* d_n)
 {
     CTX_ENTER(ctx);
-    MSG_TRY(check_img(ctx, d_src, sstep, w, h, 3, "segment src"));
-    if (!p) return msg_fail(ctx, MSG_EINVAL, "segment: params is NULL");
-    if (d_filtered) MSG_TRY(check_img(ctx, d_filtered, fstep, w, h, 3, "segment filtered"));
-    if (d_labels) MSG_TRY(check_img(ctx, d_labels, lstep, w, h, 4, "segment labels"));
-    if (d_rendered) MSG_TRY(check_img(ctx, d_rendered, rstep, w, h, 3, "segment rendered"));
     ms_config cfg;
-    MSG_TRY(ms_validate(ctx, w, h, p->sp, p->sr, p->max_level, p->term_type, p->max_count, p->eps, &cfg));
-    if (p->min_size < 0 || p->color_dist < 0) return msg_fail(ctx, MSG_EINVAL, "min_size and color_dist must be >= 0");
-    return segment_core_dev(ctx, d_src, sstep, w, h, p, cfg, d_filtered, fstep, d_labels, lstep, d_rendered, rstep, d_n);
+    MSG_TRY(segment_validate(ctx, d_src, sstep, w, h, p, d_filtered, fstep, d_labels, lstep, d_rendered, rstep, &cfg));
+    return segment_core_dev(ctx, d_src, sstep, w, h, p, cfg, d_filtered, fstep, d_labels, lstep, d_rendered, rstep, d_n, nullptr);
 }
 
 int msg_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
-                uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered, size_t rstep,
+                uint8_t* filtered, size_t fstep, void* labels, size_t lstep, uint8_t* rendered, size_t rstep,
                 int32_t* n_regions)
 {
     CTX_ENTER(ctx);
@@ -762,11 +989,13 @@ int msg_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, co
     ctx->tm.render_ms = ev_ms(ctx->ev[4], ctx->ev[5]);
     ctx->tm.d2h_ms = ev_ms(ctx->ev[5], ctx->ev[6]);
     ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[6]);
+    if (labels && p->labels_type == MSG_LABELS_16U && ctx->h_counters[16] > 65535)
+        return msg_fail(ctx, MSG_ERANGE, "segment: %d regions do not fit 16-bit labels", ctx->h_counters[16]);
     return MSG_OK;
 }
 
 int msg_submit_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, int h, const msg_segment_params* p,
-                       uint8_t* filtered, size_t fstep, int32_t* labels, size_t lstep, uint8_t* rendered, size_t rstep,
+                       uint8_t* filtered, size_t fstep, void* labels, size_t lstep, uint8_t* rendered, size_t rstep,
                        int* ticket)
 {
     CTX_ENTER(ctx);
@@ -782,34 +1011,62 @@ int msg_submit_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, in
     msg_ctx::pending& q = ctx->pend[slot];
     const bool do_label = p->lo_diff >= 0;
     const bool do_render = do_label && p->render_depth >= 0 && rendered;
-    const size_t rb = (size_t)w * 3;
-    MSG_TRY(copy_in_on(ctx, ctx->h2d_stream, src, sstep, rb, h, &q.d_in, &q.d_in_cap));
-    MSG_CUDA(ctx, cudaEventRecord(q.ev_in, ctx->h2d_stream));
+    const bool l16 = p->labels_type == MSG_LABELS_16U;
+    const size_t rb = (size_t)w * 3, lb = (size_t)w * (l16 ? 2 : 4);
+    // ---- every reservation first (device buffers of the frame, pinned staging for pageable destinations): a failure here
+    //      returns before anything touches the caller's buffers
+    MSG_TRY(msg_reserve(ctx, (void**)&q.d_in, &q.d_in_cap, rb * h));
     if (filtered) MSG_TRY(msg_reserve(ctx, (void**)&q.d_filt, &q.d_filt_cap, rb * h));
-    if (do_label) MSG_TRY(msg_reserve(ctx, (void**)&q.d_lab, &q.d_lab_cap, (size_t)w * h * 4));
+    if (do_label && !l16) MSG_TRY(msg_reserve(ctx, (void**)&q.d_lab, &q.d_lab_cap, (size_t)w * h * 4));
+    if (do_label && labels && l16) MSG_TRY(msg_reserve(ctx, (void**)&q.d_lab16, &q.d_lab16_cap, lb * h));
     if (do_render) MSG_TRY(msg_reserve(ctx, (void**)&q.d_ren, &q.d_ren_cap, rb * h));
-    int32_t* d_n = ctx->d_counters + 40 + slot;
+    struct out_desc { void* host; size_t hstep; const void* dev; size_t row_bytes; bool staged; size_t off; } outs[3];
+    int n_out = 0;
+    size_t stage_bytes = 0;
+    auto add_out = [&](void* host, size_t hstep, const void* dev, size_t row_bytes) {
+        out_desc& o = outs[n_out++];
+        o.host = host; o.hstep = hstep; o.dev = dev; o.row_bytes = row_bytes;
+        o.staged = !host_is_pinned(ctx, host);
+        o.off = stage_bytes;
+        if (o.staged) stage_bytes += (row_bytes * (size_t)h + 255) & ~(size_t)255;
+    };
+    if (filtered) add_out(filtered, fstep, q.d_filt, rb);
+    if (do_label && labels) add_out(labels, lstep, l16 ? (const void*)q.d_lab16 : (const void*)q.d_lab, lb);
+    if (do_render) add_out(rendered, rstep, q.d_ren, rb);
+    if (stage_bytes > q.h_out_cap) {
+        if (q.h_out) { cudaFreeHost(q.h_out); q.h_out = nullptr; q.h_out_cap = 0; }
+        cudaError_t e = cudaMallocHost((void**)&q.h_out, stage_bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); q.h_out = nullptr; return msg_fail(ctx, MSG_ENOMEM, "pinned output staging (%zu bytes): %s", stage_bytes, cudaGetErrorString(e)); }
+        q.h_out_cap = stage_bytes;
+    }
+    // ---- upload
+    MSG_TRY(upload_on(ctx, ctx->h2d_stream, src, sstep, rb, h, q.d_in));
+    MSG_CUDA(ctx, cudaEventRecord(q.ev_in, ctx->h2d_stream));
+    int32_t* d_n = q.d_cnt;
     MSG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, q.ev_in, 0));
     // The kernel sequence of a frame is fixed by (geometry, parameters, buffers): replay it as a CUDA graph.  The first
     // submission of a configuration runs eagerly (it sizes the workspace), the second is captured, later ones replay.
     unsigned char key[sizeof(q.g_key)];
     memset(key, 0, sizeof(key));
+    void* d_lab_out = !do_label ? nullptr : (l16 ? (labels ? (void*)q.d_lab16 : nullptr) : (void*)q.d_lab);
     {
         size_t o = 0;
         auto put = [&](const void* v, size_t nbytes) { memcpy(key + o, v, nbytes); o += nbytes; };
-        const void* ptrs[6] = {q.d_in, filtered ? q.d_filt : nullptr, do_label ? q.d_lab : nullptr, do_render ? q.d_ren : nullptr,
-                               (void*)ctx->stream, d_n};
+        const void* ptrs[7] = {q.d_in, filtered ? q.d_filt : nullptr, (do_label && !l16) ? q.d_lab : nullptr, d_lab_out,
+                               do_render ? q.d_ren : nullptr, (void*)ctx->stream, d_n};
         const double dv[3] = {p->sp, p->sr, p->eps};
-        const int iv[10] = {w, h, p->max_level, p->term_type, p->max_count, p->lo_diff, p->min_size, p->color_dist,
-                            p->render_depth, p->connectivity};
+        const int iv[11] = {w, h, p->max_level, p->term_type, p->max_count, p->lo_diff, p->min_size, p->color_dist,
+                            p->render_depth, p->connectivity, p->labels_type};
         put(dv, sizeof(dv)); put(iv, sizeof(iv)); put(ptrs, sizeof(ptrs));     // field by field: no struct padding in the key
         static_assert(sizeof(dv) + sizeof(iv) + sizeof(ptrs) <= sizeof(q.g_key), "graph key too small");
     }
-    static const bool graphs_off = getenv("MSG_NO_GRAPH") != nullptr;
+    const bool graphs_off = ctx->tune.no_graph != 0;
     const bool same = q.g_state > 0 && memcmp(key, q.g_key, sizeof(key)) == 0 && q.g_epoch == ctx->ws_epoch;
     auto run_core = [&]() {
-        return segment_core_dev(ctx, q.d_in, rb, w, h, p, cfg, filtered ? q.d_filt : nullptr, rb, do_label ? q.d_lab : nullptr,
-                                (size_t)w * 4, do_render ? q.d_ren : nullptr, rb, d_n);
+        // with 16-bit labels the int32 working map stays in the context workspace; only the converted map belongs to the frame
+        return segment_core_dev(ctx, q.d_in, rb, w, h, p, cfg, filtered ? q.d_filt : nullptr, rb,
+                                l16 ? d_lab_out : (void*)(do_label ? q.d_lab : nullptr), lb, do_render ? q.d_ren : nullptr, rb, d_n,
+                                q.d_cnt + 2);
     };
     ctx->no_events = 1;
     int rc = MSG_OK;
@@ -831,7 +1088,7 @@ int msg_submit_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, in
                 q.g_launches = ctx->st.kernel_launches - l0;
                 ctx->st.kernel_launches = l0;        // counted again below, when the graph is launched
             } else {                                 // capture not possible here: stay on the eager path for this slot
-                if (getenv("MSG_GRAPH_DEBUG"))
+                if (ctx->tune.graph_debug)
                     fprintf(stderr, "[msegment] graph capture failed: begin=%s core=%d end=%s\n", cudaGetErrorString(e), crc,
                             cudaGetErrorString(e2));
                 cudaGetLastError();
@@ -843,24 +1100,45 @@ int msg_submit_segment(msg_ctx* ctx, const uint8_t* src, size_t sstep, int w, in
         }
         if (q.g_state == 2) {
             cudaError_t e = cudaGraphLaunch(q.g_exec, ctx->stream);
-            if (e != cudaSuccess) { ctx->no_events = 0; ctx->cuda_failed = 1; return msg_fail(ctx, MSG_ECUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); }
+            if (e != cudaSuccess) {
+                ctx->no_events = 0; ctx->cuda_failed = 1;
+                cudaStreamSynchronize(ctx->h2d_stream);
+                return msg_fail(ctx, MSG_ECUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+            }
             ctx->st.kernel_launches += q.g_launches;
         } else {
             rc = run_core();
         }
     }
     ctx->no_events = 0;
-    if (rc != MSG_OK) return rc;
+    if (rc != MSG_OK) {
+        cudaStreamSynchronize(ctx->h2d_stream);      // the caller is told the call failed: no DMA may still read its buffer
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
     MSG_CUDA(ctx, cudaEventRecord(q.ev_core, ctx->stream));
     cudaStream_t ds = ctx->d2h_stream;
     MSG_CUDA(ctx, cudaStreamWaitEvent(ds, q.ev_core, 0));
-    if (filtered) MSG_TRY(copy_out_on(ctx, ds, filtered, fstep, q.d_filt, rb, h));
-    if (do_label && labels) MSG_TRY(copy_out_on(ctx, ds, labels, lstep, q.d_lab, (size_t)w * 4, h));
-    if (do_render) MSG_TRY(copy_out_on(ctx, ds, rendered, rstep, q.d_ren, rb, h));
-    MSG_CUDA(ctx, cudaMemcpyAsync(q.n_regions_host, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, ds));
-    MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ds));
+    q.n_defer = 0;
+    for (int k = 0; k < n_out; k++) {
+        const out_desc& o = outs[k];
+        const size_t total = o.row_bytes * (size_t)h;
+        if (!o.staged) {
+            if (o.hstep == o.row_bytes) MSG_CUDA(ctx, cudaMemcpyAsync(o.host, o.dev, total, cudaMemcpyDeviceToHost, ds));
+            else MSG_CUDA(ctx, cudaMemcpy2DAsync(o.host, o.hstep, o.dev, o.row_bytes, o.row_bytes, h, cudaMemcpyDeviceToHost, ds));
+        } else {   // pageable destination: DMA into the frame's pinned staging now, memcpy to the caller inside msg_wait
+            MSG_CUDA(ctx, cudaMemcpyAsync(q.h_out + o.off, o.dev, total, cudaMemcpyDeviceToHost, ds));
+            q.defer[q.n_defer].dst = o.host; q.defer[q.n_defer].dstep = o.hstep; q.defer[q.n_defer].off = o.off;
+            q.defer[q.n_defer].row_bytes = o.row_bytes; q.defer[q.n_defer].rows = h;
+            q.n_defer++;
+            ctx->st.staged_bytes += total;
+        }
+        ctx->st.d2h_bytes += total;
+    }
+    MSG_CUDA(ctx, cudaMemcpyAsync(q.h_cnt, q.d_cnt, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ds));
     MSG_CUDA(ctx, cudaEventRecord(q.done, ds));
-    ctx->pend[slot].used = 1;
+    q.l16 = (labels && l16) ? 1 : 0;
+    q.used = 1;
     *ticket = slot;
     return MSG_OK;
 }
@@ -870,10 +1148,68 @@ int msg_wait(msg_ctx* ctx, int ticket, int32_t* n_regions)
     CTX_ENTER(ctx);
     if (ticket < 0 || ticket >= MSG_MAX_INFLIGHT || !ctx->pend[ticket].used)
         return msg_fail(ctx, MSG_ESTATE, "wait: invalid ticket %d", ticket);
-    MSG_CUDA(ctx, cudaEventSynchronize(ctx->pend[ticket].done));
-    ctx->pend[ticket].used = 0;
-    if (n_regions) *n_regions = *ctx->pend[ticket].n_regions_host;
-    publish_ms_stats(ctx);
+    msg_ctx::pending& q = ctx->pend[ticket];
+    q.used = 0;                                      // whatever happens below, the slot is free again
+    MSG_CUDA(ctx, cudaEventSynchronize(q.done));
+    for (int k = 0; k < q.n_defer; k++)
+        host_scatter((uint8_t*)q.defer[k].dst, q.defer[k].dstep, q.defer[k].row_bytes, 0, q.h_out + q.defer[k].off,
+                     q.defer[k].row_bytes * (size_t)q.defer[k].rows);
+    q.n_defer = 0;
+    const int32_t n = q.h_cnt[0];
+    if (n_regions) *n_regions = n;
+    unsigned long long a, o;
+    memcpy(&a, q.h_cnt + 2, 8);
+    memcpy(&o, q.h_cnt + 4, 8);
+    ctx->st.ms_active_items = a;
+    ctx->st.ms_overflow_items = o;
+    if (q.l16 && n > 65535) return msg_fail(ctx, MSG_ERANGE, "wait: %d regions do not fit 16-bit labels", n);
+    return MSG_OK;
+}
+
+// ============================================================================ watershed (f1)
+
+int msg_watershed_batch_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, size_t image_stride, int32_t* d_markers, size_t mstep,
+                            size_t markers_stride, int w, int h, int count, unsigned long long* d_pops)
+{
+    CTX_ENTER(ctx);
+    if (count < 1 || count > 65535) return msg_fail(ctx, MSG_EINVAL, "watershed: count must be in [1, 65535]");
+    MSG_TRY(check_img(ctx, d_bgr, step, w, h, 3, "watershed image"));
+    MSG_TRY(check_img(ctx, d_markers, mstep, w, h, 4, "watershed markers"));
+    if (mstep % 4 || markers_stride % 4) return msg_fail(ctx, MSG_EINVAL, "watershed: marker steps must be multiples of 4");
+    if (count > 1 && (image_stride < step * (size_t)h || markers_stride < mstep * (size_t)h))
+        return msg_fail(ctx, MSG_EINVAL, "watershed: batch strides smaller than one image");
+    return k_watershed(ctx, d_bgr, step, image_stride, d_markers, mstep, markers_stride, w, h, count, d_pops);
+}
+
+int msg_watershed_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32_t* d_markers, size_t mstep, int w, int h)
+{
+    return msg_watershed_batch_dev(ctx, d_bgr, step, 0, d_markers, mstep, 0, w, h, 1, nullptr);
+}
+
+int msg_watershed(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* markers, size_t mstep, int w, int h)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, bgr, step, w, h, 3, "watershed image"));
+    MSG_TRY(check_img(ctx, markers, mstep, w, h, 4, "watershed markers"));
+    const size_t rb = (size_t)w * 3, lb = (size_t)w * 4;
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, rb * h));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, lb * h));
+    cudaStream_t st = ctx->stream;
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    MSG_TRY(upload_on(ctx, st, bgr, step, rb, h, ctx->d_in));
+    MSG_TRY(upload_on(ctx, st, markers, mstep, lb, h, (uint8_t*)ctx->d_labels));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    int rc = k_watershed(ctx, ctx->d_in, rb, 0, ctx->d_labels, lb, 0, w, h, 1, nullptr);
+    if (rc != MSG_OK) { cudaStreamSynchronize(st); return rc; }
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    MSG_TRY(copy_out(ctx, markers, mstep, ctx->d_labels, lb, h));
+    MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    MSG_CUDA(ctx, cudaStreamSynchronize(st));
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    ctx->tm.h2d_ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->tm.filter_ms = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->tm.d2h_ms = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->tm.total_ms = ev_ms(ctx->ev[0], ctx->ev[3]);
     return MSG_OK;
 }
 
@@ -1169,11 +1505,29 @@ int msg_subtract(msg_ctx* ctx, const uint8_t* a, size_t astep, const uint8_t* b,
     size_t n = (size_t)w * h;
     MSG_TRY(copy_in(ctx, a, astep, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_aux, &ctx->d_aux_cap, n));
-    MSG_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_aux, (size_t)w, b, bstep, (size_t)w, h, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->st.h2d_bytes += n;
+    MSG_TRY(upload_on(ctx, ctx->stream, b, bstep, (size_t)w, h, ctx->d_aux));
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, n));
     MSG_TRY(k_subtract(ctx, ctx->d_in, (size_t)w, ctx->d_aux, (size_t)w, ctx->d_out, (size_t)w, w, h));
     MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w, h));
+    MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSG_OK;
+}
+
+int msg_copy_masked(msg_ctx* ctx, const uint8_t* src, size_t sstep, const uint8_t* mask, size_t mstep, uint8_t* dst, size_t dstep,
+                    int w, int h)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, src, sstep, w, h, 3, "copyTo src"));
+    MSG_TRY(check_img(ctx, mask, mstep, w, h, 1, "copyTo mask"));
+    MSG_TRY(check_img(ctx, dst, dstep, w, h, 3, "copyTo dst"));
+    const size_t n = (size_t)w * h;
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, 3 * n));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_aux, &ctx->d_aux_cap, n));
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, 3 * n));
+    MSG_TRY(upload_on(ctx, ctx->stream, src, sstep, (size_t)w * 3, h, ctx->d_in));
+    MSG_TRY(upload_on(ctx, ctx->stream, mask, mstep, (size_t)w, h, ctx->d_aux));
+    MSG_TRY(k_copy_masked(ctx, ctx->d_in, (size_t)w * 3, ctx->d_aux, (size_t)w, ctx->d_out, (size_t)w * 3, w, h));
+    MSG_TRY(copy_out(ctx, dst, dstep, ctx->d_out, (size_t)w * 3, h));
     MSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MSG_OK;
 }

@@ -583,6 +583,26 @@ __global__ void __launch_bounds__(CCL_THREADS) strip_finalize_kernel(int32_t* __
 
 inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
+// dense int32 labels -> 16-bit labels, saturating (the caller reports MSG_ERANGE when the region count exceeds 65535)
+__global__ void __launch_bounds__(CCL_THREADS) labels_to_u16_kernel(const int32_t* __restrict__ L, int w, uint16_t* __restrict__ dst,
+                                                                   size_t dstep)
+{
+    int x = (blockIdx.x * CCL_THREADS + threadIdx.x) * 2;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const int32_t* s = L + (size_t)y * w;
+    uint16_t* d = (uint16_t*)((char*)dst + (size_t)y * dstep);
+    int a = s[x];
+    a = a < 0 ? 0 : (a > 65535 ? 65535 : a);
+    if (x + 1 < w) {
+        int b = s[x + 1];
+        b = b < 0 ? 0 : (b > 65535 ? 65535 : b);
+        if (((uintptr_t)(d + x) & 3) == 0) { *(uint32_t*)(d + x) = (uint32_t)a | ((uint32_t)b << 16); return; }
+        d[x + 1] = (uint16_t)b;
+    }
+    d[x] = (uint16_t)a;
+}
+
 // ---------------------------------------------------------------- Canny hysteresis on top of the binary union-find
 // cls: 0 none, 1 candidate, 2 strong candidate (k_seeds.cu).  L = union-find parents of the 8-connected candidate set.
 __global__ void __launch_bounds__(CCL_THREADS) hyst_mark_kernel(const uint8_t* __restrict__ cls, const int32_t* __restrict__ L,
@@ -804,4 +824,20 @@ int k_strip_finalize(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int r
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;
+}
+
+int k_labels_to_u16(msg_ctx* ctx, const int32_t* d_labels, int w, int h, uint16_t* d_dst, size_t dstep)
+{
+    dim3 grid(((w + 1) / 2 + CCL_THREADS - 1) / CCL_THREADS, h);
+    labels_to_u16_kernel<<<grid, CCL_THREADS, 0, ctx->stream>>>(d_labels, w, d_dst, dstep);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_label_canonical(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int conn, int32_t* d_labels,
+                      int32_t* d_n)
+{
+    MSG_TRY(k_ccl_color(ctx, d_plane, pitch, w, h, d, conn, d_labels, -1, w));
+    return k_relabel_canonical(ctx, d_labels, w, h, 1, d_n, 0);
 }

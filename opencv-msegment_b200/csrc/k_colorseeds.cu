@@ -592,11 +592,11 @@ int k_bilateral(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst
     size_t smem = (size_t)(32 + 2 * radius) * (8 + 2 * radius) * cn;
     dim3 grid((w + 31) / 32, (h + 7) / 8);
     if (cn == 1) {
-        MSG_CUDA(ctx, cudaFuncSetAttribute(bilateral_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MSG_TRY(msg_func_smem(ctx, (const void*)bilateral_kernel<1>, smem));
         bilateral_kernel<1><<<grid, 256, smem, ctx->stream>>>(d_src, sstep, d_dst, dstep, w, h, radius, maxk, d_space_w,
                                                              (const short2*)d_space_ofs, d_color_w);
     } else {
-        MSG_CUDA(ctx, cudaFuncSetAttribute(bilateral_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MSG_TRY(msg_func_smem(ctx, (const void*)bilateral_kernel<3>, smem));
         bilateral_kernel<3><<<grid, 256, smem, ctx->stream>>>(d_src, sstep, d_dst, dstep, w, h, radius, maxk, d_space_w,
                                                              (const short2*)d_space_ofs, d_color_w);
     }

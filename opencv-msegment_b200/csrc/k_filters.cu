@@ -14,11 +14,14 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
-__constant__ int8_t c_taps[1024];   // sharpen kernel taps (krows * kcols <= 1024)
+// sharpen kernel taps (krows * kcols <= 1024), passed BY VALUE as a kernel argument: several contexts per GPU may run
+// different kernels concurrently, so a shared __constant__ symbol would race between them
+struct sharpen_taps { int8_t t[1024]; };
 
 // dst = saturate_u8(src - sum_K taps * src), correlation, anchor at the kernel centre, BORDER_REFLECT_101
 __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict__ src, size_t sstep, uint8_t* __restrict__ dst,
-                                                      size_t dstep, int w, int h, int krows, int kcols)
+                                                      size_t dstep, int w, int h, int krows, int kcols,
+                                                      const __grid_constant__ sharpen_taps taps)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
@@ -29,7 +32,7 @@ __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict_
         const uint8_t* row = src + (size_t)reflect101(y + a - ay, h) * sstep;
         for (int b = 0; b < kcols; b++) {
             const uint8_t* p = row + 3 * (size_t)reflect101(x + b - ax, w);
-            int t = c_taps[a * kcols + b];
+            int t = taps.t[a * kcols + b];
             a0 += t * p[0]; a1 += t * p[1]; a2 += t * p[2];
         }
     }
@@ -41,13 +44,16 @@ __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict_
 }
 
 __global__ void __launch_bounds__(256) gray_kernel(const uint8_t* __restrict__ src, size_t sstep, uint8_t* __restrict__ dst,
-                                                   size_t dstep, int w)
+                                                   size_t dstep, int w, int compat342)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     if (x >= w) return;
     const uint8_t* p = src + (size_t)y * sstep + 3 * (size_t)x;
-    dst[(size_t)y * dstep + x] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15);
+    // OpenCV 4.x: 15-bit coefficients; OpenCV 3.4.2 (the version the reference binds, pom.xml:39-43): 14-bit ones
+    int g = compat342 ? (1868 * p[0] + 9617 * p[1] + 4899 * p[2] + 8192) >> 14
+                      : (3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15;
+    dst[(size_t)y * dstep + x] = (uint8_t)g;
 }
 
 // median of the k x k window (BORDER_REPLICATE): tile 32x8 + halo in shared memory, then 8 bisection steps on the value
@@ -87,9 +93,11 @@ __global__ void __launch_bounds__(MED_TW * MED_TH) median_kernel(const uint8_t* 
 int k_sharpen(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, const int8_t* taps,
               int krows, int kcols)
 {
-    MSG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_taps, taps, (size_t)krows * kcols, 0, cudaMemcpyHostToDevice, ctx->stream));
+    sharpen_taps t;
+    memset(&t, 0, sizeof(t));
+    memcpy(t.t, taps, (size_t)krows * kcols);
     dim3 grid((w + 255) / 256, h);
-    sharpen_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, sstep, d_dst, dstep, w, h, krows, kcols);
+    sharpen_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, sstep, d_dst, dstep, w, h, krows, kcols, t);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;
@@ -98,7 +106,7 @@ int k_sharpen(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, 
 int k_gray(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h)
 {
     dim3 grid((w + 255) / 256, h);
-    gray_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, sstep, d_dst, dstep, w);
+    gray_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, sstep, d_dst, dstep, w, ctx->tune.gray_compat);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;
@@ -108,7 +116,7 @@ int k_median(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, s
 {
     int r = k / 2;
     size_t smem = (size_t)(MED_TW + 2 * r) * (MED_TH + 2 * r);
-    MSG_CUDA(ctx, cudaFuncSetAttribute(median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSG_TRY(msg_func_smem(ctx, (const void*)median_kernel, smem));
     dim3 grid((w + MED_TW - 1) / MED_TW, (h + MED_TH - 1) / MED_TH);
     median_kernel<<<grid, MED_TW * MED_TH, smem, ctx->stream>>>(d_src, sstep, d_dst, dstep, w, h, k);
     MSG_LAUNCHED(ctx);

@@ -533,9 +533,8 @@ template <int NX, int TW, int ACC>
 cudaError_t launch_tile(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_params& prm, const tile_geom& g, int tiles,
                         size_t smem, int* ovf_count, unsigned long long* active, unsigned long long* work)
 {
-    // attribute is per function AND per device: set it on every launch (cheap, no sync)
-    cudaError_t e = cudaFuncSetAttribute(meanshift_tile_kernel<NX, TW, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    // attribute is per function AND per device: issued once per (kernel, size) and context (msg_func_smem caches it)
+    if (msg_func_smem(ctx, (const void*)meanshift_tile_kernel<NX, TW, ACC>, smem) != MSG_OK) return cudaErrorInvalidValue;
     meanshift_tile_kernel<NX, TW, ACC><<<tiles, TW * 4, smem, ctx->stream>>>(S, D, prm, g, ctx->d_ovf, ovf_count, active, work);
     return cudaGetLastError();
 }
@@ -574,8 +573,8 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     int TWsel = tiles64 >= (long long)ctx->sm_count ? 64 : 32;
     int acc = (prm.sp == (float)(int)prm.sp && 2 * (int)prm.sp + 1 >= 21) ? 0 : 1;
     // tuning overrides (experiments only): MSG_TILE_W = 32 | 64, MSG_ACC = 0 | 1
-    if (const char* e = getenv("MSG_TILE_W")) { int v = atoi(e); if (v == 32 || v == 64) TWsel = v; }
-    if (const char* e = getenv("MSG_ACC")) acc = atoi(e) ? 1 : 0;
+    if (ctx->tune.tile_w == 32 || ctx->tune.tile_w == 64) TWsel = ctx->tune.tile_w;
+    if (ctx->tune.acc >= 0) acc = ctx->tune.acc ? 1 : 0;
 
     // tile path limits: sentinel distance 254^2 must exceed isr2; staged tile must fit shared memory
     const int R = prm.radius;
@@ -595,8 +594,8 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
             // neighbouring rows land 8 banks apart (measured at 1080p, sp = 10: residue 8 / 24: 0.342 ms, 16: 0.359, 0: 0.425)
             g.swp = g.sw;
             while (g.swp % 32 != 8 && g.swp % 32 != 24) g.swp += 4;
-            if (const char* e = getenv("MSG_PITCH_RES")) {     // experiment switch: force the pitch residue mod 32 banks
-                const int want = atoi(e) & 28;
+            if (ctx->tune.pitch_res >= 0) {     // experiment switch: force the pitch residue mod 32 banks
+                const int want = ctx->tune.pitch_res & 28;
                 g.swp = g.sw;
                 while (g.swp % 32 != want) g.swp += 4;
             }
@@ -618,11 +617,10 @@ int k_meanshift_level(msg_ctx* ctx, msg_plane S, msg_plane D, const msg_ms_param
     MSG_CUDA(ctx, cudaMemsetAsync(ovf_count, 0, sizeof(int), ctx->stream));
     g.tiles_x = (S.w + TWsel - 1) / TWsel;
     g.order = nullptr;
-    g.use_tma = 1;
-    if (const char* e = getenv("MSG_TMA")) g.use_tma = atoi(e) ? 1 : 0;   // A/B switch (experiments)
+    g.use_tma = ctx->tune.use_tma;   // A/B switch (experiments)
     int tiles_y = (S.rows + TH - 1) / TH;
     int tiles = g.tiles_x * tiles_y;
-    if (prm.use_mask && ctx->d_cells && !getenv("MSG_NO_ORDER")) {
+    if (prm.use_mask && ctx->d_cells && !ctx->tune.no_order) {
         int cells_x = (S.w + 31) / 32, cells_y = (S.rows + 31) / 32;
         int* order = ctx->d_cells + (size_t)cells_x * cells_y;       // second half of the cell buffer
         tile_order_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_cells, cells_x, cells_y, g.tiles_x, tiles_y, TWsel / 32, order);

@@ -739,9 +739,8 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     A.rounds_out = ctx->d_counters + 10;
     A.n_out = d_n_out ? d_n_out : ctx->d_counters + 11;
     A.min_size = min_size; A.color_dist = color_dist;
-    A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !getenv("MSG_MERGE_SCALAR")) ? 1 : 0;
-    const char* sm_env = getenv("MSG_MERGE_SMALL_MAX");            // test hook: 0 forces the cooperative path
-    A.small_max = sm_env ? atoi(sm_env) : SMALL_MAX_LABELS;
+    A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !ctx->tune.merge_scalar) ? 1 : 0;
+    A.small_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : SMALL_MAX_LABELS;   // test hook: 0 forces the cooperative path
     if (A.small_max > SMALL_MAX_LABELS) A.small_max = SMALL_MAX_LABELS;
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;                              // CTAs of the streaming kernels (grid-stride)
@@ -752,7 +751,7 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     merge_stats_kernel<<<blocks_for(stat_threads), MT, 0, st>>>(A);
     MSG_LAUNCHED(ctx);
     const size_t small_smem = ((size_t)(SMALL_MAX_LABELS + 1) * 7 + SMALL_HSET) * sizeof(uint32_t);
-    MSG_CUDA(ctx, cudaFuncSetAttribute(merge_rounds_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+    MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel, small_smem));
     merge_rounds_small_kernel<<<1, ST, small_smem, st>>>(A);
     MSG_LAUNCHED(ctx);
     void* args[] = {&A};

@@ -104,7 +104,30 @@ __global__ void __launch_bounds__(256) subtract_kernel(const uint8_t* __restrict
     dst[(size_t)y * dstep + x] = (uint8_t)max(v, 0);
 }
 
+// Mat.copyTo(dst, mask) onto a zero Mat (PictureService.java:417-418, the "borders" step): dst = mask ? src : 0
+__global__ void __launch_bounds__(256) copy_masked_kernel(const uint8_t* __restrict__ src, size_t sstep, const uint8_t* __restrict__ mask,
+                                                          size_t mstep, uint8_t* __restrict__ dst, size_t dstep, int w)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const bool on = mask[(size_t)y * mstep + x] != 0;
+    const uint8_t* s = src + (size_t)y * sstep + 3 * (size_t)x;
+    uint8_t* d = dst + (size_t)y * dstep + 3 * (size_t)x;
+    d[0] = on ? s[0] : 0; d[1] = on ? s[1] : 0; d[2] = on ? s[2] : 0;
+}
+
 }  // namespace
+
+int k_copy_masked(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, const uint8_t* d_mask, size_t mstep, uint8_t* d_dst, size_t dstep,
+                  int w, int h)
+{
+    dim3 grid((w + 255) / 256, h);
+    copy_masked_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, sstep, d_mask, mstep, d_dst, dstep, w);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
 
 int k_canny_nms(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_cls, size_t cstep, int w, int h, int low, int high)
 {
@@ -118,7 +141,7 @@ int k_canny_nms(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_cls
 int k_dilate(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, int kw, int kh)
 {
     size_t smem = (size_t)(DL_TW + kw - 1) * (DL_TH + kh - 1);
-    MSG_CUDA(ctx, cudaFuncSetAttribute(dilate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSG_TRY(msg_func_smem(ctx, (const void*)dilate_kernel, smem));
     dim3 grid((w + DL_TW - 1) / DL_TW, (h + DL_TH - 1) / DL_TH);
     dilate_kernel<<<grid, DL_TW * DL_TH, smem, ctx->stream>>>(d_src, sstep, d_dst, dstep, w, h, kw, kh);
     MSG_LAUNCHED(ctx);

@@ -41,8 +41,35 @@ struct msg_ovf_item {    // mean-shift item that left its staged tile; finished 
     uint32_t iter;       // iterations already done
 };
 
+// Tuning / experiment switches.  Read from the environment ONCE in msg_create (MSG_TILE_W, MSG_ACC, MSG_PITCH_RES, MSG_TMA,
+// MSG_NO_ORDER, MSG_MERGE_SCALAR, MSG_MERGE_SMALL_MAX, MSG_NO_GRAPH, MSG_GRAPH_DEBUG, MSG_CCL_LEGACY) and changeable per context
+// with msg_set_option; nothing on the launch path calls getenv.
+struct msg_tuning {
+    int tile_w;            // 0 = automatic, else 32 | 64
+    int acc;               // -1 = automatic, else 0 | 1
+    int pitch_res;         // -1 = automatic, else forced residue of the staged row pitch mod 32 banks
+    int use_tma;           // 1
+    int no_order;          // 0
+    int merge_scalar;      // 0
+    int merge_small_max;   // -1 = compiled default
+    int no_graph, graph_debug;
+    int ccl_legacy;        // 1 = row-run union-find of round 1 instead of the tile-local one
+    int gray_compat;       // 0 = OpenCV 4.x 15-bit BGR2GRAY coefficients, 1 = OpenCV 3.4.2 14-bit ones
+    int dt_fixed;          // 0 = IPP float chamfer arithmetic (cv2 4.13 build), 1 = OpenCV's own 16.16 fixed-point fallback
+    int staging;           // 1 = pageable caller buffers go through the pinned staging ring (0: handed to cudaMemcpyAsync as is)
+};
+
+// Pinned staging ring for pageable caller buffers (SURVEY 8(b) "Ownership"): MSG_RING_CHUNKS chunks, each with the event of the
+// DMA that last used it.
+#define MSG_RING_CHUNKS 4
+#define MSG_RING_CHUNK_BYTES ((size_t)4 << 20)
+
 struct msg_ctx {
     int device;
+    msg_tuning tune;
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is issued once per (kernel, size) and context, not per launch
+    struct { const void* func; size_t smem; } attr_cache[64];
+    int n_attr;
     cudaStream_t own_stream;
     cudaStream_t stream;
     cudaEvent_t ev[8];
@@ -64,10 +91,17 @@ struct msg_ctx {
     uint8_t* d_colors; size_t d_colors_cap;
     uint8_t* d_aux;    size_t d_aux_cap;     // 8-bit planes of the seed generator (gray, blurred, classes, edges, ...)
     uint8_t* d_small;  size_t d_small_cap;   // small tables of the colour-seed generator / bilateral filter (histogram, spans, weights)
+    uint8_t* d_ws;     size_t d_ws_cap;      // watershed queues / per-image state (k_watershed.cu)
     int32_t* d_cells;  size_t d_cells_cap;   // active pixels per 32x32 cell of the current level + tile order (K1 scheduling)
 
-    // pinned host staging for pageable caller buffers
-    uint8_t* h_stage; size_t h_stage_cap;
+    // pinned host staging for pageable caller buffers: a small ring for uploads and synchronous downloads
+    uint8_t* h_ring;                          // MSG_RING_CHUNKS * MSG_RING_CHUNK_BYTES, allocated on first use
+    cudaEvent_t ring_ev[MSG_RING_CHUNKS];
+    int ring_busy[MSG_RING_CHUNKS];
+    int ring_next;
+    // explicitly registered caller ranges (msg_register_host): treated as pinned
+    struct { const uint8_t* base; size_t bytes; } reg[16];
+    int n_reg;
 
     uint64_t ws_epoch;        // bumped by every (re)allocation of a workspace buffer: invalidates captured graphs
     int no_events;            // 1 while enqueueing for the asynchronous path: no timing events (not meaningful there)
@@ -97,14 +131,21 @@ struct msg_ctx {
         uint8_t* d_filt; size_t d_filt_cap;
         uint8_t* d_ren;  size_t d_ren_cap;
         int32_t* d_lab;  size_t d_lab_cap;
+        uint16_t* d_lab16; size_t d_lab16_cap;   // labels_type = MSG_LABELS_16U
+        int32_t* d_cnt;               // 16 device counters of this frame: [0] n_regions, [1] u16 overflow flag, [2..5] mean-shift stats
+        int32_t* h_cnt;               // pinned mirror
+        // deferred copies to pageable destinations: the frame's outputs land in pinned staging (h_out, grow-only) and are
+        // copied to the caller's buffers by msg_wait
+        uint8_t* h_out;  size_t h_out_cap;
+        struct { void* dst; size_t dstep; size_t off; size_t row_bytes; int rows; } defer[3];
+        int n_defer;
+        int l16;                      // the frame's labels were requested as 16-bit
         // CUDA graph of the frame's kernel sequence (one launch call per frame instead of ~35); re-captured whenever
         // the geometry, the parameters, a buffer or the stream changes
         cudaGraphExec_t g_exec;
         int g_state;              // 0 nothing, 1 the configuration ran eagerly once (buffers sized), 2 g_exec valid, -1 disabled
         uint64_t g_epoch, g_launches;
         unsigned char g_key[160];
-        // deferred host copies (pageable destinations) are not supported asynchronously:
-        // submit requires pinned or registered memory, otherwise it degrades to synchronous.
     } pend[MSG_MAX_INFLIGHT];
 };
 
@@ -114,7 +155,11 @@ int msg_fail(msg_ctx* ctx, int code, const char* fmt, ...);
     do {                                                                                      \
         cudaError_t e__ = (call);                                                             \
         if (e__ != cudaSuccess) {                                                             \
-            (ctx)->cuda_failed = 1;                                                           \
+            /* argument / configuration / allocation errors are not sticky: the context stays usable */ \
+            if (e__ != cudaErrorInvalidConfiguration && e__ != cudaErrorInvalidValue &&       \
+                e__ != cudaErrorMemoryAllocation)                                             \
+                (ctx)->cuda_failed = 1;                                                       \
+            cudaGetLastError();                                                               \
             return msg_fail((ctx), MSG_ECUDA, "%s failed: %s (%s:%d)", #call,                 \
                             cudaGetErrorString(e__), __FILE__, __LINE__);                     \
         }                                                                                     \
@@ -126,6 +171,8 @@ int msg_fail(msg_ctx* ctx, int code, const char* fmt, ...);
     } while (0)
 
 int msg_reserve(msg_ctx* ctx, void** p, size_t* cap, size_t bytes);
+// opt-in dynamic shared memory of `func` is at least `smem` bytes on this context's device (cached per context)
+int msg_func_smem(msg_ctx* ctx, const void* func, size_t smem);
 
 static inline int msg_align_up(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -152,6 +199,11 @@ int k_merge(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels,
 int k_render(msg_ctx* ctx, const int32_t* d_labels, size_t lstep, uint8_t* d_dst, size_t dstep, int w, int h,
              int depth, const uint8_t* d_colors);
 int k_copy_labels_2d(msg_ctx* ctx, const int32_t* src, size_t sstep, int32_t* dst, size_t dstep, int w, int h);
+// colour-predicate labelling with canonical numbering (1..n in raster order of first pixel) in one call; *d_n = n
+int k_label_canonical(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int conn, int32_t* d_labels,
+                      int32_t* d_n);
+// dense int32 labels -> 16-bit labels (saturating at 65535), dstep in bytes
+int k_labels_to_u16(msg_ctx* ctx, const int32_t* d_labels, int w, int h, uint16_t* d_dst, size_t dstep);
 int k_seam_pairs(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const uint8_t* lo_bgr,
                  const int32_t* lo_lab, int w, int d, int32_t* pairs, int32_t* count);
 int k_apply_map(msg_ctx* ctx, int32_t* labels, size_t lstep, int w, int rows, const int32_t* from,
@@ -177,6 +229,8 @@ int k_median(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, s
 int k_canny_nms(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_cls, size_t cstep, int w, int h, int low, int high);
 int k_hysteresis(msg_ctx* ctx, const uint8_t* d_cls, int w, int h, int32_t* d_labels, uint8_t* d_flag, uint8_t* d_dst, size_t dstep);
 int k_dilate(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst, size_t dstep, int w, int h, int kw, int kh);
+int k_copy_masked(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, const uint8_t* d_mask, size_t mstep, uint8_t* d_dst, size_t dstep,
+                  int w, int h);
 int k_subtract(msg_ctx* ctx, const uint8_t* d_a, size_t astep, const uint8_t* d_b, size_t bstep, uint8_t* d_dst, size_t dstep,
                int w, int h);
 
@@ -198,6 +252,10 @@ int k_bilateral(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst
                 int maxk, const float* d_space_w, const short* d_space_ofs, const float* d_color_w);
 int k_contour_markers(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int32_t* d_markers, size_t mstep,
                       int32_t* n_contours_host);
+
+// k_watershed.cu: exact cv::watershed, `count` images of one geometry per call
+int k_watershed(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, size_t image_stride, int32_t* d_markers, size_t mstep,
+                size_t markers_stride, int w, int h, int count, unsigned long long* d_pops);
 
 #define MSG_LAUNCHED(ctx) ((ctx)->st.kernel_launches++)
 #define MSG_CHECK_LAUNCH(ctx) MSG_CUDA(ctx, cudaGetLastError())

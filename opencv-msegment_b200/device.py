@@ -9,9 +9,9 @@ from . import _lib as L
 
 
 def params(sp=10.0, sr=10.0, max_level=1, termcrit=(3, 5, 1.0), lo_diff=2, min_size=0, color_dist=0, render_depth=0,
-           connectivity=4):
+           connectivity=4, labels_type=0):
     return L.SegmentParams(float(sp), float(sr), int(max_level), int(termcrit[0]), int(termcrit[1]), float(termcrit[2]),
-                           int(lo_diff), int(min_size), int(color_dist), int(render_depth), int(connectivity))
+                           int(lo_diff), int(min_size), int(color_dist), int(render_depth), int(connectivity), int(labels_type))
 
 
 def _p(v):
@@ -101,6 +101,11 @@ def merge_regions(ctx, d_bgr, step, d_labels, lstep, w, h, min_size, color_dist,
 
 def render_labels(ctx, d_labels, lstep, d_dst, dstep, w, h, depth, d_colors=0):
     ctx.check(ctx._lib.msg_render_labels_dev(ctx._h, _p(d_labels), lstep, _p(d_dst), dstep, w, h, int(depth), _p(d_colors)))
+
+
+def watershed_batch(ctx, d_bgr, step, image_stride, d_markers, mstep, markers_stride, w, h, count, d_pops=0):
+    ctx.check(ctx._lib.msg_watershed_batch_dev(ctx._h, _p(d_bgr), step, image_stride, _p(d_markers), mstep, markers_stride, w, h,
+                                               int(count), _p(d_pops)))
 
 
 # ---- asynchronous host-buffer interface (pinned memory)

@@ -101,6 +101,29 @@ public:
         return n;
     }
 
+    // Imgproc.watershed(image, markers) -- PictureService.java:909; markers CV_32SC1, modified in place
+    static void watershed(const Mat& image, Mat& markers)
+    {
+        require(image.type == CV_8UC3 && markers.type == CV_32SC1, "watershed: image CV_8UC3, markers CV_32SC1");
+        require(image.rows == markers.rows && image.cols == markers.cols, "watershed: markers must have the size of image");
+        check(msg_watershed(ctx(), image.data(), image.step(), (int32_t*)markers.data(), markers.step(), image.cols, image.rows));
+    }
+
+    // PictureService.watershed(src, markers, depth, colored) -- PictureService.java:908-911
+    static Mat watershedAndColor(const Mat& src, Mat& markers, int depth, const uint8_t* colorsBgr = nullptr)
+    {
+        watershed(src, markers);
+        return colorByIndexes(markers, depth, colorsBgr);
+    }
+
+    // src.copyTo(dst, mask) on a zero dst -- PictureService.java:417-418
+    static void copyToMasked(const Mat& src, const Mat& mask, Mat& dst)
+    {
+        require(src.type == CV_8UC3 && mask.type == CV_8UC1, "copyTo: src CV_8UC3, mask CV_8UC1");
+        dst.create(src.rows, src.cols, CV_8UC3);
+        check(msg_copy_masked(ctx(), src.data(), src.step(), mask.data(), mask.step(), dst.data(), dst.step(), src.cols, src.rows));
+    }
+
     // PictureService.colorByIndexes(markers, depth, colored) -- PictureService.java:913-936 (colors == nullptr: white)
     static Mat colorByIndexes(const Mat& markers, int depth, const uint8_t* colorsBgr = nullptr)
     {

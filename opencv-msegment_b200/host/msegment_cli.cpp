@@ -177,9 +177,8 @@ int main(int argc, char** argv)
         Mat result = GpuImgproc::colorByIndexes(labels, n);           // colored=false -> white (CLI path, PictureService.java:293)
         save(++step, "result", result, 1);
         if (env_or("MSG_REFERENCE_MARKERS", 1) != 0) {
-            // The marker halves of the reference's two pipelines, step names and multipliers as it saves them
-            // (PictureService.java:320-369 and :410-444); their last two steps ("result", "bw_result") need Imgproc.watershed,
-            // which has no exact parallel form and is not produced here.
+            // The reference's two pipelines, all 8 + 8 Results, step names and multipliers as it saves them
+            // (PictureService.java:301-382 and :396-467), Imgproc.watershed included (msg_watershed: exact flood).
             method = "COLOR_METHOD";                                  // SegMethod.COLOR_METHOD
             step = 0;
             Mat black, sharp, gray, bw, dist, peaks, peaks8, markers;
@@ -200,8 +199,15 @@ int main(int argc, char** argv)
             GpuImgproc::convertToU8(peaks, peaks8);
             int depth = GpuImgproc::contourMarkers(peaks8, markers);
             GpuImgproc::circle(markers, 5, 5, 3, 255);
-            save(++step, "markers", markers, 10000);
+            save(++step, "markers", markers, 10000);                  // cloned BEFORE watershed (PictureService.java:369)
             std::cout << "colour-method contours: " << depth << std::endl;
+            {
+                Mat dst = GpuImgproc::watershedAndColor(sharp, markers, depth);    // :372: src is the sharpened image by now
+                save(++step, "result", dst, 1);
+                Mat bwres;
+                GpuImgproc::cvtColorBGR2GRAY(dst, bwres);                          // :376-379
+                save(++step, "bw_result", bwres, 1);
+            }
             method = "SHAPE_METHOD";                                  // SegMethod.SHAPE_METHOD
             step = 0;
             Mat sgray, edges, d3, d5, dde, dde3, smarkers;
@@ -210,7 +216,11 @@ int main(int argc, char** argv)
             GpuImgproc::medianBlur(sgray, sgray, k);
             save(++step, "blured_by_" + std::to_string(k) + "x" + std::to_string(k), sgray, 1);
             GpuImgproc::Canny(sgray, edges, 5, 50);
-            ++step;                                                   // "borders" (src.copyTo(dst, mask)) is a display step, not computed
+            {
+                Mat borders;
+                GpuImgproc::copyToMasked(src, edges, borders);        // src.copyTo(zeros, edges), PictureService.java:417-418
+                save(++step, "borders", borders, 1);
+            }
             save(++step, "gray_borders", edges, 1);
             GpuImgproc::dilate(edges, d3, 3, 3);
             GpuImgproc::dilate(d3, d5, 5, 5);
@@ -221,6 +231,21 @@ int main(int argc, char** argv)
             int nlab = GpuImgproc::connectedComponents(dde3, smarkers, 8);
             save(++step, "markers", smarkers, 10000);
             std::cout << "shape-method labels: " << nlab << std::endl;
+            {
+                // depth = contours.size() of findContours(markerMask, RETR_CCOMP): outer contours AND holes
+                // (PictureService.java:450-455; empty -> the reference returns null, no further Results)
+                Mat scratch;
+                const int sdepth = GpuImgproc::contourMarkers(dde3, scratch);
+                if (sdepth == 0) {
+                    std::cout << "contours is empty" << std::endl;
+                } else {
+                    Mat dst = GpuImgproc::watershedAndColor(src, smarkers, sdepth);   // :457
+                    save(++step, "result", dst, 1);
+                    Mat bwres;
+                    GpuImgproc::cvtColorBGR2GRAY(dst, bwres);                         // :461-464
+                    save(++step, "bw_result", bwres, 1);
+                }
+            }
         }
         std::cout << "results written to " << odir << std::endl;
     } catch (const CvException& e) {                // the reference lets CvException propagate: uncaught -> non-zero exit

@@ -16,6 +16,7 @@ import numpy as np
 from . import _lib as L
 
 CV_32S = 4                     # org.opencv.core.CvType.CV_32S
+CV_16U = 2                     # org.opencv.core.CvType.CV_16U
 TERM_COUNT, TERM_EPS = L.TERM_COUNT, L.TERM_EPS
 DEFAULT_TERMCRIT = (TERM_COUNT | TERM_EPS, 5, 1.0)   # Imgproc.pyrMeanShiftFiltering 4-arg overload
 
@@ -71,6 +72,21 @@ class Context:
         s = L.Stats()
         self.check(self._lib.msg_get_stats(self._h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in L.Stats._fields_}
+
+    def set_option(self, name, value):
+        self.check(self._lib.msg_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int()
+        self.check(self._lib.msg_get_option(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def register_host(self, array):
+        """Page-lock a long-lived numpy array (msg_register_host); unregister_host before it is freed."""
+        self.check(self._lib.msg_register_host(self._h, array.ctypes.data, array.nbytes))
+
+    def unregister_host(self, array):
+        self.check(self._lib.msg_unregister_host(self._h, array.ctypes.data))
 
     def set_profiling(self, enable):
         self.check(self._lib.msg_set_profiling(self._h, 1 if enable else 0))
@@ -132,8 +148,11 @@ class GpuImgproc:
         if dst is None:
             dst = np.empty((h, w, 3), np.uint8)
         else:
-            if dst.shape != src.shape or dst.dtype != np.uint8:
+            if not isinstance(dst, np.ndarray) or dst.shape != src.shape or dst.dtype != np.uint8:
                 raise CvException(L.MSG_EINVAL, "dst must have the size and type of src")
+            # a Mat's pixels are contiguous and its rows ascend: a sliced / reversed view would be written to the wrong place
+            if dst.strides[2] != 1 or dst.strides[1] != 3 or dst.strides[0] < 3 * w:
+                raise CvException(L.MSG_EINVAL, "dst must have contiguous pixels and a positive row stride (got strides %s)" % (dst.strides,))
         self.ctx.check(self._lib.msg_meanshift_filter(self.ctx._h, src.ctypes.data, src.strides[0], dst.ctypes.data,
                                                       dst.strides[0], w, h, float(sp), float(sr), int(maxLevel),
                                                       int(termcrit[0]), int(termcrit[1]), float(termcrit[2])))
@@ -192,6 +211,19 @@ class GpuImgproc:
         self.ctx.check(self._lib.msg_render_labels(self.ctx._h, markers.ctypes.data, markers.strides[0], dst.ctypes.data,
                                                    dst.strides[0], w, h, int(depth), cptr))
         return dst
+
+    # Imgproc.watershed(Mat image, Mat markers) -- PictureService.java:908-911; markers is modified IN PLACE like the Mat
+    def watershed(self, image, markers):
+        image = _mat8uc3(image, "image")
+        if not (isinstance(markers, np.ndarray) and markers.dtype == np.int32 and markers.ndim == 2 and markers.strides[1] == 4
+                and markers.strides[0] >= 4 * markers.shape[1]):
+            raise CvException(L.MSG_EINVAL, "markers must be a CV_32SC1 ndarray with contiguous pixels")
+        if markers.shape != image.shape[:2]:
+            raise CvException(L.MSG_EINVAL, "markers must have the size of image")
+        h, w = markers.shape
+        self.ctx.check(self._lib.msg_watershed(self.ctx._h, image.ctypes.data, image.strides[0], markers.ctypes.data,
+                                               markers.strides[0], w, h))
+        return markers
 
     # ---- pre-filters the reference calls around the segmentation stage
     # filter2D + convertTo + subtract + convertTo chain of PictureService.java:323-333 as one call; kernel = integer taps
@@ -425,14 +457,19 @@ class GpuImgproc:
 
     # fused pipeline
     def segment(self, src, sp=10.0, sr=10.0, maxLevel=1, termcrit=DEFAULT_TERMCRIT, loDiff=2, minSize=0, colorDist=0,
-                renderDepth=0, want=("filtered", "labels", "rendered"), connectivity=4):
+                renderDepth=0, want=("filtered", "labels", "rendered"), connectivity=4, labelsType=CV_32S):
+        """want = the download mask: products not named are neither converted nor copied back.  labelsType = CV_32S (the
+        reference's markers Mat) or CV_16U (2 bytes per pixel; CvException MSG_ERANGE beyond 65535 regions)."""
         src = _mat8uc3(src, "src")
         h, w = src.shape[:2]
+        if labelsType not in (CV_32S, CV_16U):
+            raise CvException(L.MSG_EINVAL, "labelsType must be CV_32S or CV_16U")
         p = L.SegmentParams(float(sp), float(sr), int(maxLevel), int(termcrit[0]), int(termcrit[1]), float(termcrit[2]),
-                            int(loDiff), int(minSize), int(colorDist), int(renderDepth), int(connectivity))
+                            int(loDiff), int(minSize), int(colorDist), int(renderDepth), int(connectivity),
+                            L.LABELS_16U if labelsType == CV_16U else L.LABELS_32S)
         out = {}
         f = np.empty((h, w, 3), np.uint8) if "filtered" in want else None
-        lab = np.empty((h, w), np.int32) if "labels" in want else None
+        lab = np.empty((h, w), np.uint16 if labelsType == CV_16U else np.int32) if "labels" in want else None
         r = np.empty((h, w, 3), np.uint8) if "rendered" in want else None
         n = C.c_int32()
         self.ctx.check(self._lib.msg_segment(

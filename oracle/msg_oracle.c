@@ -624,6 +624,18 @@ void orc_bgr2gray(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, 
         }
 }
 
+/* The same conversion with the coefficients of OpenCV 3.4.2's scalar path -- the version the reference binds
+ * (pom.xml:39-43): B2Y = 1868, G2Y = 9617, R2Y = 4899, yuv_shift = 14 ([recalled]: that build is not
+ * available offline, so this mode is pinned on the published constants only, not on golden vectors). */
+void orc_bgr2gray_342(const uint8_t* src, size_t sstep, uint8_t* dst, size_t dstep, int w, int h)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p = src + (size_t)y * sstep + 3 * x;
+            dst[(size_t)y * dstep + x] = (uint8_t)((1868 * p[0] + 9617 * p[1] + 4899 * p[2] + 8192) >> 14);
+        }
+}
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Shape-method seeds (PictureService.java:416-442): Canny, dilate, subtract.  Restated from the published OpenCV
  * algorithm (imgproc canny.cpp / morph.cpp semantics), pinned on cv2 4.13.0 by tests/golden/seeds.npz.

@@ -60,6 +60,7 @@ def lib():
         L.orc_laplacian_sharpen.argtypes = [u8p, sz, u8p, sz, i, i, C.c_void_p, i, i]
         L.orc_median_blur_8uc1.argtypes = [u8p, sz, u8p, sz, i, i, i]
         L.orc_bgr2gray.argtypes = [u8p, sz, u8p, sz, i, i]
+        L.orc_bgr2gray_342.argtypes = [u8p, sz, u8p, sz, i, i]
         L.orc_canny.argtypes = [u8p, sz, u8p, sz, i, i, d, d]
         L.orc_dilate_rect.argtypes = [u8p, sz, u8p, sz, i, i, i, i]
         L.orc_subtract_u8.argtypes = [u8p, sz, u8p, sz, u8p, sz, i, i]
@@ -208,11 +209,12 @@ def median_blur(gray, k):
     return dst
 
 
-def bgr2gray(src):
+def bgr2gray(src, compat342=False):
     src = _img(src)
     h, w = src.shape[:2]
     dst = np.empty((h, w), np.uint8)
-    lib().orc_bgr2gray(src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h)
+    fn = lib().orc_bgr2gray_342 if compat342 else lib().orc_bgr2gray
+    fn(src.ctypes.data, src.strides[0], dst.ctypes.data, dst.strides[0], w, h)
     return dst
 
 

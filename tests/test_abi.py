@@ -37,7 +37,7 @@ def test_python_binding_covers_the_header():
 
 def test_version_and_no_cpu_fallback():
     lib = mseg.lib.load()
-    assert lib.msg_version() == 100
+    assert lib.msg_version() == 200
     if lib.msg_device_count() == 0:
         with pytest.raises(mseg.CvException) as ei:
             mseg.Context(0)

@@ -194,15 +194,17 @@ def test_cli_batch_matches_oracle(tmp_path):
     ms = [f for f in files if f.startswith("MEANSHIFT_METHOD_")]
     assert ms == ["MEANSHIFT_METHOD_input_00001_meanshift_filtered.png", "MEANSHIFT_METHOD_input_00002_markers.png",
                   "MEANSHIFT_METHOD_input_00003_merged_markers.png", "MEANSHIFT_METHOD_input_00004_result.png"]
-    # the marker halves of the reference's two pipelines under its own step names (PictureService.java:320-369, :410-444)
+    # the reference's two pipelines, all 8 + 8 Results under its own step names (PictureService.java:301-382, :396-467;
+    # SURVEY App. C#4)
     assert [f for f in files if f.startswith("COLOR_METHOD_")] == [
         "COLOR_METHOD_input_00001_black_bg.png", "COLOR_METHOD_input_00002_laplassian_sharp.png", "COLOR_METHOD_input_00003_bw.png",
         "COLOR_METHOD_input_00004_distance_transform.png", "COLOR_METHOD_input_00005_distance_peaks.png",
-        "COLOR_METHOD_input_00006_markers.png"]
+        "COLOR_METHOD_input_00006_markers.png", "COLOR_METHOD_input_00007_result.png", "COLOR_METHOD_input_00008_bw_result.png"]
     assert [f for f in files if f.startswith("SHAPE_METHOD_")] == [
-        "SHAPE_METHOD_input_00001_blured_by_%dx%d.png" % ((orc.blur_mask_size(200, 150),) * 2), "SHAPE_METHOD_input_00003_gray_borders.png",
+        "SHAPE_METHOD_input_00001_blured_by_%dx%d.png" % ((orc.blur_mask_size(200, 150),) * 2), "SHAPE_METHOD_input_00002_borders.png",
+        "SHAPE_METHOD_input_00003_gray_borders.png",
         "SHAPE_METHOD_input_00004_dde_step.png", "SHAPE_METHOD_input_00005_dde_step_blurred_3x3.png",
-        "SHAPE_METHOD_input_00006_markers.png"]
+        "SHAPE_METHOD_input_00006_markers.png", "SHAPE_METHOD_input_00007_result.png", "SHAPE_METHOD_input_00008_bw_result.png"]
     cn, cm, cst = orc.color_seeds(im)
     rd = lambda name: _read_png(str(outdir / stamp / name))
     assert np.array_equal(rd("COLOR_METHOD_input_00002_laplassian_sharp.png"), cst["sharp"])
@@ -212,7 +214,19 @@ def test_cli_batch_matches_oracle(tmp_path):
     assert np.array_equal(rd("COLOR_METHOD_input_00005_distance_peaks.png"), cst["peaks"] * 255)
     assert np.array_equal(rd("COLOR_METHOD_input_00006_markers.png"), np.clip(cm.astype(np.int64) * 10000, 0, 255).astype(np.uint8))
     assert "colour-method contours: %d" % cn in r.stdout
+    # result / bw_result: Imgproc.watershed on the SHARPENED image (the reference copies it into src, :333) + colorByIndexes
+    ws = orc.watershed(cst["sharp"], cm.copy())
+    res = orc.render_labels(ws, cn)
+    assert np.array_equal(rd("COLOR_METHOD_input_00007_result.png"), res)
+    assert np.array_equal(rd("COLOR_METHOD_input_00008_bw_result.png"), orc.bgr2gray(res))
     sn, sm, sst = orc.shape_seeds(im)
+    want_borders = np.where((sst["edges"] != 0)[..., None], im, 0).astype(np.uint8)
+    assert np.array_equal(rd("SHAPE_METHOD_input_00002_borders.png"), want_borders)
+    sdepth, _ = orc.contour_markers(sst["dde3"])                     # contours.size() incl. holes (:450-455)
+    ws = orc.watershed(im, sm.copy())
+    res = orc.render_labels(ws, sdepth)
+    assert np.array_equal(rd("SHAPE_METHOD_input_00007_result.png"), res)
+    assert np.array_equal(rd("SHAPE_METHOD_input_00008_bw_result.png"), orc.bgr2gray(res))
     assert np.array_equal(rd("SHAPE_METHOD_input_00003_gray_borders.png"), sst["edges"])
     assert np.array_equal(rd("SHAPE_METHOD_input_00005_dde_step_blurred_3x3.png"), sst["dde3"])
     assert np.array_equal(rd("SHAPE_METHOD_input_00006_markers.png"), np.clip(sm.astype(np.int64) * 10000, 0, 255).astype(np.uint8))

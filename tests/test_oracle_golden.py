@@ -70,6 +70,15 @@ def test_watershed_golden(golden_dir):
         assert np.array_equal(got, g["out/%d" % k]), k
 
 
+def test_watershed_golden_extended(golden_dir):
+    """27 more cv2.watershed cases (tests/golden/gen_watershed.py): degenerate sizes, noise, flat images, border seeds, negative
+    input markers, and the markers of the reference's two pipelines on its sample images and on synthetic frames."""
+    g = _load(golden_dir, "watershed2.npz")
+    for name in g["names"]:
+        got = orc.watershed(g["img/%s" % name], g["markers/%s" % name])
+        assert np.array_equal(got, g["out/%s" % name]), name
+
+
 def test_render_rule():
     # PictureService.java:928: 0 < index <= depth -> colour, else background
     rng = np.random.default_rng(1)
