@@ -19,5 +19,7 @@ pkg = sys.modules[_NAME]
 Context, CvException, GpuImgproc = pkg.Context, pkg.CvException, pkg.GpuImgproc
 lib = pkg._lib
 device = pkg.device
+imgproc = pkg.imgproc
+CV_32S, CV_16U = pkg.imgproc.CV_32S, pkg.imgproc.CV_16U
 synth_bgr = pkg.synth.synth_bgr
 PKG_DIR = _PKG_DIR

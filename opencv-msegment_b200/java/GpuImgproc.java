@@ -63,6 +63,55 @@ public final class GpuImgproc {
 		return n[0];
 	}
 
+	/** Same contract as Imgproc.watershed(image, markers) -- PictureService.java:909: markers CV_32SC1, modified in place. */
+	public static void watershed(Mat image, Mat markers) {
+		require(image.type() == CvType.CV_8UC3 && markers.type() == CvType.CV_32SC1, "image CV_8UC3, markers CV_32SC1");
+		require(image.rows() == markers.rows() && image.cols() == markers.cols(), "markers must have the size of image");
+		status(nWatershed(CTX.get(), image.dataAddr(), image.step1(), markers.dataAddr(), markers.step1() * 4, image.cols(),
+			image.rows()));
+	}
+
+	/** src.copyTo(dst, mask) onto Mat.zeros -- PictureService.java:417-418 ("borders"). */
+	public static void copyToMasked(Mat src, Mat mask, Mat dst) {
+		require(src.type() == CvType.CV_8UC3 && mask.type() == CvType.CV_8UC1, "src CV_8UC3, mask CV_8UC1");
+		dst.create(src.size(), src.type());
+		status(nCopyMasked(CTX.get(), src.dataAddr(), src.step1(), mask.dataAddr(), mask.step1(), dst.dataAddr(), dst.step1(),
+			src.cols(), src.rows()));
+	}
+
+	/**
+	 * Fused mean shift + labelling + merge, intermediates in HBM (msg_segment).  labels is created as CV_32SC1, or as CV_16UC1
+	 * when labels16 is set (half the download; CvException beyond 65535 regions).  filtered may be null (not downloaded).
+	 * Returns the region count.
+	 */
+	public static int segment(Mat src, Mat filtered, Mat labels, double sp, double sr, int maxLevel, int loDiff, int minSize,
+		int colorDist, boolean labels16) {
+		require(src.type() == CvType.CV_8UC3, "src must be CV_8UC3");
+		if (filtered != null) {
+			filtered.create(src.size(), src.type());
+		}
+		labels.create(src.size(), labels16 ? CvType.CV_16UC1 : CvType.CV_32SC1);
+		int[] n = new int[1];
+		status(nSegment(CTX.get(), src.dataAddr(), src.step1(), src.cols(), src.rows(), sp, sr, maxLevel, loDiff, minSize, colorDist,
+			labels16 ? 1 : 0, filtered == null ? 0 : filtered.dataAddr(), filtered == null ? 0 : filtered.step1(),
+			labels.dataAddr(), labels.step1() * labels.elemSize1(), n));
+		return n[0];
+	}
+
+	/** msg_set_option, e.g. ("gray_compat", 1) for the OpenCV 3.4.2 BGR2GRAY coefficients the reference's natives use. */
+	public static void setOption(String name, int value) {
+		status(nSetOption(CTX.get(), name, value));
+	}
+
+	/** Page-lock a long-lived Mat so that calls copy from / to it without staging; unregister before releasing it. */
+	public static void registerMat(Mat m) {
+		status(nRegisterHost(CTX.get(), m.dataAddr(), m.step1() * m.elemSize1() * m.rows()));
+	}
+
+	public static void unregisterMat(Mat m) {
+		status(nUnregisterHost(CTX.get(), m.dataAddr()));
+	}
+
 	/** PictureService.colorByIndexes (PictureService.java:913-936); colors == null renders white. */
 	public static Mat colorByIndexes(Mat markers, int depth, byte[] colorsBgr) {
 		Mat dst = new Mat(markers.size(), CvType.CV_8UC3);
@@ -293,6 +342,14 @@ public final class GpuImgproc {
 		double peakThresh, long markers, long mstep, int[] n);
 	private static native int nBilateral(long ctx, long src, long sstep, long dst, long dstep, int w, int h, int channels,
 		int d, double sigmaColor, double sigmaSpace);
+	private static native int nWatershed(long ctx, long img, long step, long markers, long mstep, int w, int h);
+	private static native int nCopyMasked(long ctx, long src, long sstep, long mask, long mstep, long dst, long dstep, int w,
+		int h);
+	private static native int nSegment(long ctx, long src, long sstep, int w, int h, double sp, double sr, int maxLevel,
+		int loDiff, int minSize, int colorDist, int labels16, long filtered, long fstep, long labels, long lstep, int[] n);
+	private static native int nSetOption(long ctx, String name, int value);
+	private static native int nRegisterHost(long ctx, long ptr, long bytes);
+	private static native int nUnregisterHost(long ctx, long ptr);
 	private static native int nRender(long ctx, long labels, long lstep, long dst, long dstep, int w, int h, int depth,
 		byte[] colors);
 }

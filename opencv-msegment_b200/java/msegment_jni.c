@@ -2,7 +2,8 @@
  * forwards its arguments to the C ABI of include/msegment.h.  Build (on a machine with a JDK):
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include msegment_jni.c \
  *       -L.. -lmsegment_b200 -o libmsegment_jni.so
- * Not built in this repository: the build image has no jni.h. */
+ * Not built in this repository (the build image has no JDK), but type-checked on every test run against tests/stubs/jni.h
+ * (gcc -fsyntax-only -Wall -Werror, tests/test_abi.py). */
 #include <jni.h>
 #include <stdint.h>
 
@@ -201,4 +202,50 @@ JNIEXPORT jint JNICALL J(nBilateral)(JNIEnv* e, jclass c, jlong ctx, jlong src, 
 {
     return msg_bilateral_filter((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (uint8_t*)P(dst), (size_t)dstep, w, h,
                                 channels, d, sigma_color, sigma_space);
+}
+
+JNIEXPORT jint JNICALL J(nWatershed)(JNIEnv* e, jclass c, jlong ctx, jlong img, jlong step, jlong markers, jlong mstep, jint w, jint h)
+{
+    return msg_watershed((msg_ctx*)P(ctx), (const uint8_t*)P(img), (size_t)step, (int32_t*)P(markers), (size_t)mstep, w, h);
+}
+
+JNIEXPORT jint JNICALL J(nCopyMasked)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jlong mask, jlong mstep, jlong dst,
+                                      jlong dstep, jint w, jint h)
+{
+    return msg_copy_masked((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, (const uint8_t*)P(mask), (size_t)mstep,
+                           (uint8_t*)P(dst), (size_t)dstep, w, h);
+}
+
+JNIEXPORT jint JNICALL J(nSegment)(JNIEnv* e, jclass c, jlong ctx, jlong src, jlong sstep, jint w, jint h, jdouble sp, jdouble sr,
+                                   jint max_level, jint lo_diff, jint min_size, jint color_dist, jint labels16, jlong filtered,
+                                   jlong fstep, jlong labels, jlong lstep, jintArray n)
+{
+    msg_segment_params p;
+    int32_t count = 0;
+    msg_segment_params_default(&p);
+    p.sp = sp; p.sr = sr; p.max_level = max_level; p.lo_diff = lo_diff; p.min_size = min_size; p.color_dist = color_dist;
+    p.render_depth = -1;
+    p.labels_type = labels16 ? MSG_LABELS_16U : MSG_LABELS_32S;
+    int rc = msg_segment((msg_ctx*)P(ctx), (const uint8_t*)P(src), (size_t)sstep, w, h, &p, (uint8_t*)P(filtered), (size_t)fstep,
+                         P(labels), (size_t)lstep, NULL, 0, &count);
+    if (n) { jint v = count; (*e)->SetIntArrayRegion(e, n, 0, 1, &v); }
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nSetOption)(JNIEnv* e, jclass c, jlong ctx, jstring name, jint value)
+{
+    const char* s = (*e)->GetStringUTFChars(e, name, NULL);
+    int rc = s ? msg_set_option((msg_ctx*)P(ctx), s, value) : MSG_EINVAL;
+    if (s) (*e)->ReleaseStringUTFChars(e, name, s);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL J(nRegisterHost)(JNIEnv* e, jclass c, jlong ctx, jlong ptr, jlong bytes)
+{
+    return msg_register_host((msg_ctx*)P(ctx), P(ptr), (size_t)bytes);
+}
+
+JNIEXPORT jint JNICALL J(nUnregisterHost)(JNIEnv* e, jclass c, jlong ctx, jlong ptr)
+{
+    return msg_unregister_host((msg_ctx*)P(ctx), P(ptr));
 }

@@ -98,6 +98,17 @@ def test_bench_cpu_binding_is_best_effort():
     os.sched_setaffinity(0, before)
 
 
+def test_jni_glue_type_checks_against_stub_jni_h():
+    """No JDK in this image: compile-check java/msegment_jni.c against tests/stubs/jni.h (the JNI types and the JNIEnv entries
+    the glue uses, with the specification's signatures) and the real include/msegment.h, warnings as errors -- every call
+    into the C ABI is checked for argument count and types."""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-std=c99", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Werror",
+                        "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "opencv-msegment_b200", "java", "msegment_jni.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_java_natives_match_jni_glue():
     """No JDK here, so the Java shim cannot be compiled: check at least that every `native` method of GpuImgproc.java has a JNI
     function of the same name and arity in msegment_jni.c (JNIEnv*, jclass + the Java parameters), and vice versa, and that
@@ -110,7 +121,7 @@ def test_java_natives_match_jni_glue():
                for m in re.finditer(r"private static native \w+(?:\[\])? (\w+)\(([^)]*)\)", java, re.S)}
     jni = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()]) - 2
            for m in re.finditer(r"JNICALL J\((\w+)\)\(([^)]*)\)", glue, re.S)}
-    assert len(natives) >= 25
+    assert len(natives) >= 31
     assert natives == jni, (sorted(set(natives.items()) ^ set(jni.items())))
     declared = set(re.findall(r"\b(msg_\w+)\s*\(", header))
     called = set(re.findall(r"\b(msg_\w+)\s*\(", glue))
