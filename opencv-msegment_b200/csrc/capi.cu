@@ -220,7 +220,7 @@ void msg_destroy(msg_ctx* ctx)
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_out2); cudaFree(ctx->d_labels);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_ovf); cudaFree(ctx->d_scratch); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_colors); cudaFree(ctx->d_work); cudaFree(ctx->d_cells); cudaFree(ctx->d_aux); cudaFree(ctx->d_small);
-    cudaFree(ctx->d_ws);
+    cudaFree(ctx->d_ws); cudaFree(ctx->d_ccl);
     for (int l = 0; l < MSG_MAX_LEVELS; l++)
         for (int k = 0; k < 3; k++)
             if (ctx->prof_ev[l][k]) cudaEventDestroy(ctx->prof_ev[l][k]);
@@ -633,6 +633,26 @@ int msg_meanshift_filter(msg_ctx* ctx, const uint8_t* src, size_t sstep, uint8_t
 
 // ============================================================================ labelling
 
+}  // extern "C"
+
+// labels 1..n of an 8UC3 device image into a dense int32 map.  Tile-local path: the kernels read the BGR bytes themselves
+// (no packed plane); legacy path (option ccl_legacy): plane + row-run union-find + separate relabel.
+static int label_from_bgr(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int w, int h, int lo_diff, int connectivity,
+                          int32_t* d_dense_labels, int32_t* d_n)
+{
+    if (!ctx->tune.ccl_legacy)
+        return k_label_canonical_src(ctx, d_bgr, step, 2, w, h, lo_diff, connectivity, d_dense_labels, d_n);
+    msg_plane s;
+    s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
+    s.p = ctx->d_planes;
+    MSG_TRY(k_bgr_to_plane(ctx, d_bgr, step, s));
+    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, connectivity, d_dense_labels, -1, w));
+    return k_relabel_canonical(ctx, d_dense_labels, w, h, 1, d_n, 0);
+}
+
+extern "C" {
+
 int msg_label_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32_t* d_labels, size_t lstep, int w, int h,
                           int lo_diff, int connectivity, int32_t* d_n)
 {
@@ -642,19 +662,13 @@ int msg_label_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32
     if (lo_diff < 0) return msg_fail(ctx, MSG_EINVAL, "lo_diff must be >= 0");
     if (connectivity != 4 && connectivity != 8) return msg_fail(ctx, MSG_EINVAL, "connectivity must be 4 or 8");
     if (lstep % 4) return msg_fail(ctx, MSG_EINVAL, "labels step must be a multiple of 4");
-    msg_plane s;
-    s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
-    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
-    s.p = ctx->d_planes;
-    MSG_TRY(k_bgr_to_plane(ctx, d_bgr, step, s));
     bool dense = lstep == (size_t)w * 4;
     int32_t* work = d_labels;
     if (!dense) {
         MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
         work = ctx->d_labels;
     }
-    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, connectivity, work, -1, w));
-    MSG_TRY(k_relabel_canonical(ctx, work, w, h, 1, d_n, 0));
+    MSG_TRY(label_from_bgr(ctx, d_bgr, step, w, h, lo_diff, connectivity, work, d_n));
     if (!dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
     return MSG_OK;
 }
@@ -673,8 +687,7 @@ int msg_connected_components_dev(msg_ctx* ctx, const uint8_t* d_mask, size_t ste
         MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
         work = ctx->d_labels;
     }
-    MSG_TRY(k_ccl_binary(ctx, d_mask, step, w, h, connectivity, work));
-    MSG_TRY(k_relabel_canonical(ctx, work, w, h, 1, d_n, 1));   // + background label, as OpenCV counts
+    MSG_TRY(k_cc_canonical(ctx, d_mask, step, w, h, connectivity, work, d_n));   // count includes the background, as OpenCV's
     if (!dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
     return MSG_OK;
 }
@@ -754,14 +767,7 @@ int msg_label_regions(msg_ctx* ctx, const uint8_t* bgr, size_t step, int32_t* la
     MSG_TRY(copy_in(ctx, bgr, step, rb, h, &ctx->d_in, &ctx->d_in_cap));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
-    // dense device labels: msg_label_regions_dev would alias ctx->d_labels for a strided target, so go direct
-    msg_plane s;
-    s.w = w; s.rows = h; s.y0 = 0; s.hfull = h; s.pitch = msg_align_up(w, 32);
-    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * h * sizeof(uint32_t)));
-    s.p = ctx->d_planes;
-    MSG_TRY(k_bgr_to_plane(ctx, ctx->d_in, rb, s));
-    MSG_TRY(k_ccl_color(ctx, s.p, s.pitch, w, h, lo_diff, connectivity, ctx->d_labels, -1, w));
-    MSG_TRY(k_relabel_canonical(ctx, ctx->d_labels, w, h, 1, ctx->d_counters + 16, 0));
+    MSG_TRY(label_from_bgr(ctx, ctx->d_in, rb, w, h, lo_diff, connectivity, ctx->d_labels, ctx->d_counters + 16));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -785,8 +791,7 @@ int msg_connected_components(msg_ctx* ctx, const uint8_t* mask, size_t step, int
     MSG_TRY(copy_in(ctx, mask, step, (size_t)w, h, &ctx->d_in, &ctx->d_in_cap));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_labels, &ctx->d_labels_cap, (size_t)w * h * 4));
-    MSG_TRY(k_ccl_binary(ctx, ctx->d_in, (size_t)w, w, h, connectivity, ctx->d_labels));
-    MSG_TRY(k_relabel_canonical(ctx, ctx->d_labels, w, h, 1, ctx->d_counters + 16, 1));
+    MSG_TRY(k_cc_canonical(ctx, ctx->d_in, (size_t)w, w, h, connectivity, ctx->d_labels, ctx->d_counters + 16));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     MSG_TRY(copy_out(ctx, labels, lstep, ctx->d_labels, (size_t)w * 4, h));
     MSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));

@@ -267,6 +267,397 @@ __global__ void __launch_bounds__(CCL_THREADS) scan_block_sums_kernel(int32_t* _
     if (threadIdx.x == 0 && total_out) *total_out = carry + add_to_total;
 }
 
+// ================================================================ round 2: tile-local union-find
+// The row-run passes above make five sweeps over HBM (rows: R+W, merge: R + atomics, flatten: R+W, apply: R+W).  The
+// tile-local form does the bulk of the unions in shared memory and touches HBM twice:
+//   A  ccl_tile_kernel    one CTA per 128 x 16 tile: pixels -> shared memory (exactly the tile, no halo: 4 B/px coalesced
+//                         read), row runs by ballot, vertical (and diagonal) unions inside the tile with shared-memory
+//                         atomicMin, flatten; writes L[p] = GLOBAL index of the tile-local root (4 B/px) and one bit per
+//                         pixel "is a tile-local root" (1/8 B/px)
+//   B  ccl_border_kernel  only the pixels on tile borders: the unions whose two pixels lie in different tiles, global
+//                         atomicMin (the only global atomics of the stage); top rows are coalesced, left columns are not but
+//                         there are 8 x fewer of them (tiles are 128 wide, 16 high)
+//   C  ccl_roots_kernel   over the root BITMAP (n/32 words, not the pixels): tile-local roots that were linked away are
+//                         pointed straight at their final root (so every chain is <= 2 links) and lose their bit; per-block
+//                         counts of the surviving = global roots
+//   D  scan of the block counts;  E  ccl_rank_kernel: global roots get L[root] = -(label + 1), label = 1 + rank in raster order
+//   F  ccl_final_kernel   out[p] = label of L[p]'s root: one coalesced 16-byte read, <= 2 gathers that hit L1/L2 (neighbouring
+//                         pixels share their tile-local root), one coalesced 16-byte write (4 + 4 B/px)
+// Unions are decided per pixel exactly as in ccl_merge_kernel (same redundancy rules); a rule that cannot be evaluated inside
+// the tile is simply not applied (an extra union is harmless, a missing one is not), and every cross-tile pair is visited by B.
+constexpr int CT_W = 128, CT_H = 16, CT_THREADS = 256;
+constexpr uint32_t CT_INVALID = 0xFF000000u;       // colour predicates: byte3 set = "no pixel"; binary: 0 = background
+
+// PRED: 0 = packed plane (u32 per pixel, pitch in pixels), 1 = binary mask (u8, pitch in bytes), 2 = BGR bytes (pitch in bytes)
+template <int PRED>
+__device__ __forceinline__ uint32_t ct_load(const void* __restrict__ img, size_t pitch, int x, int y)
+{
+    if (PRED == 0) return __ldg((const uint32_t*)img + (size_t)y * pitch + x) & 0x00FFFFFFu;
+    if (PRED == 1) return ((const uint8_t*)img)[(size_t)y * pitch + x] != 0 ? 1u : 0u;
+    const uint8_t* p = (const uint8_t*)img + (size_t)y * pitch + 3 * (size_t)x;
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+}
+
+template <int PRED>
+__device__ __forceinline__ bool ct_fg(uint32_t v) { return PRED == 1 ? v != 0u : (v >> 24) == 0u; }
+
+template <int PRED>
+__device__ __forceinline__ bool ct_conn(uint32_t a, uint32_t b, int d)
+{
+    if (PRED == 1) return a != 0u && b != 0u;
+    uint32_t e = __vabsdiffu4(a, b);                // byte3: 0 when both are pixels, 255 when exactly one is
+    return (int)(e & 0xFF) <= d && (int)((e >> 8) & 0xFF) <= d && (int)((e >> 16) & 0xFF) <= d && (e >> 24) == 0u;
+}
+
+// the same test for two REAL pixels (byte3 = 0 on both sides) in 16-bit lanes: a lane of (|delta| + 255 - d) carries into
+// bit 8 exactly when |delta| > d.  kd = 0x00FF00FF - d * 0x00010001 (d <= 255).
+template <int PRED>
+__device__ __forceinline__ bool ct_conn_px(uint32_t a, uint32_t b, uint32_t kd)
+{
+    if (PRED == 1) return a != 0u && b != 0u;
+    const uint32_t e = __vabsdiffu4(a, b);
+    return ((((e & 0x00FF00FFu) + kd) | (((e >> 8) & 0x00FF00FFu) + kd)) & 0x01000100u) == 0u;
+}
+
+__device__ __forceinline__ int uf_find_s(const int* lab, int a)
+{
+    int p = lab[a];
+    while (p != a) { a = p; p = lab[a]; }
+    return a;
+}
+
+__device__ __forceinline__ void uf_union_s(int* lab, int a, int b)     // shared-memory union-find, smaller index wins
+{
+    for (;;) {
+        a = uf_find_s(lab, a);
+        b = uf_find_s(lab, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(lab + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// Per 32-pixel chunk the connectivity lives in two ballot words: clb = "connected to the left pixel" (run structure of the
+// row) and vb = "connected to the pixel above".  A vertical union is needed only at the first column of an overlap of two
+// runs: need = vb & ~(clb & clb_of_the_row_above & (vb << 1)) -- the ccl_merge_kernel redundancy rule in bit-parallel form
+// (pixel x is redundant when x-1 is in its run, x-1's upper neighbour is in the upper run, and x-1 is connected upwards).
+// Per-PIXEL work is the load, two predicate tests, two ballots and the final store; the union-find work (unions, find,
+// conversion to the global index, root flags) is done once per RUN by the lane that starts it.  The kernel is bound by the
+// instruction issue rate (ncu: 70 % of the issue slots at 14 % of the DRAM bandwidth; 162 thread-instructions per pixel in
+// the first per-pixel form).  A variant that compacted the unions / finds into shared-memory task lists processed one task per
+// thread was SLOWER (521 vs 380 us at 8192^2): the pointer chases then sit between block-wide barriers instead of
+// overlapping other warps' streaming work (profiles/r02_ccl_history.md).
+template <int PRED, int CONN>
+__global__ void __launch_bounds__(CT_THREADS) ccl_tile_kernel(const void* __restrict__ img, size_t pitch, int w, int h, int d,
+                                                              int32_t* __restrict__ L, uint32_t* __restrict__ bitmap, int wp)
+{
+    __shared__ uint32_t s_col[CT_H * CT_W];   // pixels; after the unions: global index of the root, stored at every run start
+    __shared__ int s_lab[CT_H * CT_W];        // union-find parents (tile-local indices); a pixel points at the start of its run
+    __shared__ unsigned s_clb[CT_H * (CT_W / 32)];
+    constexpr int CHUNKS = CT_W / 32;                            // 4
+    constexpr int ROWS_PER_WARP = CT_H / (CT_THREADS / 32);      // 2
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
+    const uint32_t kd = 0x00FF00FFu - (uint32_t)min(d, 255) * 0x00010001u;
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+    uint32_t vreg[ROWS_PER_WARP][CHUNKS];
+    unsigned clb[ROWS_PER_WARP][CHUNKS];
+    int sreg[ROWS_PER_WARP][CHUNKS];          // tile-local index of the start of my run
+
+    // ---- load + row runs
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int r = wq * ROWS_PER_WARP + rr, gy = ty0 + r;
+        int carry = r * CT_W;                 // start of the run that reaches the end of the previous chunk
+        uint32_t prev_last = 0u;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; c++) {
+            const int x = c * 32 + lane, gx = tx0 + x;
+            const bool in = gx < w && gy < h;
+            const uint32_t v = in ? ct_load<PRED>(img, pitch, gx, gy) : (PRED == 1 ? 0u : CT_INVALID);
+            vreg[rr][c] = v;
+            s_col[r * CT_W + x] = v;
+            uint32_t left = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) left = prev_last;
+            // the left neighbour of a real pixel is a real pixel, except for the first column of the tile (no link inside the tile)
+            const bool cl = ct_fg<PRED>(v) && x > 0 && ct_conn_px<PRED>(v, left, kd);
+            const unsigned bits = __ballot_sync(0xffffffffu, cl);
+            clb[rr][c] = bits;
+            if (lane == 0) s_clb[r * CHUNKS + c] = bits;
+            const unsigned starts = ~bits & le_mask;
+            const int sp = starts ? r * CT_W + c * 32 + (31 - __clz(starts)) : carry;
+            sreg[rr][c] = sp;
+            s_lab[r * CT_W + x] = ct_fg<PRED>(v) ? sp : -1;
+            if (bits != 0xffffffffu) carry = r * CT_W + c * 32 + (31 - __clz(~bits));
+            prev_last = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+
+    // ---- unions with the row above, inside the tile
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int r = wq * ROWS_PER_WARP + rr;
+        if (r == 0) continue;                 // the tile's top row unites with the tile above in ccl_border_kernel
+        unsigned vcarry = 0;                  // "connected upwards" of the last pixel of the previous chunk
+#pragma unroll
+        for (int c = 0; c < CHUNKS; c++) {
+            const int x = c * 32 + lane, p = r * CT_W + x;
+            const uint32_t v = vreg[rr][c];
+            const uint32_t u = rr > 0 ? vreg[rr > 0 ? rr - 1 : 0][c] : s_col[p - CT_W];
+            // the pixel above a real pixel is a real pixel (r >= 1)
+            const bool vup = ct_fg<PRED>(v) && ct_conn_px<PRED>(v, u, kd);
+            const unsigned vb = __ballot_sync(0xffffffffu, vup);
+            const unsigned clup = rr > 0 ? clb[rr > 0 ? rr - 1 : 0][c] : s_clb[(r - 1) * CHUNKS + c];
+            const unsigned need = vb & ~(clb[rr][c] & clup & ((vb << 1) | vcarry));
+            vcarry = vb >> 31;
+            if ((need >> lane) & 1u) uf_union_s(s_lab, sreg[rr][c], rr > 0 ? sreg[rr > 0 ? rr - 1 : 0][c] : s_lab[p - CT_W]);
+            if (CONN == 8) {
+                if (PRED != 1) {              // floodFill's 8-connectivity: both upper diagonals are edges of their own
+                    if (ct_fg<PRED>(v)) {
+                        if (x > 0 && ct_conn_px<PRED>(v, s_col[p - CT_W - 1], kd)) uf_union_s(s_lab, p, p - CT_W - 1);
+                        if (x + 1 < CT_W && ct_conn<PRED>(v, s_col[p - CT_W + 1], d)) uf_union_s(s_lab, p, p - CT_W + 1);
+                    }
+                } else if (v && !u) {         // connectedComponents(8): diagonals matter only under a background pixel
+                    const uint32_t lf = x > 0 ? s_col[p - 1] : 0u, ul = x > 0 ? s_col[p - CT_W - 1] : 0u;
+                    const uint32_t rt = x + 1 < CT_W ? s_col[p + 1] : 0u, ur = x + 1 < CT_W ? s_col[p - CT_W + 1] : 0u;
+                    if (ul && !lf) uf_union_s(s_lab, p, p - CT_W - 1);
+                    if (ur && !rt) uf_union_s(s_lab, p, p - CT_W + 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- per run: find the root, leave its GLOBAL index at the run start (s_col is free now), flag tile-local roots
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int r = wq * ROWS_PER_WARP + rr, gy = ty0 + r;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; c++) {
+            const int x = c * 32 + lane, p = r * CT_W + x;
+            bool is_root = false;
+            if (ct_fg<PRED>(vreg[rr][c]) && !((clb[rr][c] >> lane) & 1u)) {          // I start a run
+                const int root = uf_find_s(s_lab, p);
+                is_root = root == p;
+                s_col[p] = (uint32_t)((ty0 + root / CT_W) * w + tx0 + (root % CT_W));
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, is_root);
+            if (lane == 0 && gy < h && tx0 + c * 32 < w) bitmap[(size_t)gy * wp + (tx0 >> 5) + c] = bal;
+        }
+    }
+    __syncthreads();
+
+    // ---- per pixel: the label of my run
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int gy = ty0 + wq * ROWS_PER_WARP + rr;
+        if (gy >= h) continue;
+        int32_t* __restrict__ Lrow = L + (size_t)gy * w + tx0;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; c++) {
+            const int x = c * 32 + lane;
+            if (tx0 + x < w) Lrow[x] = ct_fg<PRED>(vreg[rr][c]) ? (int32_t)s_col[sreg[rr][c]] : -1;
+        }
+    }
+}
+
+// unions across tile borders.  Threads [0, n_hb): pixels of the top rows of the tiles (y = k * CT_H, k >= 1), the per-pixel
+// rules of ccl_merge_kernel with the row above; threads [n_hb, n_hb + n_vb): pixels of the left columns of the tiles
+// (x = j * CT_W, j >= 1) against the column to their left (and its diagonals for 8-connectivity).
+template <int PRED, int CONN>
+__global__ void __launch_bounds__(CT_THREADS) ccl_border_kernel(const void* __restrict__ img, size_t pitch, int w, int h, int d,
+                                                                int32_t* __restrict__ L, long long n_hb, long long n_vb)
+{
+    const long long idx = (long long)blockIdx.x * CT_THREADS + threadIdx.x;
+    const uint32_t none = PRED == 1 ? 0u : CT_INVALID;
+    auto get = [&](int x, int y) -> uint32_t { return (x >= 0 && x < w && y >= 0 && y < h) ? ct_load<PRED>(img, pitch, x, y) : none; };
+    if (idx < n_hb) {
+        const int x = (int)(idx % w), y = (int)(idx / w + 1) * CT_H;
+        const uint32_t v = get(x, y);
+        if (!ct_fg<PRED>(v)) return;
+        const int p = y * w + x;
+        const uint32_t u = get(x, y - 1), lf = get(x - 1, y), ul = get(x - 1, y - 1), ur = get(x + 1, y - 1);
+        if (PRED != 1) {
+            if (ct_conn<PRED>(v, u, d)) {
+                const bool redundant = ct_conn<PRED>(v, lf, d) && ct_conn<PRED>(u, ul, d) && ct_conn<PRED>(lf, ul, d);
+                if (!redundant) uf_union(L, p, p - w);
+            }
+            if (CONN == 8) {
+                if (ct_conn<PRED>(v, ul, d)) uf_union(L, p, p - w - 1);
+                if (ct_conn<PRED>(v, ur, d)) uf_union(L, p, p - w + 1);
+            }
+        } else {
+            if (u) {
+                if (!(lf && ul)) uf_union(L, p, p - w);
+            } else if (CONN == 8) {
+                const uint32_t rt = get(x + 1, y);
+                if (ul && !lf) uf_union(L, p, p - w - 1);
+                if (ur && !rt) uf_union(L, p, p - w + 1);
+            }
+        }
+    } else if (idx < n_hb + n_vb) {
+        const long long k = idx - n_hb;
+        const int y = (int)(k % h), x = (int)(k / h + 1) * CT_W;
+        const uint32_t v = get(x, y);
+        if (!ct_fg<PRED>(v)) return;
+        const int p = y * w + x;
+        const uint32_t lf = get(x - 1, y);
+        if (ct_conn<PRED>(v, lf, d)) {
+            // the pixel above unites the same two tile-local components when it is connected to me, its left neighbour to mine,
+            // and it to its left neighbour -- unless it sits in the tile row above (then my link to it is not made yet)
+            bool redundant = false;
+            if (y % CT_H != 0) {
+                const uint32_t u = get(x, y - 1), ul = get(x - 1, y - 1);
+                redundant = ct_conn<PRED>(v, u, d) && ct_conn<PRED>(lf, ul, d) && ct_conn<PRED>(u, ul, d);
+            }
+            if (!redundant) uf_union(L, p, p - 1);
+        }
+        if (CONN == 8) {
+            if (ct_conn<PRED>(v, get(x - 1, y - 1), d)) uf_union(L, p, p - w - 1);
+            if (ct_conn<PRED>(v, get(x - 1, y + 1), d)) uf_union(L, p, p + w - 1);
+        }
+    }
+}
+
+constexpr int RB_WORDS = 4;                               // bitmap words per thread in the root kernels
+constexpr int RB_BLOCK = CT_THREADS * RB_WORDS;           // 1024 words = 32768 pixels per block
+
+// C: which tile-local roots are still roots after the border pass?  One independent load per candidate (L[p] == p), no
+// pointer chasing; the surviving bits go to a second bitmap, the per-block counts to block_sums.
+__global__ void __launch_bounds__(CT_THREADS) ccl_roots_kernel(const int32_t* __restrict__ L, const uint32_t* __restrict__ bitmap,
+                                                               uint32_t* __restrict__ rootmap, int w, int wp, size_t nwords,
+                                                               int32_t* __restrict__ block_sums)
+{
+    const size_t base = (size_t)blockIdx.x * RB_BLOCK + (size_t)threadIdx.x * RB_WORDS;
+    unsigned bits[RB_WORDS];
+#pragma unroll
+    for (int k = 0; k < RB_WORDS; k++) bits[k] = base + k < nwords ? bitmap[base + k] : 0u;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < RB_WORDS; k++) {
+        const size_t wi = base + k;
+        unsigned keep = 0;
+        if (bits[k]) {
+            const int p0 = (int)(wi / wp) * w + (int)(wi % wp) * 32;
+            for (unsigned b = bits[k]; b;) {                      // four independent loads in flight
+                int q[4], v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { q[j] = b ? __ffs(b) - 1 : -1; b &= b - 1; }
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = q[j] >= 0 ? __ldcg(L + p0 + q[j]) : -1;
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (q[j] >= 0 && v[j] == p0 + q[j]) keep |= 1u << q[j];
+            }
+        }
+        if (wi < nwords) rootmap[wi] = keep;
+        cnt += __popc(keep);
+    }
+    int total;
+    block_exclusive_scan(cnt, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// D: exclusive scan of up to 1024 * per entries by one CTA: every thread sums `per` consecutive entries, one block scan,
+// then the entries are rewritten with their exclusive prefixes; *total_out = sum + add_to_total.
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int32_t* __restrict__ sums, int nb, int per, int32_t* __restrict__ total_out,
+                                                         int add_to_total)
+{
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int i0 = threadIdx.x * per;
+    int s = 0;
+    for (int k = 0; k < per; k++) s += i0 + k < nb ? sums[i0 + k] : 0;
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[wq] = incl;
+    __syncthreads();
+    if (wq == 0) {
+        int v = wsum[lane], inc2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (lane >= o) inc2 += t;
+        }
+        wsum[lane] = inc2 - v;
+        if (lane == 31 && total_out) *total_out = inc2 + add_to_total;
+    }
+    __syncthreads();
+    int run = wsum[wq] + incl - s;
+    for (int k = 0; k < per; k++) {
+        if (i0 + k < nb) { int v = sums[i0 + k]; sums[i0 + k] = run; run += v; }
+    }
+}
+
+// E: the roots get L[root] = -(label + 1), label = 1 + rank in raster order (-1 stays "background")
+__global__ void __launch_bounds__(CT_THREADS) ccl_rank_kernel(int32_t* __restrict__ L, const uint32_t* __restrict__ rootmap, int w,
+                                                              int wp, size_t nwords, const int32_t* __restrict__ block_offs)
+{
+    const size_t base = (size_t)blockIdx.x * RB_BLOCK + (size_t)threadIdx.x * RB_WORDS;
+    unsigned bits[RB_WORDS];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < RB_WORDS; k++) {
+        bits[k] = base + k < nwords ? rootmap[base + k] : 0u;
+        cnt += __popc(bits[k]);
+    }
+    int label = block_exclusive_scan(cnt, nullptr) + block_offs[blockIdx.x] + 1;
+#pragma unroll
+    for (int k = 0; k < RB_WORDS; k++) {
+        if (!bits[k]) continue;
+        const size_t wi = base + k;
+        const int p0 = (int)(wi / wp) * w + (int)(wi % wp) * 32;
+        for (unsigned b = bits[k]; b; b &= b - 1) {
+            L[p0 + __ffs(b) - 1] = -(label + 1);
+            label++;
+        }
+    }
+}
+
+// E': every tile-local root that was linked away takes the encoded label of its final root, so that the per-pixel pass needs
+// one gather only.  One thread per bitmap word (few candidates per thread: the chains of a warp run side by side).  A
+// concurrent traversal that meets an already rewritten entry stops there with the same label.
+__global__ void __launch_bounds__(CT_THREADS) ccl_spread_kernel(int32_t* __restrict__ L, const uint32_t* __restrict__ bitmap,
+                                                                const uint32_t* __restrict__ rootmap, int w, int wp, size_t nwords)
+{
+    const size_t wi = (size_t)blockIdx.x * CT_THREADS + threadIdx.x;
+    if (wi >= nwords) return;
+    unsigned b = bitmap[wi] & ~rootmap[wi];
+    if (!b) return;
+    const int p0 = (int)(wi / wp) * w + (int)(wi % wp) * 32;
+    for (; b; b &= b - 1) {
+        const int p = p0 + __ffs(b) - 1;
+        int v = __ldcg(L + p);
+        while (v >= 0) v = __ldcg(L + v);
+        L[p] = v;
+    }
+}
+
+__device__ __forceinline__ int ccl_resolve(const int32_t* __restrict__ L, int v)
+{
+    while (v >= 0) v = __ldcg(L + v);         // own entry -> tile root (which holds the encoded label after ccl_spread_kernel)
+    return -(v + 1);                          // -1 (background) -> 0
+}
+
+__global__ void __launch_bounds__(CT_THREADS) ccl_final_kernel(const int32_t* __restrict__ L, int32_t* __restrict__ out, size_t n)
+{
+    const size_t i4 = ((size_t)blockIdx.x * CT_THREADS + threadIdx.x) * 4;
+    if (i4 + 3 < n && ((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const int4 v = __ldcs(reinterpret_cast<const int4*>(L + i4));
+        int4 o;
+        o.x = ccl_resolve(L, v.x); o.y = ccl_resolve(L, v.y); o.z = ccl_resolve(L, v.z); o.w = ccl_resolve(L, v.w);
+        __stcs(reinterpret_cast<int4*>(out + i4), o);
+    } else {
+        for (size_t i = i4; i < n && i < i4 + 4; i++) out[i] = ccl_resolve(L, L[i]);
+    }
+}
+
 // rank[] is indexed by pixel (MODE 0: at the root pixel) or by label id (MODE 1)
 template <int MODE>
 __global__ void __launch_bounds__(CCL_THREADS) assign_rank_kernel(const int32_t* __restrict__ L,
@@ -683,7 +1074,66 @@ int k_relabel_canonical(msg_ctx* ctx, int32_t* d_labels, int w, int h, int roots
     return relabel_impl(ctx, d_labels, (size_t)w * h, roots_are_pixels ? 0 : 1, d_n_out, add_to_count);
 }
 
-// label_base < 0: canonical labels 1..n (n -> d_n via caller's relabel); otherwise strip mode
+// ---- tile-local union-find launchers.  Scratch of the stage lives in ctx->d_ccl (callers keep their label arrays in
+// d_scratch / d_labels): [L: n ints (canonical path only)][root bitmap: h * wp words][block sums]
+struct ccl_ws { int32_t* L; uint32_t* bitmap; uint32_t* rootmap; int32_t* block_sums; int wp; size_t nwords; int nblocks; };
+
+static int ccl_workspace(msg_ctx* ctx, int w, int h, bool with_labels, ccl_ws* ws)
+{
+    const size_t n = (size_t)w * h;
+    ws->wp = (w + 31) / 32;
+    ws->nwords = (size_t)ws->wp * h;
+    ws->nblocks = (int)((ws->nwords + RB_BLOCK - 1) / RB_BLOCK);
+    const size_t lab_bytes = with_labels ? ((n * 4 + 255) & ~(size_t)255) : 0;
+    const size_t bm_bytes = (ws->nwords * 4 + 255) & ~(size_t)255;
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ccl, &ctx->d_ccl_cap, lab_bytes + 2 * bm_bytes + ((size_t)ws->nblocks + 64) * 4));
+    ws->L = with_labels ? (int32_t*)ctx->d_ccl : nullptr;
+    ws->bitmap = (uint32_t*)(ctx->d_ccl + lab_bytes);
+    ws->rootmap = (uint32_t*)(ctx->d_ccl + lab_bytes + bm_bytes);
+    ws->block_sums = (int32_t*)(ctx->d_ccl + lab_bytes + 2 * bm_bytes);
+    return MSG_OK;
+}
+
+// phases A + B: union-find parents in L (roots = first pixels of the components, background -1), root bitmap in ws
+template <int PRED>
+static int ccl_tiles(msg_ctx* ctx, const void* img, size_t pitch, int w, int h, int d, int conn, int32_t* L, const ccl_ws& ws)
+{
+    cudaStream_t st = ctx->stream;
+    dim3 grid((w + CT_W - 1) / CT_W, (h + CT_H - 1) / CT_H);
+    const long long n_hb = (long long)(grid.y - 1) * w, n_vb = (long long)(grid.x - 1) * h;
+    const unsigned bblocks = (unsigned)((n_hb + n_vb + CT_THREADS - 1) / CT_THREADS);
+    if (conn == 8) ccl_tile_kernel<PRED, 8><<<grid, CT_THREADS, 0, st>>>(img, pitch, w, h, d, L, ws.bitmap, ws.wp);
+    else ccl_tile_kernel<PRED, 4><<<grid, CT_THREADS, 0, st>>>(img, pitch, w, h, d, L, ws.bitmap, ws.wp);
+    MSG_LAUNCHED(ctx);
+    if (bblocks) {
+        if (conn == 8) ccl_border_kernel<PRED, 8><<<bblocks, CT_THREADS, 0, st>>>(img, pitch, w, h, d, L, n_hb, n_vb);
+        else ccl_border_kernel<PRED, 4><<<bblocks, CT_THREADS, 0, st>>>(img, pitch, w, h, d, L, n_hb, n_vb);
+        MSG_LAUNCHED(ctx);
+    }
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+// phases C .. F: canonical labels 1..n (raster order of first pixel) from the forest in ws.L into d_out; *d_n = n + add
+static int ccl_canonical(msg_ctx* ctx, int w, int h, const ccl_ws& ws, int32_t* d_out, int32_t* d_n, int add_to_count)
+{
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)w * h;
+    ccl_roots_kernel<<<ws.nblocks, CT_THREADS, 0, st>>>(ws.L, ws.bitmap, ws.rootmap, w, ws.wp, ws.nwords, ws.block_sums);
+    MSG_LAUNCHED(ctx);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(ws.block_sums, ws.nblocks, (ws.nblocks + 1023) / 1024, d_n, add_to_count);
+    MSG_LAUNCHED(ctx);
+    ccl_rank_kernel<<<ws.nblocks, CT_THREADS, 0, st>>>(ws.L, ws.rootmap, w, ws.wp, ws.nwords, ws.block_sums);
+    MSG_LAUNCHED(ctx);
+    ccl_spread_kernel<<<blocks_for(ws.nwords, CT_THREADS), CT_THREADS, 0, st>>>(ws.L, ws.bitmap, ws.rootmap, w, ws.wp, ws.nwords);
+    MSG_LAUNCHED(ctx);
+    ccl_final_kernel<<<blocks_for((n + 3) / 4, CT_THREADS), CT_THREADS, 0, st>>>(ws.L, d_out, n);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+// label_base < 0: union-find parents (the caller relabels); otherwise strip mode: 1 + global index of the strip-local root
 int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int conn, int32_t* d_labels,
                 int64_t label_base, int full_w)
 {
@@ -691,11 +1141,17 @@ int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, 
     size_t n = (size_t)w * h;
     cudaStream_t st = ctx->stream;
     if (w > CCL_MAX_CHUNKS * 32) return msg_fail(ctx, MSG_EINVAL, "labelling supports rows up to %d pixels", CCL_MAX_CHUNKS * 32);
-    ccl_rows_kernel<0><<<h, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
-    MSG_LAUNCHED(ctx);
-    if (conn == 8) ccl_merge_kernel<0, 8><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
-    else ccl_merge_kernel<0, 4><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
-    MSG_LAUNCHED(ctx);
+    if (!ctx->tune.ccl_legacy) {
+        ccl_ws ws;
+        MSG_TRY(ccl_workspace(ctx, w, h, false, &ws));
+        MSG_TRY(ccl_tiles<0>(ctx, d_plane, (size_t)pitch, w, h, d, conn, d_labels, ws));
+    } else {
+        ccl_rows_kernel<0><<<h, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
+        MSG_LAUNCHED(ctx);
+        if (conn == 8) ccl_merge_kernel<0, 8><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
+        else ccl_merge_kernel<0, 4><<<grid, CCL_THREADS, 0, st>>>(d_plane, (size_t)pitch, w, h, d, d_labels);
+        MSG_LAUNCHED(ctx);
+    }
     if (label_base >= 0) {      // strip mode: no canonical relabel follows, flatten here
         ccl_flatten_kernel<<<blocks_for(n, CCL_THREADS), CCL_THREADS, 0, st>>>(d_labels, n);
         MSG_LAUNCHED(ctx);
@@ -709,10 +1165,13 @@ int k_ccl_color(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, 
 int k_ccl_binary(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int conn, int32_t* d_labels)
 {
     dim3 grid((w + CCL_THREADS - 1) / CCL_THREADS, h);
-    size_t n = (size_t)w * h;
     cudaStream_t st = ctx->stream;
     if (w > CCL_MAX_CHUNKS * 32) return msg_fail(ctx, MSG_EINVAL, "labelling supports rows up to %d pixels", CCL_MAX_CHUNKS * 32);
-    (void)n;
+    if (!ctx->tune.ccl_legacy) {
+        ccl_ws ws;
+        MSG_TRY(ccl_workspace(ctx, w, h, false, &ws));
+        return ccl_tiles<1>(ctx, d_mask, step, w, h, 0, conn, d_labels, ws);
+    }
     ccl_rows_kernel<1><<<h, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
     MSG_LAUNCHED(ctx);
     if (conn == 8) ccl_merge_kernel<1, 8><<<grid, CCL_THREADS, 0, st>>>(d_mask, step, w, h, 0, d_labels);
@@ -835,9 +1294,39 @@ int k_labels_to_u16(msg_ctx* ctx, const int32_t* d_labels, int w, int h, uint16_
     return MSG_OK;
 }
 
+// Colour-predicate labelling with canonical numbering in one call (the fused pipeline's label stage): phases A .. F.
+// src_kind 0: packed plane (pitch in pixels); 2: BGR bytes (pitch in bytes) -- the stand-alone operator needs no plane.
+int k_label_canonical_src(msg_ctx* ctx, const void* d_img, size_t pitch, int src_kind, int w, int h, int d, int conn,
+                          int32_t* d_labels, int32_t* d_n)
+{
+    if (w > CCL_MAX_CHUNKS * 32) return msg_fail(ctx, MSG_EINVAL, "labelling supports rows up to %d pixels", CCL_MAX_CHUNKS * 32);
+    ccl_ws ws;
+    MSG_TRY(ccl_workspace(ctx, w, h, true, &ws));
+    if (src_kind == 2) MSG_TRY(ccl_tiles<2>(ctx, d_img, pitch, w, h, d, conn, ws.L, ws));
+    else MSG_TRY(ccl_tiles<0>(ctx, d_img, pitch, w, h, d, conn, ws.L, ws));
+    return ccl_canonical(ctx, w, h, ws, d_labels, d_n, 0);
+}
+
 int k_label_canonical(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int conn, int32_t* d_labels,
                       int32_t* d_n)
 {
-    MSG_TRY(k_ccl_color(ctx, d_plane, pitch, w, h, d, conn, d_labels, -1, w));
-    return k_relabel_canonical(ctx, d_labels, w, h, 1, d_n, 0);
+    if (ctx->tune.ccl_legacy) {
+        MSG_TRY(k_ccl_color(ctx, d_plane, pitch, w, h, d, conn, d_labels, -1, w));
+        return k_relabel_canonical(ctx, d_labels, w, h, 1, d_n, 0);
+    }
+    return k_label_canonical_src(ctx, d_plane, (size_t)pitch, 0, w, h, d, conn, d_labels, d_n);
+}
+
+// Imgproc.connectedComponents: binary predicate, canonical numbering; *d_n = number of labels INCLUDING the background
+int k_cc_canonical(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int conn, int32_t* d_labels, int32_t* d_n)
+{
+    if (ctx->tune.ccl_legacy) {
+        MSG_TRY(k_ccl_binary(ctx, d_mask, step, w, h, conn, d_labels));
+        return k_relabel_canonical(ctx, d_labels, w, h, 1, d_n, 1);
+    }
+    if (w > CCL_MAX_CHUNKS * 32) return msg_fail(ctx, MSG_EINVAL, "labelling supports rows up to %d pixels", CCL_MAX_CHUNKS * 32);
+    ccl_ws ws;
+    MSG_TRY(ccl_workspace(ctx, w, h, true, &ws));
+    MSG_TRY(ccl_tiles<1>(ctx, d_mask, step, w, h, 0, conn, ws.L, ws));
+    return ccl_canonical(ctx, w, h, ws, d_labels, d_n, 1);
 }

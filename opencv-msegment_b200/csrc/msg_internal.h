@@ -91,6 +91,7 @@ struct msg_ctx {
     uint8_t* d_colors; size_t d_colors_cap;
     uint8_t* d_aux;    size_t d_aux_cap;     // 8-bit planes of the seed generator (gray, blurred, classes, edges, ...)
     uint8_t* d_small;  size_t d_small_cap;   // small tables of the colour-seed generator / bilateral filter (histogram, spans, weights)
+    uint8_t* d_ccl;    size_t d_ccl_cap;     // labelling stage: union-find forest (canonical path), root bitmap, block sums
     uint8_t* d_ws;     size_t d_ws_cap;      // watershed queues / per-image state (k_watershed.cu)
     int32_t* d_cells;  size_t d_cells_cap;   // active pixels per 32x32 cell of the current level + tile order (K1 scheduling)
 
@@ -202,6 +203,9 @@ int k_copy_labels_2d(msg_ctx* ctx, const int32_t* src, size_t sstep, int32_t* ds
 // colour-predicate labelling with canonical numbering (1..n in raster order of first pixel) in one call; *d_n = n
 int k_label_canonical(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int w, int h, int d, int conn, int32_t* d_labels,
                       int32_t* d_n);
+int k_label_canonical_src(msg_ctx* ctx, const void* d_img, size_t pitch, int src_kind, int w, int h, int d, int conn,
+                          int32_t* d_labels, int32_t* d_n);
+int k_cc_canonical(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int conn, int32_t* d_labels, int32_t* d_n);
 // dense int32 labels -> 16-bit labels (saturating at 65535), dstep in bytes
 int k_labels_to_u16(msg_ctx* ctx, const int32_t* d_labels, int w, int h, uint16_t* d_dst, size_t dstep);
 int k_seam_pairs(msg_ctx* ctx, const uint8_t* up_bgr, const int32_t* up_lab, const uint8_t* lo_bgr,
