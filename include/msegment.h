@@ -375,6 +375,49 @@ MSG_API int msg_strip_finalize_dense_dev(msg_ctx* ctx, int32_t* d_labels, size_t
                                  int full_width, int offset, const int32_t* d_frm_sorted, const int32_t* d_dense, int n_map,
                                  int frm_lo);
 
+/* ---- strip sharding as a library feature (round 2): plan, device-side seam resolution, sharded merge ------------------------
+ * The collectives themselves stay with the host (NCCL: ncclSend / ncclRecv of halo rows and one boundary row per seam, ONE
+ * ncclAllGather of the seam payloads, ncclAllReduce + ncclAllGather for the merge tables -- "NCCL only for that exchange",
+ * BASELINE.json north_star); everything else is behind this ABI, so a Java / C host drives the same sequence the Python tool
+ * tools/shard_large_image.py drives (INTEGRATION.md section 6 lists the calls in order). */
+#define MSG_MAX_STRIPS 64
+#define MSG_SHARD_TABLE_HEADER 192
+typedef struct msg_shard_plan {
+    int n_strips, width, height, max_level, halo_rows;
+    int row0[MSG_MAX_STRIPS], row1[MSG_MAX_STRIPS];      /* rows [row0, row1) a rank filters and labels */
+    int halo0[MSG_MAX_STRIPS], halo1[MSG_MAX_STRIPS];    /* source rows [halo0, halo1) it must hold to do so */
+} msg_shard_plan;
+/* Pure host function: contiguous strips whose first rows are multiples of 2^max_level (pyramid phase) + their halo ranges
+ * (msg_meanshift_halo_rows).  MSG_EINVAL if the image is too small for n_strips. */
+MSG_API int msg_shard_plan_make(int width, int height, int n_strips, double sp, int max_level, int term_type, int max_count,
+                        msg_shard_plan* out);
+/* Device-side form of step (3) of the single-exchange seam resolution above (no host round trip, no host union-find):
+ * d_gathered = the all-gathered payloads, n_strips x (width + 1) x 4 int32, row 0 of every payload = (quad count, root count,
+ * 0, 0), rows 1.. = the quads of msg_seam_quads_dev; row0[s] = first row of strip s.  d_tables (int32, at least
+ * MSG_SHARD_TABLE_HEADER + 2 * n_strips * width entries) receives: [0] n_map, [1] total number of regions of the image,
+ * [2 + s] offset of strip s, [2 + MSG_MAX_STRIPS + s] frm_lo of strip s, then frm[n_strips * width], dense[n_strips * width]. */
+MSG_API int msg_strip_resolve_dense_dev(msg_ctx* ctx, const int32_t* d_gathered, int n_strips, int width, const int* row0,
+                                int32_t* d_tables, size_t tables_capacity_ints);
+/* Step (4) reading everything from d_tables: rewrites the strip with the dense global ids (identical to the unsharded call). */
+MSG_API int msg_strip_finalize_tables_dev(msg_ctx* ctx, int32_t* d_labels, size_t labels_step, int width, int rows, int row0,
+                                  int full_width, int strip, int n_strips, const int32_t* d_tables);
+/* Region merge across strips: labels are the dense global ids 1..n_total.
+ *  (1) every rank: msg_strip_merge_stats_dev accumulates the area / colour sums of ITS strip into the caller-owned tables
+ *      d_area[n_total + 1] (uint32) and d_sum[3 * (n_total + 1)] (uint64, B G R per label; both are zeroed by the call) and
+ *      appends the adjacent (label, label) pairs of the strip -- including the seam with the strip above when
+ *      d_up_row_labels (the dense labels of that strip's last row) is given -- to d_pairs (2 int32 per pair, at most pair_cap
+ *      pairs; *d_npairs = pairs found, the call fails later if it exceeded pair_cap);
+ *  (2) host: all-reduce(sum) d_area and d_sum over the ranks, all-gather the pair lists;
+ *  (3) every rank: msg_strip_merge_finish_dev runs the merge rounds on the (identical) tables -- identical decisions on every
+ *      rank -- and rewrites its strip; *d_n_out = regions after the merge.  d_area / d_sum are modified.
+ * The result equals msg_merge_regions_dev on the whole image bit for bit. */
+MSG_API int msg_strip_merge_stats_dev(msg_ctx* ctx, const uint8_t* d_bgr_rows, size_t step, const int32_t* d_labels, size_t labels_step,
+                              int width, int rows, const int32_t* d_up_row_labels, int n_total, uint32_t* d_area,
+                              unsigned long long* d_sum, int32_t* d_pairs, long long pair_cap, int32_t* d_npairs);
+MSG_API int msg_strip_merge_finish_dev(msg_ctx* ctx, int32_t* d_labels, size_t labels_step, int width, int rows, long long full_pixels,
+                               int n_total, uint32_t* d_area, unsigned long long* d_sum, const int32_t* d_all_pairs,
+                               long long n_all_pairs, int min_size, int color_dist, int32_t* d_n_out);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 typedef struct msg_timings { /* milliseconds of the last host-buffer call, CUDA events */
     float h2d_ms, filter_ms, label_ms, merge_ms, render_ms, d2h_ms, total_ms;

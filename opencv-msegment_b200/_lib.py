@@ -18,6 +18,14 @@ class SegmentParams(C.Structure):
                 ("color_dist", C.c_int), ("render_depth", C.c_int), ("connectivity", C.c_int), ("labels_type", C.c_int)]
 
 
+MAX_STRIPS, SHARD_TABLE_HEADER = 64, 192
+
+
+class ShardPlan(C.Structure):
+    _fields_ = [("n_strips", C.c_int), ("width", C.c_int), ("height", C.c_int), ("max_level", C.c_int), ("halo_rows", C.c_int),
+                ("row0", C.c_int * 64), ("row1", C.c_int * 64), ("halo0", C.c_int * 64), ("halo1", C.c_int * 64)]
+
+
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "filter_ms", "label_ms", "merge_ms", "render_ms", "d2h_ms", "total_ms")]
 
@@ -104,6 +112,11 @@ SIGNATURES = {
     "msg_strip_apply_dense_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _I, _P, _P, _I]),
     "msg_seam_quads_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "msg_strip_finalize_dense_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _I, _P, _P, _I, _I]),
+    "msg_shard_plan_make": (_I, [_I, _I, _I, _D, _I, _I, _I, C.POINTER(ShardPlan)]),
+    "msg_strip_resolve_dense_dev": (_I, [_P, _P, _I, _I, C.POINTER(_I), _P, _SZ]),
+    "msg_strip_finalize_tables_dev": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _I, _I, _P]),
+    "msg_strip_merge_stats_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _I, _P, _I, _P, _P, _P, C.c_longlong, _P]),
+    "msg_strip_merge_finish_dev": (_I, [_P, _P, _SZ, _I, _I, C.c_longlong, _I, _P, _P, _P, C.c_longlong, _I, _I, _P]),
     "msg_get_timings": (_I, [_P, C.POINTER(Timings)]),
     "msg_get_stats": (_I, [_P, C.POINTER(Stats)]),
     "msg_debug_get_plane": (_I, [_P, _I, _I, _P, _SZ, C.POINTER(_I), C.POINTER(_I)]),

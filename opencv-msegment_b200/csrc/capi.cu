@@ -1171,6 +1171,70 @@ int msg_wait(msg_ctx* ctx, int ticket, int32_t* n_regions)
     return MSG_OK;
 }
 
+// ============================================================================ strip sharding, round 2: device-side tables, merge
+
+int msg_strip_resolve_dense_dev(msg_ctx* ctx, const int32_t* d_gathered, int n_strips, int width, const int* row0, int32_t* d_tables,
+                                size_t tables_capacity_ints)
+{
+    CTX_ENTER(ctx);
+    if (!d_gathered || !row0 || !d_tables || n_strips < 1 || n_strips > MSG_MAX_STRIPS || width < 1)
+        return msg_fail(ctx, MSG_EINVAL, "strip resolve: bad arguments");
+    if (tables_capacity_ints < (size_t)MSG_SHARD_TABLE_HEADER + 2 * (size_t)n_strips * width)
+        return msg_fail(ctx, MSG_EINVAL, "strip resolve: d_tables needs MSG_SHARD_TABLE_HEADER + 2 * n_strips * width ints");
+    for (int s = 1; s < n_strips; s++)
+        if (row0[s] <= row0[s - 1]) return msg_fail(ctx, MSG_EINVAL, "strip resolve: row0 must be ascending");
+    return k_strip_resolve(ctx, d_gathered, n_strips, width, row0, d_tables);
+}
+
+int msg_strip_finalize_tables_dev(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, int row0, int full_w, int strip,
+                                  int n_strips, const int32_t* d_tables)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, rows, 4, "labels"));
+    if (lstep % 4 || full_w != w || !d_tables || strip < 0 || strip >= n_strips || n_strips > MSG_MAX_STRIPS)
+        return msg_fail(ctx, MSG_EINVAL, "strip finalize: bad arguments");
+    if (!ctx->d_scratch) return msg_fail(ctx, MSG_ESTATE, "strip finalize: msg_strip_rank_dev must run first on this context");
+    return k_strip_finalize_tables(ctx, d_labels, lstep, w, rows, (long long)row0 * full_w, d_tables, n_strips * w, strip);
+}
+
+int msg_strip_merge_stats_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, const int32_t* d_labels, size_t lstep, int w, int rows,
+                              const int32_t* d_up_row_labels, int n_total, uint32_t* d_area, unsigned long long* d_sum,
+                              int32_t* d_pairs, long long pair_cap, int32_t* d_npairs)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_bgr, step, w, rows, 3, "strip merge image"));
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, rows, 4, "strip merge labels"));
+    if (lstep != (size_t)w * 4) return msg_fail(ctx, MSG_EINVAL, "strip merge: labels must be dense");
+    if (n_total < 0 || !d_area || !d_sum || !d_pairs || !d_npairs || pair_cap < 0)
+        return msg_fail(ctx, MSG_EINVAL, "strip merge: bad table arguments");
+    msg_plane s;
+    s.w = w; s.rows = rows; s.y0 = 0; s.hfull = rows; s.pitch = msg_align_up(w, 32);
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_planes, &ctx->d_planes_cap, (size_t)s.pitch * rows * sizeof(uint32_t)));
+    s.p = ctx->d_planes;
+    MSG_TRY(k_bgr_to_plane(ctx, d_bgr, step, s));
+    return k_strip_merge_stats(ctx, s.p, s.pitch, d_labels, w, rows, d_up_row_labels, n_total, d_area, d_sum, d_pairs, pair_cap, d_npairs);
+}
+
+int msg_strip_merge_finish_dev(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, long long full_pixels, int n_total,
+                               uint32_t* d_area, unsigned long long* d_sum, const int32_t* d_all_pairs, long long n_all_pairs,
+                               int min_size, int color_dist, int32_t* d_n_out)
+{
+    CTX_ENTER(ctx);
+    MSG_TRY(check_img(ctx, d_labels, lstep, w, rows, 4, "strip merge labels"));
+    if (lstep != (size_t)w * 4) return msg_fail(ctx, MSG_EINVAL, "strip merge: labels must be dense");
+    if (n_total < 0 || !d_area || !d_sum || n_all_pairs < 0 || (n_all_pairs > 0 && !d_all_pairs) || min_size < 0 || color_dist < 0)
+        return msg_fail(ctx, MSG_EINVAL, "strip merge: bad arguments");
+    if (min_size <= 0 && color_dist <= 0) {
+        if (d_n_out) {
+            ctx->h_counters[20] = n_total;
+            MSG_CUDA(ctx, cudaMemcpyAsync(d_n_out, ctx->h_counters + 20, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        return MSG_OK;
+    }
+    return k_strip_merge_finish(ctx, d_labels, w, rows, full_pixels, n_total, d_area, d_sum, d_all_pairs, n_all_pairs, min_size,
+                                color_dist, d_n_out);
+}
+
 // ============================================================================ watershed (f1)
 
 int msg_watershed_batch_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, size_t image_stride, int32_t* d_markers, size_t mstep,

@@ -72,7 +72,21 @@ struct merge_persist_args {
     int min_size, color_dist;
     int vec;                  // 1: w % 4 == 0 and labels 16-byte aligned -> 16-byte loads in the statistics pass
     int small_max;            // labels up to which the single-CTA rounds kernel is used (0 forces the large path)
+    int nin_host;             // >= 0: the label count is known on the host (strip-sharded merge) and overrides *n_saved
+    long long npairs_host;    // >= 0: number of valid entries of `pairs` (all-gathered list), overrides *npairs
 };
+
+__device__ __forceinline__ int merge_nin(const merge_persist_args& A)
+{
+    int nin = A.nin_host >= 0 ? A.nin_host : *A.n_saved;
+    return nin > A.cap ? A.cap : nin;
+}
+
+__device__ __forceinline__ long long merge_npairs(const merge_persist_args& A)
+{
+    long long np = A.npairs_host >= 0 ? A.npairs_host : (long long)*A.npairs;
+    return np > A.pair_cap ? A.pair_cap : np;
+}
 
 __device__ __forceinline__ bool merge_is_small(const merge_persist_args& A, int nin)
 {
@@ -227,8 +241,7 @@ __global__ void __launch_bounds__(MT) merge_stats_kernel(merge_persist_args A)
     const long long gtid = (long long)blockIdx.x * MT + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * MT;
     const long long gwarp = gtid >> 5, nwarps = nthreads >> 5;
-    int nin = *A.n_saved;
-    if (nin > A.cap) nin = A.cap;
+    const int nin = merge_nin(A);
     const int w = A.w, h = A.h;
     const merge_tables t = A.t;
     if (A.vec) { stats_pass_vec4(A, t, nin, lane, gwarp, nwarps); return; }
@@ -322,12 +335,11 @@ __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist
     uint32_t* hset = sm_tab + 7 * NS;          // set of adjacent label pairs
     __shared__ int s_accepted, s_overflow;
     __shared__ int s_wsum[ST / 32];
-    int nin = *A.n_saved;
-    if (nin > A.cap) nin = A.cap;
+    const int nin = merge_nin(A);
     if (!merge_is_small(A, nin)) return;
     const int nl = nin + 1;
     const int tid = threadIdx.x, lane = tid & 31;
-    long long npairs = *A.npairs;
+    long long npairs = merge_npairs(A);
     if (npairs > A.pair_cap) npairs = A.pair_cap;
     for (int i = tid; i < nl; i += ST) {
         par[i] = i;
@@ -481,13 +493,11 @@ __global__ void __launch_bounds__(MT) merge_rounds_large_kernel(merge_persist_ar
     const int lane = threadIdx.x & 31;
     const long long gtid = (long long)blockIdx.x * MT + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * MT;
-    int nin = *A.n_saved;
-    if (nin > A.cap) nin = A.cap;
+    const int nin = merge_nin(A);
     if (merge_is_small(A, nin)) return;                  // uniform over the grid: the small-path kernel did the work
     const int nl = nin + 1;
     merge_tables t = A.t;
-    long long npairs = *A.npairs;
-    if (npairs > A.pair_cap) npairs = A.pair_cap;
+    const long long npairs = merge_npairs(A);
 
     const long long INF = 1ll << 40;
     int rounds = 0;
@@ -610,8 +620,7 @@ __global__ void __launch_bounds__(MT) merge_rounds_large_kernel(merge_persist_ar
 // Labels outside 1..n_in are left as they are.  16-byte loads, two in flight per thread, when the buffer is aligned.
 __global__ void __launch_bounds__(MT) merge_rewrite_kernel(merge_persist_args A)
 {
-    int nin = *A.n_saved;
-    if (nin > A.cap) nin = A.cap;
+    const int nin = merge_nin(A);
     const int32_t* __restrict__ fin = reinterpret_cast<const int32_t*>(A.t.mean);
     const long long gtid = (long long)blockIdx.x * MT + threadIdx.x, nthreads = (long long)gridDim.x * MT;
     const long long n = (long long)A.w * A.h;
@@ -739,6 +748,7 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     A.rounds_out = ctx->d_counters + 10;
     A.n_out = d_n_out ? d_n_out : ctx->d_counters + 11;
     A.min_size = min_size; A.color_dist = color_dist;
+    A.nin_host = -1; A.npairs_host = -1;
     A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !ctx->tune.merge_scalar) ? 1 : 0;
     A.small_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : SMALL_MAX_LABELS;   // test hook: 0 forces the cooperative path
     if (A.small_max > SMALL_MAX_LABELS) A.small_max = SMALL_MAX_LABELS;
@@ -790,5 +800,130 @@ int k_merge(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_t* d_labels,
     }
     MSG_TRY(merge_launch(ctx, d_plane, pitch, d_labels, w, h, min_size, color_dist, d_n_in, d_n_out));
     MSG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 10, ctx->d_counters + 10, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return MSG_OK;
+}
+
+
+// ================================================================ strip-sharded merge (one very large image over several GPUs)
+// regions are global (dense labels 1..n_total after the seam resolution); every rank accumulates the statistics
+// and the adjacency list of ITS strip into caller-owned tables, the host sums the tables over the ranks (all-reduce) and
+// concatenates the pair lists (all-gather), and every rank then runs the same rounds on the same tables -- identical decisions
+// without any further exchange -- and rewrites its strip.  Integer sums are order independent, duplicates in the pair list are
+// harmless (the rounds take minima over it), so the result equals the unsharded merge bit for bit.
+namespace {
+
+__global__ void __launch_bounds__(MT) strip_merge_init_kernel(unsigned int* __restrict__ area, unsigned long long* __restrict__ sum,
+                                                              int nl, int32_t* __restrict__ npairs)
+{
+    const long long gtid = (long long)blockIdx.x * MT + threadIdx.x, nthreads = (long long)gridDim.x * MT;
+    for (long long i = gtid; i < nl; i += nthreads) { area[i] = 0; sum[3 * i] = 0; sum[3 * i + 1] = 0; sum[3 * i + 2] = 0; }
+    if (gtid == 0) *npairs = 0;
+}
+
+// adjacency across the seam above this strip: last row of the strip above (dense labels) against my first row
+__global__ void __launch_bounds__(MT) seam_adjacency_kernel(const int32_t* __restrict__ up, const int32_t* __restrict__ lo, int w,
+                                                            int nin, int2* __restrict__ pairs, long long cap,
+                                                            int32_t* __restrict__ npairs)
+{
+    const int x = blockIdx.x * MT + threadIdx.x;
+    int a = 0, b = 0;
+    if (x < w) { a = up[x]; b = lo[x]; }
+    bool emit = a > 0 && b > 0 && a != b && a <= nin && b <= nin;
+    if (emit && x > 0 && up[x - 1] == a && lo[x - 1] == b) emit = false;      // same pair as the column to the left
+    const unsigned m = __ballot_sync(0xffffffffu, emit);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    long long pos = 0;
+    if (lane == 0) pos = (long long)atomicAdd(npairs, __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+    if (emit && pos < cap) pairs[pos] = make_int2(a, b);
+}
+
+__global__ void __launch_bounds__(MT) strip_merge_par_kernel(int32_t* __restrict__ par, int nl, int32_t* __restrict__ accepted,
+                                                             int32_t* __restrict__ rounds)
+{
+    const long long gtid = (long long)blockIdx.x * MT + threadIdx.x, nthreads = (long long)gridDim.x * MT;
+    for (long long i = gtid; i < nl; i += nthreads) par[i] = (int)i;
+    if (gtid == 0) { *accepted = 0; *rounds = 0; }
+}
+
+}  // namespace
+
+int k_strip_merge_stats(msg_ctx* ctx, const uint32_t* d_plane, int pitch, const int32_t* d_labels, int w, int rows,
+                        const int32_t* d_up_row_labels, int n_total, unsigned int* d_area, unsigned long long* d_sum,
+                        int32_t* d_pairs, long long pair_cap, int32_t* d_npairs)
+{
+    merge_persist_args A;
+    memset(&A, 0, sizeof(A));
+    A.t.area = d_area; A.t.sum = d_sum;
+    A.pairs = (int2*)d_pairs; A.pair_cap = pair_cap; A.npairs = d_npairs;
+    A.plane = d_plane; A.pitch = pitch; A.labels = const_cast<int32_t*>(d_labels); A.w = w; A.h = rows;
+    A.cap = n_total; A.nin_host = n_total; A.npairs_host = -1;
+    A.n_saved = ctx->d_counters + 14;
+    A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !ctx->tune.merge_scalar) ? 1 : 0;
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)w * rows;
+    const int wide = ctx->sm_count * 8;
+    auto blocks_for = [&](size_t items) { size_t b = (items + MT - 1) / MT; return (int)(b < 1 ? 1 : (b > (size_t)wide ? (size_t)wide : b)); };
+    strip_merge_init_kernel<<<blocks_for((size_t)n_total + 1), MT, 0, st>>>(d_area, d_sum, n_total + 1, d_npairs);
+    MSG_LAUNCHED(ctx);
+    size_t stat_threads = A.vec ? ((n + 127) / 128) * 32 : ((size_t)((w + 31) / 32) * rows) * 32;
+    merge_stats_kernel<<<blocks_for(stat_threads), MT, 0, st>>>(A);
+    MSG_LAUNCHED(ctx);
+    if (d_up_row_labels) {
+        seam_adjacency_kernel<<<(w + MT - 1) / MT, MT, 0, st>>>(d_up_row_labels, d_labels, w, n_total, (int2*)d_pairs, pair_cap, d_npairs);
+        MSG_LAUNCHED(ctx);
+    }
+    MSG_CHECK_LAUNCH(ctx);
+    return MSG_OK;
+}
+
+int k_strip_merge_finish(msg_ctx* ctx, int32_t* d_labels, int w, int rows, long long full_pixels, int n_total, unsigned int* d_area,
+                         unsigned long long* d_sum, const int32_t* d_all_pairs, long long n_all_pairs, int min_size, int color_dist,
+                         int32_t* d_n_out)
+{
+    int blocks_per_sm = 0;
+    MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
+    if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
+    const int grid = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+    const size_t nl = (size_t)n_total + 1;
+    const size_t bytes = nl * (8 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256;
+    MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));
+    char* base = (char*)ctx->d_ovf;
+    merge_persist_args A;
+    memset(&A, 0, sizeof(A));
+    A.t.area = d_area; A.t.sum = d_sum;
+    A.t.best = (unsigned long long*)base;  base += nl * 8;
+    A.t.mean = (uint32_t*)base;            base += nl * 4;
+    A.t.par = (int32_t*)base;              base += nl * 4;
+    A.newid = (int32_t*)base;              base += nl * 4;
+    A.bsum = (int32_t*)base;
+    A.pairs = (int2*)const_cast<int32_t*>(d_all_pairs); A.pair_cap = n_all_pairs; A.npairs = ctx->d_counters + 13;
+    A.labels = d_labels; A.w = w; A.h = rows;
+    A.cap = n_total; A.nin_host = n_total; A.npairs_host = n_all_pairs;
+    A.n_saved = ctx->d_counters + 14;
+    A.accepted = ctx->d_counters + 9;
+    A.rounds_out = ctx->d_counters + 10;
+    A.n_out = d_n_out ? d_n_out : ctx->d_counters + 11;
+    A.min_size = min_size; A.color_dist = color_dist;
+    A.small_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : SMALL_MAX_LABELS;
+    if (A.small_max > SMALL_MAX_LABELS) A.small_max = SMALL_MAX_LABELS;
+    if (full_pixels > SMALL_MAX_PIXELS) A.small_max = 0;      // the single-CTA path keeps 32-bit colour sums: whole image <= 2^24 pixels
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)w * rows;
+    const int wide = ctx->sm_count * 8;
+    auto blocks_for = [&](size_t items) { size_t b = (items + MT - 1) / MT; return (int)(b < 1 ? 1 : (b > (size_t)wide ? (size_t)wide : b)); };
+    strip_merge_par_kernel<<<blocks_for(nl), MT, 0, st>>>(A.t.par, (int)nl, A.accepted, A.rounds_out);
+    MSG_LAUNCHED(ctx);
+    const size_t small_smem = ((size_t)(SMALL_MAX_LABELS + 1) * 7 + SMALL_HSET) * sizeof(uint32_t);
+    MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel, small_smem));
+    merge_rounds_small_kernel<<<1, ST, small_smem, st>>>(A);
+    MSG_LAUNCHED(ctx);
+    void* args[] = {&A};
+    MSG_CUDA(ctx, cudaLaunchCooperativeKernel((void*)merge_rounds_large_kernel, dim3(grid), dim3(MT), args, 0, st));
+    MSG_LAUNCHED(ctx);
+    merge_rewrite_kernel<<<blocks_for((n / 4 + 1) / 2 + 1), MT, 0, st>>>(A);
+    MSG_LAUNCHED(ctx);
+    MSG_CHECK_LAUNCH(ctx);
     return MSG_OK;
 }

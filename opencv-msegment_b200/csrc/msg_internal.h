@@ -257,6 +257,17 @@ int k_bilateral(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_dst
 int k_contour_markers(msg_ctx* ctx, const uint8_t* d_mask, size_t step, int w, int h, int32_t* d_markers, size_t mstep,
                       int32_t* n_contours_host);
 
+// k_shard.cu / k_merge.cu: device-side seam resolution and the strip-sharded merge
+int k_strip_resolve(msg_ctx* ctx, const int32_t* d_gathered, int n_strips, int width, const int* row0, int32_t* d_tables);
+int k_strip_finalize_tables(msg_ctx* ctx, int32_t* d_labels, size_t lstep, int w, int rows, long long base, const int32_t* d_tables,
+                            int cap, int strip);
+int k_strip_merge_stats(msg_ctx* ctx, const uint32_t* d_plane, int pitch, const int32_t* d_labels, int w, int rows,
+                        const int32_t* d_up_row_labels, int n_total, unsigned int* d_area, unsigned long long* d_sum,
+                        int32_t* d_pairs, long long pair_cap, int32_t* d_npairs);
+int k_strip_merge_finish(msg_ctx* ctx, int32_t* d_labels, int w, int rows, long long full_pixels, int n_total, unsigned int* d_area,
+                         unsigned long long* d_sum, const int32_t* d_all_pairs, long long n_all_pairs, int min_size, int color_dist,
+                         int32_t* d_n_out);
+
 // k_watershed.cu: exact cv::watershed, `count` images of one geometry per call
 int k_watershed(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, size_t image_stride, int32_t* d_markers, size_t mstep,
                 size_t markers_stride, int w, int h, int count, unsigned long long* d_pops);

@@ -89,6 +89,37 @@ def strip_finalize_dense(ctx, d_labels, lstep, w, rows, row0, full_w, offset, d_
                                                     _p(d_dense), int(n_map), int(frm_lo)))
 
 
+def shard_plan(w, h, n_strips, sp, max_level=1, termcrit=(3, 5, 1.0)):
+    """msg_shard_plan_make -> (halo_rows, [(row0, row1)], [(halo0, halo1)])"""
+    p = L.ShardPlan()
+    rc = L.load().msg_shard_plan_make(int(w), int(h), int(n_strips), float(sp), int(max_level), int(termcrit[0]), int(termcrit[1]),
+                                      C.byref(p))
+    if rc != L.MSG_OK:
+        raise ValueError("msg_shard_plan_make(%d x %d, %d strips, max_level %d) failed: %d" % (w, h, n_strips, max_level, rc))
+    return (p.halo_rows, [(p.row0[k], p.row1[k]) for k in range(n_strips)], [(p.halo0[k], p.halo1[k]) for k in range(n_strips)])
+
+
+def strip_resolve_dense(ctx, d_gathered, n_strips, w, row0s, d_tables, tables_ints):
+    arr = (C.c_int * n_strips)(*[int(r) for r in row0s])
+    ctx.check(ctx._lib.msg_strip_resolve_dense_dev(ctx._h, _p(d_gathered), int(n_strips), int(w), arr, _p(d_tables), int(tables_ints)))
+
+
+def strip_finalize_tables(ctx, d_labels, lstep, w, rows, row0, full_w, strip, n_strips, d_tables):
+    ctx.check(ctx._lib.msg_strip_finalize_tables_dev(ctx._h, _p(d_labels), lstep, w, rows, row0, full_w, int(strip), int(n_strips),
+                                                     _p(d_tables)))
+
+
+def strip_merge_stats(ctx, d_bgr, step, d_labels, lstep, w, rows, d_up_row_labels, n_total, d_area, d_sum, d_pairs, pair_cap, d_npairs):
+    ctx.check(ctx._lib.msg_strip_merge_stats_dev(ctx._h, _p(d_bgr), step, _p(d_labels), lstep, w, rows, _p(d_up_row_labels), int(n_total),
+                                                 _p(d_area), _p(d_sum), _p(d_pairs), int(pair_cap), _p(d_npairs)))
+
+
+def strip_merge_finish(ctx, d_labels, lstep, w, rows, full_pixels, n_total, d_area, d_sum, d_all_pairs, n_all_pairs, min_size, color_dist,
+                       d_n_out=0):
+    ctx.check(ctx._lib.msg_strip_merge_finish_dev(ctx._h, _p(d_labels), lstep, w, rows, int(full_pixels), int(n_total), _p(d_area),
+                                                  _p(d_sum), _p(d_all_pairs), int(n_all_pairs), int(min_size), int(color_dist), _p(d_n_out)))
+
+
 def connected_components(ctx, d_mask, step, d_labels, lstep, w, h, connectivity=8, d_n=0):
     ctx.check(ctx._lib.msg_connected_components_dev(ctx._h, _p(d_mask), step, _p(d_labels), lstep, w, h, int(connectivity),
                                                     _p(d_n)))

@@ -149,6 +149,101 @@ def test_strips_single_exchange_dense(w, h, n, sp, sr, ml):
     ctx.close()
 
 
+@pytest.mark.parametrize("w,h,n,sp,sr,ml,min_size,cd", [(600, 518, 3, 10, 10, 1, 30, 8), (333, 400, 4, 6, 15, 2, 20, 0),
+                                                        (420, 300, 5, 10, 10, 1, 0, 12), (512, 96, 6, 4, 30, 0, 25, 6),
+                                                        (1024, 700, 8, 10, 10, 1, 50, 10)])
+def test_strips_device_resolve_and_sharded_merge(w, h, n, sp, sr, ml, min_size, cd):
+    """Round 2: the whole strip pipeline without host arithmetic.  msg_shard_plan_make; per strip label + rank + seam quads; the
+    "all-gathered" payload buffer is resolved ON THE DEVICE (msg_strip_resolve_dense_dev) and consumed by
+    msg_strip_finalize_tables_dev -> labels identical to the unsharded call; then the strip-sharded merge (per-strip tables,
+    summed = the all-reduce, pair lists concatenated = the all-gather, identical rounds per strip) -> identical to
+    msg_merge_regions_dev on the whole image and to the oracle."""
+    im = orc.synth_bgr(w, h, 29)
+    src = torch.from_numpy(im).cuda()
+    ctx = mseg.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    full = torch.empty_like(src)
+    dev.meanshift(ctx, src.data_ptr(), 3 * w, full.data_ptr(), 3 * w, w, h, sp, sr, ml)
+    lab_full = torch.empty((h, w), dtype=torch.int32, device="cuda")
+    nfull = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dev.label_regions(ctx, full.data_ptr(), 3 * w, lab_full.data_ptr(), 4 * w, w, h, 2, nfull.data_ptr())
+    ctx.synchronize()
+    halo, strips, halos = dev.shard_plan(w, h, n, sp, ml)
+    ctxs = [mseg.Context(0) for _ in strips]
+    for c in ctxs:
+        c.set_stream(torch.cuda.current_stream().cuda_stream)
+    labs = []
+    gathered = torch.zeros((n, w + 1, 4), dtype=torch.int32, device="cuda")       # what ONE all-gather delivers to every rank
+    for k, (r0, r1) in enumerate(strips):
+        rows = full[r0:r1].contiguous()
+        l = torch.empty((r1 - r0, w), dtype=torch.int32, device="cuda")
+        dev.label_strip(ctxs[k], rows.data_ptr(), 3 * w, l.data_ptr(), 4 * w, w, r1 - r0, r0, w, 2)
+        dev.strip_rank(ctxs[k], l.data_ptr(), 4 * w, w, r1 - r0, r0, w, gathered[k, 0, 1:].data_ptr())
+        labs.append(l)
+    for k in range(1, n):
+        (u0, u1), (r0, r1) = strips[k - 1], strips[k]
+        up_lab = labs[k - 1][-1].contiguous()
+        up_rank1 = torch.zeros(w, dtype=torch.int32, device="cuda")
+        dev.strip_query_dense(ctxs[k - 1], up_lab.data_ptr(), w, w, u1 - u0, u0, w, 0, up_rank1.data_ptr())
+        dev.seam_quads(ctxs[k], full[r0 - 1].data_ptr(), up_lab.data_ptr(), up_rank1.data_ptr(), full[r0].data_ptr(),
+                       labs[k][0].data_ptr(), w, 2, r1 - r0, r0, w, gathered[k, 1:].data_ptr(), gathered[k, 0, 0:].data_ptr())
+    tables_ints = mseg.lib.SHARD_TABLE_HEADER + 2 * n * w
+    tables = torch.zeros(tables_ints, dtype=torch.int32, device="cuda")
+    for k, (r0, r1) in enumerate(strips):            # every rank resolves the same payload and rewrites its strip
+        dev.strip_resolve_dense(ctxs[k], gathered.data_ptr(), n, w, [s[0] for s in strips], tables.data_ptr(), tables_ints)
+        dev.strip_finalize_tables(ctxs[k], labs[k].data_ptr(), 4 * w, w, r1 - r0, r0, w, k, n, tables.data_ptr())
+    torch.cuda.synchronize()
+    got = torch.cat(labs)
+    total = int(tables[1].item())
+    assert total == int(nfull.item()) == int(lab_full.max().item())
+    assert torch.equal(got, lab_full), int((got != lab_full).sum().item())
+    # the host tables of round 1 agree with the device tables
+    host = gathered.cpu().numpy()
+    quads = np.concatenate([host[r, 1:1 + int(host[r, 0, 0])] for r in range(n)], axis=0)
+    frm, dense, offsets, frm_lo, total_h = sh.resolve_dense(quads, host[:, 0, 1], strips, w)
+    t = tables.cpu().numpy()
+    assert t[0] == len(frm) and t[1] == total_h
+    assert np.array_equal(t[2:2 + n], offsets) and np.array_equal(t[2 + 64:2 + 64 + n], frm_lo)
+    hdr = mseg.lib.SHARD_TABLE_HEADER
+    assert np.array_equal(t[hdr:hdr + len(frm)], frm) and np.array_equal(t[hdr + n * w:hdr + n * w + len(frm)], dense)
+    # ---- sharded merge
+    want = lab_full.clone()
+    nwant = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dev.merge_regions(ctx, full.data_ptr(), 3 * w, want.data_ptr(), 4 * w, w, h, min_size, cd, nwant.data_ptr())
+    area = torch.zeros((n, total + 1), dtype=torch.int32, device="cuda")
+    sums = torch.zeros((n, 3 * (total + 1)), dtype=torch.int64, device="cuda")
+    cap = 2 * w * max(r1 - r0 for r0, r1 in strips)
+    pairs = torch.zeros((n, cap, 2), dtype=torch.int32, device="cuda")
+    npairs = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for k, (r0, r1) in enumerate(strips):
+        up = labs[k - 1][-1].contiguous() if k else None
+        dev.strip_merge_stats(ctxs[k], full[r0:r1].contiguous().data_ptr(), 3 * w, labs[k].data_ptr(), 4 * w, w, r1 - r0,
+                              up.data_ptr() if up is not None else 0, total, area[k].data_ptr(), sums[k].data_ptr(),
+                              pairs[k].data_ptr(), cap, npairs[k:].data_ptr())
+    torch.cuda.synchronize()
+    assert int(area.sum().item()) == w * h                                           # every pixel counted exactly once
+    area_all, sums_all = area.sum(dim=0, dtype=torch.int32), sums.sum(dim=0)          # = all-reduce(sum)
+    cnts = npairs.cpu().tolist()
+    assert max(cnts) <= cap
+    all_pairs = torch.cat([pairs[k, :cnts[k]] for k in range(n)]).contiguous()        # = all-gather
+    nout = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for k, (r0, r1) in enumerate(strips):
+        a_k, s_k = area_all.clone(), sums_all.clone()                                 # every rank owns its copy of the tables
+        dev.strip_merge_finish(ctxs[k], labs[k].data_ptr(), 4 * w, w, r1 - r0, w * h, total, a_k.data_ptr(), s_k.data_ptr(),
+                               all_pairs.data_ptr(), all_pairs.shape[0], min_size, cd, nout[k:].data_ptr())
+    torch.cuda.synchronize()
+    got = torch.cat(labs)
+    assert len(set(nout.cpu().tolist())) == 1 and int(nout[0].item()) == int(nwant.item())
+    assert torch.equal(got, want), int((got != want).sum().item())
+    f = full.cpu().numpy()
+    n0, l0 = orc.label_regions(f, 2)
+    n1, l1 = orc.merge_regions(f, l0, min_size, cd)
+    assert n1 == int(nwant.item()) and np.array_equal(got.cpu().numpy(), l1)
+    for c in ctxs:
+        c.close()
+    ctx.close()
+
+
 def test_synth_rows_matches_full():
     ctx = mseg.Context(0)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)

@@ -79,6 +79,20 @@ def test_watershed_golden_extended(golden_dir):
         assert np.array_equal(got, g["out/%s" % name]), name
 
 
+def test_oracle_reproduces_cv2_whole_frame_digest_1080p(golden_dir):
+    """The 1080p unit of tests/golden/fullsize_digests.json (cv2 on the whole frame) against the oracle; the 4K units are
+    checked by tests/golden/campaign_digests.py (25 CPU-minutes, result in PROVENANCE.txt) and, on the GPU, by
+    tests/test_gpu_fullsize_cv2.py."""
+    import hashlib
+    import json
+    u = json.load(open(os.path.join(golden_dir, "fullsize_digests.json")))["units"]["c2_seed2"]
+    im = orc.synth_bgr(u["w"], u["h"], u["seed"])
+    f = orc.meanshift_filter(im, u["sp"], u["sr"], 1)
+    assert hashlib.sha256(np.ascontiguousarray(f).tobytes()).hexdigest() == u["filtered_sha256"]
+    n, lab = orc.label_regions(f, 2)
+    assert n == u["n_regions"] and hashlib.sha256(np.ascontiguousarray(lab).tobytes()).hexdigest() == u["labels_sha256"]
+
+
 def test_render_rule():
     # PictureService.java:928: 0 < index <= depth -> colour, else background
     rng = np.random.default_rng(1)

@@ -166,3 +166,22 @@ def test_resolve_dense_single_exchange(w, h, n_strips, seed):
         own = offsets[s] + np.searchsorted(ranks[s], v) - (j - frm_lo[s]) + 1
         got[r0:r1] = np.where(hit, dense[np.minimum(j, max(len(dense) - 1, 0))] if len(dense) else 0, own)
     assert np.array_equal(got, want)
+
+
+def test_c_shard_plan_matches_python_planner():
+    """msg_shard_plan_make (pure host C, what a Java / C host calls) gives the strips and halo ranges of the Python planner."""
+    import msegment_b200 as mseg
+    dev = mseg.device
+    sh = mseg.pkg.sharded
+    for (w, h, n, sp, ml) in [(16384, 16384, 8, 10, 1), (8192, 8192, 8, 10, 1), (4096, 4096, 2, 10, 1), (600, 518, 3, 10, 1),
+                              (333, 400, 4, 6, 2), (257, 300, 2, 8, 0), (512, 96, 6, 4, 0), (1000, 1001, 7, 20, 3), (50, 64, 64, 2, 0)]:
+        halo, strips, halos = dev.shard_plan(w, h, n, sp, ml)
+        assert halo == dev.halo_rows(sp, ml)
+        assert strips == sh.plan_strips(h, n, ml), (w, h, n, ml)
+        assert halos == [sh.halo_range(r0, r1, h, halo, ml) for r0, r1 in strips]
+        assert strips[0][0] == 0 and strips[-1][1] == h and all(a < b for a, b in strips)
+    import pytest
+    with pytest.raises(ValueError):
+        dev.shard_plan(100, 10, 8, 10, 2)          # too small for 8 strips at alignment 4
+    with pytest.raises(ValueError):
+        dev.shard_plan(100, 1000, 65, 10, 0)       # more than MSG_MAX_STRIPS
