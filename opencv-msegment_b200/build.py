@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmsegment_b200.so")
-SOURCES = ["capi.cu", "k_convert.cu", "k_meanshift.cu", "k_ccl.cu", "k_merge.cu", "k_filters.cu", "k_seeds.cu", "k_colorseeds.cu", "k_contours.cu", "k_watershed.cu", "k_shard.cu"]
+SOURCES = ["capi.cu", "k_convert.cu", "k_meanshift.cu", "k_ccl.cu", "k_merge.cu", "k_filters.cu", "k_seeds.cu", "k_colorseeds.cu", "k_dt_fixed.cu", "k_contours.cu", "k_watershed.cu", "k_shard.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden", "--use_fast_math=false" if False else "-Xptxas", "-v"]
 

@@ -490,11 +490,15 @@ int k_threshold_u8(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_
     return MSG_OK;
 }
 
-int k_distance_transform_max_width(msg_ctx* ctx) { (void)ctx; return DT_THREADS * DT_PMAXMAX; }
+int k_distance_transform_max_width(msg_ctx* ctx)
+{
+    return ctx->tune.dt_fixed ? k_distance_transform_fixed_max_dim() : DT_THREADS * DT_PMAXMAX;
+}
 
 // d_dist: dense w*h floats; d_max (device float, may not be NULL): maximum of the result
 int k_distance_transform(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, float* d_dist, int w, int h, float* d_max)
 {
+    if (ctx->tune.dt_fixed) return k_distance_transform_fixed(ctx, d_src, sstep, d_dist, w, h, d_max);
     if (w > k_distance_transform_max_width(ctx))
         return msg_fail(ctx, MSG_EINVAL, "distanceTransform supports rows up to %d pixels", k_distance_transform_max_width(ctx));
     int need = (w + DT_THREADS - 1) / DT_THREADS;

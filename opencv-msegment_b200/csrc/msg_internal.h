@@ -246,6 +246,9 @@ int k_threshold_u8(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, uint8_t* d_
                    const int32_t* d_thresh, int thresh, int maxval);
 int k_distance_transform_max_width(msg_ctx* ctx);
 int k_distance_transform(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, float* d_dist, int w, int h, float* d_max);
+// k_dt_fixed.cu: the same call in OpenCV's own 16.16 fixed-point arithmetic (option "dt_fixed"); k_distance_transform dispatches
+int k_distance_transform_fixed_max_dim();
+int k_distance_transform_fixed(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, float* d_dist, int w, int h, float* d_max);
 int k_normalize_minmax_f32(msg_ctx* ctx, const float* d_src, float* d_dst, int w, int h, double alpha, double beta, float* d_mm);
 int k_threshold_f32(msg_ctx* ctx, const float* d_src, float* d_dst, int w, int h, float thresh, float maxval);
 int k_dilate_f32(msg_ctx* ctx, const float* d_src, float* d_dst, int w, int h, int kw, int kh);

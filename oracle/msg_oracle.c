@@ -836,6 +836,61 @@ void orc_distance_transform_l2_5(const uint8_t* src, size_t sstep, float* dst, s
     free(t);
 }
 
+/* The same call as a NON-IPP OpenCV build computes it (distransform.cpp, distanceTransform_5x5: what the openpnp 3.4.2 natives
+ * the reference binds would run): 16.16 fixed point.  Metrics HV = cvRound(1 * 65536), DIAG = cvRound(1.4 * 65536),
+ * LONG = cvRound(2.1969 * 65536); a 2-pixel border of DIST_MAX = INT_MAX >> 2 around an int plane; forward pass = min over the
+ * eight forward mask cells, backward pass the same mirrored (skipped where the value is already <= HV: no candidate can be
+ * smaller), output = (float)(t * (1.f / 65536)) with t clamped to DIST_MAX = UINT_MAX - LONG (cv2 4.13: a pixel no zero pixel
+ * reaches -- only possible when the source has none -- reads 65533.805).  Integer min-plus: order independent.
+ * Pinned on cv2 4.13.0 with cv2.ipp.setUseIPP(False) (tests/golden/gen_dt_fixed.py -> dt_fixed.npz). */
+void orc_distance_transform_l2_5_fixed(const uint8_t* src, size_t sstep, float* dst, size_t dstep, int w, int h)
+{
+    const int HV = 65536, DIAG = 91750, LONG_ = 143976;      /* cvRound(1.4f * 65536) = 91750, cvRound(2.1969f * 65536) = 143976 */
+    const long long DIST_MAX = 4294967295ll - LONG_;
+    const float scale = 1.f / 65536;
+    const size_t tp = (size_t)w + 4;
+    long long* t = (long long*)malloc(tp * ((size_t)h + 4) * sizeof(long long));     /* 64-bit: sums cannot wrap */
+    for (size_t i = 0; i < tp * ((size_t)h + 4); i++) t[i] = DIST_MAX;
+#define T_(y, x) t[(size_t)((y) + 2) * tp + (size_t)((x) + 2)]
+#define MIN_(v) do { long long q_ = (v); if (q_ < t0) t0 = q_; } while (0)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            long long t0;
+            if (!src[(size_t)y * sstep + x]) t0 = 0;
+            else {
+                t0 = T_(y - 2, x - 1) + LONG_;
+                MIN_(T_(y - 2, x + 1) + LONG_);
+                MIN_(T_(y - 1, x - 2) + LONG_);
+                MIN_(T_(y - 1, x - 1) + DIAG);
+                MIN_(T_(y - 1, x) + HV);
+                MIN_(T_(y - 1, x + 1) + DIAG);
+                MIN_(T_(y - 1, x + 2) + LONG_);
+                MIN_(T_(y, x - 1) + HV);
+            }
+            T_(y, x) = t0;
+        }
+    for (int y = h - 1; y >= 0; y--)
+        for (int x = w - 1; x >= 0; x--) {
+            long long t0 = T_(y, x);
+            if (t0 > HV) {
+                MIN_(T_(y + 2, x + 1) + LONG_);
+                MIN_(T_(y + 2, x - 1) + LONG_);
+                MIN_(T_(y + 1, x + 2) + LONG_);
+                MIN_(T_(y + 1, x + 1) + DIAG);
+                MIN_(T_(y + 1, x) + HV);
+                MIN_(T_(y + 1, x - 1) + DIAG);
+                MIN_(T_(y + 1, x - 2) + LONG_);
+                MIN_(T_(y, x + 1) + HV);
+                T_(y, x) = t0;
+            }
+            if (t0 > DIST_MAX) t0 = DIST_MAX;
+            *(float*)((uint8_t*)dst + (size_t)y * dstep + (size_t)x * 4) = (float)((float)(unsigned int)t0 * scale);
+        }
+#undef T_
+#undef MIN_
+    free(t);
+}
+
 /* Core.normalize(src 32F, dst, 0, 1, NORM_MINMAX) (PictureService.java:1021): scale = 1 * (1 / (max - min)) in double,
  * shift = 0 - min * scale; dst = src * (float)scale + (float)shift in float; a constant image becomes all zero. */
 void orc_normalize_minmax01_f32(const float* src, size_t sstep, float* dst, size_t dstep, int w, int h)

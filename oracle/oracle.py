@@ -68,6 +68,7 @@ def lib():
         L.orc_otsu_threshold.restype = i
         L.orc_threshold_binary_u8.argtypes = [u8p, sz, u8p, sz, i, i, i, i]
         L.orc_distance_transform_l2_5.argtypes = [u8p, sz, C.c_void_p, sz, i, i]
+        L.orc_distance_transform_l2_5_fixed.argtypes = [u8p, sz, C.c_void_p, sz, i, i]
         L.orc_normalize_minmax01_f32.argtypes = [C.c_void_p, sz, C.c_void_p, sz, i, i]
         L.orc_peaks_u8.argtypes = [C.c_void_p, sz, u8p, sz, i, i, d]
         L.orc_contour_markers.argtypes = [u8p, sz, i32p, sz, i, i]
@@ -288,11 +289,13 @@ def threshold_binary(gray, thresh, maxval=255):
     return dst
 
 
-def distance_transform(mask):
+def distance_transform(mask, fixed=False):
+    """fixed=False: the float arithmetic of the IPP-backed cv2 build; fixed=True: OpenCV's own 16.16 fixed-point chamfer."""
     mask = _u8(mask)
     h, w = mask.shape
     dst = np.empty((h, w), np.float32)
-    lib().orc_distance_transform_l2_5(mask.ctypes.data, mask.strides[0], dst.ctypes.data, dst.strides[0], w, h)
+    fn = lib().orc_distance_transform_l2_5_fixed if fixed else lib().orc_distance_transform_l2_5
+    fn(mask.ctypes.data, mask.strides[0], dst.ctypes.data, dst.strides[0], w, h)
     return dst
 
 
@@ -348,14 +351,15 @@ def bilateral_filter(img, d, sigma_color, sigma_space):
 SHARPEN_TAPS_9x1 = np.array([1, 1, 1, 1, -8, 1, 1, 1, 1], np.int8).reshape(9, 1)   # literal MatOfFloat reading (App. C#2)
 
 
-def color_seeds(bgr, taps=SHARPEN_TAPS_9x1, peak_thresh=0.4):
-    """Colour-method marker generator (PictureService.java:309-366): returns (n_contours, markers int32, stages dict)."""
+def color_seeds(bgr, taps=SHARPEN_TAPS_9x1, peak_thresh=0.4, dt_fixed=False, gray_compat=False):
+    """Colour-method marker generator (PictureService.java:309-366): returns (n_contours, markers int32, stages dict).
+    dt_fixed / gray_compat: the arithmetic of a non-IPP OpenCV 3.4.2 build (the library's options of the same names)."""
     black = white_to_black(bgr)
     sharp = laplacian_sharpen(black, taps)
-    gray = bgr2gray(sharp)
+    gray = bgr2gray(sharp, compat342=gray_compat)
     t = otsu_threshold(gray)
     bw = threshold_binary(gray, t, 255)
-    dist = distance_transform(bw)
+    dist = distance_transform(bw, fixed=dt_fixed)
     nrm = normalize_minmax01(dist)
     pk = peaks(nrm, peak_thresh)
     n, markers = contour_markers(pk)

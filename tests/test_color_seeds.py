@@ -73,6 +73,69 @@ def test_oracle_distance_transform_tie_cases_golden(golden_dir):
     assert plain_differs >= 3
 
 
+def _dt_fixed_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "dt_fixed.npz"))
+
+
+def test_oracle_distance_transform_fixed_golden(golden_dir):
+    """cv2.distanceTransform with IPP switched off (OpenCV's own 16.16 fixed-point chamfer: what a non-IPP build such as the
+    openpnp 3.4.2 natives computes, tests/golden/gen_dt_fixed.py) == orc_distance_transform_l2_5_fixed, incl. the images
+    without any zero pixel (65533.805 everywhere) and the cases where the two arithmetics differ."""
+    g = _dt_fixed_golden(golden_dir)
+    names = [str(n) for n in g["names"]]
+    assert len(names) >= 12
+    differs_from_float_mode = 0
+    for n in names:
+        m, want = g["mask/" + n], g["dist/" + n]
+        assert np.array_equal(orc.distance_transform(m, fixed=True), want), n
+        differs_from_float_mode += int(not np.array_equal(orc.distance_transform(m), want))
+    assert differs_from_float_mode >= 5
+
+
+@pytest.mark.gpu
+def test_gpu_distance_transform_fixed_mode(golden_dir):
+    """Option dt_fixed = 1: the whole-GPU closed-form kernels (k_dt_fixed.cu) == cv2 without IPP on the golden vectors and ==
+    the oracle's two-pass fixed-point recurrence on larger blobs, noise, single zero pixels far away, ragged sizes; the option
+    switches back; the whole colour-seed chain follows the mode."""
+    g = _dt_fixed_golden(golden_dir)
+    with mseg.Context(0) as ctx:
+        gi = mseg.GpuImgproc(ctx)
+        ctx.set_option("dt_fixed", 1)
+        assert ctx.get_option("dt_fixed") == 1
+        for n in (str(n) for n in g["names"]):
+            assert np.array_equal(gi.distanceTransform(g["mask/" + n]), g["dist/" + n]), n
+        for (w, h, sigma, level) in ((640, 360, 6, .5), (1920, 1080, 12, .45), (2500, 300, 9, .3), (333, 517, 3, .6), (1031, 77, 2, .5)):
+            mask = _blobs(w, h, 5, sigma, level) * 255
+            assert np.array_equal(gi.distanceTransform(mask), orc.distance_transform(mask, fixed=True)), (w, h)
+            noise = ((np.random.default_rng(w).random((h, w)) < .97) * 255).astype(np.uint8)
+            assert np.array_equal(gi.distanceTransform(noise), orc.distance_transform(noise, fixed=True)), (w, h)
+        for (w, h, zy, zx) in ((3000, 40, 0, 0), (3000, 40, 39, 2999), (1500, 700, 350, 750), (70, 2000, 1999, 0), (5000, 9, 4, 17),
+                               (33, 65, 64, 32), (129, 31, 0, 128)):
+            m = np.full((h, w), 255, np.uint8)
+            m[zy, zx] = 0
+            assert np.array_equal(gi.distanceTransform(m), orc.distance_transform(m, fixed=True)), (w, h, zy, zx)
+        for shape in ((1, 1), (1, 40), (40, 1), (2, 2), (5, 3), (33, 1), (1, 257)):
+            for fill in (0, 255):
+                m = np.full(shape, fill, np.uint8)
+                assert np.array_equal(gi.distanceTransform(m), orc.distance_transform(m, fixed=True)), (shape, fill)
+        # strided ROI views in and out
+        big = ((np.random.default_rng(3).random((90, 140)) < .95) * 255).astype(np.uint8)
+        view = big[7:71, 13:120]
+        assert np.array_equal(gi.distanceTransform(view), orc.distance_transform(np.ascontiguousarray(view), fixed=True))
+        # the chain follows the mode (and differs from the float mode's distances on this frame)
+        im = orc.synth_bgr(640, 360, 31)
+        want_n, want_m, want = orc.color_seeds(im, dt_fixed=True)
+        n, m, st = gi.colorSeeds(im, stages=True)
+        assert n == want_n and np.array_equal(m, want_m)
+        for key in ("bw", "norm", "peaks"):
+            assert np.array_equal(st[key], want[key]), key
+        with pytest.raises(mseg.CvException):
+            gi.distanceTransform(np.zeros((2, 16385), np.uint8))
+        ctx.set_option("dt_fixed", 0)
+        m = _blobs(300, 200, 5, 4, .5) * 255
+        assert np.array_equal(gi.distanceTransform(m), orc.distance_transform(m))
+
+
 def _plain_float_chamfer(mask):
     """Two-pass 5x5 chamfer with every addition rounded to float32 (the textbook order)."""
     f = np.float32

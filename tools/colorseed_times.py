@@ -46,6 +46,14 @@ def main():
                          "color_seeds_chain": best(lambda: gi.colorSeeds(im)),
                          "bilateral_gray_d11": best(lambda: gi.bilateralFilter(gray, 11, 22, 22)),
                          "bilateral_bgr_d11": best(lambda: gi.bilateralFilter(im, 11, 22, 22))}
+        ctx.set_option("dt_fixed", 1)       # OpenCV's own 16.16 fixed-point chamfer: order independent, whole-GPU kernels
+        out["gpu_ms"]["distance_transform_fixed_mode"] = best(lambda: gi.distanceTransform(bw))
+        out["gpu_ms"]["color_seeds_chain_fixed_mode"] = best(lambda: gi.colorSeeds(im))
+        gi.distanceTransform(bw)
+        out["gpu_kernel_ms"] = {"distance_transform_fixed_mode": round(ctx.timings()["filter_ms"], 4)}
+        ctx.set_option("dt_fixed", 0)
+        gi.distanceTransform(bw)
+        out["gpu_kernel_ms"]["distance_transform"] = round(ctx.timings()["filter_ms"], 4)
         ev = ctx.stats()
         out["kernel_launches_total"] = ev["kernel_launches"]
     if cv2 is not None:
