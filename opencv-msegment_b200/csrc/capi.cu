@@ -65,7 +65,7 @@ static const opt_entry g_opts[] = {
     OPT("tile_w", tile_w, 0),           OPT("acc", acc, -1),           OPT("pitch_res", pitch_res, -1),
     OPT("tma", use_tma, 1),             OPT("no_order", no_order, 0),  OPT("merge_scalar", merge_scalar, 0),
     OPT("merge_small_max", merge_small_max, -1), OPT("no_graph", no_graph, 0), OPT("graph_debug", graph_debug, 0),
-    OPT("ccl_legacy", ccl_legacy, 0),   OPT("gray_compat", gray_compat, 0), OPT("dt_fixed", dt_fixed, 0),
+    OPT("ccl_legacy", ccl_legacy, 0),   OPT("gray_compat", gray_compat, 0), OPT("dt_fixed", dt_fixed, 0), OPT("dt_legacy", dt_legacy, 0),
     OPT("staging", staging, 1),
 };
 #undef OPT
@@ -1341,27 +1341,26 @@ int msg_meanshift_halo_rows(double sp, int max_level, int term_type, int max_cou
     if (!(term_type & MSG_TERM_COUNT)) max_count = 5;
     if (max_count < 1) max_count = 1;
     if (max_count > 100) max_count = 100;
-    // Dependency cone of an output row, in level-0 rows (DESIGN.md "strip sharding"):
-    //  at level l a pixel reads S[l] within max_count*ceil(sp_l) + ceil(sp_l) rows of itself; S[l] reads S[l-1]
-    //  within 2 rows (pyrDown taps, scaled by 2); the level-l mask/pyrUp reads D[l+1] within 3 rows.
-    long need = 0;  // rows needed at the current level, accumulated from level 0 upwards
-    long halo0 = 0;
-    for (int l = 0; l <= max_level; l++) {
+    // Dependency of an output row on source rows (DESIGN.md "strip sharding").  need(l) = rows of S[l] (level-l
+    // units) that a pixel of the level-l result D[l] can depend on, either side:
+    //   * its own windows: the centre moves <= r_l = ceil(sp_l) per iteration and max_count windows are evaluated, the k-th one
+    //     reaching k * r_l rows from the pixel  ->  max_count * r_l   (windows read the SOURCE plane S[l], never D[l]);
+    //   * below the top level, its initial value and its change-mask bit come from D[l+1] within 3 level-(l+1) rows (pyrUp
+    //     taps +-1, the 8-neighbour test of the mask rule, the 3x3 dilate); a row of D[l+1] depends on S[l+1] within
+    //     need(l+1) rows, a row of S[l+1] on S[l] within 2 rows of its double (pyrDown taps)  ->  2 * (need(l+1) + 3) + 2.
+    // The two are alternatives, not a chain: need(l) = max of them.  Defaults: max(50, 2 * (25 + 3) + 2) = 58.
+    // The bound is proven tight enough by the bit-identity gates (tests/test_gpu_sharded.py: strips == unsharded call for
+    // maxLevel 0 / 1 / 2, several sp and termcrits; tools/shard_large_image.py --verify on real ranks).
+    long need = 0;
+    for (int l = max_level; l >= 0; l--) {
         double spl = sp / (double)(1 << l);
         if (!(spl >= 1.0)) spl = 1.0;
-        long r = (long)ceil(spl);
-        long reach_l = (long)(max_count + 1) * r;          // rows of S[l] a level-l pixel can touch
-        // to have D[l] valid on the rows that level l-1 needs (need rows at level l), S[l] is needed on need + reach_l
-        long s_rows_l = need + reach_l;
-        // rows of level 0 that S[l] on +-s_rows_l depends on: each pyrDown adds 2 rows then doubles
-        long v = s_rows_l;
-        for (int k = l; k > 0; k--) v = 2 * v + 2;
-        if (v > halo0) halo0 = v;
-        // the level l+1 rows needed by level l's pyrUp + mask (3 rows margin), for pixels within `need + 0` rows
-        need = (need + reach_l) / 2 + 4;
+        const long own = (long)max_count * (long)ceil(spl);
+        const long via_up = 2 * (need + 3) + 2;
+        need = (l == max_level || own > via_up) ? own : via_up;
     }
-    long a = 1L << max_level;
-    halo0 = (halo0 + 2 * a + a - 1) / a * a;   // multiple of 2^max_level, plus slack
+    const long a = 1L << max_level;
+    long halo0 = (need + a - 1) / a * a + a;   // multiple of 2^max_level (strip origins keep the pyramid phase), one unit of slack
     return (int)halo0;
 }
 

@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include "msg_internal.h"
+#include <type_traits>
 
 namespace {
 
@@ -304,6 +305,233 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dt_wave_kernel(float* __restric
     }
 }
 
+// ---------------------------------------------------------------- the same wavefront, second form (default)
+// What bounded dt_wave_kernel (ncu, profiles/r01_dt_kernel_history.md): one SM's issue slots and its FP64 pipe, not the chain
+// latency -- half of the lanes idle at every step (lane G works when s - G is even) and the forward pass spent ~25 double
+// operations and ~10 conversions per pixel.  Here
+//   * every thread owns TWO adjacent chunks ("virtual lanes" 2t and 2t+1) and works at every step: the even one at even
+//     steps, the odd one at odd steps (virtual lane v handles row r at step s = 2r + v, exactly the schedule above), so the
+//     halo of a step comes half from the thread's own registers and half from ONE neighbour thread (3-4 shuffles, not 7);
+//   * candidates that share a metric are reduced in float first -- min(v1 + c, v2 + c) = min(v1, v2) + c holds for exact sums
+//     and for rounded ones (rounding is monotone) -- so a pixel costs three additions and two minima instead of seven and
+//     seven;
+//   * float -> double is exact widening, done with two integer operations instead of the quarter-rate F2F (0 widens to
+//     2^-127, which every use adds to a metric >= 1 where it vanishes in the rounding; zero pixels are selected explicitly);
+//   * the rule "round at every pixel" of the last columns (x >= lim) is compiled separately and taken by the one or two
+//     virtual lanes it concerns.
+// Same arithmetic, same results (tests/test_color_seeds.py), 8192 columns at most.
+constexpr int DT2_THREADS = 256, DT2_WARPS = DT2_THREADS / 32, DT2_PMAX = 16;
+
+struct dt2_shared {
+    float4 right[DT2_WARPS];      // lane 31's ODD chunk after an odd step: A[P-1], B[P-2], B[P-1], Clast (read at the next even step)
+    float4 left[DT2_WARPS];       // lane 0's EVEN chunk after an even step: A[0], A[1], B[0] (read at the next odd step)
+};
+
+__device__ __forceinline__ double dt_widen(float f)        // exact for normal non-negative floats; 0 -> 2^-127
+{
+    const unsigned b = __float_as_uint(f);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+__device__ __forceinline__ double dt_dmin(double a, double b) { return a < b ? a : b; }
+
+template <int P, int DIR, int V>
+__device__ __forceinline__ float dt2_pass(float* __restrict__ dist, int w, int h, dt2_shared& sh)
+{
+    typedef typename dt_vec<V>::type vec_t;
+    const int T = threadIdx.x, lane = T & 31, warp = T >> 5;
+    const int NVL = (w + P - 1) / P;                 // virtual lanes in use
+    const int nsteps = 2 * h + NVL - 2;
+    const int lim = ((w - 2) / 4) * 4;               // forward pass: columns >= lim round at every pixel
+    float A[2][P], B[2][P], Cl[2] = {FLT_MAX, FLT_MAX}, vmax = 0.f;
+    float q0[P], q1[P], q2[P], q3[P];                // initial values, loaded four steps ahead; set = step mod 4
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        A[0][j] = A[1][j] = B[0][j] = B[1][j] = FLT_MAX;
+        q0[j] = q1[j] = q2[j] = q3[j] = FLT_MAX;
+    }
+    auto m0_of = [&](int par) { return (2 * T + par) * P; };
+    auto cnt_of = [&](int par) { return max(0, min(w - m0_of(par), P)); };
+    auto load_row = [&](int par, int it, float (&pre)[P]) {              // only called with cnt > 0
+        const int m0 = m0_of(par), cnt = cnt_of(par);
+        const int y = DIR > 0 ? it : h - 1 - it;
+        const int xlo = DIR > 0 ? m0 : w - m0 - P;
+        const float* p = dist + (size_t)y * w + xlo;
+        if (cnt == P) {
+#pragma unroll
+            for (int e = 0; e < P; e += V) {
+                vec_t v = __ldcg((const vec_t*)(p + e));
+                const float* f = (const float*)&v;
+#pragma unroll
+                for (int i = 0; i < V; i++) pre[DIR > 0 ? e + i : P - 1 - (e + i)] = f[i];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const int jj = min(j, cnt - 1);
+                float v = __ldcg(p + (DIR > 0 ? jj : P - 1 - jj));
+                pre[j] = j < cnt ? v : FLT_MAX;
+            }
+        }
+    };
+    auto store_row = [&](int par, int it, const float (&val)[P]) {
+        const int m0 = m0_of(par), cnt = cnt_of(par);
+        const int y = DIR > 0 ? it : h - 1 - it;
+        const int xlo = DIR > 0 ? m0 : w - m0 - P;
+        float* p = dist + (size_t)y * w + xlo;
+        if (cnt == P) {
+#pragma unroll
+            for (int e = 0; e < P; e += V) {
+                vec_t v;
+                float* f = (float*)&v;
+#pragma unroll
+                for (int i = 0; i < V; i++) f[i] = val[DIR > 0 ? e + i : P - 1 - (e + i)];
+                *(vec_t*)(p + e) = v;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; j++)
+                if (j < cnt) p[DIR > 0 ? j : P - 1 - j] = val[j];
+        }
+    };
+    // virtual lane v uses row 0 at step v and row 1 at step v + 2
+    if (cnt_of(0) > 0) {
+        if ((T & 1) == 0) { load_row(0, 0, q0); if (h > 1) load_row(0, 1, q2); }
+        else { load_row(0, 0, q2); if (h > 1) load_row(0, 1, q0); }
+    }
+    if (cnt_of(1) > 0) {
+        if ((T & 1) == 0) { load_row(1, 0, q1); if (h > 1) load_row(1, 1, q3); }
+        else { load_row(1, 0, q3); if (h > 1) load_row(1, 1, q1); }
+    }
+    if (T < DT2_WARPS) {
+        const float4 inf = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+        sh.right[T] = inf;
+        sh.left[T] = inf;
+    }
+    __syncthreads();
+
+    // one row of one chunk.  Ac / Bc: the chunk's last two rows; halo values as in dt_wave_pass
+    auto row = [&](auto tail_tag, int m0, int cnt, float (&t)[P], const float (&Ac)[P], const float (&Bc)[P], float Lc, float Lb0,
+                   float Lb1, float Lcl, float Ra0, float Ra1, float Rb0) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        // candidates of one metric reduced in float
+        float mC[P], mB[P];
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            const float b0 = dt_pick<P>(Bc, j - 1, FLT_MAX, Lcl, Rb0, FLT_MAX), b1 = dt_pick<P>(Bc, j + 1, FLT_MAX, Lcl, Rb0, FLT_MAX);
+            const float a0 = dt_pick<P>(Ac, j - 2, Lb0, Lb1, Ra0, Ra1), a1 = dt_pick<P>(Ac, j + 2, Lb0, Lb1, Ra0, Ra1);
+            mC[j] = fminf(fminf(b0, b1), fminf(a0, a1));
+            mB[j] = fminf(dt_pick<P>(Ac, j - 1, Lb0, Lb1, Ra0, Ra1), dt_pick<P>(Ac, j + 1, Lb0, Lb1, Ra0, Ra1));
+        }
+        if constexpr (DIR > 0) {
+            double runv = dt_widen(Lc);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const double cand = dt_dmin(dt_dmin(dt_widen(mC[j]) + (double)DT_C, dt_widen(mB[j]) + (double)DT_B),
+                                            dt_widen(Ac[j]) + (double)DT_A);
+                const double tu = t[j] == 0.f ? 0.0 : cand;                   // initial value: 0 on zero pixels, "infinite" elsewhere
+                bool round_in = (j & 3) == 0 && j > 0;                        // j == 0: Lc is a stored (rounded) pixel already
+                if (TAIL) round_in = round_in || (j > 0 && m0 + j >= lim);
+                const double rin = round_in ? dt_widen(__double2float_rn(runv)) : runv;
+                runv = dt_dmin(tu, rin + 1.0);
+                t[j] = j < cnt ? __double2float_rn(runv) : FLT_MAX;           // outside the image: "infinite"
+            }
+        } else {
+            float run = Lc;
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const float cand = fminf(fminf(__fadd_rn(mC[j], DT_C), __fadd_rn(mB[j], DT_B)), __fadd_rn(Ac[j], DT_A));
+                run = fminf(fminf(t[j], cand), __fadd_rn(run, DT_A));
+                t[j] = j < cnt ? run : FLT_MAX;
+                vmax = fmaxf(vmax, j < cnt ? run : 0.f);
+            }
+        }
+    };
+
+    auto step = [&](auto par_tag, int s, float (&pre)[P]) {
+        constexpr int PAR = decltype(par_tag)::value;
+        const int vl = 2 * T + PAR, d = s - vl, it = d >> 1;
+        const int m0 = vl * P, cnt = max(0, min(w - m0, P));
+        const bool active = cnt > 0 && d >= 0 && it < h;
+        float Lc, Lb0, Lb1, Lcl, Ra0, Ra1, Rb0;
+        if (PAR == 0) {
+            // left = the odd chunk of thread T-1 (row r done one step ago), right = my own odd chunk (row r-1)
+            Lc = __shfl_up_sync(0xffffffffu, A[1][P - 1], 1);
+            Lb0 = __shfl_up_sync(0xffffffffu, B[1][P - 2], 1);
+            Lb1 = __shfl_up_sync(0xffffffffu, B[1][P - 1], 1);
+            Lcl = __shfl_up_sync(0xffffffffu, Cl[1], 1);
+            if (lane == 0) {
+                const float4 v = warp > 0 ? sh.right[warp - 1] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+                Lc = v.x; Lb0 = v.y; Lb1 = v.z; Lcl = v.w;
+            }
+            Ra0 = A[1][0]; Ra1 = A[1][1]; Rb0 = B[1][0];
+        } else {
+            // left = my own even chunk (row r done one step ago), right = the even chunk of thread T+1 (row r-1)
+            Lc = A[0][P - 1]; Lb0 = B[0][P - 2]; Lb1 = B[0][P - 1]; Lcl = Cl[0];
+            Ra0 = __shfl_down_sync(0xffffffffu, A[0][0], 1);
+            Ra1 = __shfl_down_sync(0xffffffffu, A[0][1], 1);
+            Rb0 = __shfl_down_sync(0xffffffffu, B[0][0], 1);
+            if (lane == 31) {
+                const float4 v = warp + 1 < DT2_WARPS ? sh.left[warp + 1] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+                Ra0 = v.x; Ra1 = v.y; Rb0 = v.z;
+            }
+        }
+        if (active) {
+            float t[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) t[j] = pre[j];
+            if (it + 2 < h) load_row(PAR, it + 2, pre);       // consumed four steps later, from the same register set
+            if (DIR > 0 && m0 + P > lim)
+                row(std::true_type(), m0, cnt, t, A[PAR], B[PAR], Lc, Lb0, Lb1, Lcl, Ra0, Ra1, Rb0);
+            else
+                row(std::false_type(), m0, cnt, t, A[PAR], B[PAR], Lc, Lb0, Lb1, Lcl, Ra0, Ra1, Rb0);
+            store_row(PAR, it, t);
+            Cl[PAR] = B[PAR][P - 1];
+#pragma unroll
+            for (int j = 0; j < P; j++) { B[PAR][j] = A[PAR][j]; A[PAR][j] = t[j]; }
+        }
+        if (PAR == 1 && lane == 31) sh.right[warp] = make_float4(A[1][P - 1], B[1][P - 2], B[1][P - 1], Cl[1]);
+        if (PAR == 0 && lane == 0) sh.left[warp] = make_float4(A[0][0], A[0][1], B[0][0], 0.f);
+        __syncthreads();
+    };
+    typedef std::integral_constant<int, 0> even_t;
+    typedef std::integral_constant<int, 1> odd_t;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; s += 4) {                     // nsteps is uniform over the CTA: every thread meets every barrier
+        step(even_t(), s, q0);
+        if (s + 1 < nsteps) step(odd_t(), s + 1, q1);
+        if (s + 2 < nsteps) step(even_t(), s + 2, q2);
+        if (s + 3 < nsteps) step(odd_t(), s + 3, q3);
+    }
+    __syncthreads();
+    return vmax;
+}
+
+template <int P, int V>
+__global__ void __launch_bounds__(DT2_THREADS, 1) dt_wave2_kernel(float* __restrict__ dist, int w, int h, float* d_max)
+{
+    __shared__ dt2_shared sh;
+    __shared__ float s_max[DT2_WARPS];
+    dt2_pass<P, 1, V>(dist, w, h, sh);
+    float vmax = dt2_pass<P, -1, V>(dist, w, h, sh);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) s_max[warp] = vmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = s_max[0];
+        for (int i = 1; i < DT2_WARPS; i++) v = fmaxf(v, s_max[i]);
+        *d_max = v;
+    }
+}
+
+template <int P>
+void dt2_launch(cudaStream_t st, float* d_dist, int w, int h, float* d_max)
+{
+    if (w % 4 == 0 && ((uintptr_t)d_dist & 15) == 0) dt_wave2_kernel<P, 4><<<1, DT2_THREADS, 0, st>>>(d_dist, w, h, d_max);
+    else dt_wave2_kernel<P, 1><<<1, DT2_THREADS, 0, st>>>(d_dist, w, h, d_max);
+}
+
 // initial values of the forward pass: 0 on the zero pixels of the source, "infinite" elsewhere
 __global__ void __launch_bounds__(256) dt_init_kernel(const uint8_t* __restrict__ src, size_t sstep, float* __restrict__ dist, int w)
 {
@@ -506,7 +734,12 @@ int k_distance_transform(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, float
     dim3 grid((w + 255) / 256, h);
     dt_init_kernel<<<grid, 256, 0, st>>>(d_src, sstep, d_dist, w);
     MSG_LAUNCHED(ctx);
-    if (need <= 4) dt_launch<4>(st, d_dist, w, h, d_max);           // a lane's chunk is a whole number of 4-column groups
+    if (!ctx->tune.dt_legacy) {
+        const int need2 = (w + 2 * DT2_THREADS - 1) / (2 * DT2_THREADS);
+        if (need2 <= 4) dt2_launch<4>(st, d_dist, w, h, d_max);     // a chunk is a whole number of 4-column groups
+        else if (need2 <= 8) dt2_launch<8>(st, d_dist, w, h, d_max);
+        else dt2_launch<16>(st, d_dist, w, h, d_max);
+    } else if (need <= 4) dt_launch<4>(st, d_dist, w, h, d_max);
     else if (need <= 8) dt_launch<8>(st, d_dist, w, h, d_max);
     else if (need <= 16) dt_launch<16>(st, d_dist, w, h, d_max);
     else dt_launch<32>(st, d_dist, w, h, d_max);

@@ -19,7 +19,8 @@
 //      and stopped as soon as HV * |x - x'| reaches the best value so far (work per pixel = 2 * dist, 5-20 tests on the
 //      pipeline's Otsu masks).
 // An image without any zero pixel reads DIST_MAX * 2^-16 = 65533.805 everywhere (cv2 4.13 clamps there).
-// Checked bit for bit against orc_distance_transform_l2_5_fixed (pinned on cv2 with IPP switched off, tests/golden/dt_fixed.npz).
+// Checked bit for bit against the CPU oracle's two-pass fixed-point recurrence, itself pinned on cv2 with IPP switched off
+// (tests/golden/dt_fixed.npz, tests/test_color_seeds.py).
 #include "msg_internal.h"
 
 namespace {

@@ -55,6 +55,7 @@ struct msg_tuning {
     int no_graph, graph_debug;
     int ccl_legacy;        // 1 = row-run union-find of round 1 instead of the tile-local one
     int gray_compat;       // 0 = OpenCV 4.x 15-bit BGR2GRAY coefficients, 1 = OpenCV 3.4.2 14-bit ones
+    int dt_legacy;         // 1 = the first wavefront kernel of the float distance transform (dt_wave_kernel) instead of dt_wave2_kernel
     int dt_fixed;          // 0 = IPP float chamfer arithmetic (cv2 4.13 build), 1 = OpenCV's own 16.16 fixed-point fallback
     int staging;           // 1 = pageable caller buffers go through the pinned staging ring (0: handed to cudaMemcpyAsync as is)
 };

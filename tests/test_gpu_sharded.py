@@ -256,3 +256,51 @@ def test_synth_rows_matches_full():
     assert torch.equal(a[70:130], b)
     assert np.array_equal(a.cpu().numpy(), orc.synth_bgr(w, h, 5))
     ctx.close()
+
+
+def _smooth_field(w, h, seed, k):
+    """Low-frequency colour field (box-filtered noise, stretched to 0..255): mean-shift windows drift far on it."""
+    rng = np.random.default_rng(seed)
+    f = rng.random((h + 2 * k, w + 2 * k, 3))
+    for axis in (0, 1):
+        c = np.cumsum(f, axis=axis)
+        n = f.shape[axis] - 2 * k
+        f = np.take(c, np.arange(2 * k, 2 * k + n), axis=axis) - np.take(c, np.arange(0, n), axis=axis)
+    f = (f - f.min()) / (f.max() - f.min())
+    return np.ascontiguousarray((f * 255).astype(np.uint8))
+
+
+@pytest.mark.parametrize("w,h,n,sp,sr,ml,term", [(200, 1200, 3, 10, 30, 1, (3, 5, 1.0)), (160, 1400, 4, 10, 40, 1, (1, 9, 0.0)),
+                                                (180, 900, 2, 7.5, 25, 2, (3, 5, 1.0)), (150, 1000, 3, 12, 50, 0, (1, 7, 0.0)),
+                                                (140, 1100, 3, 4, 60, 3, (3, 6, 1.0))])
+def test_halo_bound_on_far_drifting_windows(w, h, n, sp, sr, ml, term):
+    """The halo of msg_meanshift_halo_rows is the derived dependency bound max(own windows, via the level above), not a chain
+    of the two.  Tall strips (far more rows than the halo), smooth fields and large sr make the windows travel
+    as far as they can; every strip filtered from its rows + halo only must equal the unsharded call bit for bit -- and the
+    drift statistics show that the windows did travel (the test would be vacuous otherwise)."""
+    ctx = mseg.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    im = _smooth_field(w, h, 100 + ml, 9)
+    src = torch.from_numpy(im).cuda()
+    full = torch.empty_like(src)
+    dev.meanshift(ctx, src.data_ptr(), 3 * w, full.data_ptr(), 3 * w, w, h, sp, sr, ml, term)
+    ctx.synchronize()
+    halo = dev.halo_rows(sp, ml, term)
+    mc = term[1] if term[0] & 1 else 5
+    own = mc * int(np.ceil(max(sp, 1.0)))
+    assert own <= halo <= 2 * own + 16 * (1 << ml), (halo, own)            # not the old chained bound
+    strips = sh.plan_strips(h, n, ml)
+    assert min(r1 - r0 for r0, r1 in strips) > 2 * halo
+    for (r0, r1) in strips:
+        h0, h1 = sh.halo_range(r0, r1, h, halo, ml)
+        rows = src[h0:h1].contiguous()
+        out = torch.empty((r1 - r0, w, 3), dtype=torch.uint8, device="cuda")
+        dev.meanshift_strip(ctx, rows.data_ptr(), 3 * w, h0, h1, out.data_ptr(), 3 * w, w, h, r0, r1, sp, sr, ml, term)
+        bad = (out != full[r0:r1]).any(dim=2)
+        assert not bad.any(), "strip %d..%d differs at %d pixels, rows %s" % (
+            r0, r1, int(bad.sum()), (torch.nonzero(bad.any(dim=1)).flatten()[:8] + r0).tolist())
+    # the unsharded GPU result is the oracle's on this image too
+    assert np.array_equal(full.cpu().numpy(), orc.meanshift_filter(im, sp, sr, ml, term))
+    # the windows did move: a large share of the pixels changed colour by more than the noise level
+    moved = (np.abs(full.cpu().numpy().astype(int) - im.astype(int)).max(axis=2) > 3).mean()
+    assert moved > 0.05, moved

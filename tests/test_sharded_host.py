@@ -185,3 +185,17 @@ def test_c_shard_plan_matches_python_planner():
         dev.shard_plan(100, 10, 8, 10, 2)          # too small for 8 strips at alignment 4
     with pytest.raises(ValueError):
         dev.shard_plan(100, 1000, 65, 10, 0)       # more than MSG_MAX_STRIPS
+
+
+def test_halo_rows_is_the_derived_bound():
+    """msg_meanshift_halo_rows (pure host arithmetic, no GPU): need(l) = max(maxCount * ceil(sp_l), 2 * (need(l+1) + 3) + 2),
+    rounded up to the pyramid phase + one unit (58 at defaults, not the 134 of a chained cone)."""
+    import msegment_b200 as mseg
+    hr = mseg.device.halo_rows
+    assert hr(10, 1) == 60                       # max(50, 2 * (25 + 3) + 2 = 58) -> 58 + 2
+    assert hr(10, 0) == 51                       # 5 * 10, + 1
+    assert hr(10, 0, (1, 9, 0.0)) == 91          # COUNT only, 9 iterations
+    assert hr(10, 1, (2, 0, 1.0)) == 60          # EPS only: OpenCV runs 5 iterations
+    assert hr(20, 1) == 110                      # max(100, 2 * (50 + 3) + 2 = 108) -> 108 + 2
+    assert hr(4, 3) == 104                       # levels 3..0: 5 -> 18 -> 44 -> 96, rounded to a multiple of 8, + 8
+    assert hr(10, 9) == -1
