@@ -80,6 +80,10 @@ MSG_API int msg_synchronize(msg_ctx* ctx);
  *                     reference binds (pom.xml:39-43); differs by 1 LSB on 0.26 % of colours (INTEGRATION.md "version skew")
  *   "dt_fixed"        0 (default): distanceTransform(L2, 5) in the float arithmetic of the IPP-backed cv2 4.13 build;
  *                     1: OpenCV's own 16.16 fixed-point chamfer (what a non-IPP build, e.g. the openpnp 3.4.2 natives, runs)
+ *   "labels_canonical" 0 (default): msg_merge_regions_dev validates and renumbers arbitrary positive labels (two extra passes over
+ *                     the pixels); 1: the caller vouches that the labels are canonical -- 1..n in raster order of first pixel, what
+ *                     msg_label_regions / msg_connected_components write -- and passes n in *d_n_regions
+ *   "dt_legacy"       1: the first wavefront kernel of the float distance transform (A/B hook)
  *   "staging"         1 (default): pageable caller buffers are staged through the context's pinned ring; 0: handed to
  *                     cudaMemcpyAsync as they are (driver staging, serialises the asynchronous path)
  *   "merge_small_max", "tile_w", "acc", "pitch_res", "tma", "no_order", "merge_scalar", "no_graph", "ccl_legacy":

@@ -66,6 +66,7 @@ static const opt_entry g_opts[] = {
     OPT("tma", use_tma, 1),             OPT("no_order", no_order, 0),  OPT("merge_scalar", merge_scalar, 0),
     OPT("merge_small_max", merge_small_max, -1), OPT("no_graph", no_graph, 0), OPT("graph_debug", graph_debug, 0),
     OPT("ccl_legacy", ccl_legacy, 0),   OPT("gray_compat", gray_compat, 0), OPT("dt_fixed", dt_fixed, 0), OPT("dt_legacy", dt_legacy, 0),
+    OPT("labels_canonical", labels_canonical, 0),
     OPT("staging", staging, 1),
 };
 #undef OPT
@@ -712,7 +713,11 @@ int msg_merge_regions_dev(msg_ctx* ctx, const uint8_t* d_bgr, size_t step, int32
         work = ctx->d_labels;
         MSG_TRY(k_copy_labels_2d(ctx, d_labels, lstep, work, (size_t)w * 4, w, h));
     }
-    MSG_TRY(k_merge(ctx, s.p, s.pitch, work, w, h, min_size, color_dist, nullptr, d_n));
+    // option "labels_canonical": the caller vouches that the labels are 1..n in raster order of first pixel (what
+    // msg_label_regions / msg_connected_components write) with n = *d_n on entry: no validation, no renumbering pass
+    if (ctx->tune.labels_canonical && !d_n)
+        return msg_fail(ctx, MSG_EINVAL, "merge: option labels_canonical needs the label count in *d_n_regions on entry");
+    MSG_TRY(k_merge(ctx, s.p, s.pitch, work, w, h, min_size, color_dist, ctx->tune.labels_canonical ? d_n : nullptr, d_n));
     if (!dense) MSG_TRY(k_copy_labels_2d(ctx, work, (size_t)w * 4, d_labels, lstep, w, h));
     return MSG_OK;
 }

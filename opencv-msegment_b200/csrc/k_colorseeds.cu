@@ -320,11 +320,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dt_wave_kernel(float* __restric
 //   * the rule "round at every pixel" of the last columns (x >= lim) is compiled separately and taken by the one or two
 //     virtual lanes it concerns.
 // Same arithmetic, same results (tests/test_color_seeds.py), 8192 columns at most.
-constexpr int DT2_THREADS = 256, DT2_WARPS = DT2_THREADS / 32, DT2_PMAX = 16;
+constexpr int DT2_MAX_WARPS = 16;          // CTAs of 256 (rows up to 2048 pixels) or 512 threads, chunks of 4 / 8 columns
 
 struct dt2_shared {
-    float4 right[DT2_WARPS];      // lane 31's ODD chunk after an odd step: A[P-1], B[P-2], B[P-1], Clast (read at the next even step)
-    float4 left[DT2_WARPS];       // lane 0's EVEN chunk after an even step: A[0], A[1], B[0] (read at the next odd step)
+    float4 right[DT2_MAX_WARPS];      // lane 31's ODD chunk after an odd step: A[P-1], B[P-2], B[P-1], Clast (read at the next even step)
+    float4 left[DT2_MAX_WARPS];       // lane 0's EVEN chunk after an even step: A[0], A[1], B[0] (read at the next odd step)
 };
 
 __device__ __forceinline__ double dt_widen(float f)        // exact for normal non-negative floats; 0 -> 2^-127
@@ -334,8 +334,22 @@ __device__ __forceinline__ double dt_widen(float f)        // exact for normal n
 }
 __device__ __forceinline__ double dt_dmin(double a, double b) { return a < b ? a : b; }
 
-template <int P, int DIR, int V>
-__device__ __forceinline__ float dt2_pass(float* __restrict__ dist, int w, int h, dt2_shared& sh)
+// Row prefetch: the initial values of a chunk's row are fetched FOUR STEPS ahead with cp.async (LDGSTS) into the thread's own
+// shared-memory slot of the step's set (s mod 4) and read back with one LDS when the row is processed.  (Prefetching into
+// registers, as dt_wave_kernel does, made ptxas stage the load in scratch registers and move it "home" right behind the load:
+// every step then waited a full L2 round trip -- 47 % of the stall samples of the first capture, profiles/r02_dt_wave2_ncu.md.)
+// One commit group per step, so cp.async.wait_group 3 = "the group of four steps ago has landed".  The prefetch is
+// unconditional with clamped coordinates (a lane that has not started yet fetches exactly its rows 0 and 1 during the four
+// steps before its first, and anything fetched past the last row or chunk is never used), so there is no prologue.
+template <int BYTES>
+__device__ __forceinline__ void dt_cp_async(void* smem, const void* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(gmem), "n"(BYTES) : "memory");
+}
+
+template <int NT, int P, int DIR, int V>
+__device__ __forceinline__ float dt2_pass(float* __restrict__ dist, int w, int h, dt2_shared& sh, float* s_pre)
 {
     typedef typename dt_vec<V>::type vec_t;
     const int T = threadIdx.x, lane = T & 31, warp = T >> 5;
@@ -343,38 +357,37 @@ __device__ __forceinline__ float dt2_pass(float* __restrict__ dist, int w, int h
     const int nsteps = 2 * h + NVL - 2;
     const int lim = ((w - 2) / 4) * 4;               // forward pass: columns >= lim round at every pixel
     float A[2][P], B[2][P], Cl[2] = {FLT_MAX, FLT_MAX}, vmax = 0.f;
-    float q0[P], q1[P], q2[P], q3[P];                // initial values, loaded four steps ahead; set = step mod 4
 #pragma unroll
-    for (int j = 0; j < P; j++) {
-        A[0][j] = A[1][j] = B[0][j] = B[1][j] = FLT_MAX;
-        q0[j] = q1[j] = q2[j] = q3[j] = FLT_MAX;
-    }
-    auto m0_of = [&](int par) { return (2 * T + par) * P; };
-    auto cnt_of = [&](int par) { return max(0, min(w - m0_of(par), P)); };
-    auto load_row = [&](int par, int it, float (&pre)[P]) {              // only called with cnt > 0
-        const int m0 = m0_of(par), cnt = cnt_of(par);
-        const int y = DIR > 0 ? it : h - 1 - it;
+    for (int j = 0; j < P; j++) A[0][j] = A[1][j] = B[0][j] = B[1][j] = FLT_MAX;
+    // slot of (set, element group e / V) of this thread: consecutive threads are V floats apart -> conflict-free
+    auto slot = [&](int set, int eg) { return s_pre + ((size_t)(set * (P / V) + eg) * NT + T) * V; };
+    // element e (ascending image column xlo + e) of the chunk is pixel j = e (forward) or P - 1 - e (backward) in pass order
+    auto prefetch_row = [&](int par, int it, int set) {
+        const int vl = min(2 * T + par, NVL - 1);                        // clamped: always a chunk of the image
+        const int m0 = vl * P, cnt = min(w - m0, P);
+        const int y = DIR > 0 ? min(max(it, 0), h - 1) : h - 1 - min(max(it, 0), h - 1);
         const int xlo = DIR > 0 ? m0 : w - m0 - P;
         const float* p = dist + (size_t)y * w + xlo;
-        if (cnt == P) {
 #pragma unroll
-            for (int e = 0; e < P; e += V) {
-                vec_t v = __ldcg((const vec_t*)(p + e));
-                const float* f = (const float*)&v;
+        for (int e = 0; e < P; e += V) {
+            // groups outside the row (partial last chunk) re-fetch a valid group; their pixels are masked at use
+            const int ec = DIR > 0 ? min(e, (cnt - 1) / V * V) : max(e, (P - cnt) / V * V);
+            dt_cp_async<4 * V>(slot(set, e / V), p + ec);
+        }
+    };
+    auto read_row = [&](int set, int cnt, float (&pre)[P]) {
 #pragma unroll
-                for (int i = 0; i < V; i++) pre[DIR > 0 ? e + i : P - 1 - (e + i)] = f[i];
-            }
-        } else {
+        for (int e = 0; e < P; e += V) {
+            const vec_t v = *(const vec_t*)slot(set, e / V);
+            const float* f = (const float*)&v;
 #pragma unroll
-            for (int j = 0; j < P; j++) {
-                const int jj = min(j, cnt - 1);
-                float v = __ldcg(p + (DIR > 0 ? jj : P - 1 - jj));
-                pre[j] = j < cnt ? v : FLT_MAX;
+            for (int i = 0; i < V; i++) {
+                const int j = DIR > 0 ? e + i : P - 1 - (e + i);
+                pre[j] = j < cnt ? f[i] : FLT_MAX;
             }
         }
     };
-    auto store_row = [&](int par, int it, const float (&val)[P]) {
-        const int m0 = m0_of(par), cnt = cnt_of(par);
+    auto store_row = [&](int m0, int cnt, int it, const float (&val)[P]) {
         const int y = DIR > 0 ? it : h - 1 - it;
         const int xlo = DIR > 0 ? m0 : w - m0 - P;
         float* p = dist + (size_t)y * w + xlo;
@@ -393,16 +406,14 @@ __device__ __forceinline__ float dt2_pass(float* __restrict__ dist, int w, int h
                 if (j < cnt) p[DIR > 0 ? j : P - 1 - j] = val[j];
         }
     };
-    // virtual lane v uses row 0 at step v and row 1 at step v + 2
-    if (cnt_of(0) > 0) {
-        if ((T & 1) == 0) { load_row(0, 0, q0); if (h > 1) load_row(0, 1, q2); }
-        else { load_row(0, 0, q2); if (h > 1) load_row(0, 1, q0); }
+    // what steps -4 .. -1 would have prefetched: virtual lane v uses row 0 at step v, row 1 at step v + 2
+#pragma unroll
+    for (int s = -4; s < 0; s++) {
+        const int par = s & 1;
+        prefetch_row(par, ((s - (2 * T + par)) >> 1) + 2, s & 3);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (cnt_of(1) > 0) {
-        if ((T & 1) == 0) { load_row(1, 0, q1); if (h > 1) load_row(1, 1, q3); }
-        else { load_row(1, 0, q3); if (h > 1) load_row(1, 1, q1); }
-    }
-    if (T < DT2_WARPS) {
+    if (T < NT / 32) {
         const float4 inf = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
         sh.right[T] = inf;
         sh.left[T] = inf;
@@ -447,7 +458,7 @@ __device__ __forceinline__ float dt2_pass(float* __restrict__ dist, int w, int h
         }
     };
 
-    auto step = [&](auto par_tag, int s, float (&pre)[P]) {
+    auto step = [&](auto par_tag, int s) {
         constexpr int PAR = decltype(par_tag)::value;
         const int vl = 2 * T + PAR, d = s - vl, it = d >> 1;
         const int m0 = vl * P, cnt = max(0, min(w - m0, P));
@@ -471,24 +482,25 @@ __device__ __forceinline__ float dt2_pass(float* __restrict__ dist, int w, int h
             Ra1 = __shfl_down_sync(0xffffffffu, A[0][1], 1);
             Rb0 = __shfl_down_sync(0xffffffffu, B[0][0], 1);
             if (lane == 31) {
-                const float4 v = warp + 1 < DT2_WARPS ? sh.left[warp + 1] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+                const float4 v = warp + 1 < NT / 32 ? sh.left[warp + 1] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
                 Ra0 = v.x; Ra1 = v.y; Rb0 = v.z;
             }
         }
+        asm volatile("cp.async.wait_group 3;" ::: "memory");      // the prefetch of four steps ago (this step's set) has landed
         if (active) {
             float t[P];
-#pragma unroll
-            for (int j = 0; j < P; j++) t[j] = pre[j];
-            if (it + 2 < h) load_row(PAR, it + 2, pre);       // consumed four steps later, from the same register set
+            read_row(s & 3, cnt, t);
             if (DIR > 0 && m0 + P > lim)
                 row(std::true_type(), m0, cnt, t, A[PAR], B[PAR], Lc, Lb0, Lb1, Lcl, Ra0, Ra1, Rb0);
             else
                 row(std::false_type(), m0, cnt, t, A[PAR], B[PAR], Lc, Lb0, Lb1, Lcl, Ra0, Ra1, Rb0);
-            store_row(PAR, it, t);
+            store_row(m0, cnt, it, t);
             Cl[PAR] = B[PAR][P - 1];
 #pragma unroll
             for (int j = 0; j < P; j++) { B[PAR][j] = A[PAR][j]; A[PAR][j] = t[j]; }
         }
+        prefetch_row(PAR, it + 2, s & 3);                          // consumed at step s + 4 from the same slot
+        asm volatile("cp.async.commit_group;" ::: "memory");
         if (PAR == 1 && lane == 31) sh.right[warp] = make_float4(A[1][P - 1], B[1][P - 2], B[1][P - 1], Cl[1]);
         if (PAR == 0 && lane == 0) sh.left[warp] = make_float4(A[0][0], A[0][1], B[0][0], 0.f);
         __syncthreads();
@@ -497,22 +509,24 @@ __device__ __forceinline__ float dt2_pass(float* __restrict__ dist, int w, int h
     typedef std::integral_constant<int, 1> odd_t;
 #pragma unroll 1
     for (int s = 0; s < nsteps; s += 4) {                     // nsteps is uniform over the CTA: every thread meets every barrier
-        step(even_t(), s, q0);
-        if (s + 1 < nsteps) step(odd_t(), s + 1, q1);
-        if (s + 2 < nsteps) step(even_t(), s + 2, q2);
-        if (s + 3 < nsteps) step(odd_t(), s + 3, q3);
+        step(even_t(), s);
+        if (s + 1 < nsteps) step(odd_t(), s + 1);
+        if (s + 2 < nsteps) step(even_t(), s + 2);
+        if (s + 3 < nsteps) step(odd_t(), s + 3);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");      // no copy of this pass is still in flight when the next one reuses the slots
     __syncthreads();
     return vmax;
 }
 
-template <int P, int V>
-__global__ void __launch_bounds__(DT2_THREADS, 1) dt_wave2_kernel(float* __restrict__ dist, int w, int h, float* d_max)
+template <int NT, int P, int V>
+__global__ void __launch_bounds__(NT, 1) dt_wave2_kernel(float* __restrict__ dist, int w, int h, float* d_max)
 {
     __shared__ dt2_shared sh;
-    __shared__ float s_max[DT2_WARPS];
-    dt2_pass<P, 1, V>(dist, w, h, sh);
-    float vmax = dt2_pass<P, -1, V>(dist, w, h, sh);
+    __shared__ float s_max[DT2_MAX_WARPS];
+    extern __shared__ __align__(16) float s_pre[];            // 4 sets x P floats per thread
+    dt2_pass<NT, P, 1, V>(dist, w, h, sh, s_pre);
+    float vmax = dt2_pass<NT, P, -1, V>(dist, w, h, sh, s_pre);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
@@ -520,16 +534,23 @@ __global__ void __launch_bounds__(DT2_THREADS, 1) dt_wave2_kernel(float* __restr
     __syncthreads();
     if (threadIdx.x == 0) {
         float v = s_max[0];
-        for (int i = 1; i < DT2_WARPS; i++) v = fmaxf(v, s_max[i]);
+        for (int i = 1; i < NT / 32; i++) v = fmaxf(v, s_max[i]);
         *d_max = v;
     }
 }
 
-template <int P>
-void dt2_launch(cudaStream_t st, float* d_dist, int w, int h, float* d_max)
+template <int NT, int P>
+int dt2_launch(msg_ctx* ctx, cudaStream_t st, float* d_dist, int w, int h, float* d_max)
 {
-    if (w % 4 == 0 && ((uintptr_t)d_dist & 15) == 0) dt_wave2_kernel<P, 4><<<1, DT2_THREADS, 0, st>>>(d_dist, w, h, d_max);
-    else dt_wave2_kernel<P, 1><<<1, DT2_THREADS, 0, st>>>(d_dist, w, h, d_max);
+    const size_t smem = (size_t)4 * P * NT * sizeof(float);                // 16 / 32 / 64 KB
+    if (w % 4 == 0 && ((uintptr_t)d_dist & 15) == 0) {
+        MSG_TRY(msg_func_smem(ctx, (const void*)dt_wave2_kernel<NT, P, 4>, smem));
+        dt_wave2_kernel<NT, P, 4><<<1, NT, smem, st>>>(d_dist, w, h, d_max);
+    } else {
+        MSG_TRY(msg_func_smem(ctx, (const void*)dt_wave2_kernel<NT, P, 1>, smem));
+        dt_wave2_kernel<NT, P, 1><<<1, NT, smem, st>>>(d_dist, w, h, d_max);
+    }
+    return MSG_OK;
 }
 
 // initial values of the forward pass: 0 on the zero pixels of the source, "infinite" elsewhere
@@ -735,10 +756,10 @@ int k_distance_transform(msg_ctx* ctx, const uint8_t* d_src, size_t sstep, float
     dt_init_kernel<<<grid, 256, 0, st>>>(d_src, sstep, d_dist, w);
     MSG_LAUNCHED(ctx);
     if (!ctx->tune.dt_legacy) {
-        const int need2 = (w + 2 * DT2_THREADS - 1) / (2 * DT2_THREADS);
-        if (need2 <= 4) dt2_launch<4>(st, d_dist, w, h, d_max);     // a chunk is a whole number of 4-column groups
-        else if (need2 <= 8) dt2_launch<8>(st, d_dist, w, h, d_max);
-        else dt2_launch<16>(st, d_dist, w, h, d_max);
+        // threads x 2 chunks x P columns (a chunk is a whole number of 4-column groups); short chunks = short steps
+        if (w <= 2048) MSG_TRY((dt2_launch<256, 4>(ctx, st, d_dist, w, h, d_max)));
+        else if (w <= 4096) MSG_TRY((dt2_launch<512, 4>(ctx, st, d_dist, w, h, d_max)));
+        else MSG_TRY((dt2_launch<512, 8>(ctx, st, d_dist, w, h, d_max)));
     } else if (need <= 4) dt_launch<4>(st, d_dist, w, h, d_max);
     else if (need <= 8) dt_launch<8>(st, d_dist, w, h, d_max);
     else if (need <= 16) dt_launch<16>(st, d_dist, w, h, d_max);

@@ -57,6 +57,7 @@ struct msg_tuning {
     int gray_compat;       // 0 = OpenCV 4.x 15-bit BGR2GRAY coefficients, 1 = OpenCV 3.4.2 14-bit ones
     int dt_legacy;         // 1 = the first wavefront kernel of the float distance transform (dt_wave_kernel) instead of dt_wave2_kernel
     int dt_fixed;          // 0 = IPP float chamfer arithmetic (cv2 4.13 build), 1 = OpenCV's own 16.16 fixed-point fallback
+    int labels_canonical;  // 1 = msg_merge_regions_dev trusts that its input labels are canonical (1..*d_n, raster order of first pixel)
     int staging;           // 1 = pageable caller buffers go through the pinned staging ring (0: handed to cudaMemcpyAsync as is)
 };
 

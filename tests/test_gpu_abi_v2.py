@@ -188,3 +188,40 @@ def test_two_contexts_with_different_sharpen_kernels():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not bad
+
+
+def test_merge_labels_canonical_option(ctx):
+    """Option labels_canonical: msg_merge_regions_dev skips the validation / renumbering passes when the caller vouches for
+    canonical labels (the output of msg_label_regions_dev) and passes their count; same result as the validating call."""
+    torch = pytest.importorskip("torch")
+    dev = mseg.device
+    for (w, h, seed) in ((640, 360, 11), (517, 233, 12)):
+        im = orc.synth_bgr(w, h, seed)
+        filt = orc.meanshift_filter(im, 8, 10, 1)
+        d_f = torch.from_numpy(filt).cuda()
+        lab = torch.empty((h, w), dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        dev.label_regions(ctx, d_f.data_ptr(), 3 * w, lab.data_ptr(), 4 * w, w, h, 2, cnt.data_ptr())
+        ctx.synchronize()
+        n0 = int(cnt[0].item())
+        want_n, want = orc.merge_regions(filt, lab.cpu().numpy(), 40, 9)
+        a, b = lab.clone(), lab.clone()
+        torch.cuda.synchronize()                     # torch ops run on torch's stream, the C-ABI calls on the context's
+        dev.merge_regions(ctx, d_f.data_ptr(), 3 * w, a.data_ptr(), 4 * w, w, h, 40, 9, cnt.data_ptr())
+        ctx.synchronize()
+        assert int(cnt[0].item()) == want_n and np.array_equal(a.cpu().numpy(), want)
+        ctx.set_option("labels_canonical", 1)
+        try:
+            base = ctx.stats()["kernel_launches"]
+            cnt[0] = n0
+            torch.cuda.synchronize()
+            dev.merge_regions(ctx, d_f.data_ptr(), 3 * w, b.data_ptr(), 4 * w, w, h, 40, 9, cnt.data_ptr())
+            ctx.synchronize()
+            trusted_launches = ctx.stats()["kernel_launches"] - base
+            assert int(cnt[0].item()) == want_n and np.array_equal(b.cpu().numpy(), want)
+            with pytest.raises(mseg.CvException):
+                dev.merge_regions(ctx, d_f.data_ptr(), 3 * w, b.data_ptr(), 4 * w, w, h, 40, 9, 0)
+        finally:
+            ctx.set_option("labels_canonical", 0)
+        assert trusted_launches <= 8

@@ -17,6 +17,7 @@ def main():
     dev = mseg.device
     ctx = mseg.Context(0)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_option("labels_canonical", 1)     # the labels come straight from msg_label_regions_dev: no validation passes
     src = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
     filt = torch.empty_like(src)
     ren = torch.empty_like(src)

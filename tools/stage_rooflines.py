@@ -42,6 +42,7 @@ def main():
     torch.cuda.set_device(0)
     with mseg.Context(0) as ctx:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.set_option("labels_canonical", 1)     # the labels come straight from msg_label_regions_dev: no validation passes
         for w, h in sizes:
             n = w * h
             src = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
@@ -54,11 +55,13 @@ def main():
             dev.meanshift(ctx, src.data_ptr(), 3 * w, filt.data_ptr(), 3 * w, w, h, 10, 10)
             t_label = timed(lambda: dev.label_regions(ctx, filt.data_ptr(), 3 * w, lab0.data_ptr(), 4 * w, w, h, 2, cnt.data_ptr()), reps)
             n0 = int(cnt[0].item())
+            cnt0 = cnt.clone()
 
             def merge():
                 lab.copy_(lab0)
+                cnt.copy_(cnt0)                     # option labels_canonical: the label count goes in through *d_n_regions
                 dev.merge_regions(ctx, filt.data_ptr(), 3 * w, lab.data_ptr(), 4 * w, w, h, 50, 10, cnt.data_ptr())
-            t_copy = timed(lambda: lab.copy_(lab0), reps)
+            t_copy = timed(lambda: (lab.copy_(lab0), cnt.copy_(cnt0)), reps)
             t_merge = timed(merge, reps) - t_copy
             n1 = int(cnt[0].item())
             t_render = timed(lambda: dev.render_labels(ctx, lab.data_ptr(), 4 * w, ren.data_ptr(), 3 * w, w, h, n1), reps)
