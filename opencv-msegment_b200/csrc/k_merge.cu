@@ -724,7 +724,14 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     int blocks_per_sm = 0;
     MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
-    int grid = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+    const int grid_max = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+    // The large-path rounds are latency-bound (four grid-wide barriers per round, a few items per thread): a barrier costs
+    // roughly in proportion to the CTAs that arrive at it, and a 296-CTA cooperative grid also holds thread slots on every SM
+    // that the mean-shift kernels of other streams want.  The label count is only known on the device, so the grid is sized
+    // from the pixel count (one CTA per 2^18 pixels: 32 at 4K, 256 at 8192^2); option "merge_grid" overrides it.
+    int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : (int)(n >> 18);
+    if (grid < 16) grid = 16;
+    if (grid > grid_max) grid = grid_max;
     size_t nl = (size_t)cap + 1;
     size_t pair_cap = 2 * n;                        // every pixel has at most a right and a down neighbour
     size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256 + pair_cap * sizeof(int2);
@@ -885,7 +892,10 @@ int k_strip_merge_finish(msg_ctx* ctx, int32_t* d_labels, int w, int rows, long 
     int blocks_per_sm = 0;
     MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
-    const int grid = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+    const int grid_max = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+    int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : (int)(((long long)n_total + n_all_pairs / 4) >> 9);
+    if (grid < 16) grid = 16;
+    if (grid > grid_max) grid = grid_max;
     const size_t nl = (size_t)n_total + 1;
     const size_t bytes = nl * (8 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256;
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));

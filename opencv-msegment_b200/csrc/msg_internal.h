@@ -52,6 +52,7 @@ struct msg_tuning {
     int no_order;          // 0
     int merge_scalar;      // 0
     int merge_small_max;   // -1 = compiled default
+    int merge_grid;        // 0 = automatic, else CTAs of the cooperative large-path rounds kernel
     int no_graph, graph_debug;
     int ccl_legacy;        // 1 = row-run union-find of round 1 instead of the tile-local one
     int gray_compat;       // 0 = OpenCV 4.x 15-bit BGR2GRAY coefficients, 1 = OpenCV 3.4.2 14-bit ones

@@ -38,10 +38,13 @@ def main():
     if os.environ.get("SIZES"):
         sizes = [tuple(int(v) for v in s.split("x")) for s in os.environ["SIZES"].split(",")]
     reps = int(os.environ.get("REPS", "5"))
-    out = {"peak_gbs": hbm, "rows": []}
+    grid = int(os.environ.get("MERGE_GRID", "0"))
+    out = {"peak_gbs": hbm, "merge_grid": grid or "auto", "rows": []}
     torch.cuda.set_device(0)
     with mseg.Context(0) as ctx:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        if grid:
+            ctx.set_option("merge_grid", grid)
         ctx.set_option("labels_canonical", 1)     # the labels come straight from msg_label_regions_dev: no validation passes
         for w, h in sizes:
             n = w * h
@@ -64,8 +67,10 @@ def main():
             t_copy = timed(lambda: (lab.copy_(lab0), cnt.copy_(cnt0)), reps)
             t_merge = timed(merge, reps) - t_copy
             n1 = int(cnt[0].item())
+            ctx.synchronize()
+            rounds = int(ctx.stats()["merge_rounds"])
             t_render = timed(lambda: dev.render_labels(ctx, lab.data_ptr(), 4 * w, ren.data_ptr(), 3 * w, w, h, n1), reps)
-            row = {"size": "%dx%d" % (w, h), "mpix": round(n / 1e6, 2), "regions": n0, "regions_after_merge": n1}
+            row = {"size": "%dx%d" % (w, h), "mpix": round(n / 1e6, 2), "regions": n0, "regions_after_merge": n1, "merge_rounds": rounds}
             for name, t, bpp in (("label", t_label, 7), ("merge", t_merge, 11), ("render", t_render, 7)):
                 gbs = bpp * n / (t * 1e-3) / 1e9
                 row[name] = {"ms": round(t, 4), "gbs": round(gbs, 1), "frac": round(gbs / hbm, 4)}
