@@ -73,6 +73,12 @@ struct merge_persist_args {
     int vec;                  // 1: w % 4 == 0 and labels 16-byte aligned -> 16-byte loads in the statistics pass
     int small_max;            // labels up to which the single-CTA rounds kernel is used (0 forces the large path)
     int nin_host;             // >= 0: the label count is known on the host (strip-sharded merge) and overrides *n_saved
+    // large path: the pair list holds one entry per boundary corner (10-15 x more than there are adjacent region pairs); the
+    // rounds kernel first builds the SET of pairs in a global hash table and walks the unique list instead
+    unsigned long long* htab; // [1 << hbits] open-addressing set, key = min label << 32 | max label (0 = empty)
+    int hbits;
+    int2* uniq;               // [1 << hbits] unique pairs in insertion order
+    int32_t* nuniq;           // device: [0] entries of uniq, [1] overflow flag (table full: the rounds use the raw list)
     long long npairs_host;    // >= 0: number of valid entries of `pairs` (all-gathered list), overrides *npairs
 };
 
@@ -497,7 +503,52 @@ __global__ void __launch_bounds__(MT) merge_rounds_large_kernel(merge_persist_ar
     if (merge_is_small(A, nin)) return;                  // uniform over the grid: the small-path kernel did the work
     const int nl = nin + 1;
     merge_tables t = A.t;
-    const long long npairs = merge_npairs(A);
+    long long npairs = merge_npairs(A);
+    const int2* __restrict__ pairs = A.pairs;
+
+    // ---- the set of adjacent pairs (every round walks it; the raw list repeats a pair once per boundary corner)
+    if (A.htab) {
+        const long long slots = 1ll << A.hbits;
+        for (long long i = gtid; i < slots; i += nthreads) A.htab[i] = 0ull;
+        if (gtid == 0) { A.nuniq[0] = 0; A.nuniq[1] = 0; }
+        grid.sync();
+        const unsigned long long hmask = (unsigned long long)slots - 1;
+        for (long long base = (gtid - lane); base < npairs; base += nthreads) {     // warp-uniform trip count
+            const long long i = base + lane;
+            bool fresh = false;
+            int2 pr = make_int2(0, 0);
+            if (i < npairs) {
+                pr = A.pairs[i];
+                if (pr.x > 0 && pr.y > 0 && pr.x != pr.y) {
+                    const unsigned lo = (unsigned)min(pr.x, pr.y), hi = (unsigned)max(pr.x, pr.y);
+                    const unsigned long long key = ((unsigned long long)lo << 32) | hi;
+                    unsigned long long slot = (key * 0x9E3779B97F4A7C15ull) >> (64 - A.hbits);
+                    int probes = 0;
+                    for (; probes < 64; probes++) {
+                        const unsigned long long old = atomicCAS(A.htab + slot, 0ull, key);
+                        if (old == 0ull) { fresh = true; break; }
+                        if (old == key) break;
+                        slot = (slot + 1) & hmask;
+                    }
+                    if (probes == 64) A.nuniq[1] = 1;                                  // table too full for this image
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, fresh);
+            if (m) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(A.nuniq, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+                if (fresh) {
+                    if (pos < slots) A.uniq[pos] = pr; else A.nuniq[1] = 1;
+                }
+            }
+        }
+        grid.sync();
+        if (*((volatile int32_t*)A.nuniq + 1) == 0) {
+            pairs = A.uniq;
+            npairs = *((volatile int32_t*)A.nuniq);
+        }
+    }
 
     const long long INF = 1ll << 40;
     int rounds = 0;
@@ -521,7 +572,7 @@ __global__ void __launch_bounds__(MT) merge_rounds_large_kernel(merge_persist_ar
             grid.sync();
             // region adjacency through the (flattened) parent table: both ends of every recorded pair
             for (long long i = gtid; i < npairs; i += nthreads) {
-                int2 pr = A.pairs[i];
+                int2 pr = pairs[i];
                 int ra = __ldcg(t.par + pr.x), rb = __ldcg(t.par + pr.y);
                 if (ra == rb) continue;
                 bool pa = (long long)t.area[ra] < size_thr, pb = (long long)t.area[rb] < size_thr;
@@ -725,16 +776,17 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
     const int grid_max = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
-    // The large-path rounds are latency-bound (four grid-wide barriers per round, a few items per thread): a barrier costs
-    // roughly in proportion to the CTAs that arrive at it, and a 296-CTA cooperative grid also holds thread slots on every SM
-    // that the mean-shift kernels of other streams want.  The label count is only known on the device, so the grid is sized
-    // from the pixel count (one CTA per 2^18 pixels: 32 at 4K, 256 at 8192^2); option "merge_grid" overrides it.
-    int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : (int)(n >> 18);
-    if (grid < 16) grid = 16;
+    // Option "merge_grid" (A/B hook): CTAs of the cooperative rounds kernel.  Measured (4K / 8192^2, merge stage): 16 CTAs 0.52 /
+    // 4.79 ms, 32: 0.37 / 2.84, 64: 0.28 / 1.83, 148: 0.24 / 1.25, 296: 0.22 / 1.04 -- the passes are bound by the work over the
+    // pair list, not by the grid barriers, so the full grid stays the default.
+    int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : grid_max;
     if (grid > grid_max) grid = grid_max;
     size_t nl = (size_t)cap + 1;
     size_t pair_cap = 2 * n;                        // every pixel has at most a right and a down neighbour
-    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256 + pair_cap * sizeof(int2);
+    int hbits = 16;                                 // pair set of the large path: one slot per 16 pixels, at least 2^16
+    while (((size_t)1 << hbits) < n / 16 && hbits < 28) hbits++;
+    const size_t hslots = (size_t)1 << hbits;
+    size_t bytes = nl * (24 + 8 + 4 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256 + pair_cap * sizeof(int2) + hslots * 16 + 64;
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));
     char* base = (char*)ctx->d_ovf;
     merge_persist_args A;
@@ -745,7 +797,11 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     A.t.par = (int32_t*)base;              base += nl * 4;
     A.newid = (int32_t*)base;              base += nl * 4;
     A.bsum = (int32_t*)base;               base += ((size_t)(grid + 1) * 4 + 15) / 16 * 16;
-    A.pairs = (int2*)base;
+    A.pairs = (int2*)base;                 base += pair_cap * sizeof(int2);
+    A.htab = (unsigned long long*)base;    base += hslots * 8;
+    A.uniq = (int2*)base;
+    A.hbits = hbits;
+    A.nuniq = ctx->d_counters + 18;
     A.pair_cap = (long long)pair_cap;
     A.npairs = ctx->d_counters + 13;
     A.plane = d_plane; A.pitch = pitch; A.labels = d_labels; A.w = w; A.h = h;
@@ -893,11 +949,14 @@ int k_strip_merge_finish(msg_ctx* ctx, int32_t* d_labels, int w, int rows, long 
     MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
     const int grid_max = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
-    int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : (int)(((long long)n_total + n_all_pairs / 4) >> 9);
-    if (grid < 16) grid = 16;
+    int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : grid_max;
     if (grid > grid_max) grid = grid_max;
     const size_t nl = (size_t)n_total + 1;
-    const size_t bytes = nl * (8 + 4 + 4 + 4) + (size_t)(grid + 1) * 4 + 256;
+    int hbits = 16;                                 // pair set: 8 slots per region (a planar adjacency graph has < 3 edges per region)
+    while (((size_t)1 << hbits) < 8 * nl && hbits < 28) hbits++;
+    const size_t hslots = (size_t)1 << hbits;
+    const size_t bsum_bytes = ((size_t)(grid + 1) * 4 + 255) / 256 * 256;
+    const size_t bytes = nl * (8 + 4 + 4 + 4) + bsum_bytes + 256 + hslots * 16;
     MSG_TRY(msg_reserve(ctx, (void**)&ctx->d_ovf, &ctx->d_ovf_cap, bytes));
     char* base = (char*)ctx->d_ovf;
     merge_persist_args A;
@@ -907,7 +966,12 @@ int k_strip_merge_finish(msg_ctx* ctx, int32_t* d_labels, int w, int rows, long 
     A.t.mean = (uint32_t*)base;            base += nl * 4;
     A.t.par = (int32_t*)base;              base += nl * 4;
     A.newid = (int32_t*)base;              base += nl * 4;
-    A.bsum = (int32_t*)base;
+    A.bsum = (int32_t*)base;               base += bsum_bytes;
+    base = (char*)(((uintptr_t)base + 15) & ~(uintptr_t)15);
+    A.htab = (unsigned long long*)base;    base += hslots * 8;
+    A.uniq = (int2*)base;
+    A.hbits = hbits;
+    A.nuniq = ctx->d_counters + 18;
     A.pairs = (int2*)const_cast<int32_t*>(d_all_pairs); A.pair_cap = n_all_pairs; A.npairs = ctx->d_counters + 13;
     A.labels = d_labels; A.w = w; A.h = rows;
     A.cap = n_total; A.nin_host = n_total; A.npairs_host = n_all_pairs;
