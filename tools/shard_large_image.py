@@ -18,7 +18,7 @@ calls between two collectives is a C-ABI entry point of include/msegment.h, in t
   [4-byte read]  total number of regions (sizes the tables)
   [P2P]  last row of dense labels to the rank below
   msg_strip_merge_stats_dev
-  [ALL-REDUCE] area, colour sums   [ALL-GATHER] adjacent-pair lists
+  [ALL-REDUCE] area + colour sums (one buffer)   [ALL-GATHER] adjacent-pair lists
   msg_strip_merge_finish_dev                            identical rounds on every rank, strip rewritten
 
 --verify (sizes that fit one GPU) gathers the result on rank 0 and compares it bit for bit with the unsharded single-GPU
@@ -164,15 +164,18 @@ def run(args, oracle_hook=None):
             if rank > 0:
                 ops.append(dist.P2POp(dist.irecv, up_dense, rank - 1))
             p2p(ops)
-            area = torch.empty(n_total + 1, dtype=torch.int32, device="cuda")
-            sums = torch.empty(3 * (n_total + 1), dtype=torch.int64, device="cuda")
+            # one buffer, ONE all-reduce: 3 x int64 colour sums per label, then the int32 areas packed two per int64 (the areas
+            # of a label summed over the ranks stay below 2^32 -- they are pixel counts -- so no carry crosses the halves)
+            nl = n_total + 1
+            stats = torch.zeros(3 * nl + (nl + 1) // 2, dtype=torch.int64, device="cuda")
+            sums = stats[:3 * nl]
+            area = stats[3 * nl:].view(torch.int32)[:nl]
             cap = 2 * w * rows
             pairs = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
             npairs = torch.zeros(1, dtype=torch.int32, device="cuda")
             dev.strip_merge_stats(ctx, filt.data_ptr(), 3 * w, lab.data_ptr(), 4 * w, w, rows, up_dense.data_ptr() if rank > 0 else 0,
                                   n_total, area.data_ptr(), sums.data_ptr(), pairs.data_ptr(), cap, npairs.data_ptr())
-            dist.all_reduce(area)
-            dist.all_reduce(sums)
+            dist.all_reduce(stats)
             counts = torch.empty(world, dtype=torch.int32, device="cuda")
             dist.all_gather_into_tensor(counts, npairs)
             cl = counts.cpu().tolist()
