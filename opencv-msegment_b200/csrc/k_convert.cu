@@ -70,32 +70,37 @@ __global__ void __launch_bounds__(256) plane_to_bgr_v4_kernel(const uint32_t* __
 }
 
 // ------------------------------------------------------------------ pyrDown: 5x5 [1 4 6 4 1]^2, (acc+128)>>8
+// Separable in 16-bit lanes: the horizontal sums of a row are at most 16 * 255, the vertical weights add up to 16 again, so
+// (B, R) and (G) stay below 2^16 in two registers and `(acc + 128) >> 8` is applied to both lanes at once.  The five reflected
+// column indices are computed once per thread, not once per tap (the kernel was instruction-bound: ~250 instructions per pixel).
 __global__ void __launch_bounds__(256) pyr_down_kernel(msg_plane s, msg_plane d)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int r = blockIdx.y;  // stored row of d
     if (x >= d.w || r >= d.rows) return;
     int y = d.y0 + r;    // global row at the coarse level
-    const int k[5] = {1, 4, 6, 4, 1};
-    int a0 = 0, a1 = 0, a2 = 0;
+    int xi[5];
+#pragma unroll
+    for (int b = 0; b < 5; b++) xi[b] = reflect101(2 * x + b - 2, s.w);
+    uint32_t lo = 0, hi = 0;
 #pragma unroll
     for (int a = -2; a <= 2; a++) {
         int yy = reflect101(2 * y + a, s.hfull) - s.y0;
         yy = clampi(yy, 0, s.rows - 1);  // rows outside a strip's halo: value unused by valid outputs
         const uint32_t* row = s.p + (size_t)yy * s.pitch;
-#pragma unroll
-        for (int b = -2; b <= 2; b++) {
-            int xx = reflect101(2 * x + b, s.w);
-            uint32_t v = __ldg(row + xx);
-            int wgt = k[a + 2] * k[b + 2];
-            a0 += wgt * (int)(v & 0xFF);
-            a1 += wgt * (int)((v >> 8) & 0xFF);
-            a2 += wgt * (int)((v >> 16) & 0xFF);
-        }
+        const uint32_t v0 = __ldg(row + xi[0]), v1 = __ldg(row + xi[1]), v2 = __ldg(row + xi[2]), v3 = __ldg(row + xi[3]),
+                       v4 = __ldg(row + xi[4]);
+        const uint32_t M = 0x00FF00FFu;
+        const uint32_t hl = (v0 & M) + (v4 & M) + 4u * ((v1 & M) + (v3 & M)) + 6u * (v2 & M);
+        const uint32_t hh = ((v0 >> 8) & 0xFFu) + ((v4 >> 8) & 0xFFu) + 4u * (((v1 >> 8) & 0xFFu) + ((v3 >> 8) & 0xFFu)) +
+                            6u * ((v2 >> 8) & 0xFFu);
+        const uint32_t wy = (a == 0) ? 6u : ((a == -1 || a == 1) ? 4u : 1u);
+        lo += wy * hl;
+        hi += wy * hh;
     }
-    uint32_t o = (uint32_t)((a0 + 128) >> 8) | ((uint32_t)((a1 + 128) >> 8) << 8) |
-                 ((uint32_t)((a2 + 128) >> 8) << 16) | 0x01000000u;
-    d.p[(size_t)r * d.pitch + x] = o;
+    lo = ((lo + 0x00800080u) >> 8) & 0x00FF00FFu;        // (B, R)
+    hi = ((hi + 128u) >> 8) & 0xFFu;                     // G
+    d.p[(size_t)r * d.pitch + x] = lo | (hi << 8) | 0x01000000u;
 }
 
 // ------------------------------------------------------------------ change flags of D[l+1] (App. A.2)
@@ -191,6 +196,78 @@ __global__ void __launch_bounds__(256) pyr_up_mask_kernel(msg_plane s /*D[l+1] w
     if (cell_count) {   // active pixels per 32x32 cell (one atomic per warp): lets the mean-shift kernel run heavy tiles first
         unsigned bal = __ballot_sync(__activemask(), m != 0);
         if ((threadIdx.x & 31) == 0 && bal) atomicAdd(cell_count + (r / 32) * cells_x + (x / 32), __popc(bal));
+    }
+}
+
+// The same, one 2 x 2 output quad per thread (d.y0 even): the four pixels (2i, 2j) .. (2i+1, 2j+1) read the same 3 x 3 source
+// neighbourhood (rows i-1, i, i+1 x columns j-1, j, j+1 with pyrUp's border rule) and the four flags they need are byte 3 of
+// words that are loaded anyway, so a quad costs 9 loads and ~100 instructions instead of 4 x (13 loads + ~150 instructions).
+// (ncu launch list of the 4K step: 73 us per frame for a 41 MB pass -- instruction-bound, and not hidden by the other streams.)
+__global__ void __launch_bounds__(256) pyr_up_mask_quad_kernel(msg_plane s /*D[l+1] with flags*/, msg_plane d,
+                                                               int* __restrict__ cell_count, int cells_x)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;       // source column; output columns 2j, 2j + 1
+    const int r0 = 2 * blockIdx.y;                              // stored output rows r0, r0 + 1
+    const int i = (d.y0 >> 1) + blockIdx.y;                     // source row (global, level l+1)
+    const int h1 = s.hfull, w1 = s.w;
+    const bool inx = 2 * j < d.w;
+    int act = 0;
+    if (inx && r0 < d.rows) {
+        const int jm = (j - 1 >= 0) ? j - 1 : (w1 > 1 ? 1 : 0), jp = (j + 1 < w1) ? j + 1 : w1 - 1;
+        const int jc = j < w1 ? j : w1 - 1;
+        const int im = (i - 1 >= 0) ? i - 1 : (h1 > 1 ? 1 : 0), ip = (i + 1 < h1) ? i + 1 : h1 - 1;
+        const int ic = i < h1 ? i : h1 - 1;
+        const int rows3[3] = {im, ic, ip};
+        const uint32_t M = 0x00FF00FFu;
+        uint32_t El[3], Eh[3], Ol[3], Oh[3], F1[3], F2[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int rr = clampi(rows3[a] - s.y0, 0, s.rows - 1);
+            const uint32_t* row = s.p + (size_t)rr * s.pitch;
+            const uint32_t v0 = __ldg(row + jm), v1 = __ldg(row + jc), v2 = __ldg(row + jp);
+            const uint32_t a0 = v0 & M, a1 = v1 & M, a2 = v2 & M;
+            const uint32_t g0 = (v0 >> 8) & 0xFFu, g1 = (v1 >> 8) & 0xFFu, g2 = (v2 >> 8) & 0xFFu;
+            El[a] = a0 + 6u * a1 + a2;  Eh[a] = g0 + 6u * g1 + g2;          // even output column: (1, 6, 1) on (j-1, j, j+1)
+            Ol[a] = 4u * (a1 + a2);     Oh[a] = 4u * (g1 + g2);              // odd output column: (4, 4) on (j, j+1)
+            F1[a] = v1 >> 24;           F2[a] = v2 >> 24;
+        }
+        auto fin = [&](uint32_t lo, uint32_t hi) {
+            return (((lo + 0x00200020u) >> 6) & M) | ((((hi + 32u) >> 6) & 0xFFu) << 8);
+        };
+        const uint32_t cEE = fin(El[0] + 6u * El[1] + El[2], Eh[0] + 6u * Eh[1] + Eh[2]);     // (2i, 2j)
+        const uint32_t cEO = fin(Ol[0] + 6u * Ol[1] + Ol[2], Oh[0] + 6u * Oh[1] + Oh[2]);     // (2i, 2j+1)
+        const uint32_t cOE = fin(4u * (El[1] + El[2]), 4u * (Eh[1] + Eh[2]));                 // (2i+1, 2j)
+        const uint32_t cOO = fin(4u * (Ol[1] + Ol[2]), 4u * (Oh[1] + Oh[2]));                 // (2i+1, 2j+1)
+        // mask = OR of the flags whose raw position (2 i' + 1, 2 j' - 1) lies in the 3 x 3 neighbourhood of the pixel (the rule of
+        // pyr_up_mask_kernel above, specialised to the four parities)
+        const bool RH = (2 * i + 1 < d.hfull) && i >= 1 && i <= h1 - 2 && (i - s.y0) >= 0 && (i - s.y0) < s.rows;
+        const bool RL = (i - 1) >= 1 && (i - 1) <= h1 - 2 && (i - 1 - s.y0) >= 0 && (i - 1 - s.y0) < s.rows;
+        const bool Cj = j >= 1 && j <= w1 - 2, Cj1 = (j + 1) >= 1 && (j + 1) <= w1 - 2;
+        const bool CH = Cj1 && (2 * j + 1 < d.w);
+        const uint32_t hi_j = (RH && Cj) ? F1[1] : 0u, hi_j1h = (RH && CH) ? F2[1] : 0u, hi_j1 = (RH && Cj1) ? F2[1] : 0u;
+        const uint32_t lo_j = (RL && Cj) ? F1[0] : 0u, lo_j1h = (RL && CH) ? F2[0] : 0u, lo_j1 = (RL && Cj1) ? F2[0] : 0u;
+        const uint32_t mEE = (hi_j | hi_j1h | lo_j | lo_j1h) ? 1u : 0u;
+        const uint32_t mEO = (hi_j1 | lo_j1) ? 1u : 0u;
+        const uint32_t mOE = (hi_j | hi_j1h) ? 1u : 0u;
+        const uint32_t mOO = hi_j1 ? 1u : 0u;
+        const bool two_cols = 2 * j + 1 < d.w, two_rows = r0 + 1 < d.rows;
+        uint32_t* o0 = d.p + (size_t)r0 * d.pitch + 2 * j;
+        if (two_cols) *reinterpret_cast<uint2*>(o0) = make_uint2(cEE | (mEE << 24), cEO | (mEO << 24));
+        else o0[0] = cEE | (mEE << 24);
+        act = (int)mEE + (two_cols ? (int)mEO : 0);
+        if (two_rows) {
+            uint32_t* o1 = o0 + d.pitch;
+            if (two_cols) *reinterpret_cast<uint2*>(o1) = make_uint2(cOE | (mOE << 24), cOO | (mOO << 24));
+            else o1[0] = cOE | (mOE << 24);
+            act += (int)mOE + (two_cols ? (int)mOO : 0);
+        }
+    }
+    if (cell_count) {   // active pixels per 32 x 32 cell: a warp covers 64 output columns = two cells of one cell row
+        const int lane = threadIdx.x & 31;
+        const int half = __reduce_add_sync(0xffffffffu, lane < 16 ? act : 0);
+        const int other = __reduce_add_sync(0xffffffffu, lane < 16 ? 0 : act);
+        if (lane == 0 && half) atomicAdd(cell_count + (r0 / 32) * cells_x + (2 * j) / 32, half);
+        if (lane == 16 && other) atomicAdd(cell_count + (r0 / 32) * cells_x + (2 * j) / 32, other);
     }
 }
 
@@ -293,6 +370,13 @@ int k_pyr_up_mask(msg_ctx* ctx, msg_plane dsrc, msg_plane ddst, int isr22, int* 
     flag_kernel<<<g1, 256, 0, ctx->stream>>>(dsrc, isr22);
     MSG_LAUNCHED(ctx);
     MSG_CHECK_LAUNCH(ctx);
+    if ((ddst.y0 & 1) == 0 && ddst.pitch % 2 == 0) {       // 2 x 2 quads need even strip origins (they are multiples of 2^maxLevel)
+        dim3 gq(((ddst.w + 1) / 2 + 255) / 256, (ddst.rows + 1) / 2);
+        pyr_up_mask_quad_kernel<<<gq, 256, 0, ctx->stream>>>(dsrc, ddst, d_cell_count, cells_x);
+        MSG_LAUNCHED(ctx);
+        MSG_CHECK_LAUNCH(ctx);
+        return MSG_OK;
+    }
     dim3 g2((ddst.w + 255) / 256, ddst.rows);
     pyr_up_mask_kernel<<<g2, 256, 0, ctx->stream>>>(dsrc, ddst, d_cell_count, cells_x);
     MSG_LAUNCHED(ctx);

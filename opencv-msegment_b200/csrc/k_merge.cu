@@ -776,10 +776,14 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
     const int grid_max = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
-    // Option "merge_grid" (A/B hook): CTAs of the cooperative rounds kernel.  Measured (4K / 8192^2, merge stage): 16 CTAs 0.52 /
-    // 4.79 ms, 32: 0.37 / 2.84, 64: 0.28 / 1.83, 148: 0.24 / 1.25, 296: 0.22 / 1.04 -- the passes are bound by the work over the
-    // pair list, not by the grid barriers, so the full grid stays the default.
-    int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : grid_max;
+    // CTAs of the cooperative rounds kernel (option "merge_grid" overrides).  Alone, more CTAs are faster (merge stage at 4K /
+    // 8192^2: 16 CTAs 0.52 / 4.79 ms, 32: 0.37 / 2.84, 64: 0.28 / 1.83, 148: 0.24 / 1.25, 296: 0.22 / 1.04: the passes are bound by
+    // the work over the pair list, not by the grid barriers).  But a frame-sized image is one of many in flight: two CTAs of this
+    // kernel per SM do not fit next to three mean-shift CTAs (registers), and a cooperative grid holds its slots on EVERY SM while
+    // it mostly waits at barriers -- the 4K bench step runs 4663 Mpix/s with 296 CTAs, 4728 with 148, 4764 with 74, 4758 with 37
+    // (tools/overlap_probe.py, profiles/r02_overlap_probe.txt).  So: half a CTA per SM up to 2^24 pixels, the full grid beyond
+    // (a single very large image has the GPU to itself).
+    int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : (n <= ((size_t)1 << 24) ? (ctx->sm_count + 1) / 2 : grid_max);
     if (grid > grid_max) grid = grid_max;
     size_t nl = (size_t)cap + 1;
     size_t pair_cap = 2 * n;                        // every pixel has at most a right and a down neighbour
