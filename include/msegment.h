@@ -86,7 +86,7 @@ MSG_API int msg_synchronize(msg_ctx* ctx);
  *   "dt_legacy"       1: the first wavefront kernel of the float distance transform (A/B hook)
  *   "staging"         1 (default): pageable caller buffers are staged through the context's pinned ring; 0: handed to
  *                     cudaMemcpyAsync as they are (driver staging, serialises the asynchronous path)
- *   "merge_small_max", "merge_grid", "tile_w", "acc", "pitch_res", "tma", "no_order", "merge_scalar", "no_graph", "ccl_legacy":
+ *   "merge_small_max", "merge_medium_only", "merge_grid", "tile_w", "acc", "pitch_res", "tma", "no_order", "merge_scalar", "no_graph", "ccl_legacy":
  *                     tuning / test hooks */
 MSG_API int msg_set_option(msg_ctx* ctx, const char* name, int value);
 MSG_API int msg_get_option(msg_ctx* ctx, const char* name, int* value);

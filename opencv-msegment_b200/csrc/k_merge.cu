@@ -25,10 +25,11 @@ namespace {
 
 constexpr int MT = 256;
 constexpr int MERGE_MAX_ROUNDS = 64;
+constexpr size_t MEDIUM_SMEM = (size_t)8192 * 7 * sizeof(uint32_t);
+constexpr int MEDIUM_MAX_LABELS = 8191;         // medium path: 13-bit label field, every table of the CTA in 224 KB of shared memory
 constexpr int SMALL_MAX_LABELS = 4095;          // small path: labels 1..4095 -> 12-bit label field in the 32-bit selection key
 constexpr long long SMALL_MAX_PIXELS = 1ll << 24;   // small path: colour sums of a region fit 32 bits (255 * 2^24 < 2^32)
 constexpr int ST = 1024;                        // threads of the small-path CTA
-constexpr int SMALL_HSET_BITS = 14, SMALL_HSET = 1 << SMALL_HSET_BITS;   // slots of its adjacent-pair set
 
 struct merge_tables {
     unsigned int* area;            // [nl]
@@ -71,14 +72,17 @@ struct merge_persist_args {
     long long pair_cap;
     int min_size, color_dist;
     int vec;                  // 1: w % 4 == 0 and labels 16-byte aligned -> 16-byte loads in the statistics pass
-    int small_max;            // labels up to which the single-CTA rounds kernel is used (0 forces the large path)
+    int small_max;            // labels up to which the single-CTA rounds kernel with the shared-memory pair set is used
+    int medium_max;           // labels up to which the single-CTA rounds kernel with the global pair set is used (0 / 0: large path)
     int nin_host;             // >= 0: the label count is known on the host (strip-sharded merge) and overrides *n_saved
-    // large path: the pair list holds one entry per boundary corner (10-15 x more than there are adjacent region pairs); the
-    // rounds kernel first builds the SET of pairs in a global hash table and walks the unique list instead
-    unsigned long long* htab; // [1 << hbits] open-addressing set, key = min label << 32 | max label (0 = empty)
+    // The raw pair list holds one entry per boundary corner (10-15 x more than there are adjacent region pairs) and every round
+    // walks the pairs, so the SET of pairs is built once in a global hash table: by the statistics pass itself (whole GPU, set_in_stats
+    // = 1: unsharded merge) or by the cooperative rounds kernel (strip-sharded merge: the raw lists of all ranks arrive gathered).
+    unsigned long long* htab; // [1 << hbits] open-addressing set, key = min label << 32 | max label (0 = empty); zeroed by the host
     int hbits;
     int2* uniq;               // [1 << hbits] unique pairs in insertion order
     int32_t* nuniq;           // device: [0] entries of uniq, [1] overflow flag (table full: the rounds use the raw list)
+    int set_in_stats;
     long long npairs_host;    // >= 0: number of valid entries of `pairs` (all-gathered list), overrides *npairs
 };
 
@@ -94,9 +98,14 @@ __device__ __forceinline__ long long merge_npairs(const merge_persist_args& A)
     return np > A.pair_cap ? A.pair_cap : np;
 }
 
-__device__ __forceinline__ bool merge_is_small(const merge_persist_args& A, int nin)
+// Which rounds kernel serves this image: 0 = single CTA, <= 4095 labels, pair set in shared memory; 1 = single CTA, <= 8191
+// labels, pair set in a global hash table (a 4K frame of the bench: 5.5 k regions); 2 = cooperative grid.  Uniform over a launch.
+__device__ __forceinline__ int merge_regime(const merge_persist_args& A, int nin)
 {
-    return nin <= A.small_max && (long long)A.w * A.h <= SMALL_MAX_PIXELS;
+    if ((long long)A.w * A.h > SMALL_MAX_PIXELS) return 2;       // colour sums of a region must fit 32 bits
+    if (nin <= A.small_max) return 0;
+    if (nin <= A.medium_max) return 1;
+    return 2;
 }
 
 __device__ __forceinline__ void persist_union(int32_t* par, int a, int b)
@@ -124,7 +133,10 @@ __global__ void __launch_bounds__(MT) merge_init_kernel(merge_persist_args A)
         A.t.sum[3 * i] = 0; A.t.sum[3 * i + 1] = 0; A.t.sum[3 * i + 2] = 0;
         A.t.par[i] = (int)i;
     }
-    if (gtid == 0) { *A.accepted = 0; *A.rounds_out = 0; *A.npairs = 0; *A.n_saved = nin; }
+    if (gtid == 0) {
+        *A.accepted = 0; *A.rounds_out = 0; *A.npairs = 0; *A.n_saved = nin;
+        if (A.nuniq) { A.nuniq[0] = 0; A.nuniq[1] = 0; }
+    }
 }
 
 // ---------------------------------------------------------------- statistics + adjacency pairs (one pass over the pixels)
@@ -135,6 +147,23 @@ __device__ __forceinline__ void stats_flush(const merge_tables& t, int lab, unsi
     atomicAdd(t.sum + 3 * (size_t)lab, (unsigned long long)b);
     atomicAdd(t.sum + 3 * (size_t)lab + 1, (unsigned long long)g);
     atomicAdd(t.sum + 3 * (size_t)lab + 2, (unsigned long long)r);
+}
+
+// insert an adjacent pair into the global set; true if it was not there yet (the caller appends it to A.uniq)
+__device__ __forceinline__ bool pair_set_insert(const merge_persist_args& A, int a, int b)
+{
+    const unsigned lo = (unsigned)min(a, b), hi = (unsigned)max(a, b);
+    const unsigned long long key = ((unsigned long long)lo << 32) | hi;
+    const unsigned long long hmask = (1ull << A.hbits) - 1;
+    unsigned long long slot = (key * 0x9E3779B97F4A7C15ull) >> (64 - A.hbits);
+    for (int probes = 0; probes < 64; probes++) {
+        const unsigned long long old = atomicCAS(A.htab + slot, 0ull, key);
+        if (old == 0ull) return true;
+        if (old == key) return false;
+        slot = (slot + 1) & hmask;
+    }
+    A.nuniq[1] = 1;                                        // table too full for this image: the rounds walk the raw list
+    return false;
 }
 
 // Statistics + adjacency pass, 16-byte loads (requires w % 4 == 0 and 16-byte aligned label rows): a warp walks the image
@@ -236,6 +265,33 @@ __device__ __forceinline__ void stats_pass_vec4(const merge_persist_args& A, con
                 if (er[k]) { if (pos < A.pair_cap) A.pairs[pos] = make_int2(lab[k], rn[k]); pos++; }
                 if (ed[k]) { if (pos < A.pair_cap) A.pairs[pos] = make_int2(lab[k], dn[k]); pos++; }
             }
+            if (A.set_in_stats) {                           // the set of pairs, built here by the whole GPU
+                unsigned fresh = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (er[k] && pair_set_insert(A, lab[k], rn[k])) fresh |= 1u << (2 * k);
+                    if (ed[k] && pair_set_insert(A, lab[k], dn[k])) fresh |= 2u << (2 * k);
+                }
+                const int nf = __popc(fresh);
+                if (__any_sync(FULL, nf)) {
+                    int inc2 = nf;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int v = __shfl_up_sync(FULL, inc2, o);
+                        if (lane >= o) inc2 += v;
+                    }
+                    const int tot2 = __shfl_sync(FULL, inc2, 31);
+                    int upos = 0;
+                    if (lane == 0) upos = atomicAdd(A.nuniq, tot2);
+                    upos = __shfl_sync(FULL, upos, 0) + inc2 - nf;
+                    const int ucap = 1 << A.hbits;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (fresh & (1u << (2 * k))) { if (upos < ucap) A.uniq[upos] = make_int2(lab[k], rn[k]); else A.nuniq[1] = 1; upos++; }
+                        if (fresh & (2u << (2 * k))) { if (upos < ucap) A.uniq[upos] = make_int2(lab[k], dn[k]); else A.nuniq[1] = 1; upos++; }
+                    }
+                }
+            }
         }
     }
 }
@@ -300,6 +356,19 @@ __global__ void __launch_bounds__(MT) merge_stats_kernel(merge_persist_args A)
             unsigned lt = (1u << lane) - 1;
             if (lr > 0) { long long k = pos + __popc(mr & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, lr); }
             if (ld > 0) { long long k = pos + __popc(mr) + __popc(md & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, ld); }
+            if (A.set_in_stats) {
+                const bool fr = lr > 0 && pair_set_insert(A, lab, lr), fd = ld > 0 && pair_set_insert(A, lab, ld);
+                const unsigned ur = __ballot_sync(0xffffffffu, fr), ud = __ballot_sync(0xffffffffu, fd);
+                const int tot2 = __popc(ur) + __popc(ud);
+                if (tot2) {
+                    int upos = 0;
+                    if (lane == 0) upos = atomicAdd(A.nuniq, tot2);
+                    upos = __shfl_sync(0xffffffffu, upos, 0);
+                    const int ucap = 1 << A.hbits;
+                    if (fr) { int k = upos + __popc(ur & lt); if (k < ucap) A.uniq[k] = make_int2(lab, lr); else A.nuniq[1] = 1; }
+                    if (fd) { int k = upos + __popc(ur) + __popc(ud & lt); if (k < ucap) A.uniq[k] = make_int2(lab, ld); else A.nuniq[1] = 1; }
+                }
+            }
         }
     }
 }
@@ -327,10 +396,12 @@ __device__ __forceinline__ void sm_union(int* par, int a, int b)
     }
 }
 
+template <int LBITS>
 __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist_args A)
 {
     extern __shared__ uint32_t sm_tab[];
-    constexpr int NS = SMALL_MAX_LABELS + 1;
+    constexpr int NS = 1 << LBITS;                   // labels 0 .. NS - 1: LBITS-bit label field in the 32-bit selection key
+    constexpr uint32_t LMASK = NS - 1;
     int* par = reinterpret_cast<int*>(sm_tab);
     uint32_t* area = sm_tab + NS;
     uint32_t* mean = sm_tab + 2 * NS;
@@ -338,15 +409,18 @@ __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist
     uint32_t* sum0 = sm_tab + 4 * NS;
     uint32_t* sum1 = sm_tab + 5 * NS;
     uint32_t* sum2 = sm_tab + 6 * NS;
-    uint32_t* hset = sm_tab + 7 * NS;          // set of adjacent label pairs
-    __shared__ int s_accepted, s_overflow;
+    __shared__ int s_accepted;
     __shared__ int s_wsum[ST / 32];
     const int nin = merge_nin(A);
-    if (!merge_is_small(A, nin)) return;
+    if (merge_regime(A, nin) != (LBITS == 12 ? 0 : 1)) return;
     const int nl = nin + 1;
     const int tid = threadIdx.x, lane = tid & 31;
+    // the pairs the rounds walk: the set built by the statistics pass (read coalesced from L2), or the raw list when there is
+    // none (strip-sharded merge) or its table overflowed
+    const int2* __restrict__ pairs = A.pairs;
     long long npairs = merge_npairs(A);
     if (npairs > A.pair_cap) npairs = A.pair_cap;
+    if (A.set_in_stats && A.nuniq[1] == 0) { pairs = A.uniq; npairs = A.nuniq[0]; }
     for (int i = tid; i < nl; i += ST) {
         par[i] = i;
         area[i] = A.t.area[i];
@@ -354,43 +428,14 @@ __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist
         sum1[i] = (uint32_t)A.t.sum[3 * (size_t)i + 1];
         sum2[i] = (uint32_t)A.t.sum[3 * (size_t)i + 2];
     }
-    // The pair list holds one entry per boundary corner; the rounds only need every adjacent (label, label) pair once.
-    // Build that set in shared memory (open addressing, key = min << 12 | max): a region adjacency graph of 4095 regions
-    // has at most ~12k edges when it is planar; if the table ever fills up the rounds walk the list in global memory.
-    for (int i = tid; i < SMALL_HSET; i += ST) hset[i] = 0;
-    if (tid == 0) s_overflow = 0;
     __syncthreads();
-    for (long long base = 0; base < npairs; base += (long long)ST * 8) {
-        int2 pr[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {                      // 8 independent loads in flight per thread
-            long long k = base + (long long)u * ST + tid;
-            pr[u] = k < npairs ? A.pairs[k] : make_int2(0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            if (pr[u].x <= 0) continue;
-            uint32_t a = (uint32_t)min(pr[u].x, pr[u].y), b = (uint32_t)max(pr[u].x, pr[u].y);
-            uint32_t key = (a << 12) | b;
-            uint32_t slot = (key * 2654435761u) >> (32 - SMALL_HSET_BITS);
-            int probes = 0;
-            for (; probes < 128; probes++) {
-                uint32_t old = atomicCAS(hset + slot, 0u, key);
-                if (old == 0u || old == key) break;
-                slot = (slot + 1) & (SMALL_HSET - 1);
-            }
-            if (probes == 128) s_overflow = 1;
-        }
-    }
-    __syncthreads();
-    const bool use_set = s_overflow == 0;
     auto edge = [&](int la, int lb, uint32_t size_thr) {    // both ends of an adjacent pair bid for each other
         int ra = par[la], rb = par[lb];
         if (ra == rb) return;
         bool pa = area[ra] < size_thr, pb = area[rb] < size_thr;
         if (!pa && !pb) return;
         uint32_t e = __vabsdiffu4(mean[ra], mean[rb]);
-        uint32_t d2 = __dp4a(e, e, 0u) << 12;
+        uint32_t d2 = __dp4a(e, e, 0u) << LBITS;
         if (pa) atomicMin(best + ra, d2 | (uint32_t)rb);
         if (pb) atomicMin(best + rb, d2 | (uint32_t)ra);
     };
@@ -414,23 +459,16 @@ __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist
             }
             if (tid == 0) s_accepted = 0;
             __syncthreads();
-            if (use_set) {
-                for (int i = tid; i < SMALL_HSET; i += ST) {
-                    uint32_t key = hset[i];
-                    if (key) edge((int)(key >> 12), (int)(key & 0xfffu), size_thr);
-                }
-            } else {
-                for (long long k = tid; k < npairs; k += ST) {
-                    int2 pr = A.pairs[k];
-                    edge(pr.x, pr.y, size_thr);
-                }
+            for (long long k = tid; k < npairs; k += ST) {
+                const int2 pr = pairs[k];
+                edge(pr.x, pr.y, size_thr);
             }
             __syncthreads();
             for (int i = tid; i < nl; i += ST) {
                 if (i == 0) continue;
                 uint32_t k = best[i];
-                if (k == 0xffffffffu || (k >> 12) > dist_limit) continue;
-                sm_union(par, i, (int)(k & 0xfffu));
+                if (k == 0xffffffffu || (k >> LBITS) > dist_limit) continue;
+                sm_union(par, i, (int)(k & LMASK));
                 atomicAdd(&s_accepted, 1);
             }
             __syncthreads();
@@ -500,14 +538,16 @@ __global__ void __launch_bounds__(MT) merge_rounds_large_kernel(merge_persist_ar
     const long long gtid = (long long)blockIdx.x * MT + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * MT;
     const int nin = merge_nin(A);
-    if (merge_is_small(A, nin)) return;                  // uniform over the grid: the small-path kernel did the work
+    if (merge_regime(A, nin) != 2) return;               // uniform over the grid: a single-CTA kernel did the work
     const int nl = nin + 1;
     merge_tables t = A.t;
     long long npairs = merge_npairs(A);
     const int2* __restrict__ pairs = A.pairs;
 
     // ---- the set of adjacent pairs (every round walks it; the raw list repeats a pair once per boundary corner)
-    if (A.htab) {
+    if (A.set_in_stats) {
+        if (*((volatile int32_t*)A.nuniq + 1) == 0) { pairs = A.uniq; npairs = *((volatile int32_t*)A.nuniq); }
+    } else if (A.htab) {
         const long long slots = 1ll << A.hbits;
         for (long long i = gtid; i < slots; i += nthreads) A.htab[i] = 0ull;
         if (gtid == 0) { A.nuniq[0] = 0; A.nuniq[1] = 0; }
@@ -817,20 +857,33 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     A.min_size = min_size; A.color_dist = color_dist;
     A.nin_host = -1; A.npairs_host = -1;
     A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !ctx->tune.merge_scalar) ? 1 : 0;
-    A.small_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : SMALL_MAX_LABELS;   // test hook: 0 forces the cooperative path
+    // test hooks: merge_small_max = v caps both single-CTA regimes (0 forces the cooperative path), merge_medium_only = 1 sends
+    // every image of <= 8191 labels through the global-pair-set kernel
+    A.small_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : SMALL_MAX_LABELS;
     if (A.small_max > SMALL_MAX_LABELS) A.small_max = SMALL_MAX_LABELS;
+    A.medium_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : MEDIUM_MAX_LABELS;
+    if (A.medium_max > MEDIUM_MAX_LABELS) A.medium_max = MEDIUM_MAX_LABELS;
+    if (ctx->tune.merge_medium_only) { A.small_max = -1; A.medium_max = MEDIUM_MAX_LABELS; }
+    if (MEDIUM_SMEM + 1024 > (size_t)ctx->max_smem_optin) A.medium_max = -1;
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;                              // CTAs of the streaming kernels (grid-stride)
     auto blocks_for = [&](size_t items) { size_t b = (items + MT - 1) / MT; return (int)(b < 1 ? 1 : (b > (size_t)wide ? (size_t)wide : b)); };
+    A.set_in_stats = 1;
+    MSG_CUDA(ctx, cudaMemsetAsync(A.htab, 0, hslots * sizeof(unsigned long long), st));
     merge_init_kernel<<<blocks_for(n < 65536 ? n : 65536), MT, 0, st>>>(A);
     MSG_LAUNCHED(ctx);
     size_t stat_threads = A.vec ? ((n + 127) / 128) * 32 : ((size_t)((w + 31) / 32) * h) * 32;   // one warp per chunk
     merge_stats_kernel<<<blocks_for(stat_threads), MT, 0, st>>>(A);
     MSG_LAUNCHED(ctx);
-    const size_t small_smem = ((size_t)(SMALL_MAX_LABELS + 1) * 7 + SMALL_HSET) * sizeof(uint32_t);
-    MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel, small_smem));
-    merge_rounds_small_kernel<<<1, ST, small_smem, st>>>(A);
+    const size_t small_smem = (size_t)(SMALL_MAX_LABELS + 1) * 7 * sizeof(uint32_t);
+    MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel<12>, small_smem));
+    merge_rounds_small_kernel<12><<<1, ST, small_smem, st>>>(A);
     MSG_LAUNCHED(ctx);
+    if (A.medium_max > A.small_max) {                                                        // 224 KB: the whole SM
+        MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel<13>, MEDIUM_SMEM));
+        merge_rounds_small_kernel<13><<<1, ST, MEDIUM_SMEM, st>>>(A);
+        MSG_LAUNCHED(ctx);
+    }
     void* args[] = {&A};
     MSG_CUDA(ctx, cudaLaunchCooperativeKernel((void*)merge_rounds_large_kernel, dim3(grid), dim3(MT), args, 0, st));
     MSG_LAUNCHED(ctx);
@@ -986,17 +1039,27 @@ int k_strip_merge_finish(msg_ctx* ctx, int32_t* d_labels, int w, int rows, long 
     A.min_size = min_size; A.color_dist = color_dist;
     A.small_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : SMALL_MAX_LABELS;
     if (A.small_max > SMALL_MAX_LABELS) A.small_max = SMALL_MAX_LABELS;
-    if (full_pixels > SMALL_MAX_PIXELS) A.small_max = 0;      // the single-CTA path keeps 32-bit colour sums: whole image <= 2^24 pixels
+    A.medium_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : MEDIUM_MAX_LABELS;
+    if (A.medium_max > MEDIUM_MAX_LABELS) A.medium_max = MEDIUM_MAX_LABELS;
+    if (ctx->tune.merge_medium_only) { A.small_max = -1; A.medium_max = MEDIUM_MAX_LABELS; }
+    if (MEDIUM_SMEM + 1024 > (size_t)ctx->max_smem_optin) A.medium_max = -1;
+    // the single-CTA paths keep 32-bit colour sums: WHOLE image <= 2^24 pixels (merge_regime only sees the strip)
+    if (full_pixels > SMALL_MAX_PIXELS) { A.small_max = -1; A.medium_max = -1; }
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t)w * rows;
     const int wide = ctx->sm_count * 8;
     auto blocks_for = [&](size_t items) { size_t b = (items + MT - 1) / MT; return (int)(b < 1 ? 1 : (b > (size_t)wide ? (size_t)wide : b)); };
     strip_merge_par_kernel<<<blocks_for(nl), MT, 0, st>>>(A.t.par, (int)nl, A.accepted, A.rounds_out);
     MSG_LAUNCHED(ctx);
-    const size_t small_smem = ((size_t)(SMALL_MAX_LABELS + 1) * 7 + SMALL_HSET) * sizeof(uint32_t);
-    MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel, small_smem));
-    merge_rounds_small_kernel<<<1, ST, small_smem, st>>>(A);
+    const size_t small_smem = (size_t)(SMALL_MAX_LABELS + 1) * 7 * sizeof(uint32_t);
+    MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel<12>, small_smem));
+    merge_rounds_small_kernel<12><<<1, ST, small_smem, st>>>(A);
     MSG_LAUNCHED(ctx);
+    if (A.medium_max > A.small_max) {                                                        // 224 KB: the whole SM
+        MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel<13>, MEDIUM_SMEM));
+        merge_rounds_small_kernel<13><<<1, ST, MEDIUM_SMEM, st>>>(A);
+        MSG_LAUNCHED(ctx);
+    }
     void* args[] = {&A};
     MSG_CUDA(ctx, cudaLaunchCooperativeKernel((void*)merge_rounds_large_kernel, dim3(grid), dim3(MT), args, 0, st));
     MSG_LAUNCHED(ctx);

@@ -52,6 +52,7 @@ struct msg_tuning {
     int no_order;          // 0
     int merge_scalar;      // 0
     int merge_small_max;   // -1 = compiled default
+    int merge_medium_only; // test hook: 1 = images of <= 8191 labels use the single-CTA kernel with the global pair set
     int merge_grid;        // 0 = automatic, else CTAs of the cooperative large-path rounds kernel
     int no_graph, graph_debug;
     int ccl_legacy;        // 1 = row-run union-find of round 1 instead of the tile-local one

