@@ -868,8 +868,11 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;                              // CTAs of the streaming kernels (grid-stride)
     auto blocks_for = [&](size_t items) { size_t b = (items + MT - 1) / MT; return (int)(b < 1 ? 1 : (b > (size_t)wide ? (size_t)wide : b)); };
-    A.set_in_stats = 1;
-    MSG_CUDA(ctx, cudaMemsetAsync(A.htab, 0, hslots * sizeof(unsigned long long), st));
+    // Who builds the set of pairs: the statistics pass for frame-sized images (the single-CTA rounds kernels need it ready; 4K:
+    // merge 0.21 ms), the cooperative rounds kernel itself beyond 2^24 pixels (always the large regime; inserting from the
+    // statistics pass puts an L2 atomic round trip into its warps' critical path: 8192^2 merge 1.02 instead of 0.85 ms).
+    A.set_in_stats = n <= (size_t)SMALL_MAX_PIXELS ? 1 : 0;
+    if (A.set_in_stats) MSG_CUDA(ctx, cudaMemsetAsync(A.htab, 0, hslots * sizeof(unsigned long long), st));
     merge_init_kernel<<<blocks_for(n < 65536 ? n : 65536), MT, 0, st>>>(A);
     MSG_LAUNCHED(ctx);
     size_t stat_threads = A.vec ? ((n + 127) / 128) * 32 : ((size_t)((w + 31) / 32) * h) * 32;   // one warp per chunk
