@@ -76,13 +76,13 @@ struct merge_persist_args {
     int medium_max;           // labels up to which the single-CTA rounds kernel with the global pair set is used (0 / 0: large path)
     int nin_host;             // >= 0: the label count is known on the host (strip-sharded merge) and overrides *n_saved
     // The raw pair list holds one entry per boundary corner (10-15 x more than there are adjacent region pairs) and every round
-    // walks the pairs, so the SET of pairs is built once in a global hash table: by the statistics pass itself (whole GPU, set_in_stats
-    // = 1: unsharded merge) or by the cooperative rounds kernel (strip-sharded merge: the raw lists of all ranks arrive gathered).
+    // walks the pairs, so the SET of pairs is built once in a global hash table: by merge_pair_set_kernel (whole GPU, set_ready = 1:
+    // unsharded merge of a frame-sized image) or by the cooperative rounds kernel itself (images beyond 2^24 pixels, strip-sharded merge).
     unsigned long long* htab; // [1 << hbits] open-addressing set, key = min label << 32 | max label (0 = empty); zeroed by the host
     int hbits;
     int2* uniq;               // [1 << hbits] unique pairs in insertion order
     int32_t* nuniq;           // device: [0] entries of uniq, [1] overflow flag (table full: the rounds use the raw list)
-    int set_in_stats;
+    int set_ready;            // 1: merge_pair_set_kernel ran before the rounds kernels (unsharded merge of a frame-sized image)
     long long npairs_host;    // >= 0: number of valid entries of `pairs` (all-gathered list), overrides *npairs
 };
 
@@ -265,33 +265,6 @@ __device__ __forceinline__ void stats_pass_vec4(const merge_persist_args& A, con
                 if (er[k]) { if (pos < A.pair_cap) A.pairs[pos] = make_int2(lab[k], rn[k]); pos++; }
                 if (ed[k]) { if (pos < A.pair_cap) A.pairs[pos] = make_int2(lab[k], dn[k]); pos++; }
             }
-            if (A.set_in_stats) {                           // the set of pairs, built here by the whole GPU
-                unsigned fresh = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (er[k] && pair_set_insert(A, lab[k], rn[k])) fresh |= 1u << (2 * k);
-                    if (ed[k] && pair_set_insert(A, lab[k], dn[k])) fresh |= 2u << (2 * k);
-                }
-                const int nf = __popc(fresh);
-                if (__any_sync(FULL, nf)) {
-                    int inc2 = nf;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        int v = __shfl_up_sync(FULL, inc2, o);
-                        if (lane >= o) inc2 += v;
-                    }
-                    const int tot2 = __shfl_sync(FULL, inc2, 31);
-                    int upos = 0;
-                    if (lane == 0) upos = atomicAdd(A.nuniq, tot2);
-                    upos = __shfl_sync(FULL, upos, 0) + inc2 - nf;
-                    const int ucap = 1 << A.hbits;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (fresh & (1u << (2 * k))) { if (upos < ucap) A.uniq[upos] = make_int2(lab[k], rn[k]); else A.nuniq[1] = 1; upos++; }
-                        if (fresh & (2u << (2 * k))) { if (upos < ucap) A.uniq[upos] = make_int2(lab[k], dn[k]); else A.nuniq[1] = 1; upos++; }
-                    }
-                }
-            }
         }
     }
 }
@@ -356,18 +329,35 @@ __global__ void __launch_bounds__(MT) merge_stats_kernel(merge_persist_args A)
             unsigned lt = (1u << lane) - 1;
             if (lr > 0) { long long k = pos + __popc(mr & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, lr); }
             if (ld > 0) { long long k = pos + __popc(mr) + __popc(md & lt); if (k < A.pair_cap) A.pairs[k] = make_int2(lab, ld); }
-            if (A.set_in_stats) {
-                const bool fr = lr > 0 && pair_set_insert(A, lab, lr), fd = ld > 0 && pair_set_insert(A, lab, ld);
-                const unsigned ur = __ballot_sync(0xffffffffu, fr), ud = __ballot_sync(0xffffffffu, fd);
-                const int tot2 = __popc(ur) + __popc(ud);
-                if (tot2) {
-                    int upos = 0;
-                    if (lane == 0) upos = atomicAdd(A.nuniq, tot2);
-                    upos = __shfl_sync(0xffffffffu, upos, 0);
-                    const int ucap = 1 << A.hbits;
-                    if (fr) { int k = upos + __popc(ur & lt); if (k < ucap) A.uniq[k] = make_int2(lab, lr); else A.nuniq[1] = 1; }
-                    if (fd) { int k = upos + __popc(ur) + __popc(ud & lt); if (k < ucap) A.uniq[k] = make_int2(lab, ld); else A.nuniq[1] = 1; }
-                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the set of adjacent pairs (frame-sized images)
+// One pass over the raw pair list with the whole GPU: insert into the global hash set, append the new ones to A.uniq.  (Doing
+// this inside the statistics pass put an L2 atomic round trip into the critical path of its warps: 66 -> 89 us per 4K frame;
+// as a kernel of its own the list is spread evenly over the threads and the latency is hidden: profiles/r02_launches_4k.md.)
+__global__ void __launch_bounds__(MT) merge_pair_set_kernel(merge_persist_args A)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gtid = (long long)blockIdx.x * MT + threadIdx.x, nthreads = (long long)gridDim.x * MT;
+    const long long npairs = merge_npairs(A);
+    const int ucap = 1 << A.hbits;
+    for (long long base = gtid - lane; base < npairs; base += nthreads) {          // warp-uniform trip count
+        const long long i = base + lane;
+        int2 pr = make_int2(0, 0);
+        bool fresh = false;
+        if (i < npairs) {
+            pr = A.pairs[i];
+            fresh = pr.x > 0 && pr.y > 0 && pr.x != pr.y && pair_set_insert(A, pr.x, pr.y);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, fresh);
+        if (m) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(A.nuniq, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+            if (fresh) {
+                if (pos < ucap) A.uniq[pos] = pr; else A.nuniq[1] = 1;
             }
         }
     }
@@ -420,7 +410,7 @@ __global__ void __launch_bounds__(ST, 1) merge_rounds_small_kernel(merge_persist
     const int2* __restrict__ pairs = A.pairs;
     long long npairs = merge_npairs(A);
     if (npairs > A.pair_cap) npairs = A.pair_cap;
-    if (A.set_in_stats && A.nuniq[1] == 0) { pairs = A.uniq; npairs = A.nuniq[0]; }
+    if (A.set_ready && A.nuniq[1] == 0) { pairs = A.uniq; npairs = A.nuniq[0]; }
     for (int i = tid; i < nl; i += ST) {
         par[i] = i;
         area[i] = A.t.area[i];
@@ -545,7 +535,7 @@ __global__ void __launch_bounds__(MT) merge_rounds_large_kernel(merge_persist_ar
     const int2* __restrict__ pairs = A.pairs;
 
     // ---- the set of adjacent pairs (every round walks it; the raw list repeats a pair once per boundary corner)
-    if (A.set_in_stats) {
+    if (A.set_ready) {
         if (*((volatile int32_t*)A.nuniq + 1) == 0) { pairs = A.uniq; npairs = *((volatile int32_t*)A.nuniq); }
     } else if (A.htab) {
         const long long slots = 1ll << A.hbits;
@@ -868,16 +858,19 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;                              // CTAs of the streaming kernels (grid-stride)
     auto blocks_for = [&](size_t items) { size_t b = (items + MT - 1) / MT; return (int)(b < 1 ? 1 : (b > (size_t)wide ? (size_t)wide : b)); };
-    // Who builds the set of pairs: the statistics pass for frame-sized images (the single-CTA rounds kernels need it ready; 4K:
-    // merge 0.21 ms), the cooperative rounds kernel itself beyond 2^24 pixels (always the large regime; inserting from the
-    // statistics pass puts an L2 atomic round trip into its warps' critical path: 8192^2 merge 1.02 instead of 0.85 ms).
-    A.set_in_stats = n <= (size_t)SMALL_MAX_PIXELS ? 1 : 0;
-    if (A.set_in_stats) MSG_CUDA(ctx, cudaMemsetAsync(A.htab, 0, hslots * sizeof(unsigned long long), st));
+    // Who builds the set of pairs: a kernel of its own for frame-sized images (the single-CTA rounds kernels need it ready), the
+    // cooperative rounds kernel itself beyond 2^24 pixels (always the large regime: one launch less, same work).
+    A.set_ready = n <= (size_t)SMALL_MAX_PIXELS ? 1 : 0;
+    if (A.set_ready) MSG_CUDA(ctx, cudaMemsetAsync(A.htab, 0, hslots * sizeof(unsigned long long), st));
     merge_init_kernel<<<blocks_for(n < 65536 ? n : 65536), MT, 0, st>>>(A);
     MSG_LAUNCHED(ctx);
     size_t stat_threads = A.vec ? ((n + 127) / 128) * 32 : ((size_t)((w + 31) / 32) * h) * 32;   // one warp per chunk
     merge_stats_kernel<<<blocks_for(stat_threads), MT, 0, st>>>(A);
     MSG_LAUNCHED(ctx);
+    if (A.set_ready) {
+        merge_pair_set_kernel<<<ctx->sm_count * 4, MT, 0, st>>>(A);
+        MSG_LAUNCHED(ctx);
+    }
     const size_t small_smem = (size_t)(SMALL_MAX_LABELS + 1) * 7 * sizeof(uint32_t);
     MSG_TRY(msg_func_smem(ctx, (const void*)merge_rounds_small_kernel<12>, small_smem));
     merge_rounds_small_kernel<12><<<1, ST, small_smem, st>>>(A);
