@@ -6,14 +6,17 @@
 // simultaneously (union by smallest label); phase A = colour fuse, phase B = min-size prune.
 // K2c = PictureService.colorByIndexes (PictureService.java:913-936).
 //
-// Launch sequence of one merge (the label count lives on the device, so both round kernels are always launched and the
-// one whose regime does not apply returns at once):
-//   merge_init_kernel          tables of the n_in labels
-//   merge_stats_kernel         one pass over the pixels: area + colour sums per label, list of adjacent label pairs
-//   merge_rounds_small_kernel  <= 4095 labels (a 1080p / 4K frame): ONE CTA, every table in shared memory, __syncthreads
-//                              between the passes of a round, then the dense renumbering
-//   merge_rounds_large_kernel  more labels: cooperative grid, tables in L2/HBM, grid-wide barriers, same passes
-//   merge_rewrite_kernel       one pass over the pixels: label -> final id
+// Launch sequence of one merge (the label count lives on the device, so every rounds kernel is always launched and the
+// ones whose regime does not apply return at once):
+//   merge_init_kernel             tables of the n_in labels
+//   merge_stats_kernel            one pass over the pixels: area + colour sums per label, raw list of adjacent label pairs
+//   merge_pair_set_kernel         (images of <= 2^24 pixels) the SET of adjacent pairs: global hash table + unique list
+//   merge_rounds_small_kernel<12> <= 4095 labels (a 1080p frame): ONE CTA, every table in shared memory, __syncthreads
+//                                 between the passes of a round, then the dense renumbering
+//   merge_rounds_small_kernel<13> <= 8191 labels (a 4K frame): the same with 13-bit labels, 224 KB of shared memory
+//   merge_rounds_large_kernel     more labels: cooperative grid, tables in L2/HBM, grid-wide barriers, same passes; builds
+//                                 the pair set itself beyond 2^24 pixels and in the strip-sharded merge
+//   merge_rewrite_kernel          one pass over the pixels: label -> final id
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
