@@ -805,8 +805,9 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
 {
     size_t n = (size_t)w * h;
     int cap = (int)n;                                 // worst case: every pixel its own region
-    int blocks_per_sm = 0;
-    MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
+    if (ctx->merge_blocks_per_sm <= 0)       // occupancy of the cooperative kernel: queried once per context, not per launch
+        MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->merge_blocks_per_sm, merge_rounds_large_kernel, MT, 0));
+    const int blocks_per_sm = ctx->merge_blocks_per_sm;
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
     const int grid_max = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
     // CTAs of the cooperative rounds kernel (option "merge_grid" overrides).  Alone, more CTAs are faster (merge stage at 4K /
@@ -1001,8 +1002,9 @@ int k_strip_merge_finish(msg_ctx* ctx, int32_t* d_labels, int w, int rows, long 
                          unsigned long long* d_sum, const int32_t* d_all_pairs, long long n_all_pairs, int min_size, int color_dist,
                          int32_t* d_n_out)
 {
-    int blocks_per_sm = 0;
-    MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds_large_kernel, MT, 0));
+    if (ctx->merge_blocks_per_sm <= 0)       // occupancy of the cooperative kernel: queried once per context, not per launch
+        MSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->merge_blocks_per_sm, merge_rounds_large_kernel, MT, 0));
+    const int blocks_per_sm = ctx->merge_blocks_per_sm;
     if (blocks_per_sm < 1) return msg_fail(ctx, MSG_ECUDA, "merge: cooperative kernel does not fit");
     const int grid_max = ctx->sm_count * (blocks_per_sm < 2 ? blocks_per_sm : 2);
     int grid = ctx->tune.merge_grid > 0 ? ctx->tune.merge_grid : grid_max;

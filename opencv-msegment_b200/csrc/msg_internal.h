@@ -74,6 +74,7 @@ struct msg_ctx {
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is issued once per (kernel, size) and context, not per launch
     struct { const void* func; size_t smem; } attr_cache[64];
     int n_attr;
+    int merge_blocks_per_sm;   // resident CTAs per SM of the cooperative merge kernel (0 = not queried yet)
     cudaStream_t own_stream;
     cudaStream_t stream;
     cudaEvent_t ev[8];
