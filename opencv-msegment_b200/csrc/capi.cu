@@ -63,9 +63,9 @@ struct opt_entry { const char* name; size_t off; int dflt; };
 #define OPT(n, f, d) {n, offsetof(msg_tuning, f), d}
 static const opt_entry g_opts[] = {
     OPT("tile_w", tile_w, 0),           OPT("acc", acc, -1),           OPT("pitch_res", pitch_res, -1),
-    OPT("tma", use_tma, 1),             OPT("no_order", no_order, 0),  OPT("merge_scalar", merge_scalar, 0),
+    OPT("tma", use_tma, 1),             OPT("no_order", no_order, 0),  OPT("merge_scalar", merge_scalar, 0), OPT("merge_strips", merge_strips, 1),
     OPT("merge_small_max", merge_small_max, -1), OPT("merge_grid", merge_grid, 0), OPT("merge_medium_only", merge_medium_only, 0), OPT("no_graph", no_graph, 0), OPT("graph_debug", graph_debug, 0),
-    OPT("ccl_legacy", ccl_legacy, 0),   OPT("gray_compat", gray_compat, 0), OPT("dt_fixed", dt_fixed, 0), OPT("dt_legacy", dt_legacy, 0),
+    OPT("ccl_legacy", ccl_legacy, 0),   OPT("ccl_quad", ccl_quad, 1),   OPT("gray_compat", gray_compat, 0), OPT("dt_fixed", dt_fixed, 0), OPT("dt_legacy", dt_legacy, 0),
     OPT("labels_canonical", labels_canonical, 0),
     OPT("staging", staging, 1),
 };

@@ -464,6 +464,156 @@ __global__ void __launch_bounds__(CT_THREADS) ccl_tile_kernel(const void* __rest
     }
 }
 
+// ---- four pixels per lane (4-connectivity, colour predicates; rows that allow 16-byte / 4-byte aligned vector accesses).
+// ccl_tile_kernel above spends ~160 thread-instructions per pixel (two ballots, a shuffle and the run bookkeeping PER PIXEL).
+// Here one warp owns a whole 128-pixel tile row and a lane owns 4 consecutive pixels: the links between a lane's own pixels are
+// plain register compares, the run structure of the row needs two ballots per ROW -- C = "my first pixel is linked to the lane
+// on my left", T = "my four pixels are linked to each other": the run through my first pixel starts in the highest lane below
+// me whose bit in (C & T) is clear, at that lane's last internal break -- one shuffle.  The vertical rule is the same
+// (need = vb & ~(cl & cl_above & (vb << 1))) on 4-bit masks, with one shuffle for the carry between lanes.  Loads, parent
+// stores and label stores are 16-byte accesses; the root bits of 8 lanes are one bitmap word (__reduce_or_sync).
+// Produces exactly what ccl_tile_kernel<PRED, 4> produces (every tile-local component points at its smallest pixel).
+template <int PRED>
+__device__ __forceinline__ void ct4_load(const void* __restrict__ img, size_t pitch, int gx, int gy, uint32_t (&v)[4])
+{
+    if (PRED == 0) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>((const uint32_t*)img + (size_t)gy * pitch + gx));
+        v[0] = q.x & 0x00FFFFFFu; v[1] = q.y & 0x00FFFFFFu; v[2] = q.z & 0x00FFFFFFu; v[3] = q.w & 0x00FFFFFFu;
+    } else {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>((const uint8_t*)img + (size_t)gy * pitch + 3 * (size_t)gx);
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        v[0] = w0 & 0x00FFFFFFu;
+        v[1] = (w0 >> 24) | ((w1 & 0xFFFFu) << 8);
+        v[2] = (w1 >> 16) | ((w2 & 0xFFu) << 16);
+        v[3] = w2 >> 8;
+    }
+}
+
+template <int PRED>
+__global__ void __launch_bounds__(CT_THREADS) ccl_tile4_kernel(const void* __restrict__ img, size_t pitch, int w, int h, int d,
+                                                               int32_t* __restrict__ L, uint32_t* __restrict__ bitmap, int wp)
+{
+    __shared__ __align__(16) uint32_t s_col[CT_H * CT_W];   // pixels; after the unions: global index of the root at every run start
+    __shared__ __align__(16) int s_lab[CT_H * CT_W];        // union-find parents (tile-local indices)
+    __shared__ unsigned char s_hb[CT_H * 32];               // per lane: the four "linked to my left neighbour" bits
+    constexpr int ROWS_PER_WARP = CT_H / (CT_THREADS / 32); // 2
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_H;
+    const int gx = tx0 + 4 * lane;
+    const uint32_t kd = 0x00FF00FFu - (uint32_t)min(d, 255) * 0x00010001u;
+    const unsigned below = (1u << lane) - 1u;
+    uint32_t vreg[ROWS_PER_WARP][4];
+    unsigned hbr[ROWS_PER_WARP];              // bit j: pixel j is linked to the pixel on its left
+    int st0[ROWS_PER_WARP];                   // tile-local index of the start of the run through my first pixel
+
+    // ---- load + row runs
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int r = wq * ROWS_PER_WARP + rr, gy = ty0 + r;
+        uint32_t (&v)[4] = vreg[rr];
+        if (gx < w && gy < h) ct4_load<PRED>(img, pitch, gx, gy, v);
+        else v[0] = v[1] = v[2] = v[3] = CT_INVALID;
+        reinterpret_cast<uint4*>(s_col)[r * 32 + lane] = make_uint4(v[0], v[1], v[2], v[3]);
+        const uint32_t left = __shfl_up_sync(0xffffffffu, v[3], 1);
+        // the left neighbour of a real pixel is a real pixel, except for the first column of the tile (no link inside the tile)
+        unsigned hb = (ct_fg<PRED>(v[0]) && lane > 0 && ct_conn_px<PRED>(v[0], left, kd)) ? 1u : 0u;
+        hb |= (ct_fg<PRED>(v[1]) && ct_conn_px<PRED>(v[1], v[0], kd)) ? 2u : 0u;
+        hb |= (ct_fg<PRED>(v[2]) && ct_conn_px<PRED>(v[2], v[1], kd)) ? 4u : 0u;
+        hb |= (ct_fg<PRED>(v[3]) && ct_conn_px<PRED>(v[3], v[2], kd)) ? 8u : 0u;
+        hbr[rr] = hb;
+        s_hb[r * 32 + lane] = (unsigned char)hb;
+        const unsigned C = __ballot_sync(0xffffffffu, hb & 1u);
+        const unsigned T = __ballot_sync(0xffffffffu, (hb & 0xEu) == 0xEu);
+        // start of the run through my last pixel, as an offset inside my four: 3, 2, 1, or 0 when the four are linked
+        const int lb = !(hb & 8u) ? 3 : (!(hb & 4u) ? 2 : (!(hb & 2u) ? 1 : 0));
+        const unsigned stop = ~(C & T) & below;                      // lanes below me where the run cannot pass through
+        const int sl = (hb & 1u) ? 31 - __clz(stop) : lane;          // lane 0 never links left, so stop != 0 whenever bit 0 of hb is set
+        const int slb = __shfl_sync(0xffffffffu, lb, sl);
+        const int base = r * CT_W;
+        const int s0 = (hb & 1u) ? base + 4 * sl + slb : base + 4 * lane;
+        st0[rr] = s0;
+        int4 par;
+        par.x = s0;
+        par.y = (hb & 2u) ? par.x : base + 4 * lane + 1;
+        par.z = (hb & 4u) ? par.y : base + 4 * lane + 2;
+        par.w = (hb & 8u) ? par.z : base + 4 * lane + 3;
+        if (!ct_fg<PRED>(v[0])) par.x = -1;
+        if (!ct_fg<PRED>(v[1])) par.y = -1;
+        if (!ct_fg<PRED>(v[2])) par.z = -1;
+        if (!ct_fg<PRED>(v[3])) par.w = -1;
+        reinterpret_cast<int4*>(s_lab)[r * 32 + lane] = par;
+    }
+    __syncthreads();
+
+    // ---- unions with the row above, inside the tile.  (All rows at once: the runs of a region that crosses the tile may link
+    //      into a chain that later finds walk -- ncu: 23 % of the instructions are the find loop at 1.9 active lanes -- but
+    //      closing the seams between the warps' row pairs as a binary tree, three more block barriers, measured SLOWER:
+    //      297 -> 328 us at 8192^2, profiles/r02_ccl_quad.md.)
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int r = wq * ROWS_PER_WARP + rr;
+        if (r == 0) continue;                 // the tile's top row unites with the tile above in ccl_border_kernel
+        uint32_t u[4];
+        unsigned hbu;
+        if (rr > 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) u[j] = vreg[rr > 0 ? rr - 1 : 0][j];
+            hbu = hbr[rr > 0 ? rr - 1 : 0];
+        } else {
+            const uint4 q = reinterpret_cast<const uint4*>(s_col)[(r - 1) * 32 + lane];
+            u[0] = q.x; u[1] = q.y; u[2] = q.z; u[3] = q.w;
+            hbu = s_hb[(r - 1) * 32 + lane];
+        }
+        unsigned vb = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)           // the pixel above a real pixel is a real pixel (r >= 1)
+            vb |= (ct_fg<PRED>(vreg[rr][j]) && ct_conn_px<PRED>(vreg[rr][j], u[j], kd)) ? (1u << j) : 0u;
+        const unsigned carry = __shfl_up_sync(0xffffffffu, vb >> 3, 1) & (lane > 0 ? 1u : 0u);
+        unsigned need = vb & ~(hbr[rr] & hbu & ((vb << 1) | carry)) & 0xFu;
+        const int p0 = r * CT_W + 4 * lane;
+        while (need) {
+            const int j = __ffs(need) - 1;
+            need &= need - 1;
+            uf_union_s(s_lab, p0 + j, p0 + j - CT_W);
+        }
+    }
+    __syncthreads();
+
+    // ---- per run: find the root, leave its GLOBAL index at the run start (s_col is free now), flag tile-local roots
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int r = wq * ROWS_PER_WARP + rr, gy = ty0 + r;
+        const int p0 = r * CT_W + 4 * lane;
+        unsigned roots = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (ct_fg<PRED>(vreg[rr][j]) && !((hbr[rr] >> j) & 1u)) {               // I start a run
+                const int root = uf_find_s(s_lab, p0 + j);
+                if (root == p0 + j) roots |= 1u << j;
+                s_col[p0 + j] = (uint32_t)((ty0 + root / CT_W) * w + tx0 + (root % CT_W));
+            }
+        }
+        const unsigned word = __reduce_or_sync(0xFFu << (lane & 24), roots << (4 * (lane & 7)));
+        if ((lane & 7) == 0 && gy < h && tx0 + 4 * lane < w) bitmap[(size_t)gy * wp + (tx0 >> 5) + (lane >> 3)] = word;
+    }
+    __syncthreads();
+
+    // ---- per pixel: the label of my run
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+        const int r = wq * ROWS_PER_WARP + rr, gy = ty0 + r;
+        if (gy >= h || gx >= w) continue;
+        const int p0 = r * CT_W + 4 * lane;
+        const unsigned hb = hbr[rr];
+        int4 o;
+        o.x = ct_fg<PRED>(vreg[rr][0]) ? (int32_t)s_col[st0[rr]] : -1;
+        o.y = (hb & 2u) ? o.x : (ct_fg<PRED>(vreg[rr][1]) ? (int32_t)s_col[p0 + 1] : -1);
+        o.z = (hb & 4u) ? o.y : (ct_fg<PRED>(vreg[rr][2]) ? (int32_t)s_col[p0 + 2] : -1);
+        o.w = (hb & 8u) ? o.z : (ct_fg<PRED>(vreg[rr][3]) ? (int32_t)s_col[p0 + 3] : -1);
+        *reinterpret_cast<int4*>(L + (size_t)gy * w + gx) = o;
+    }
+}
+
 // unions across tile borders.  Threads [0, n_hb): pixels of the top rows of the tiles (y = k * CT_H, k >= 1), the per-pixel
 // rules of ccl_merge_kernel with the row above; threads [n_hb, n_hb + n_vb): pixels of the left columns of the tiles
 // (x = j * CT_W, j >= 1) against the column to their left (and its diagonals for 8-connectivity).
@@ -474,12 +624,20 @@ __global__ void __launch_bounds__(CT_THREADS) ccl_border_kernel(const void* __re
     const long long idx = (long long)blockIdx.x * CT_THREADS + threadIdx.x;
     const uint32_t none = PRED == 1 ? 0u : CT_INVALID;
     auto get = [&](int x, int y) -> uint32_t { return (x >= 0 && x < w && y >= 0 && y < h) ? ct_load<PRED>(img, pitch, x, y) : none; };
-    if (idx < n_hb) {
-        const int x = (int)(idx % w), y = (int)(idx / w + 1) * CT_H;
-        const uint32_t v = get(x, y);
+    // top rows: the lane on my left holds the pixel on my left (and the one above it) unless I am the first lane of the warp or
+    // the first pixel of a row, so the redundancy test costs two shuffles instead of two more (byte-wise, for BGR) loads
+    const bool top = idx < n_hb;
+    int x = 0, y = 0;
+    uint32_t v = none, u = none;
+    if (top) {
+        x = (int)(idx % w); y = (int)(idx / w + 1) * CT_H;
+        v = get(x, y); u = get(x, y - 1);
+    }
+    uint32_t lf = __shfl_up_sync(0xffffffffu, v, 1), ul = __shfl_up_sync(0xffffffffu, u, 1);
+    if (top) {
         if (!ct_fg<PRED>(v)) return;
+        if ((threadIdx.x & 31) == 0 || x == 0) { lf = get(x - 1, y); ul = get(x - 1, y - 1); }
         const int p = y * w + x;
-        const uint32_t u = get(x, y - 1), lf = get(x - 1, y), ul = get(x - 1, y - 1), ur = get(x + 1, y - 1);
         if (PRED != 1) {
             if (ct_conn<PRED>(v, u, d)) {
                 const bool redundant = ct_conn<PRED>(v, lf, d) && ct_conn<PRED>(u, ul, d) && ct_conn<PRED>(lf, ul, d);
@@ -487,13 +645,13 @@ __global__ void __launch_bounds__(CT_THREADS) ccl_border_kernel(const void* __re
             }
             if (CONN == 8) {
                 if (ct_conn<PRED>(v, ul, d)) uf_union(L, p, p - w - 1);
-                if (ct_conn<PRED>(v, ur, d)) uf_union(L, p, p - w + 1);
+                if (ct_conn<PRED>(v, get(x + 1, y - 1), d)) uf_union(L, p, p - w + 1);
             }
         } else {
             if (u) {
                 if (!(lf && ul)) uf_union(L, p, p - w);
             } else if (CONN == 8) {
-                const uint32_t rt = get(x + 1, y);
+                const uint32_t rt = get(x + 1, y), ur = get(x + 1, y - 1);
                 if (ul && !lf) uf_union(L, p, p - w - 1);
                 if (ur && !rt) uf_union(L, p, p - w + 1);
             }
@@ -1102,7 +1260,13 @@ static int ccl_tiles(msg_ctx* ctx, const void* img, size_t pitch, int w, int h, 
     dim3 grid((w + CT_W - 1) / CT_W, (h + CT_H - 1) / CT_H);
     const long long n_hb = (long long)(grid.y - 1) * w, n_vb = (long long)(grid.x - 1) * h;
     const unsigned bblocks = (unsigned)((n_hb + n_vb + CT_THREADS - 1) / CT_THREADS);
-    if (conn == 8) ccl_tile_kernel<PRED, 8><<<grid, CT_THREADS, 0, st>>>(img, pitch, w, h, d, L, ws.bitmap, ws.wp);
+    // four pixels per lane when the rows allow aligned vector accesses (width a multiple of 4; plane: 16-byte aligned rows,
+    // BGR: 4-byte aligned rows); option ccl_quad = 0 keeps the one-pixel-per-lane kernel (A/B hook)
+    bool quad = PRED != 1 && conn == 4 && ctx->tune.ccl_quad && w % 4 == 0 && (reinterpret_cast<uintptr_t>(L) & 15) == 0;
+    if (PRED == 0) quad = quad && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0;
+    if (PRED == 2) quad = quad && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+    if (quad) ccl_tile4_kernel<PRED == 1 ? 0 : PRED><<<grid, CT_THREADS, 0, st>>>(img, pitch, w, h, d, L, ws.bitmap, ws.wp);
+    else if (conn == 8) ccl_tile_kernel<PRED, 8><<<grid, CT_THREADS, 0, st>>>(img, pitch, w, h, d, L, ws.bitmap, ws.wp);
     else ccl_tile_kernel<PRED, 4><<<grid, CT_THREADS, 0, st>>>(img, pitch, w, h, d, L, ws.bitmap, ws.wp);
     MSG_LAUNCHED(ctx);
     if (bblocks) {

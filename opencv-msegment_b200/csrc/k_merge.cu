@@ -74,7 +74,7 @@ struct merge_persist_args {
     int32_t* npairs;          // device counter
     long long pair_cap;
     int min_size, color_dist;
-    int vec;                  // 1: w % 4 == 0 and labels 16-byte aligned -> 16-byte loads in the statistics pass
+    int vec;                  // w % 4 == 0 and labels 16-byte aligned -> 16-byte loads in the statistics pass: 2 = column strips, 1 = row chunks
     int small_max;            // labels up to which the single-CTA rounds kernel with the shared-memory pair set is used
     int medium_max;           // labels up to which the single-CTA rounds kernel with the global pair set is used (0 / 0: large path)
     int nin_host;             // >= 0: the label count is known on the host (strip-sharded merge) and overrides *n_saved
@@ -230,15 +230,15 @@ __device__ __forceinline__ void stats_pass_vec4(const merge_persist_args& A, con
         unsigned heads = __ballot_sync(FULL, head);
         unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
         int seg_end = above ? lane + __ffs(above) - 1 : 31;
+        // a chunk is 128 pixels: every sum of a segment stays below 2^16 (128 * 255), so two 16-bit lanes share a register
+        unsigned bg = b | (g << 16), rc = r | (cnt << 16);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned c2 = __shfl_down_sync(FULL, cnt, o);
-            unsigned b2 = __shfl_down_sync(FULL, b, o);
-            unsigned g2 = __shfl_down_sync(FULL, g, o);
-            unsigned r2 = __shfl_down_sync(FULL, r, o);
-            if (lane + o <= seg_end) { cnt += c2; b += b2; g += g2; r += r2; }
+            const unsigned bg2 = __shfl_down_sync(FULL, bg, o);
+            const unsigned rc2 = __shfl_down_sync(FULL, rc, o);
+            if (lane + o <= seg_end) { bg += bg2; rc += rc2; }
         }
-        if (head && cur > 0) stats_flush(t, cur, cnt, b, g, r);
+        if (head && cur > 0) stats_flush(t, cur, rc >> 16, bg & 0xFFFFu, bg >> 16, rc & 0xFFFFu);
         // ---- adjacency pairs
         int pl = __shfl_up_sync(FULL, lab[3], 1), pd = __shfl_up_sync(FULL, dn[3], 1);   // pixel left of my first one
         if (lane == 0) { pl = 0; pd = 0; }
@@ -273,6 +273,148 @@ __device__ __forceinline__ void stats_pass_vec4(const merge_persist_args& A, con
 }
 
 
+// Statistics + adjacency pass, column strips (requires w % 4 == 0 and 16-byte aligned label rows).  A warp walks DOWN a strip
+// of 128 columns (4 consecutive pixels per lane) for 16..64 rows: the labels of the row above and below are the registers of
+// the previous / next iteration (one label load and one colour load per row instead of three and one, and the next row is
+// in flight while this one is processed), and the sums stay in the lane: two register-resident entries {label, count,
+// B, G, R} per lane take the pixels of the lane's four columns row after row and go to the tables (4 atomics) only when a
+// third label shows up or the strip ends -- no segmented shuffle reduction, and a region costs a few atomics per lane and
+// strip instead of a few per 128-pixel chunk of every row.  All sums are integer: the order of the additions is free.
+// 16-bit lanes: an entry sees at most 64 rows x 4 pixels x 255 = 65 280 < 2^16 per channel.
+// Adjacent-pair list: the rules of stats_pass_vec4 (a right pair is skipped when the row above holds the same pair, a down
+// pair when the pixel to the left holds the same pair; the first pixel of a strip row never skips).
+constexpr int SS_MIN_ROWS = 16, SS_MAX_ROWS = 64;
+struct stat_entry { int lab; unsigned br, gc; };           // br = sum B | sum R << 16, gc = sum G | count << 16
+
+__device__ __forceinline__ void stat_entry_flush(const merge_tables& t, const stat_entry& e)
+{
+    if (e.lab > 0 && e.gc) stats_flush(t, e.lab, e.gc >> 16, e.br & 0xFFFFu, e.gc & 0xFFFFu, e.br >> 16);
+}
+
+// The raw pair list is ONE array with ONE counter: an atomicAdd per warp and row on that counter is a same-address atomic every
+// 128 pixels -- ~1 ns each, serialised in one L2 slice: 59 k of them per 4K frame, 476 k at 8192^2 were the duration of the
+// kernel (57 us / 0.5 ms) whatever else it did.  A warp therefore collects its pairs in shared memory and claims list space
+// once per SS_PAIR_BUF pairs (a row adds at most 32 lanes x 8 = 256).
+constexpr int SS_PAIR_BUF = 256;
+
+__device__ __forceinline__ void stat_pairs_flush(const merge_persist_args& A, const int2* buf, int nbuf, int lane)
+{
+    if (nbuf == 0) return;                                                        // warp-uniform
+    long long base = 0;
+    if (lane == 0) base = (long long)atomicAdd(A.npairs, nbuf);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = lane; i < nbuf; i += 32)
+        if (base + i < A.pair_cap) A.pairs[base + i] = buf[i];
+    __syncwarp();
+}
+
+__device__ __forceinline__ void stats_pass_strips(const merge_persist_args& A, const merge_tables& t, int nin, int lane,
+                                                  long long gwarp, long long nwarps, int2* buf)
+{
+    int nbuf = 0;
+    const int w = A.w, h = A.h;
+    const int sx = (w + 127) / 128;
+    const long long per = ((long long)h * sx + nwarps - 1) / nwarps;              // rows per unit: about one unit per warp
+    const int ru = (int)(per < SS_MIN_ROWS ? SS_MIN_ROWS : (per > SS_MAX_ROWS ? SS_MAX_ROWS : per));
+    const long long nunits = (long long)sx * ((h + ru - 1) / ru);
+    const unsigned FULL = 0xffffffffu;
+    const unsigned unin = (unsigned)nin;
+    auto clean = [&](int v) { return (unsigned)v > unin ? 0 : v; };             // negative or beyond the table: background
+    for (long long u = gwarp; u < nunits; u += nwarps) {
+        const int x = (int)(u % sx) * 128 + lane * 4;
+        const int y0 = (int)(u / sx) * ru, y1 = min(h, y0 + ru);
+        const bool in = x < w;                                                    // w % 4 == 0: all four pixels or none
+        const bool has_right = in && x + 4 < w;
+        const bool edge = lane == 31 && has_right;                                // my right neighbour is in the next strip
+        const int32_t* lrow = A.labels + (size_t)y0 * w + x;
+        int up[5] = {0, 0, 0, 0, 0};                                              // row above: my four columns + my right neighbour's
+        if (y0 > 0 && in) {
+            const int4 U4 = *reinterpret_cast<const int4*>(lrow - w);
+            up[0] = clean(U4.x); up[1] = clean(U4.y); up[2] = clean(U4.z); up[3] = clean(U4.w);
+        }
+        up[4] = __shfl_down_sync(FULL, up[0], 1);
+        if (edge) up[4] = y0 > 0 ? clean(lrow[4 - w]) : 0;
+        if (!has_right) up[4] = 0;
+        int lab[4] = {0, 0, 0, 0};
+        if (in) {
+            const int4 L4 = *reinterpret_cast<const int4*>(lrow);
+            lab[0] = clean(L4.x); lab[1] = clean(L4.y); lab[2] = clean(L4.z); lab[3] = clean(L4.w);
+        }
+        stat_entry e0 = {0, 0u, 0u}, e1 = {0, 0u, 0u};
+        for (int y = y0; y < y1; y++, lrow += w) {
+            int dn[4] = {0, 0, 0, 0};
+            uint4 C4 = make_uint4(0, 0, 0, 0);
+            int nx = 0;
+            if (in) {
+                if (y + 1 < h) {
+                    const int4 D4 = *reinterpret_cast<const int4*>(lrow + w);
+                    dn[0] = clean(D4.x); dn[1] = clean(D4.y); dn[2] = clean(D4.z); dn[3] = clean(D4.w);
+                }
+                C4 = __ldg(reinterpret_cast<const uint4*>(A.plane + (size_t)y * A.pitch + x));
+                if (edge) nx = clean(lrow[4]);
+            }
+            {
+                const int t0 = __shfl_down_sync(FULL, lab[0], 1);
+                if (!edge) nx = has_right ? t0 : 0;
+            }
+            // ---- sums
+            const uint32_t col[4] = {C4.x, C4.y, C4.z, C4.w};
+            const bool uni = lab[0] == lab[1] && lab[1] == lab[2] && lab[2] == lab[3];
+            if (uni && lab[0] == e1.lab && lab[0] != e0.lab) { const stat_entry s = e0; e0 = e1; e1 = s; }
+            if (uni && lab[0] == e0.lab) {
+                e0.br += (col[0] & 0x00FF00FFu) + (col[1] & 0x00FF00FFu) + (col[2] & 0x00FF00FFu) + (col[3] & 0x00FF00FFu);
+                e0.gc += ((col[0] >> 8) & 0xFFu) + ((col[1] >> 8) & 0xFFu) + ((col[2] >> 8) & 0xFFu) + ((col[3] >> 8) & 0xFFu) + 0x40000u;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned abr = col[k] & 0x00FF00FFu, agc = ((col[k] >> 8) & 0xFFu) + 0x10000u;
+                    if (lab[k] == e0.lab) { e0.br += abr; e0.gc += agc; }
+                    else if (lab[k] == e1.lab) { e1.br += abr; e1.gc += agc; }
+                    else { stat_entry_flush(t, e1); e1.lab = lab[k]; e1.br = abr; e1.gc = agc; }
+                }
+            }
+            // ---- adjacency pairs
+            int pl = __shfl_up_sync(FULL, lab[3], 1), pd = __shfl_up_sync(FULL, dn[3], 1);   // pixel left of my first one
+            if (lane == 0) { pl = 0; pd = 0; }
+            const int rn[4] = {lab[1], lab[2], lab[3], nx};
+            bool er[4], ed[4];
+            int mine = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                er[k] = lab[k] > 0 && rn[k] > 0 && rn[k] != lab[k] && !(up[k] == lab[k] && up[k + 1] == rn[k]);
+                const int ll = k ? lab[k - 1] : pl, ld = k ? dn[k - 1] : pd;
+                ed[k] = lab[k] > 0 && dn[k] > 0 && dn[k] != lab[k] && !(ll == lab[k] && ld == dn[k]);
+                mine += (int)er[k] + (int)ed[k];
+            }
+            if (__any_sync(FULL, mine)) {
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int tot = __shfl_sync(FULL, incl, 31);                      // <= 256 = SS_PAIR_BUF
+                if (nbuf + tot > SS_PAIR_BUF) { stat_pairs_flush(A, buf, nbuf, lane); nbuf = 0; }
+                int pos = nbuf + incl - mine;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (er[k]) buf[pos++] = make_int2(lab[k], rn[k]);
+                    if (ed[k]) buf[pos++] = make_int2(lab[k], dn[k]);
+                }
+                nbuf += tot;
+                __syncwarp();
+            }
+            // ---- next row
+#pragma unroll
+            for (int k = 0; k < 4; k++) { up[k] = lab[k]; lab[k] = dn[k]; }
+            up[4] = nx;
+        }
+        stat_entry_flush(t, e0);
+        stat_entry_flush(t, e1);
+    }
+    stat_pairs_flush(A, buf, nbuf, lane);
+}
+
 __global__ void __launch_bounds__(MT) merge_stats_kernel(merge_persist_args A)
 {
     const int lane = threadIdx.x & 31;
@@ -282,6 +424,11 @@ __global__ void __launch_bounds__(MT) merge_stats_kernel(merge_persist_args A)
     const int nin = merge_nin(A);
     const int w = A.w, h = A.h;
     const merge_tables t = A.t;
+    if (A.vec == 2) {
+        __shared__ int2 s_pairs[MT / 32][SS_PAIR_BUF];
+        stats_pass_strips(A, t, nin, lane, gwarp, nwarps, s_pairs[threadIdx.x >> 5]);
+        return;
+    }
     if (A.vec) { stats_pass_vec4(A, t, nin, lane, gwarp, nwarps); return; }
     const int cpr = (w + 31) / 32;                      // 32-pixel chunks per row
     const long long nchunks = (long long)cpr * h;
@@ -850,7 +997,7 @@ static int merge_launch(msg_ctx* ctx, const uint32_t* d_plane, int pitch, int32_
     A.n_out = d_n_out ? d_n_out : ctx->d_counters + 11;
     A.min_size = min_size; A.color_dist = color_dist;
     A.nin_host = -1; A.npairs_host = -1;
-    A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !ctx->tune.merge_scalar) ? 1 : 0;
+    A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !ctx->tune.merge_scalar) ? (ctx->tune.merge_strips ? 2 : 1) : 0;
     // test hooks: merge_small_max = v caps both single-CTA regimes (0 forces the cooperative path), merge_medium_only = 1 sends
     // every image of <= 8191 labels through the global-pair-set kernel
     A.small_max = ctx->tune.merge_small_max >= 0 ? ctx->tune.merge_small_max : SMALL_MAX_LABELS;
@@ -980,7 +1127,7 @@ int k_strip_merge_stats(msg_ctx* ctx, const uint32_t* d_plane, int pitch, const 
     A.plane = d_plane; A.pitch = pitch; A.labels = const_cast<int32_t*>(d_labels); A.w = w; A.h = rows;
     A.cap = n_total; A.nin_host = n_total; A.npairs_host = -1;
     A.n_saved = ctx->d_counters + 14;
-    A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !ctx->tune.merge_scalar) ? 1 : 0;
+    A.vec = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_labels) & 15) == 0 && !ctx->tune.merge_scalar) ? (ctx->tune.merge_strips ? 2 : 1) : 0;
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t)w * rows;
     const int wide = ctx->sm_count * 8;

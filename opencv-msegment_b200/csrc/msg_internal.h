@@ -51,11 +51,13 @@ struct msg_tuning {
     int use_tma;           // 1
     int no_order;          // 0
     int merge_scalar;      // 0
+    int merge_strips;      // 1 = statistics pass walks column strips with register-resident sums (0: row chunks + segmented shuffle reduction, A/B hook)
     int merge_small_max;   // -1 = compiled default
     int merge_medium_only; // test hook: 1 = images of <= 8191 labels use the single-CTA kernel with the global pair set
     int merge_grid;        // 0 = automatic, else CTAs of the cooperative large-path rounds kernel
     int no_graph, graph_debug;
     int ccl_legacy;        // 1 = row-run union-find of round 1 instead of the tile-local one
+    int ccl_quad;          // 1 = the tile kernel with four pixels per lane where the rows allow it (0: one pixel per lane, A/B hook)
     int gray_compat;       // 0 = OpenCV 4.x 15-bit BGR2GRAY coefficients, 1 = OpenCV 3.4.2 14-bit ones
     int dt_legacy;         // 1 = the first wavefront kernel of the float distance transform (dt_wave_kernel) instead of dt_wave2_kernel
     int dt_fixed;          // 0 = IPP float chamfer arithmetic (cv2 4.13 build), 1 = OpenCV's own 16.16 fixed-point fallback
