@@ -86,6 +86,10 @@ MSG_API int msg_synchronize(msg_ctx* ctx);
  *   "dt_legacy"       1: the first wavefront kernel of the float distance transform (A/B hook)
  *   "staging"         1 (default): pageable caller buffers are staged through the context's pinned ring; 0: handed to
  *                     cudaMemcpyAsync as they are (driver staging, serialises the asynchronous path)
+ *   "ccl_quad"        1 (default): the labelling's tile kernel handles four pixels per lane where the rows allow aligned vector
+ *                     accesses (width a multiple of 4); 0: one pixel per lane everywhere (A/B hook, same labels)
+ *   "merge_strips"    1 (default): the merge's statistics pass walks column strips with register-resident sums; 0: row chunks
+ *                     with a segmented shuffle reduction (A/B hook, same tables)
  *   "merge_small_max", "merge_medium_only", "merge_grid", "tile_w", "acc", "pitch_res", "tma", "no_order", "merge_scalar", "no_graph", "ccl_legacy":
  *                     tuning / test hooks */
 MSG_API int msg_set_option(msg_ctx* ctx, const char* name, int value);

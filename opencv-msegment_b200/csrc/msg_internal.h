@@ -42,7 +42,7 @@ struct msg_ovf_item {    // mean-shift item that left its staged tile; finished 
 };
 
 // Tuning / experiment switches.  Read from the environment ONCE in msg_create (MSG_TILE_W, MSG_ACC, MSG_PITCH_RES, MSG_TMA,
-// MSG_NO_ORDER, MSG_MERGE_SCALAR, MSG_MERGE_SMALL_MAX, MSG_NO_GRAPH, MSG_GRAPH_DEBUG, MSG_CCL_LEGACY) and changeable per context
+// MSG_NO_ORDER, MSG_MERGE_SCALAR, MSG_MERGE_STRIPS, MSG_MERGE_SMALL_MAX, MSG_NO_GRAPH, MSG_GRAPH_DEBUG, MSG_CCL_LEGACY, MSG_CCL_QUAD) and changeable per context
 // with msg_set_option; nothing on the launch path calls getenv.
 struct msg_tuning {
     int tile_w;            // 0 = automatic, else 32 | 64
